@@ -1,0 +1,46 @@
+# Top-level build: libeuler_gpu.so (CUDA, sm_100a), the host C program, the oracle.
+#   make            -> everything that can be built here (nvcc cross-compiles without a GPU)
+#   make gpu        -> euler_b200/lib/libeuler_gpu.so
+#   make host       -> euler_b200/lib/libeuler_host.so + bin/euler-gpu
+#   make oracle     -> oracle/liboracle.so (+ oracle/_ref when /root/reference is present)
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CC       ?= gcc
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false: bit-exact parity with the reference's non-contracted fp32/fp64 arithmetic
+NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xcompiler -Wall \
+            -Xptxas -warn-spills --expt-relaxed-constexpr --expt-extended-lambda
+CSRC     := euler_b200/csrc
+LIBDIR   := euler_b200/lib
+OBJDIR   := build/obj
+CU_SRCS  := $(CSRC)/api.cu $(CSRC)/grid_kernels.cu $(CSRC)/marker_kernels.cu \
+            $(CSRC)/pcg_kernels.cu $(CSRC)/wavefront.cu
+CU_OBJS  := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
+HDRS     := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/euler_gpu.h
+HOST     := euler_b200/host
+
+.PHONY: all gpu host oracle clean
+all: gpu host oracle
+
+gpu: $(LIBDIR)/libeuler_gpu.so
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+$(LIBDIR)/libeuler_gpu.so: $(CU_OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^ -ldl
+
+host: $(LIBDIR)/libeuler_host.so bin/euler-gpu
+$(LIBDIR)/libeuler_host.so: $(HOST)/scenario.c $(HOST)/scenario.h
+	@mkdir -p $(LIBDIR)
+	$(CC) -std=gnu99 -O2 -ffp-contract=off -Wall -Wextra -fPIC -shared $< -lm -o $@
+bin/euler-gpu: $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c $(HOST)/scenario.h $(HOST)/render.h include/euler_gpu.h
+	@mkdir -p bin
+	$(CC) -std=gnu99 -O2 -ffp-contract=off -Wall -Wextra -Iinclude $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c \
+	  -ldl -lm -o $@
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf build bin $(LIBDIR)/*.so
+	$(MAKE) -C oracle clean

@@ -1,0 +1,553 @@
+// euler_b200/csrc/api.cu — the C-ABI of libeuler_gpu.so (include/euler_gpu.h): handle,
+// device memory, state access and the host-side drivers of sim_step() / project()
+// (reference main.c:843-900, 709-806).  No torch, no CPU fallback: every stage is a CUDA
+// kernel from grid_kernels.cu / marker_kernels.cu / pcg_kernels.cu / wavefront.cu.
+#include "../../include/euler_gpu.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "kernels.h"
+
+using namespace euler;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(EULER_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                 \
+  } while (0)
+
+}  // namespace
+
+struct euler_gpu {
+  Ctx c;
+  euler_params prm;
+  int nx, ny;
+  bool own_stream;
+  std::vector<void*> allocs;     // raw cudaMalloc pointers
+  DevScalars* host_sc;           // pinned mirror
+  size_t device_bytes;
+  bool max_valid;                // sc.max_*_bits describe the current u, v
+  // stats
+  uint64_t frames, substeps, solves, solves_skipped, pcg_iterations;
+  int last_iterations;
+  double last_residual;
+  float last_dt;
+  bool profiling;
+  cudaEvent_t ev[4];
+  double ms_markers, ms_grid, ms_project;
+};
+
+namespace {
+
+template <class T>
+int alloc_plane(euler_gpu* h, T** out) {
+  const Grid& g = h->c.g;
+  const size_t rows = (size_t)g.ny + 2 * GUARD_ROWS;
+  const size_t bytes = rows * g.pitch * sizeof(T);
+  void* raw = nullptr;
+  CU(cudaMalloc(&raw, bytes));
+  CU(cudaMemsetAsync(raw, 0, bytes, h->c.stream));
+  h->allocs.push_back(raw);
+  h->device_bytes += bytes;
+  *out = reinterpret_cast<T*>(raw) + (size_t)GUARD_ROWS * g.pitch;
+  return 0;
+}
+
+template <class T>
+int alloc_array(euler_gpu* h, T** out, size_t n) {
+  void* raw = nullptr;
+  const size_t bytes = (n ? n : 1) * sizeof(T);
+  CU(cudaMalloc(&raw, bytes));
+  CU(cudaMemsetAsync(raw, 0, bytes, h->c.stream));
+  h->allocs.push_back(raw);
+  h->device_bytes += bytes;
+  *out = reinterpret_cast<T*>(raw);
+  return 0;
+}
+
+int pull_scalars(euler_gpu* h) {
+  CU(cudaMemcpyAsync(h->host_sc, h->c.sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->c.stream));
+  CU(cudaStreamSynchronize(h->c.stream));
+  return 0;
+}
+
+struct FieldInfo { void* ptr; size_t elem; };
+
+FieldInfo field_info(euler_gpu* h, int f) {
+  Ctx& c = h->c;
+  switch (f) {
+    case EULER_F_U: return {c.u, 4};
+    case EULER_F_V: return {c.v, 4};
+    case EULER_F_UTMP: return {c.utmp, 4};
+    case EULER_F_VTMP: return {c.vtmp, 4};
+    case EULER_F_SOLID: return {c.solid, 1};
+    case EULER_F_SOURCE: return {c.source, 1};
+    case EULER_F_SINK: return {c.sink, 1};
+    case EULER_F_COUNT: return {c.count, 1};
+    case EULER_F_PREV_COUNT: return {c.prev_count, 1};
+    case EULER_F_PRECON: return {c.precon, 8};
+    case EULER_F_Q: return {c.q, 8};
+    case EULER_F_ADIAG: return {c.adiag, 1};
+    case EULER_F_P: return {c.p, 8};
+    case EULER_F_R: return {c.r, 8};
+    case EULER_F_Z: return {c.z, 8};
+    case EULER_F_S: return {c.s, 8};
+    default: return {nullptr, 0};
+  }
+}
+
+int upload_plane(euler_gpu* h, void* dst, const void* src, size_t elem) {
+  const Grid& g = h->c.g;
+  CU(cudaMemcpy2DAsync(dst, g.pitch * elem, src, (size_t)g.nx * elem, (size_t)g.nx * elem, g.ny,
+                       cudaMemcpyHostToDevice, h->c.stream));
+  return 0;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(EULER_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+void prof_mark(euler_gpu* h, int i) {
+  if (h->profiling) cudaEventRecord(h->ev[i], h->c.stream);
+}
+
+// ---- project(), main.c:709-806 ------------------------------------------------------
+
+void enqueue_precon_apply(euler_gpu* h, bool init) {
+  if (h->prm.precon == EULER_PRECON_REDBLACK) launch_rb_apply(h->c, init);
+  else launch_ic0_apply(h->c, init);
+}
+
+void enqueue_iteration(euler_gpu* h) {
+  launch_apply_a(h->c, true);
+  launch_axpy(h->c, h->prm.tol);
+  enqueue_precon_apply(h, false);
+  launch_update_search(h->c);
+}
+
+int run_project(euler_gpu* h, float dt) {
+  Ctx& c = h->c;
+  launch_build_rhs(c, dt);
+  int rc = pull_scalars(h);
+  if (rc) return rc;
+  h->last_iterations = 0;
+  if (!h->host_sc->nonzero_rhs) {
+    h->solves_skipped++;                                    // all_zero(r), main.c:742
+  } else {
+    h->solves++;
+    launch_pcg_reset(c);
+    if (h->prm.precon == EULER_PRECON_REDBLACK) launch_rb_build(c);
+    else launch_ic0_build(c);
+    enqueue_precon_apply(h, true);                          // z = M^-1 r, sigma = z.r  (:744-748)
+    launch_copy_search(c);                                  // s = z                    (:746)
+    int remaining = h->prm.max_iterations;
+    const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
+    while (remaining > 0) {
+      const int chunk = remaining < every ? remaining : every;
+      for (int i = 0; i < chunk; ++i) enqueue_iteration(h);
+      remaining -= chunk;
+      rc = pull_scalars(h);
+      if (rc) return rc;
+      if (h->host_sc->done) break;
+    }
+    h->last_iterations = h->host_sc->iters;
+    h->last_residual = h->host_sc->resid;
+    h->pcg_iterations += (uint64_t)h->host_sc->iters;
+  }
+  launch_pressure_update(c, dt);
+  h->max_valid = true;
+  return check_launch("project");
+}
+
+int run_substep(euler_gpu* h, float dt) {
+  Ctx& c = h->c;
+  h->last_dt = dt;
+  prof_mark(h, 0);
+  launch_advect_markers(c, dt, h->prm.marker_mode);          // main.c:855
+  launch_refresh_counts(c);                                  // main.c:856
+  launch_sources(c);                                         // main.c:864
+  prof_mark(h, 1);
+  launch_extrapolate(c);                                     // main.c:865-868
+  { float* t = c.u; c.u = c.uext; c.uext = t; t = c.v; c.v = c.vext; c.vext = t; }
+  launch_advect_velocity(c, dt);                             // main.c:871-889
+  prof_mark(h, 2);
+  int rc = run_project(h, dt);                               // main.c:893
+  if (rc) return rc;
+  prof_mark(h, 3);
+  h->substeps++;
+  if (h->profiling) {
+    CU(cudaEventSynchronize(h->ev[3]));
+    float a = 0, b = 0, d = 0;
+    cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&d, h->ev[2], h->ev[3]);
+    h->ms_markers += a; h->ms_grid += b; h->ms_project += d;
+  }
+  return 0;
+}
+
+int compute_dt(euler_gpu* h, float frame_time, float* dt) {
+  if (!h->max_valid) launch_maxsq(h->c);
+  h->max_valid = true;
+  launch_timestep(h->c, frame_time, h->prm.cfl_distance);
+  int rc = pull_scalars(h);
+  if (rc) return rc;
+  *dt = h->host_sc->dt;
+  return 0;
+}
+
+}  // namespace
+
+// ======================================================================= C-ABI ====
+
+extern "C" {
+
+int euler_gpu_abi_version(void) { return EULER_GPU_ABI_VERSION; }
+const char* euler_gpu_last_error(void) { return g_err; }
+
+int euler_gpu_default_params(euler_params* p) {
+  if (!p) return fail(EULER_E_INVALID, "params is NULL");
+  memset(p, 0, sizeof *p);
+  p->h = 1.f; p->rho = 1.f; p->gravity = -10.f;              // main.c:58-60
+  p->frame_time = 0.1f; p->max_substeps = 8;                 // main.c:849-851
+  p->cfl_distance = 0.75f;                                   // main.c:838
+  p->max_iterations = 100;                                   // main.c:735
+  p->tol = (double)1e-6f;                                    // main.c:736
+  p->precon = EULER_PRECON_IC0_WAVEFRONT;
+  p->marker_mode = EULER_MARKERS_REFERENCE;
+  p->rng_state = 0x9bd185c449534b91ull;                      // main.c:204
+  p->device = 0; p->stream = nullptr; p->pcg_check_every = 8;
+  p->row0 = 0; p->global_ny = 0;
+  return 0;
+}
+
+int euler_gpu_destroy(euler_gpu* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->prm.device);
+  if (h->c.stream) cudaStreamSynchronize(h->c.stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->host_sc) cudaFreeHost(h->host_sc);
+  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->own_stream && h->c.stream) cudaStreamDestroy(h->c.stream);
+  delete h;
+  return 0;
+}
+
+int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, const uint8_t* source,
+                     const uint8_t* sink, const float* markers_xy, size_t n_markers,
+                     const euler_params* params) {
+  if (!out) return fail(EULER_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (nx < 4 || ny < 4) return fail(EULER_E_INVALID, "grid %dx%d too small (min 4x4)", nx, ny);
+  if (!solid || !source || !sink) return fail(EULER_E_INVALID, "mask planes must not be NULL");
+  if (n_markers && !markers_xy) return fail(EULER_E_INVALID, "markers is NULL");
+  const size_t max_markers = 4 * (size_t)nx * ny;            // MAX_MARKER_COUNT, main.c:92
+  if (n_markers > max_markers) return fail(EULER_E_INVALID, "too many markers");
+  if (max_markers >= 0xFFFFFFFFull) return fail(EULER_E_UNSUPPORTED, "grid too large");
+  euler_params prm;
+  if (params) prm = *params; else euler_gpu_default_params(&prm);
+  if (prm.precon != EULER_PRECON_IC0_WAVEFRONT && prm.precon != EULER_PRECON_REDBLACK)
+    return fail(EULER_E_INVALID, "unknown preconditioner %d", prm.precon);
+  if (prm.marker_mode != EULER_MARKERS_REFERENCE && prm.marker_mode != EULER_MARKERS_FAST)
+    return fail(EULER_E_INVALID, "unknown marker mode %d", prm.marker_mode);
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(EULER_E_CUDA, "no CUDA device: %s (libeuler_gpu has no CPU fallback)",
+                cudaGetErrorString(e));
+  if (prm.device < 0 || prm.device >= ndev) return fail(EULER_E_INVALID, "device %d of %d", prm.device, ndev);
+  CU(cudaSetDevice(prm.device));
+
+  euler_gpu* h = new euler_gpu();
+  memset(&h->c, 0, sizeof h->c);
+  h->prm = prm; h->nx = nx; h->ny = ny;
+  h->host_sc = nullptr; h->device_bytes = 0; h->max_valid = false;
+  h->frames = h->substeps = h->solves = h->solves_skipped = h->pcg_iterations = 0;
+  h->last_iterations = 0; h->last_residual = 0; h->last_dt = 0; h->profiling = false;
+  h->ms_markers = h->ms_grid = h->ms_project = 0;
+  for (int i = 0; i < 4; ++i) h->ev[i] = nullptr;
+  Ctx& c = h->c;
+  c.g.nx = nx; c.g.ny = ny;
+  c.g.pitch = (nx + PITCH_ALIGN - 1) / PITCH_ALIGN * PITCH_ALIGN;
+  c.g.row0 = 0; c.g.gny = ny;
+  c.lim.u_x = nextafterf((float)(nx - 2), 0.f);              // main.c:339-340, U is (X-1) x Y
+  c.lim.u_y = nextafterf((float)(ny - 1), 0.f);
+  c.lim.v_x = nextafterf((float)(nx - 1), 0.f);              // V is X x (Y-1)
+  c.lim.v_y = nextafterf((float)(ny - 2), 0.f);
+  c.h = prm.h; c.rho = prm.rho; c.gravity = prm.gravity;
+  c.max_markers = max_markers;
+
+#define TRY(x) do { int rc_ = (x); if (rc_) { euler_gpu_destroy(h); return rc_; } } while (0)
+#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { int rc_ = fail(EULER_E_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); euler_gpu_destroy(h); return rc_; } } while (0)
+
+  cudaDeviceProp prop;
+  TRYCU(cudaGetDeviceProperties(&prop, prm.device));
+  c.sm_count = prop.multiProcessorCount;
+  if (prm.stream) { c.stream = (cudaStream_t)prm.stream; h->own_stream = false; }
+  else { TRYCU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  for (int i = 0; i < 4; ++i) TRYCU(cudaEventCreate(&h->ev[i]));
+  TRYCU(cudaMallocHost((void**)&h->host_sc, sizeof(DevScalars)));
+
+  TRY(alloc_plane(h, &c.solid)); TRY(alloc_plane(h, &c.source)); TRY(alloc_plane(h, &c.sink));
+  TRY(alloc_plane(h, &c.count)); TRY(alloc_plane(h, &c.prev_count));
+  TRY(alloc_plane(h, &c.count32));
+  TRY(alloc_plane(h, &c.u)); TRY(alloc_plane(h, &c.v));
+  TRY(alloc_plane(h, &c.utmp)); TRY(alloc_plane(h, &c.vtmp));
+  TRY(alloc_plane(h, &c.uext)); TRY(alloc_plane(h, &c.vext));
+  TRY(alloc_plane(h, &c.adiag));
+  TRY(alloc_plane(h, &c.precon)); TRY(alloc_plane(h, &c.q)); TRY(alloc_plane(h, &c.p));
+  TRY(alloc_plane(h, &c.r)); TRY(alloc_plane(h, &c.z)); TRY(alloc_plane(h, &c.s));
+  TRY(alloc_array(h, &c.markers, max_markers));
+  TRY(alloc_array(h, &c.markers_alt, max_markers));
+  c.n_segments = (max_markers + 1023) / 1024;
+  TRY(alloc_array(h, &c.seg_count, c.n_segments));
+  TRY(alloc_array(h, &c.seg_offset, c.n_segments));
+  const size_t nblk2d = (size_t)((nx + 31) / 32) * (size_t)((ny + 7) / 8);
+  c.n_strips = (ny - 2 + 31) / 32;
+  c.n_partials = nblk2d > (size_t)c.n_strips ? nblk2d : (size_t)c.n_strips;
+  TRY(alloc_array(h, &c.partials, c.n_partials));
+  TRY(alloc_array(h, &c.wf_progress, (size_t)c.n_strips));
+  TRY(alloc_array(h, &c.sc, 1));
+  TRY(alloc_array(h, &c.rng_jump, 64 * 64));
+
+  TRY(upload_plane(h, c.solid, solid, 1));
+  TRY(upload_plane(h, c.source, source, 1));
+  TRY(upload_plane(h, c.sink, sink, 1));
+  if (n_markers)
+    TRYCU(cudaMemcpyAsync(c.markers, markers_xy, n_markers * sizeof(float2), cudaMemcpyHostToDevice, c.stream));
+
+  // static row-major list of source cells (main.c:284-286 visits them in this order)
+  std::vector<unsigned int> cells;
+  for (int y = 0; y < ny; ++y)
+    for (int x = 0; x < nx; ++x)
+      if (source[(size_t)y * nx + x]) cells.push_back((unsigned int)((size_t)y * c.g.pitch + x));
+  c.n_source_cells = cells.size();
+  TRY(alloc_array(h, &c.source_cells, cells.size()));
+  if (!cells.empty())
+    TRYCU(cudaMemcpyAsync(c.source_cells, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  std::vector<unsigned long long> jump(64 * 64);
+  init_rng_jump_table(jump.data());
+  TRYCU(cudaMemcpyAsync(c.rng_jump, jump.data(), jump.size() * 8, cudaMemcpyHostToDevice, c.stream));
+
+  memset(h->host_sc, 0, sizeof(DevScalars));
+  h->host_sc->n_markers = n_markers;
+  h->host_sc->rng_state = prm.rng_state;
+  TRYCU(cudaMemcpyAsync(c.sc, h->host_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, c.stream));
+  TRYCU(cudaStreamSynchronize(c.stream));   // host vectors above go out of scope
+
+  launch_refresh_counts(c);                                  // sim_init, main.c:268
+  TRY(check_launch("create"));
+  TRYCU(cudaStreamSynchronize(c.stream));
+#undef TRY
+#undef TRYCU
+  *out = h;
+  return 0;
+}
+
+#define ENTER(h)                                                   \
+  if (!(h)) return fail(EULER_E_INVALID, "handle is NULL");        \
+  CU(cudaSetDevice((h)->prm.device))
+
+int euler_gpu_calculate_timestep(euler_gpu* h, float frame_time, float* dt) {
+  ENTER(h);
+  if (!dt) return fail(EULER_E_INVALID, "dt is NULL");
+  return compute_dt(h, frame_time, dt);
+}
+
+int euler_gpu_substep(euler_gpu* h, float dt) {
+  ENTER(h);
+  int rc = run_substep(h, dt);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->c.stream));
+  return 0;
+}
+
+int euler_gpu_step_frame(euler_gpu* h, int* substeps) {
+  ENTER(h);
+  float frame_time = h->prm.frame_time;                      // main.c:849-851
+  int step = 0;
+  for (; frame_time > 0.f && step < h->prm.max_substeps; ++step) {
+    float dt;
+    int rc = compute_dt(h, frame_time, &dt);
+    if (rc) return rc;
+    frame_time -= dt;
+    rc = run_substep(h, dt);
+    if (rc) return rc;
+  }
+  h->frames++;
+  if (substeps) *substeps = step;
+  CU(cudaStreamSynchronize(h->c.stream));
+  return check_launch("step_frame");
+}
+
+int euler_gpu_run_stage(euler_gpu* h, int stage, float dt) {
+  ENTER(h);
+  Ctx& c = h->c;
+  switch (stage) {
+    case EULER_S_ADVECT_MARKERS: launch_advect_markers(c, dt, h->prm.marker_mode); break;
+    case EULER_S_REFRESH_COUNTS: launch_refresh_counts(c); break;
+    case EULER_S_SOURCES: launch_sources(c); break;
+    case EULER_S_EXTRAPOLATE: {
+      launch_extrapolate(c);
+      float* t = c.u; c.u = c.uext; c.uext = t; t = c.v; c.v = c.vext; c.vext = t;
+      h->max_valid = false;
+      break;
+    }
+    case EULER_S_ADVECT_VELOCITY: launch_advect_velocity(c, dt); break;
+    case EULER_S_PROJECT: { int rc = run_project(h, dt); if (rc) return rc; break; }
+    case EULER_S_BUILD_RHS: launch_build_rhs(c, dt); break;
+    case EULER_S_PRECONDITION:
+      launch_pcg_reset(c);
+      if (h->prm.precon == EULER_PRECON_REDBLACK) launch_rb_build(c); else launch_ic0_build(c);
+      enqueue_precon_apply(h, true);
+      break;
+    case EULER_S_APPLY_A: launch_pcg_reset(c); launch_apply_a(c, false); break;
+    case EULER_S_PRESSURE_UPDATE: launch_pressure_update(c, dt); h->max_valid = true; break;
+    default: return fail(EULER_E_INVALID, "unknown stage %d", stage);
+  }
+  int rc = check_launch("run_stage");
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->c.stream));
+  return check_launch("run_stage");
+}
+
+int euler_gpu_pcg_iterations(euler_gpu* h, int iterations) {
+  ENTER(h);
+  for (int i = 0; i < iterations; ++i) enqueue_iteration(h);
+  return check_launch("pcg_iterations");
+}
+
+int euler_gpu_read_marker_count(euler_gpu* h, uint8_t* dst) {
+  return euler_gpu_get(h, EULER_F_COUNT, dst, (size_t)(h ? h->nx : 0) * (h ? h->ny : 0));
+}
+
+int euler_gpu_get(euler_gpu* h, int field, void* dst, size_t bytes) {
+  ENTER(h);
+  if (!dst) return fail(EULER_E_INVALID, "dst is NULL");
+  const Grid& g = h->c.g;
+  if (field == EULER_F_MARKERS) {
+    int rc = pull_scalars(h);
+    if (rc) return rc;
+    const size_t want = (size_t)h->host_sc->n_markers * sizeof(float2);
+    if (bytes != want) return fail(EULER_E_INVALID, "markers: %zu bytes given, %zu needed", bytes, want);
+    if (want) CU(cudaMemcpyAsync(dst, h->c.markers, want, cudaMemcpyDeviceToHost, h->c.stream));
+    CU(cudaStreamSynchronize(h->c.stream));
+    return 0;
+  }
+  FieldInfo fi = field_info(h, field);
+  if (!fi.ptr) return fail(EULER_E_INVALID, "unknown field %d", field);
+  const size_t want = (size_t)g.nx * g.ny * fi.elem;
+  if (bytes != want) return fail(EULER_E_INVALID, "field %d: %zu bytes given, %zu needed", field, bytes, want);
+  CU(cudaMemcpy2DAsync(dst, (size_t)g.nx * fi.elem, fi.ptr, g.pitch * fi.elem, (size_t)g.nx * fi.elem,
+                       g.ny, cudaMemcpyDeviceToHost, h->c.stream));
+  CU(cudaStreamSynchronize(h->c.stream));
+  return 0;
+}
+
+int euler_gpu_set(euler_gpu* h, int field, const void* src, size_t bytes) {
+  ENTER(h);
+  if (!src && bytes) return fail(EULER_E_INVALID, "src is NULL");
+  const Grid& g = h->c.g;
+  if (field == EULER_F_MARKERS) {
+    if (bytes % sizeof(float2)) return fail(EULER_E_INVALID, "markers: size not a multiple of 8");
+    const size_t n = bytes / sizeof(float2);
+    if (n > h->c.max_markers) return fail(EULER_E_INVALID, "markers: %zu > max %zu", n, h->c.max_markers);
+    if (n) CU(cudaMemcpyAsync(h->c.markers, src, bytes, cudaMemcpyHostToDevice, h->c.stream));
+    unsigned long long nn = n;
+    CU(cudaMemcpyAsync(&h->c.sc->n_markers, &nn, sizeof nn, cudaMemcpyHostToDevice, h->c.stream));
+    CU(cudaStreamSynchronize(h->c.stream));
+    return 0;
+  }
+  if (field == EULER_F_SOURCE) return fail(EULER_E_UNSUPPORTED, "source plane is fixed at create()");
+  FieldInfo fi = field_info(h, field);
+  if (!fi.ptr) return fail(EULER_E_INVALID, "unknown field %d", field);
+  const size_t want = (size_t)g.nx * g.ny * fi.elem;
+  if (bytes != want) return fail(EULER_E_INVALID, "field %d: %zu bytes given, %zu needed", field, bytes, want);
+  int rc = upload_plane(h, fi.ptr, src, fi.elem);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->c.stream));
+  if (field == EULER_F_U || field == EULER_F_V) h->max_valid = false;
+  return 0;
+}
+
+int euler_gpu_set_rng_state(euler_gpu* h, uint64_t state) {
+  ENTER(h);
+  unsigned long long s = state;
+  CU(cudaMemcpyAsync(&h->c.sc->rng_state, &s, sizeof s, cudaMemcpyHostToDevice, h->c.stream));
+  CU(cudaStreamSynchronize(h->c.stream));
+  return 0;
+}
+
+int euler_gpu_set_source_exhausted(euler_gpu* h, int exhausted) {
+  ENTER(h);
+  int v = exhausted ? 1 : 0;
+  CU(cudaMemcpyAsync(&h->c.sc->source_exhausted, &v, sizeof v, cudaMemcpyHostToDevice, h->c.stream));
+  CU(cudaStreamSynchronize(h->c.stream));
+  return 0;
+}
+
+int euler_gpu_stats(euler_gpu* h, euler_stats* out) {
+  ENTER(h);
+  if (!out) return fail(EULER_E_INVALID, "out is NULL");
+  int rc = pull_scalars(h);
+  if (rc) return rc;
+  memset(out, 0, sizeof *out);
+  out->frames = h->frames; out->substeps = h->substeps;
+  out->solves = h->solves; out->solves_skipped = h->solves_skipped;
+  out->pcg_iterations = h->pcg_iterations;
+  out->last_iterations = h->last_iterations;
+  out->last_residual = h->last_residual;
+  out->last_dt = h->last_dt;
+  out->n_markers = h->host_sc->n_markers;
+  out->source_exhausted = h->host_sc->source_exhausted;
+  out->rng_state = h->host_sc->rng_state;
+  out->kernel_launches = h->c.launches;
+  out->device_bytes = h->device_bytes;
+  out->ms_markers = h->ms_markers; out->ms_grid = h->ms_grid; out->ms_project = h->ms_project;
+  return 0;
+}
+
+int euler_gpu_set_profiling(euler_gpu* h, int enabled) {
+  ENTER(h);
+  h->profiling = enabled != 0;
+  return 0;
+}
+
+int euler_gpu_synchronize(euler_gpu* h) {
+  ENTER(h);
+  CU(cudaStreamSynchronize(h->c.stream));
+  return check_launch("synchronize");
+}
+
+void* euler_gpu_stream(euler_gpu* h) { return h ? (void*)h->c.stream : nullptr; }
+
+int euler_gpu_comm_unique_id(void*) {
+  return fail(EULER_E_UNSUPPORTED, "multi-GPU slabs are not built into this library yet");
+}
+int euler_gpu_comm_init(euler_gpu*, int, int, const void*) {
+  return fail(EULER_E_UNSUPPORTED, "multi-GPU slabs are not built into this library yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// euler_b200/csrc/common.cuh — shared device/host definitions for libeuler_gpu.so (sm_100a).
+//
+// Data layout in HBM: every plane is row-major [ny][pitch] with x fastest,
+// pitch = nx rounded up to 32 elements so each row starts on a 128 B (float) / 256 B
+// (double) / 32 B (uint8) boundary, plus GUARD_ROWS rows of zeros before row 0 and after row
+// ny-1 so that y±1 / x±1 neighbour loads of border cells stay inside the allocation without
+// a bounds branch (the border ring is never fluid: it is all sinks, reference main.c:244-252).
+//
+// The whole library is compiled with -fmad=false: the reference is built without FMA
+// contraction in its parity configuration (oracle/build_ref.sh "strict"), and every fp32
+// expression below is written in the reference's evaluation order so results are bit-exact.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace euler {
+
+constexpr int GUARD_ROWS = 4;
+constexpr int PITCH_ALIGN = 32;
+
+enum FaceType { CELL_P = 0, FACE_U = 1, FACE_V = 2 };   // reference celltype_t, main.c:46-50
+
+struct Grid {
+  int nx, ny;      // rows stored by this handle (== global size when not slab-decomposed)
+  int pitch;       // elements per row
+  int row0;        // global index of local row 0
+  int gny;         // global ny
+};
+
+__host__ __device__ __forceinline__ size_t gidx(const Grid& g, int x, int y) {
+  return (size_t)y * (size_t)g.pitch + (size_t)x;
+}
+
+// Scalars that live in device memory and are produced/consumed by kernels without a host
+// round trip.  One instance per handle.
+struct DevScalars {
+  // calculate_timestep (main.c:834-841)
+  unsigned int max_u2_bits, max_v2_bits;   // float bit patterns (non-negative => uint order)
+  float dt, frame_left;
+  // markers (main.c:92-95, 204)
+  unsigned long long n_markers;
+  unsigned long long n_deleted;
+  int source_exhausted;
+  int pad0;
+  unsigned long long rng_state;
+  // PCG (main.c:735-767)
+  double sigma, zs, alpha, beta, resid;
+  int iters, done, nonzero_rhs, pad1;
+  // grid-wide "last block done" counters, one per reducing kernel family
+  unsigned int ctr[8];
+  // wavefront tickets
+  unsigned int ticket[4];
+  // faithful marker mode (dt carry-over): number of candidate markers, first fired index
+  unsigned long long n_candidates;
+  unsigned long long first_fired;
+};
+
+#define EULER_FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(EULER_FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(EULER_FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_maxf(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(EULER_FULL_MASK, v, o));
+  return v;
+}
+
+// Deterministic block reduction (blockDim.x*blockDim.y*blockDim.z <= 1024). Result valid in
+// thread 0.  IS_MAX selects max instead of sum.
+template <bool IS_MAX>
+__device__ __forceinline__ double block_reduce(double v) {
+  __shared__ double red_smem[32];
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+  const int lane = tid & 31, wid = tid >> 5;
+  v = IS_MAX ? warp_max(v) : warp_sum(v);
+  __syncthreads();                    // protect red_smem reuse across calls
+  if (lane == 0) red_smem[wid] = v;
+  __syncthreads();
+  const int nw = (nthreads + 31) >> 5;
+  if (wid == 0) {
+    v = lane < nw ? red_smem[lane] : 0.0;
+    v = IS_MAX ? warp_max(v) : warp_sum(v);
+  }
+  return v;
+}
+
+// Grid-wide reduction without a second launch and without floating-point atomics: every
+// block writes its partial, the block that arrives last re-reduces all partials in a fixed
+// order (deterministic for a given grid size) and runs `fin(total)` in its thread 0.
+template <bool IS_MAX, class Fin>
+__device__ __forceinline__ void grid_reduce_last_block(double block_value, double* partials,
+                                                       unsigned int* counter, Fin fin) {
+  __shared__ bool is_last;
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+  const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (tid == 0) {
+    partials[bid] = block_value;
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (unsigned int i = tid; i < nblocks; i += nthreads) {
+    double p = __ldcg(partials + i);
+    acc = IS_MAX ? fmax(acc, p) : acc + p;
+  }
+  acc = block_reduce<IS_MAX>(acc);
+  if (tid == 0) {
+    *counter = 0;
+    fin(acc);
+  }
+}
+
+}  // namespace euler

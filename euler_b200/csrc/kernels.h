@@ -1,0 +1,72 @@
+// euler_b200/csrc/kernels.h — host-side launchers of the sm_100a kernels (one per stage of
+// reference sim_step(), main.c:843-900).  Every launcher enqueues on ctx.stream and bumps
+// ctx.launches by the number of kernels it started.
+#pragma once
+#include "common.cuh"
+#include "interp.cuh"
+
+namespace euler {
+
+struct Ctx {
+  Grid g;
+  InterpLimits lim;
+  cudaStream_t stream;
+  unsigned long long launches;
+  int sm_count;
+  // constants (reference main.c:58-60, 735-736, 838)
+  float h, rho, gravity;
+  // static masks
+  uint8_t *solid, *source, *sink;
+  // dynamic cell classification: marker counts now / previous sub-step (main.c:96-97)
+  uint8_t *count, *prev_count;
+  unsigned int* count32;          // atomic binning target, folded to uint8 afterwards
+  // velocities (main.c:64-67) + one scratch pair for the out-of-place extrapolation
+  float *u, *v, *utmp, *vtmp, *uext, *vext;
+  // markers (main.c:92-95): ping-pong AoS float2 arrays
+  float2 *markers, *markers_alt;
+  size_t max_markers;
+  // compaction scratch
+  unsigned int* seg_count;        // per 1024-marker segment
+  unsigned int* seg_offset;
+  unsigned long long* del_list;   // ordered indices of deleted markers
+  size_t n_segments;
+  // source cells, row-major (static)
+  unsigned int* source_cells;
+  size_t n_source_cells;
+  unsigned long long* rng_jump;   // 64 x 64 columns of T^(2^j), xorshift64 transition
+  // pressure solve
+  int8_t* adiag;
+  double *precon, *q, *p, *r, *z, *s;
+  double* partials;               // grid-reduction scratch
+  size_t n_partials;
+  unsigned int* wf_progress;      // wavefront strip progress flags
+  int n_strips;
+  DevScalars* sc;                 // device scalars
+};
+
+// ---- grid stages (grid_kernels.cu)
+void launch_maxsq(Ctx& c);                                   // -> sc.max_u2_bits/max_v2_bits
+void launch_timestep(Ctx& c, float frame_time, float cfl);   // -> sc.dt (uses sc.max_*)
+void launch_extrapolate(Ctx& c);                             // (u,v) -> (uext,vext); caller swaps
+void launch_advect_velocity(Ctx& c, float dt);               // (u,v) -> (utmp,vtmp)
+void launch_build_rhs(Ctx& c, float dt);                     // -> r, p=0, adiag, sc.nonzero_rhs
+void launch_pressure_update(Ctx& c, float dt);               // p,utmp,vtmp -> u,v (+max u2,v2)
+
+// ---- markers (marker_kernels.cu)
+void launch_advect_markers(Ctx& c, float dt, int mode);      // in: markers, out: markers (swapped inside)
+void launch_refresh_counts(Ctx& c);                          // prev<-cur, re-bin, delete in sink/solid
+void launch_sources(Ctx& c);                                 // update_fluid_sources
+void init_rng_jump_table(unsigned long long* host_table /* 64*64 */);
+
+// ---- pressure solve (pcg_kernels.cu, wavefront.cu)
+void launch_ic0_build(Ctx& c);                               // E^-1, wavefront (once per project)
+void launch_ic0_apply(Ctx& c, bool init);                    // z = M^-1 r (+ z.r, sigma/beta)
+void launch_rb_build(Ctx& c);                                // red-black E^-1
+void launch_rb_apply(Ctx& c, bool init);                     // z = M^-1 r (+ z.r, sigma/beta)
+void launch_copy_search(Ctx& c);                             // s = z
+void launch_apply_a(Ctx& c, bool with_alpha);                // z = A s (+ z.s, alpha)
+void launch_axpy(Ctx& c, double tol);                        // p += a s, r -= a z, ||r||inf
+void launch_update_search(Ctx& c);                           // s = z + beta s
+void launch_pcg_reset(Ctx& c);                               // iters=0, done=0
+
+}  // namespace euler

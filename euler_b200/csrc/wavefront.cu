@@ -1,0 +1,210 @@
+// euler_b200/csrc/wavefront.cu — reference-faithful IC(0) ("MIC(0)-style", sigma = 0.25,
+// tau = 0) preconditioner of reference main.c:580-627, natural (row-major) ordering.
+//
+// The three loops of apply_preconditioner — E^-1 build (:586-600), L q = r (:603-613) and
+// L^T z = q (:616-626) — carry a sequential dependency on the left/lower (resp. right/upper)
+// neighbour, so cell (x,y) can only be done after (x-1,y) and (x,y-1): an anti-diagonal
+// wavefront.  Layout of the parallel sweep:
+//
+//   * the interior rows are cut into STRIPS of 32 rows; one warp owns a strip, lane l owns
+//     row y0+l and at step t works on column x = 1 + t - l (lanes are skewed by one column);
+//   * the value of the left neighbour never leaves the lane's registers; the value of the
+//     lower neighbour is what lane l-1 produced one step earlier -> one __shfl_up per step;
+//   * lane 0 needs the top row of the strip below.  Strips are chained through a progress
+//     counter per strip (st.release / ld.acquire, published every WF_PUBLISH columns), so
+//     strip k runs ~32+WF_PUBLISH columns behind strip k-1: a software pipeline of warps
+//     across the SMs.  Strip ids are handed out by an atomic ticket so a strip can only wait
+//     on a strip that has already started (no reliance on block scheduling order).
+//   * the backward solve is the mirror image (rows and columns descending).
+//
+// Arithmetic is the reference's, operation for operation (fp64, no FMA), so q, z and
+// g_precon are bit-identical to the CPU's given the same r — including quirk SURVEY §9.1:
+// the diagonal recurrence reads precon of the left/lower neighbour even when that cell is
+// not fluid (a value left over from an earlier time step; precon is only written at fluid
+// cells and never cleared).
+//
+// Byte traffic is the same 56 B/cell as a streaming kernel would need; the sweep is bound
+// by the dependent fp64 chain (mul, add, add, mul per column), not by HBM — see DESIGN.md.
+#include "kernels.h"
+
+namespace euler {
+
+namespace {
+
+constexpr int WF_PUBLISH = 8;
+constexpr int WF_PREFETCH = 32;   // columns ahead for prefetch.global.L1
+
+enum { WF_BUILD = 0, WF_FORWARD = 1, WF_BACKWARD = 2 };
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// MODE WF_BUILD   : precon(x,y) from adiag and precon(x-1,y), precon(x,y-1)   main.c:586-600
+// MODE WF_FORWARD : q = L^-1 r                                                main.c:603-613
+// MODE WF_BACKWARD: z = L^-T q, fused with the z.r reduction                  main.c:616-626
+//
+// `in`  = r (forward) / q (backward); `out` = q (forward) / z (backward).
+template <int MODE>
+__global__ void __launch_bounds__(32) k_ic0_sweep(
+    Grid g, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
+    double* precon, const double* __restrict__ in, double* out, const double* __restrict__ rvec,
+    unsigned int* progress, unsigned int* ticket, double* partials, DevScalars* sc, int init) {
+  if (MODE != WF_BUILD && sc->done) return;
+  const int lane = threadIdx.x;
+  const int n_strips = gridDim.x;
+  unsigned int strip = 0;
+  if (lane == 0) strip = atomicAdd(ticket, 1u) % (unsigned int)n_strips;
+  strip = __shfl_sync(EULER_FULL_MASK, strip, 0);
+
+  const int ncols = g.nx - 2;                       // interior columns 1 .. nx-2
+  const bool fwd = MODE != WF_BACKWARD;
+  // forward: rows ascend from 1; backward: rows descend from ny-2
+  const int y = fwd ? 1 + 32 * (int)strip + lane : (g.ny - 2) - 32 * (int)strip - lane;
+  const bool row_ok = y >= 1 && y <= g.ny - 2;
+  const int ystep = fwd ? 1 : -1;                   // direction towards "later" rows
+  const int y_dep = y - ystep;                      // row this row depends on
+  // the lane that owns the strip's last row publishes progress for the next strip
+  const bool publisher = lane == 31;
+
+  const size_t row = (size_t)(row_ok ? y : 1) * g.pitch;
+  const size_t row_dep = (size_t)(row_ok ? y_dep : 1) * g.pitch;
+
+  // carried along the row (value at the previous column of this lane's row)
+  double prev_val = 0.0;                            // q(x-1) / z(x+1); 0 outside (memset)
+  double prev_pc = 0.0;                             // precon(x-1) for build/forward
+  bool prev_fl = false;                             // fluid(x+1) for backward
+  if (row_ok && fwd) prev_pc = precon[row + 0];     // column 0: never fluid, plane value
+  // what this lane produced in the previous step (consumed by lane+1 now)
+  double last_val = 0.0, last_pc = 0.0;
+  bool last_fl = false;
+
+  unsigned int avail = 0;                           // columns of the dependency row known done
+  double acc = 0.0;
+
+  const int nsteps = ncols + 31;
+  for (int t = 0; t < nsteps; ++t) {
+    const int k = t - lane;                         // 0-based position along the sweep
+    const int x = fwd ? 1 + k : (g.nx - 2) - k;
+    const bool col_ok = k >= 0 && k < ncols;
+
+    double dep_val = __shfl_up_sync(EULER_FULL_MASK, last_val, 1);
+    double dep_pc = __shfl_up_sync(EULER_FULL_MASK, last_pc, 1);
+    bool dep_fl = __shfl_up_sync(EULER_FULL_MASK, (int)last_fl, 1) != 0;
+
+    if (lane == 0 && col_ok && row_ok) {
+      // dependency row belongs to the previous strip (or is the never-fluid border row)
+      if (strip > 0) {
+        const unsigned int need = (unsigned int)(k + 1);
+        if (avail < need) {
+          do { avail = ld_acquire(progress + (strip - 1)); } while (avail < need);
+        }
+        if (MODE != WF_BUILD) dep_val = __ldcg(out + row_dep + x);
+        dep_pc = __ldcg(precon + row_dep + x);
+      } else {
+        dep_val = 0.0;
+        dep_pc = precon[row_dep + x];
+      }
+      dep_fl = fluid[row_dep + x] != 0;
+    }
+
+    if (col_ok && row_ok) {
+      const size_t c = row + x;
+      const bool fl = fluid[c] != 0;
+      if (((x & 3) == 0)) {
+        const int xp = fwd ? x + WF_PREFETCH : x - WF_PREFETCH;
+        if (xp >= 0 && xp < g.nx) {
+          if (MODE != WF_BUILD) { prefetch_l1(in + row + xp); }
+          prefetch_l1(precon + row + xp);
+          if (MODE == WF_BACKWARD) prefetch_l1(rvec + row + xp);
+        }
+      }
+      if (MODE == WF_BUILD) {
+        double pc;
+        if (fl) {
+          const double a = (double)adiag[c];
+          const double wl = -1.0 * prev_pc;                  // get_a_minus_i == -1
+          const double wd = -1.0 * dep_pc;
+          double e = a - wl * wl - wd * wd;                  // main.c:590-593
+          if (e < 0.25 * a) e = a != 0.0 ? a : 1.0;          // main.c:594-596
+          pc = 1.0 / sqrt(e);
+          precon[c] = pc;
+        } else {
+          pc = precon[c];                                    // stale value stays
+        }
+        prev_pc = pc;
+        last_pc = pc;
+      } else if (MODE == WF_FORWARD) {
+        const double pc = precon[c];
+        double qv = 0.0;
+        if (fl) {
+          const double tt = in[c] - (-1.0 * prev_pc) * prev_val - (-1.0 * dep_pc) * dep_val;
+          qv = tt * pc;                                      // main.c:607-610
+        }
+        out[c] = qv;
+        prev_val = qv; prev_pc = pc;
+        last_val = qv; last_pc = pc;
+      } else {
+        double zv = 0.0;
+        if (fl) {
+          const double pc = precon[c];
+          const double ar = prev_fl ? -1.0 : 0.0;            // get_a_plus_i(y,x)
+          const double au = dep_fl ? -1.0 : 0.0;             // get_a_plus_j(y,x)
+          const double tt = in[c] - ar * pc * prev_val - au * pc * dep_val;
+          zv = tt * pc;                                      // main.c:620-623
+          acc += zv * rvec[c];
+        }
+        out[c] = zv;
+        prev_val = zv; prev_fl = fl;
+        last_val = zv; last_fl = fl;
+      }
+      if (publisher && (((k + 1) % WF_PUBLISH) == 0 || k == ncols - 1)) {
+        st_release(progress + strip, (unsigned int)(k + 1));
+      }
+    }
+  }
+
+  if (MODE == WF_BACKWARD) {
+    acc = warp_sum(acc);
+    grid_reduce_last_block<false>(acc, partials, &sc->ctr[3], [&](double total) {
+      if (init) { sc->sigma = total; }                       // main.c:748
+      else { sc->beta = total / sc->sigma; sc->sigma = total; }   // main.c:762-765
+    });
+  }
+}
+
+}  // namespace
+
+static void reset_wavefront(Ctx& c) {
+  cudaMemsetAsync(c.wf_progress, 0, sizeof(unsigned int) * (size_t)c.n_strips, c.stream);
+}
+
+void launch_ic0_build(Ctx& c) {
+  reset_wavefront(c);
+  k_ic0_sweep<WF_BUILD><<<c.n_strips, 32, 0, c.stream>>>(
+      c.g, c.count, c.adiag, c.precon, nullptr, nullptr, nullptr, c.wf_progress,
+      &c.sc->ticket[0], c.partials, c.sc, 0);
+  c.launches += 1;
+}
+
+void launch_ic0_apply(Ctx& c, bool init) {
+  reset_wavefront(c);
+  k_ic0_sweep<WF_FORWARD><<<c.n_strips, 32, 0, c.stream>>>(
+      c.g, c.count, c.adiag, c.precon, c.r, c.q, nullptr, c.wf_progress, &c.sc->ticket[1],
+      c.partials, c.sc, 0);
+  reset_wavefront(c);
+  k_ic0_sweep<WF_BACKWARD><<<c.n_strips, 32, 0, c.stream>>>(
+      c.g, c.count, c.adiag, c.precon, c.q, c.z, c.r, c.wf_progress, &c.sc->ticket[2],
+      c.partials, c.sc, init ? 1 : 0);
+  c.launches += 2;
+}
+
+}  // namespace euler

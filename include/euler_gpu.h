@@ -1,0 +1,206 @@
+/* include/euler_gpu.h — C-ABI of libeuler_gpu.so
+ *
+ * Drop-in boundary for ONE path of cgmb/euler: the per-timestep fluid solve, i.e.
+ * `sim_step()` (reference main.c:843-900) and everything it calls (main.c:102-841).  The
+ * reference has no plugin/FFI interface: the "API" of this path is two void functions with
+ * external linkage, `sim_init(args_t)` (main.c:209) and `sim_step()` (main.c:843), plus the
+ * ~20 file-scope globals they mutate (main.c:64-100, 552, 577-578) and that `draw_rows()`
+ * reads back (main.c:921-943).  This header turns that seam into an explicit handle-based
+ * C interface; INTEGRATION.md shows the patch a maintainer of the reference would apply.
+ *
+ * Conventions
+ *   - plain C, no CUDA/torch types in any signature; pointers are HOST pointers unless a
+ *     parameter says "device".  Host buffers are copied during the call, never retained.
+ *   - every function returns 0 on success or a negative EULER_E_* code; the message of the
+ *     last failure on the calling thread is `euler_gpu_last_error()`.  The library never
+ *     calls exit() and lets no C++ exception cross the boundary (the reference exit(1)s /
+ *     die()s instead: main.c:213-214, misc/terminal.c:48-52).
+ *   - all planes are row-major [ny][nx], x fastest, exactly the reference's [Y][X] arrays
+ *     (main.c:64).  U faces are valid for x < nx-1, V faces for y < ny-1 (main.c:36-43).
+ *   - a handle is not thread-safe; one host thread drives it.  Work is enqueued on one CUDA
+ *     stream; get/read/stats calls synchronise that stream.
+ *   - there is NO CPU fallback: if no CUDA device is usable, create() fails.
+ */
+#ifndef EULER_GPU_H
+#define EULER_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EULER_GPU_ABI_VERSION 1
+
+enum euler_error {
+  EULER_OK            =  0,
+  EULER_E_INVALID     = -1,   /* bad argument */
+  EULER_E_CUDA        = -2,   /* CUDA runtime error (message has the details) */
+  EULER_E_NOMEM       = -3,
+  EULER_E_UNSUPPORTED = -4,
+  EULER_E_COMM        = -5    /* NCCL / multi-GPU plumbing */
+};
+
+/* Preconditioner of the pressure solve (replaces apply_preconditioner, main.c:580-627). */
+enum euler_precon {
+  EULER_PRECON_IC0_WAVEFRONT = 0, /* reference-faithful natural-order IC(0) ("MIC(0)-style",
+                                     sigma=0.25, tau=0), solved by a pipelined anti-diagonal
+                                     wavefront; reproduces the reference's iterates, incl.
+                                     the stale-g_precon reads.  Single GPU. */
+  EULER_PRECON_REDBLACK      = 1  /* GPU-parallel red-black ordered IC(0): same matrix, same
+                                     tolerance, different (fully parallel) factor. */
+};
+
+/* How the marker array is kept. */
+enum euler_marker_mode {
+  EULER_MARKERS_REFERENCE = 0, /* bit-identical ARRAY, not just multiset: reference swap-delete
+                                  order (main.c:112) and the `dt -= t_prev` carry-over between
+                                  successive markers (main.c:464,501,518) are reproduced. */
+  EULER_MARKERS_FAST      = 1  /* every marker gets the full sub-step dt; order unspecified.
+                                  Required for slab-decomposed (multi-GPU) runs. */
+};
+
+/* Planes / arrays addressable through euler_gpu_get/set (reference global in brackets). */
+enum euler_field {
+  EULER_F_U = 0,          /* float  [ny][nx]  g_u            main.c:64 */
+  EULER_F_V,              /* float            g_v            main.c:65 */
+  EULER_F_UTMP,           /* float            g_utmp         main.c:66 */
+  EULER_F_VTMP,           /* float            g_vtmp         main.c:67 */
+  EULER_F_SOLID,          /* uint8            g_solid        main.c:71 */
+  EULER_F_SOURCE,         /* uint8            g_source       main.c:72 */
+  EULER_F_SINK,           /* uint8            g_sink         main.c:73 */
+  EULER_F_COUNT,          /* uint8            g_marker_count main.c:96  (== g_fluid) */
+  EULER_F_PREV_COUNT,     /* uint8            g_prev_marker_count main.c:97 */
+  EULER_F_MARKERS,        /* float  [n][2]    g_markers      main.c:95  (n = current length) */
+  EULER_F_PRECON,         /* double           g_precon       main.c:577 (persistent) */
+  EULER_F_Q,              /* double           g_q            main.c:578 */
+  EULER_F_ADIAG,          /* int8             g_a            main.c:552 */
+  EULER_F_P,              /* double           p (VLA in project, main.c:739) */
+  EULER_F_R,              /* double           r / b          main.c:716,740 */
+  EULER_F_Z,              /* double           z              main.c:743 */
+  EULER_F_S,              /* double           s              main.c:745 */
+  EULER_F__COUNT
+};
+
+/* Stages runnable one at a time from the current device state (parity harness).
+ * `dt` is the sub-step length where the stage takes one. */
+enum euler_stage {
+  EULER_S_ADVECT_MARKERS = 0, /* advect_markers(dt)            main.c:464-537 */
+  EULER_S_REFRESH_COUNTS,     /* refresh_marker_counts()       main.c:102-117 */
+  EULER_S_SOURCES,            /* update_fluid_sources()        main.c:276-298 */
+  EULER_S_EXTRAPOLATE,        /* extrapolate(u),(v) + zero_bounds(u),(v)  main.c:865-868 */
+  EULER_S_ADVECT_VELOCITY,    /* advect_u, advect_v, apply_body_forces, zero_bounds(utmp),(vtmp)
+                                 main.c:871-889: (u,v) -> (utmp,vtmp) */
+  EULER_S_PROJECT,            /* project(dt, utmp, vtmp, u, v) main.c:709-806 */
+  EULER_S_BUILD_RHS,          /* b and a_diag only             main.c:713-733: -> R, ADIAG, P=0 */
+  EULER_S_PRECONDITION,       /* z = M^-1 r                    main.c:580-627 */
+  EULER_S_APPLY_A,            /* z = A s                       main.c:679-691 */
+  EULER_S_PRESSURE_UPDATE,    /* clamp p, subtract gradient    main.c:769-805 */
+  EULER_S__COUNT
+};
+
+typedef struct euler_params {
+  /* physical constants; defaults = reference (main.c:58-60) */
+  float h;               /* k_side_length = 1 */
+  float rho;             /* k_density     = 1 */
+  float gravity;         /* k_gravity     = -10 */
+  /* sub-stepping; defaults = reference (main.c:838, 849-851) */
+  float frame_time;      /* 0.1 s of simulated time per euler_gpu_step_frame */
+  int   max_substeps;    /* 8 */
+  float cfl_distance;    /* 0.75 (cells) */
+  /* pressure solve; defaults = reference (main.c:735-736) */
+  int    max_iterations; /* 100 */
+  double tol;            /* (double)1e-6f, absolute, on ||r||inf */
+  int    precon;         /* enum euler_precon; default IC0_WAVEFRONT */
+  int    marker_mode;    /* enum euler_marker_mode; default REFERENCE */
+  /* source RNG: state of randf()'s xorshift64* stream (main.c:204) AFTER the host seeded
+   * the initial markers; default = the reference seed 0x9bd185c449534b91 */
+  uint64_t rng_state;
+  /* plumbing */
+  int   device;          /* CUDA device ordinal; default 0 */
+  void *stream;          /* cudaStream_t to enqueue on; NULL = the library creates one */
+  int   pcg_check_every; /* iterations enqueued between convergence polls; default 8 */
+  /* row-slab decomposition: this handle owns global rows [row0, row0+ny) of a
+   * grid that is global_ny rows tall; 0/0 = not decomposed.  See euler_gpu_comm_init. */
+  int   row0;
+  int   global_ny;
+} euler_params;
+
+typedef struct euler_stats {
+  uint64_t frames, substeps;        /* since create */
+  uint64_t solves, solves_skipped;  /* project() calls that ran PCG / hit all_zero (main.c:742) */
+  uint64_t pcg_iterations;          /* total */
+  int      last_iterations;         /* of the last solve */
+  double   last_residual;           /* ||r||inf at exit of the last solve */
+  float    last_dt;
+  uint64_t n_markers;
+  int      source_exhausted;        /* g_source_exhausted, main.c:94 */
+  uint64_t rng_state;
+  uint64_t kernel_launches;         /* CUDA kernels launched by this handle since create */
+  uint64_t device_bytes;            /* device memory owned by the handle */
+  double   ms_markers, ms_grid, ms_project;  /* device time per stage group, summed, only
+                                                when profiling was enabled */
+} euler_stats;
+
+typedef struct euler_gpu euler_gpu;
+
+/* Fill *p with the reference's constants. */
+int euler_gpu_default_params(euler_params *p);
+
+/* Replaces the state hand-over at the end of sim_init (main.c:209-274): the host keeps the
+ * scenario parser and the marker seeding (so file format and RNG stream stay byte-identical)
+ * and passes the three static masks, the seeded markers and the RNG state.  The ring of
+ * sinks (main.c:244-252) must already be present in `sink`.  Runs refresh_marker_counts once,
+ * like sim_init (main.c:268). */
+int euler_gpu_create(euler_gpu **out, int nx, int ny,
+                     const uint8_t *solid, const uint8_t *source, const uint8_t *sink,
+                     const float *markers_xy, size_t n_markers,
+                     const euler_params *params);
+int euler_gpu_destroy(euler_gpu *h);
+
+/* sim_step() (main.c:843-900): up to max_substeps adaptive sub-steps covering frame_time.
+ * Returns after the frame's work is complete on the device.  *substeps may be NULL. */
+int euler_gpu_step_frame(euler_gpu *h, int *substeps);
+/* calculate_timestep(frame_time) (main.c:834-841) from the current u, v. */
+int euler_gpu_calculate_timestep(euler_gpu *h, float frame_time, float *dt);
+/* One sub-step with the given dt: body of the loop main.c:855-893. */
+int euler_gpu_substep(euler_gpu *h, float dt);
+/* One stage (parity harness). */
+int euler_gpu_run_stage(euler_gpu *h, int stage, float dt);
+
+/* What draw_rows() reads every frame (main.c:933): the uint8 marker-count plane. */
+int euler_gpu_read_marker_count(euler_gpu *h, uint8_t *dst /* ny*nx */);
+
+/* State access (checkpoint / parity).  `bytes` must equal the field's size: ny*nx*sizeof(T),
+ * or n_markers*8 for EULER_F_MARKERS (set: any n <= 4*nx*ny; sets the length too). */
+int euler_gpu_get(euler_gpu *h, int field, void *dst, size_t bytes);
+int euler_gpu_set(euler_gpu *h, int field, const void *src, size_t bytes);
+int euler_gpu_set_rng_state(euler_gpu *h, uint64_t state);
+int euler_gpu_set_source_exhausted(euler_gpu *h, int exhausted);
+
+int euler_gpu_stats(euler_gpu *h, euler_stats *out);
+/* Toggle per-stage-group CUDA-event timing (adds synchronisation; off by default). */
+int euler_gpu_set_profiling(euler_gpu *h, int enabled);
+int euler_gpu_synchronize(euler_gpu *h);
+/* The CUDA stream (cudaStream_t) the handle enqueues on, for event timing by the caller. */
+void *euler_gpu_stream(euler_gpu *h);
+
+/* Benchmark hook: run exactly `iterations` PCG iterations of the current system without
+ * convergence polling (used to time the iteration kernels alone; state must hold a built
+ * rhs). */
+int euler_gpu_pcg_iterations(euler_gpu *h, int iterations);
+
+/* Multi-GPU (row slabs, one process per GPU).  `unique_id` is the 128-byte ncclUniqueId
+ * produced on rank 0 by euler_gpu_comm_unique_id and distributed by the caller (any side
+ * channel: torch.distributed, MPI, a file).  Collective over all ranks. */
+int euler_gpu_comm_unique_id(void *unique_id_128);
+int euler_gpu_comm_init(euler_gpu *h, int rank, int n_ranks, const void *unique_id_128);
+
+const char *euler_gpu_last_error(void);
+int euler_gpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EULER_GPU_H */
