@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 fluid-solve path (contract: see DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gpu|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): MAC cell-updates/s = grid cells x sub-steps / time, whole job, plus PCG
+iterations/s and the HBM-roofline fraction of the dominant kernel.  One "step" is one sub-step
+of reference sim_step() (main.c:851-894): calculate_timestep, marker advection + re-binning,
+sources, extrapolation, semi-Lagrangian velocity advection + gravity + boundaries, and the
+pressure projection (PCG capped at the reference's 100 iterations).
+
+Workload at N=1: the 16384^2 synthetic "basic-fill" scenario (walled box,
+fluid block resting on the floor so the solve is active from the first sub-step), red-black
+IC(0) preconditioner, fp64 PCG vectors as in the reference.  At N>1 every rank runs one such
+grid (independent replicas, weak scaling) until slab decomposition lands — the line says so.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, built unmodified
+from /root/reference with its own -O3 -ffast-math flags) on the box's host cores: one thread,
+because the reference is single-threaded, on a bounded sample of the same workload (same
+synthetic scenario at 1024^2; the metric is per cell, and at 16384^2 one CPU sub-step would
+take ~13 minutes).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes per cell of each kernel class, dense accounting over all cells with the
+# reference's dtypes (fields fp32, PCG vectors fp64, masks u8): SURVEY §8d / DESIGN.md §4
+ALG_BYTES_PER_CELL = {
+    "apply_a": 18.0,            # R s 8 + fluid,a_diag 2 + W z 8
+    "axpy_norm": 48.0,          # R s,p,z,r 32 + W p,r 16
+    "precon_apply": 56.0,       # fwd R r,pc 16 W q 8; bwd R q,pc 16 W z 8; R r 8
+    "update_search": 24.0,      # R z,s 16 + W s 8
+    "build_rhs": 19.0,
+    "pressure_update": 26.0,
+    "extrapolate_bounds": 19.0,
+    "advect_velocity": 18.0,
+    "maxsq": 8.0,
+}
+ALG_BYTES_PER_MARKER = {"advect_markers": 16.0}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------- GPU arm ----
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from euler_b200 import Scenario, synthetic
+    from euler_b200 import gpu as G
+
+    rank, world, local = dist_env()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    n = args.grid
+    precon = G.PRECON_REDBLACK if args.precon == "rb" else G.PRECON_IC0_WAVEFRONT
+
+    t_host0 = time.perf_counter()
+    text = synthetic(args.scenario, n, n)
+    scn = Scenario(text, n, n)
+    del text
+    t_host = time.perf_counter() - t_host0
+
+    stream = torch.cuda.Stream()          # the handle enqueues on this stream; events are recorded on it
+
+    def make():
+        return G.EulerGpu.from_scenario(scn, precon=precon, marker_mode=G.MARKERS_FAST,
+                                        device=local, stream=stream.cuda_stream,
+                                        pcg_check_every=args.check_every)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(sim):
+        dt = sim.calculate_timestep(0.1)
+        sim.substep(dt)
+
+    # ---- device-resident timing (value) --------------------------------------------
+    sim = make()
+    cells = n * n
+    for _ in range(args.warmup):
+        one_step(sim)
+    sim.set_profiling(True)
+    sim.reset_profile()
+    st0 = sim.stats()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        one_step(sim)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    st1 = sim.stats()
+    prof = sim.kernel_profile()
+    sim.set_profiling(False)
+    iters = int(st1.pcg_iterations - st0.pcg_iterations)
+    launches = int(st1.kernel_launches - st0.kernel_launches)
+    n_markers = int(st1.n_markers)
+    dev_bytes = int(st1.device_bytes)
+    sim.close()
+    del sim
+
+    # ---- end to end through the C-ABI from host buffers (e2e) ------------------------
+    # timed region: euler_gpu_create from host arrays (H2D of the three masks and the seeded
+    # markers), K sub-steps, and after every sub-step the D2H read of the marker-count plane
+    # into pinned host memory — what the reference's step/draw loop moves (main.c:1034-1038).
+    count_host = torch.empty((n, n), dtype=torch.uint8, pin_memory=True).numpy()
+    barrier()
+    t0 = time.perf_counter()
+    sim = make()
+    for _ in range(args.steps):
+        one_step(sim)
+        sim.read_marker_count(count_host)
+    sim.synchronize()
+    t_e2e = time.perf_counter() - t0
+    h2d = (3 * cells + scn.markers.nbytes) / args.steps
+    d2h = float(cells)
+    sim.close()
+
+    t = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
+    it = torch.tensor([iters, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    iters_all, launches_all = int(it[0]), int(it[1])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        total_ms = sum(v[0] for v in prof.values())
+        dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
+        roof = None
+        kernels = {}
+        for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            if name in ALG_BYTES_PER_CELL:
+                b = ALG_BYTES_PER_CELL[name] * cells
+            elif name in ALG_BYTES_PER_MARKER:
+                b = ALG_BYTES_PER_MARKER[name] * n_markers
+            else:
+                b = None
+            avg = kms / cnt
+            kernels[name] = {"ms_avg": round(avg, 4), "launches": cnt, "share": round(kms / total_ms, 4),
+                             "gbs": round(b / avg / 1e6, 1) if b else None,
+                             "frac": round(b / avg / 1e6 / peak, 4) if b else None}
+        if dom and kernels[dom[0]]["gbs"]:
+            k = kernels[dom[0]]
+            roof = {"kernel": dom[0], "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": k["frac"], "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": ALG_BYTES_PER_CELL[dom[0]] * cells,
+                    "ms_per_launch": k["ms_avg"], "share_of_step": k["share"]}
+        value = cells * args.steps * world / (ms_max * 1e-3)
+        line = {
+            "metric": "MAC cell-updates/s", "value": value, "unit": "cell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s %dx%d per GPU, one sub-step of sim_step per step, PCG cap 100 "
+                                   "(reference main.c:735), %s preconditioner, fp64 PCG vectors"
+                                   % (args.scenario, n, n, "red-black IC(0)" if args.precon == "rb" else "IC(0) wavefront"),
+                       "grid": [n, n], "markers": n_markers,
+                       "parallelism": "single GPU" if world == 1 else "independent replicas x%d" % world,
+                       "l2_policy": "inputs >> L2: every plane is %.0f MB..%.0f MB vs 126 MB L2, no flush needed"
+                                    % (cells / 1e6, cells * 8 / 1e6),
+                       "device_bytes": dev_bytes, "host_setup_s": round(t_host, 2)},
+            "pcg_iters_per_s": iters_all / (ms_max * 1e-3),
+            "pcg_iterations": iters_all,
+            "gpu_launches": launches_all,
+            "e2e": {"value": cells * args.steps * world / (e2e_ms_max * 1e-3), "unit": "cell-updates/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "euler_gpu_create from host arrays + K sub-steps + per-step D2H of the count plane"},
+            "roofline": roof,
+            "kernels": kernels,
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world >= 1:
+            line["cpu_baseline"] = cpu_baseline(args, seconds=args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------- reference arm ----
+
+def cpu_sample(args, steps, warmup):
+    """Times the UNMODIFIED reference (oracle/_ref, its own -O3 -ffast-math flags) on one host
+    core, same synthetic scenario resampled to the sample grid."""
+    from euler_b200 import synthetic
+    from oracle.oracle import Reference, ref_available, Oracle
+    n = args.cpu_grid
+    text = synthetic(args.scenario, n, n)
+    if ref_available(n, n, fast=True):
+        sim = Reference(n, n, fast=True)
+        sim.init_from_text(text)
+        kind = "reference"
+
+        def step():
+            # one sub-step == sim_step() with the frame cut after the first sub-step is not
+            # expressible without touching the reference; time its own stages in sim_step order
+            dt = sim.calculate_timestep(0.1)
+            sim.advect_markers(dt); sim.refresh_marker_counts(); sim.update_fluid_sources()
+            sim.extrapolate(sim.u, 1); sim.extrapolate(sim.v, 2)
+            sim.zero_bounds(sim.u, 1); sim.zero_bounds(sim.v, 2)
+            sim.advect_u(dt); sim.advect_v(dt); sim.apply_body_forces(dt)
+            sim.zero_bounds(sim.utmp, 1); sim.zero_bounds(sim.vtmp, 2)
+            sim.project(dt)
+    else:
+        sim = Oracle(n, n, text)
+        kind = "port"
+
+        def step():
+            sim.substep(sim.calculate_timestep(0.1))
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": n * n * steps / dt, "unit": "cell-updates/s", "cores": 1, "kind": kind,
+            "host_cores_available": os.cpu_count(),
+            "sample": "%s resampled to %dx%d, %d sub-steps (PCG cap 100), single thread: the reference "
+                      "is single-threaded" % (args.scenario, n, n, steps),
+            "seconds": dt, "ms_per_step": dt / steps * 1e3}
+
+
+def cpu_baseline(args, seconds=20.0):
+    # ~3 s per sub-step at 1024^2: 1 warm-up + enough steps for ~seconds
+    steps = max(1, int(seconds / 3.5))
+    return cpu_sample(args, steps, 1)
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 6))
+    warm = 1 if args.warmup > 0 else 0
+    b = cpu_sample(args, steps, warm)
+    line = {"impl": "reference", "metric": "MAC cell-updates/s", "value": b["value"],
+            "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": b["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s, reference CPU path on a %dx%d sample of the %dx%d workload"
+                                   % (args.scenario, args.cpu_grid, args.cpu_grid, args.grid, args.grid)},
+            "cpu_baseline": b,
+            "e2e": {"value": b["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
+    ap.add_argument("--grid", type=int, default=16384)
+    ap.add_argument("--scenario", default="basic-fill")
+    ap.add_argument("--precon", default="rb", choices=["rb", "ic0"])
+    ap.add_argument("--check-every", type=int, default=25)
+    ap.add_argument("--cpu-grid", type=int, default=1024)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,6 +149,7 @@ void enqueue_iteration(euler_gpu* h) {
 int run_project(euler_gpu* h, float dt) {
   Ctx& c = h->c;
   launch_build_rhs(c, dt);
+  launch_tile_flags(c);
   int rc = pull_scalars(h);
   if (rc) return rc;
   h->last_iterations = 0;
@@ -198,6 +199,8 @@ int run_substep(euler_gpu* h, float dt) {
   h->substeps++;
   if (h->profiling) {
     CU(cudaEventSynchronize(h->ev[3]));
+    CU(cudaStreamSynchronize(c.stream));
+    prof_collect(c);
     float a = 0, b = 0, d = 0;
     cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
@@ -249,6 +252,10 @@ int euler_gpu_destroy(euler_gpu* h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->host_sc) cudaFreeHost(h->host_sc);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->c.prof.ev) {
+    for (int i = 0; i < 2 * h->c.prof.cap; ++i) if (h->c.prof.ev[i]) cudaEventDestroy(h->c.prof.ev[i]);
+    delete[] h->c.prof.ev; delete[] h->c.prof.cls;
+  }
   if (h->own_stream && h->c.stream) cudaStreamDestroy(h->c.stream);
   delete h;
   return 0;
@@ -308,6 +315,9 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   if (prm.stream) { c.stream = (cudaStream_t)prm.stream; h->own_stream = false; }
   else { TRYCU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); h->own_stream = true; }
   for (int i = 0; i < 4; ++i) TRYCU(cudaEventCreate(&h->ev[i]));
+  c.prof.cap = 4096;
+  c.prof.ev = new cudaEvent_t[2 * c.prof.cap]();
+  c.prof.cls = new int[c.prof.cap]();
   TRYCU(cudaMallocHost((void**)&h->host_sc, sizeof(DevScalars)));
 
   TRY(alloc_plane(h, &c.solid)); TRY(alloc_plane(h, &c.source)); TRY(alloc_plane(h, &c.sink));
@@ -326,7 +336,9 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   TRY(alloc_array(h, &c.seg_offset, c.n_segments));
   const size_t nblk2d = (size_t)((nx + 31) / 32) * (size_t)((ny + 7) / 8);
   c.n_strips = (ny - 2 + 31) / 32;
-  c.n_partials = nblk2d > (size_t)c.n_strips ? nblk2d : (size_t)c.n_strips;
+  c.n_partials = 65536 > (size_t)c.n_strips ? 65536 : (size_t)c.n_strips;
+  (void)nblk2d;
+  TRY(alloc_array(h, &c.tile_active, (size_t)pcg_tile_count(c.g)));
   TRY(alloc_array(h, &c.partials, c.n_partials));
   TRY(alloc_array(h, &c.wf_progress, (size_t)c.n_strips));
   TRY(alloc_array(h, &c.sc, 1));
@@ -417,13 +429,14 @@ int euler_gpu_run_stage(euler_gpu* h, int stage, float dt) {
     }
     case EULER_S_ADVECT_VELOCITY: launch_advect_velocity(c, dt); break;
     case EULER_S_PROJECT: { int rc = run_project(h, dt); if (rc) return rc; break; }
-    case EULER_S_BUILD_RHS: launch_build_rhs(c, dt); break;
+    case EULER_S_BUILD_RHS: launch_build_rhs(c, dt); launch_tile_flags(c); break;
     case EULER_S_PRECONDITION:
       launch_pcg_reset(c);
+      launch_tile_flags(c);
       if (h->prm.precon == EULER_PRECON_REDBLACK) launch_rb_build(c); else launch_ic0_build(c);
       enqueue_precon_apply(h, true);
       break;
-    case EULER_S_APPLY_A: launch_pcg_reset(c); launch_apply_a(c, false); break;
+    case EULER_S_APPLY_A: launch_pcg_reset(c); launch_tile_flags(c); launch_apply_a(c, false); break;
     case EULER_S_PRESSURE_UPDATE: launch_pressure_update(c, dt); h->max_valid = true; break;
     default: return fail(EULER_E_INVALID, "unknown stage %d", stage);
   }
@@ -435,7 +448,13 @@ int euler_gpu_run_stage(euler_gpu* h, int stage, float dt) {
 
 int euler_gpu_pcg_iterations(euler_gpu* h, int iterations) {
   ENTER(h);
-  for (int i = 0; i < iterations; ++i) enqueue_iteration(h);
+  for (int i = 0; i < iterations; ++i) {
+    enqueue_iteration(h);
+    if (h->c.prof.on && h->c.prof.n + 16 > h->c.prof.cap) {
+      CU(cudaStreamSynchronize(h->c.stream));
+      prof_collect(h->c);
+    }
+  }
   return check_launch("pcg_iterations");
 }
 
@@ -526,13 +545,38 @@ int euler_gpu_stats(euler_gpu* h, euler_stats* out) {
   out->kernel_launches = h->c.launches;
   out->device_bytes = h->device_bytes;
   out->ms_markers = h->ms_markers; out->ms_grid = h->ms_grid; out->ms_project = h->ms_project;
+  out->active_cells = (uint64_t)h->host_sc->active_tiles * (uint64_t)pcg_tile_cells();
+  for (int i = 0; i < KC__COUNT; ++i) { out->kernel_ms[i] = h->c.prof.ms[i]; out->kernel_count[i] = h->c.prof.count[i]; }
   return 0;
 }
 
 int euler_gpu_set_profiling(euler_gpu* h, int enabled) {
   ENTER(h);
+  CU(cudaStreamSynchronize(h->c.stream));
   h->profiling = enabled != 0;
+  h->c.prof.on = h->profiling;
+  h->c.prof.n = 0;
+  if (h->profiling)
+    for (int i = 0; i < 2 * h->c.prof.cap; ++i)
+      if (!h->c.prof.ev[i]) CU(cudaEventCreate(&h->c.prof.ev[i]));
   return 0;
+}
+
+int euler_gpu_reset_profile(euler_gpu* h) {
+  ENTER(h);
+  CU(cudaStreamSynchronize(h->c.stream));
+  prof_collect(h->c);
+  for (int i = 0; i < KC__COUNT; ++i) { h->c.prof.ms[i] = 0; h->c.prof.count[i] = 0; }
+  h->ms_markers = h->ms_grid = h->ms_project = 0;
+  return 0;
+}
+
+const char* euler_gpu_kernel_class_name(int i) {
+  static const char* names[KC__COUNT] = {
+      "maxsq", "advect_markers", "refresh_counts", "sources", "extrapolate_bounds",
+      "advect_velocity", "build_rhs", "precon_build", "precon_apply", "apply_a", "axpy_norm",
+      "update_search", "pressure_update", "misc"};
+  return (i >= 0 && i < KC__COUNT) ? names[i] : nullptr;
 }
 
 int euler_gpu_synchronize(euler_gpu* h) {

@@ -52,6 +52,7 @@ struct DevScalars {
   unsigned int ticket[4];
   // faithful marker mode (dt carry-over): number of candidate markers, first fired index
   unsigned long long n_candidates;
+  unsigned int active_tiles, pad2;
   unsigned long long first_fired;
 };
 

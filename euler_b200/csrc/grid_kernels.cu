@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(BX* BY) k_pressure_update(
 // ----------------------------------------------------------------- launchers ----
 
 void launch_maxsq(Ctx& c) {
+  ProfScope ps(c, KC_MAXSQ);
   cudaMemsetAsync(&c.sc->max_u2_bits, 0, 2 * sizeof(unsigned int), c.stream);
   const int blocks = c.sm_count * 8;
   k_maxsq<<<blocks, 256, 0, c.stream>>>(c.g, c.u, c.v, c.sc);
@@ -215,23 +216,27 @@ void launch_maxsq(Ctx& c) {
 }
 
 void launch_timestep(Ctx& c, float frame_time, float cfl) {
+  ProfScope ps(c, KC_MISC);
   k_timestep<<<1, 1, 0, c.stream>>>(c.sc, cfl * c.h, frame_time);
   c.launches += 1;
 }
 
 void launch_extrapolate(Ctx& c) {
+  ProfScope ps(c, KC_EXTRAPOLATE);
   k_extrapolate_bounds<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
       c.g, c.u, c.v, c.count, c.prev_count, c.solid, c.uext, c.vext);
   c.launches += 1;
 }
 
 void launch_advect_velocity(Ctx& c, float dt) {
+  ProfScope ps(c, KC_ADVECT_VELOCITY);
   k_advect_velocity<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
       c.g, c.lim, c.u, c.v, c.count, c.solid, c.utmp, c.vtmp, dt, c.h, c.gravity);
   c.launches += 1;
 }
 
 void launch_build_rhs(Ctx& c, float dt) {
+  ProfScope ps(c, KC_BUILD_RHS);
   cudaMemsetAsync(&c.sc->nonzero_rhs, 0, sizeof(int), c.stream);
   const double scale = (double)((c.h * c.h) * c.rho / dt);     // fp32 expression, main.c:713
   k_build_rhs<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
@@ -240,6 +245,7 @@ void launch_build_rhs(Ctx& c, float dt) {
 }
 
 void launch_pressure_update(Ctx& c, float dt) {
+  ProfScope ps(c, KC_PRESSURE_UPDATE);
   cudaMemsetAsync(&c.sc->max_u2_bits, 0, 2 * sizeof(unsigned int), c.stream);
   const float k = 1.f / (c.rho * c.h);                          // invf(rho*h), main.c:706
   k_pressure_update<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(

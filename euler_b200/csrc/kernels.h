@@ -7,7 +7,24 @@
 
 namespace euler {
 
+// Kernel classes for the per-kernel timers (euler_stats.kernel_ms); order is ABI.
+enum KernelClass {
+  KC_MAXSQ = 0, KC_ADVECT_MARKERS, KC_REFRESH_COUNTS, KC_SOURCES, KC_EXTRAPOLATE,
+  KC_ADVECT_VELOCITY, KC_BUILD_RHS, KC_PRECON_BUILD, KC_PRECON_APPLY, KC_APPLY_A, KC_AXPY,
+  KC_UPDATE_SEARCH, KC_PRESSURE_UPDATE, KC_MISC, KC__COUNT
+};
+
+struct Prof {
+  bool on;
+  int n, cap;
+  cudaEvent_t* ev;     // 2*cap events
+  int* cls;            // class of each recorded pair
+  double ms[KC__COUNT];
+  unsigned long long count[KC__COUNT];
+};
+
 struct Ctx {
+  Prof prof;
   Grid g;
   InterpLimits lim;
   cudaStream_t stream;
@@ -37,12 +54,34 @@ struct Ctx {
   // pressure solve
   int8_t* adiag;
   double *precon, *q, *p, *r, *z, *s;
+  uint8_t* tile_active;           // per PCG tile: contains fluid (pcg_kernels.cu)
   double* partials;               // grid-reduction scratch
   size_t n_partials;
   unsigned int* wf_progress;      // wavefront strip progress flags
   int n_strips;
   DevScalars* sc;                 // device scalars
 };
+
+// RAII: when profiling is on, brackets the launches of one kernel class with CUDA events on
+// ctx.stream; prof_collect() (after a stream sync) folds them into Prof::ms.
+struct ProfScope {
+  Ctx& c; int slot;
+  ProfScope(Ctx& ctx, int cls) : c(ctx), slot(-1) {
+    Prof& p = c.prof;
+    if (p.on && p.n < p.cap) { slot = p.n++; p.cls[slot] = cls; cudaEventRecord(p.ev[2 * slot], c.stream); }
+  }
+  ~ProfScope() { if (slot >= 0) cudaEventRecord(c.prof.ev[2 * slot + 1], c.stream); }
+};
+inline void prof_collect(Ctx& c) {
+  Prof& p = c.prof;
+  for (int i = 0; i < p.n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.ev[2 * i], p.ev[2 * i + 1]) == cudaSuccess) {
+      p.ms[p.cls[i]] += ms; p.count[p.cls[i]] += 1;
+    }
+  }
+  p.n = 0;
+}
 
 // ---- grid stages (grid_kernels.cu)
 void launch_maxsq(Ctx& c);                                   // -> sc.max_u2_bits/max_v2_bits
@@ -68,5 +107,8 @@ void launch_apply_a(Ctx& c, bool with_alpha);                // z = A s (+ z.s, 
 void launch_axpy(Ctx& c, double tol);                        // p += a s, r -= a z, ||r||inf
 void launch_update_search(Ctx& c);                           // s = z + beta s
 void launch_pcg_reset(Ctx& c);                               // iters=0, done=0
+void launch_tile_flags(Ctx& c);                              // per-tile fluid flags from count
+int pcg_tile_count(const Grid& g);
+int pcg_tile_cells();
 
 }  // namespace euler

@@ -402,6 +402,7 @@ void init_rng_jump_table(unsigned long long* t) {
 }
 
 void launch_advect_markers(Ctx& c, float dt, int /*mode*/) {
+  ProfScope ps(c, KC_ADVECT_MARKERS);
   const int blocks = c.sm_count * 8;
   k_advect_markers<<<blocks, MTHREADS, 0, c.stream>>>(c.g, c.lim, c.u, c.v, c.count, c.solid,
                                                       c.h, c.markers, c.markers_alt, c.sc, dt);
@@ -410,6 +411,7 @@ void launch_advect_markers(Ctx& c, float dt, int /*mode*/) {
 }
 
 void launch_refresh_counts(Ctx& c) {
+  ProfScope ps(c, KC_REFRESH_COUNTS);
   // prev <- cur (main.c:103) by swapping planes; cur is rebuilt from scratch (main.c:104)
   uint8_t* t = c.prev_count; c.prev_count = c.count; c.count = t;
   const int blocks = c.sm_count * 8;
@@ -426,6 +428,7 @@ void launch_refresh_counts(Ctx& c) {
 
 void launch_sources(Ctx& c) {
   if (c.n_source_cells == 0) return;
+  ProfScope ps(c, KC_SOURCES);
   k_sources<<<1, 1024, 0, c.stream>>>(c.g, c.h, c.source_cells, c.n_source_cells, c.count,
                                       c.markers, c.max_markers, c.rng_jump, c.sc);
   c.launches += 1;

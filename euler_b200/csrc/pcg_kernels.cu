@@ -9,72 +9,214 @@
 //
 // The reference-faithful natural-order IC(0) lives in wavefront.cu.
 //
-// Scalars never visit the host: each reducing kernel leaves per-block partials, the block
-// that finishes last folds them in a fixed order and writes alpha / beta / sigma / the stop
-// flag into DevScalars (common.cuh grid_reduce_last_block).  Once `done` is set every later
-// kernel of the solve returns immediately, so the host may enqueue iterations in batches and
-// poll rarely; the iterate sequence is the same as with a per-iteration test.
+// Execution shape (all kernels here): a PERSISTENT grid of sm_count x PCG_BLOCKS_PER_SM blocks
+// walks the grid in tiles of TW x TH = 512 x 16 cells.  A thread owns 4 consecutive x (one
+// uchar4 / two double2 loads per plane and row, 16 B-aligned, fully coalesced) and marches
+// up the TH rows of the tile keeping a three-row window of the stencil operand in
+// REGISTERS, so every operand row is loaded from HBM/L2 once per tile (plus one halo row
+// above and below).  Left/right neighbours come from the adjacent lane by warp shuffle; only
+// the two edge lanes of a warp issue one extra scalar load.  Tiles without any fluid cell are
+// skipped through a per-tile flag built once per sub-step (k_tile_flags) — like the
+// reference, which touches only is_fluid cells.
 //
-// All vectors are fp64 like the reference's; only fluid cells are read or written
-// (is_fluid(y,x) guards every loop body of the reference).
+// Scalars never visit the host: each reducing kernel leaves ONE partial per block, the block
+// that finishes last folds them in a fixed order (deterministic) and writes alpha / beta /
+// sigma / the stop flag into DevScalars.  Once `done` is set every later kernel of the solve
+// returns immediately, so the host may enqueue iterations in batches and poll rarely; the
+// iterate sequence is the same as with the reference's per-iteration test.
+//
+// All vectors are fp64 like the reference's.  -fmad=false + source-order arithmetic make
+// every element-wise result bit-identical to the CPU's; only the order of the dot-product
+// sums differs.
 #include "kernels.h"
 
 namespace euler {
 
 namespace {
 
-constexpr int BX = 32, BY = 8;
-inline dim3 grid2d(const Grid& g) { return dim3((g.nx + BX - 1) / BX, (g.ny + BY - 1) / BY); }
-
+constexpr int TW = 512, TH = 16, TT = 128;     // tile width/height in cells, threads per block
 enum { CTR_ZS = 0, CTR_NORM = 1, CTR_ZR = 2 };
 
-// z = A s on fluid cells; off-diagonals are -1 towards fluid neighbours, a_diag = number of
-// non-solid neighbours.  Subtraction order as in main.c:683-687: right, up, left, down.
-__global__ void __launch_bounds__(BX* BY) k_apply_a(
-    Grid g, const double* __restrict__ s, const uint8_t* __restrict__ fluid,
-    const int8_t* __restrict__ adiag, double* __restrict__ z, double* partials, DevScalars* sc) {
-  if (sc->done) return;
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
-  double prod = 0.0;
-  if (x < g.nx && y < g.ny) {
-    const size_t c = gidx(g, x, y);
-    if (fluid[c]) {
-      const double sc_ = s[c];
-      double out = (double)adiag[c] * sc_;
-      out -= fluid[c + 1] ? s[c + 1] : 0.0;
-      out -= fluid[c + g.pitch] ? s[c + g.pitch] : 0.0;
-      out -= fluid[c - 1] ? s[c - 1] : 0.0;
-      out -= fluid[c - g.pitch] ? s[c - g.pitch] : 0.0;
-      z[c] = out;
-      prod = out * sc_;
+struct Tiles { int tx, ty, n; };
+__host__ __device__ inline Tiles tiles_of(const Grid& g) {
+  Tiles t;
+  t.tx = (g.pitch + TW - 1) / TW;
+  t.ty = (g.ny + TH - 1) / TH;
+  t.n = t.tx * t.ty;
+  return t;
+}
+
+struct D4 { double v[4]; };
+
+__device__ __forceinline__ D4 ld4(const double* __restrict__ p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  D4 r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  return r;
+}
+__device__ __forceinline__ void st4(double* __restrict__ p, const D4& d) {
+  *reinterpret_cast<double2*>(p) = make_double2(d.v[0], d.v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(d.v[2], d.v[3]);
+}
+__device__ __forceinline__ unsigned ldmask(const uint8_t* __restrict__ p) {
+  return *reinterpret_cast<const unsigned*>(p);            // 4 cells, one byte each
+}
+__device__ __forceinline__ bool mbit(unsigned m, int k) { return ((m >> (8 * k)) & 0xffu) != 0; }
+
+// per-tile "contains fluid" flags
+__global__ void __launch_bounds__(TT) k_tile_flags(Grid g, const uint8_t* __restrict__ fluid,
+                                                   uint8_t* __restrict__ active, DevScalars* sc) {
+  const Tiles T = tiles_of(g);
+  for (int tile = blockIdx.x; tile < T.n; tile += gridDim.x) {
+    const int x0 = (tile % T.tx) * TW + threadIdx.x * 4, y0 = (tile / T.tx) * TH;
+    const int y1 = min(y0 + TH, g.ny);
+    unsigned any = 0;
+    if (x0 < g.pitch)
+      for (int y = y0; y < y1; ++y) any |= ldmask(fluid + gidx(g, x0, y));
+    const int has = __syncthreads_or(any != 0);
+    if (threadIdx.x == 0) {
+      active[tile] = has ? 1 : 0;
+      if (has) atomicAdd(&sc->active_tiles, 1u);
     }
   }
-  const double bsum = block_reduce<false>(prod);
+}
+
+// ---------------------------------------------------------------------------------------
+// Three-row register window over a per-cell operand W (what the 5-point stencil reads from
+// the neighbours) plus the fluid mask.  `Op` supplies:
+//   D4   Op::operand(c)            W of the 4 cells starting at flat index c
+//   double Op::operand1(c)         W of the single cell c (edge lanes)
+//   void Op::cell(c, k, m, wc, wl, fl, wr, fr, wd, fd, wu, fu)   consume one cell
+//   operand(c, slot) is called once per row entering the window (slot says where), so an Op
+//   may stash other planes of that row; rotate() is called when UP becomes CENTER.
+// Call order inside a tile row is k = 0..3 for ascending x.
+enum { SLOT_DOWN = 0, SLOT_CENTER = 1, SLOT_UP = 2 };
+
+template <class Op>
+__device__ __forceinline__ void stencil_tile(const Grid& g, const uint8_t* __restrict__ fluid,
+                                             int x0, int y0, int y1, bool live, Op& op) {
+  const int lane = threadIdx.x & 31;
+  const unsigned keep = live ? 0xffffffffu : 0u;   // threads past the row end present no fluid
+  size_t c = gidx(g, x0, y0);
+  D4 wd = op.operand(c - g.pitch, SLOT_DOWN);
+  unsigned md = ldmask(fluid + c - g.pitch) & keep;
+  D4 wc = op.operand(c, SLOT_CENTER);
+  unsigned mc = ldmask(fluid + c) & keep;
+  for (int y = y0; y < y1; ++y, c += g.pitch) {
+    const D4 wu = op.operand(c + g.pitch, SLOT_UP);
+    const unsigned mu = ldmask(fluid + c + g.pitch) & keep;
+    // horizontal neighbours of the quad's two end cells
+    double wl = __shfl_up_sync(EULER_FULL_MASK, wc.v[3], 1);
+    double wr = __shfl_down_sync(EULER_FULL_MASK, wc.v[0], 1);
+    unsigned ml = __shfl_up_sync(EULER_FULL_MASK, mc, 1) >> 24;
+    unsigned mr = __shfl_down_sync(EULER_FULL_MASK, mc, 1) & 0xffu;
+    if (lane == 0) { ml = fluid[c - 1]; wl = ml ? op.operand1(c - 1) : 0.0; }
+    if (lane == 31) { mr = fluid[c + 4]; wr = mr ? op.operand1(c + 4) : 0.0; }
+    if (mc) {
+      op.begin_row(c, mc);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!mbit(mc, k)) continue;
+        const double l = k == 0 ? wl : wc.v[k - 1];
+        const bool fl = k == 0 ? (ml != 0) : mbit(mc, k - 1);
+        const double r = k == 3 ? wr : wc.v[k + 1];
+        const bool fr = k == 3 ? (mr != 0) : mbit(mc, k + 1);
+        op.cell(c, k, wc.v[k], l, fl, r, fr, wd.v[k], mbit(md, k), wu.v[k], mbit(mu, k), x0 + k, y);
+      }
+      op.end_row(c, mc);
+    }
+    wd = wc; md = mc; wc = wu; mc = mu;
+    op.rotate();
+  }
+}
+
+template <class Body>
+__device__ __forceinline__ void for_each_tile(const Grid& g, const uint8_t* __restrict__ active,
+                                              Body body) {
+  const Tiles T = tiles_of(g);
+  for (int tile = blockIdx.x; tile < T.n; tile += gridDim.x) {
+    if (!active[tile]) continue;
+    const int x0 = (tile % T.tx) * TW + threadIdx.x * 4, y0 = (tile / T.tx) * TH;
+    // threads past the row end keep participating in the shuffles with a clamped, harmless
+    // address (their mask is the zero padding / they are never asked for a valid neighbour)
+    const int xs = min(x0, g.pitch - 4);
+    body(xs, y0, min(y0 + TH, g.ny), x0 < g.pitch);
+  }
+}
+
+// ---- z = A s --------------------------------------------------------------------------
+struct ApplyA {
+  const double* __restrict__ s;
+  const int8_t* __restrict__ adiag;
+  double* __restrict__ z;
+  double acc;
+  unsigned am;
+  D4 out;
+  __device__ __forceinline__ D4 operand(size_t c, int) const { return ld4(s + c); }
+  __device__ __forceinline__ double operand1(size_t c) const { return s[c]; }
+  __device__ __forceinline__ void rotate() {}
+  __device__ __forceinline__ void begin_row(size_t c, unsigned) {
+    am = ldmask(reinterpret_cast<const uint8_t*>(adiag) + c);
+    out.v[0] = out.v[1] = out.v[2] = out.v[3] = 0.0;
+  }
+  __device__ __forceinline__ void cell(size_t, int k, double sc, double l, bool fl, double r, bool fr,
+                                       double d, bool fd, double u, bool fu, int, int) {
+    // main.c:683-687: a_diag*s - right - up - left - down, each only towards fluid
+    double o = (double)(int)(signed char)((am >> (8 * k)) & 0xffu) * sc;
+    o -= fr ? r : 0.0;
+    o -= fu ? u : 0.0;
+    o -= fl ? l : 0.0;
+    o -= fd ? d : 0.0;
+    out.v[k] = o;
+    acc += o * sc;
+  }
+  __device__ __forceinline__ void end_row(size_t c, unsigned) { st4(z + c, out); }
+};
+
+__global__ void __launch_bounds__(TT) k_apply_a(
+    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ s,
+    const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ z,
+    double* partials, DevScalars* sc) {
+  if (sc->done) return;
+  ApplyA op{s, adiag, z, 0.0, 0u, {}};
+  for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
+    stencil_tile(g, fluid, x0, y0, y1, live, op);
+  });
+  const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZS], [&](double total) {
     sc->zs = total;
     sc->alpha = sc->sigma / total;                           // main.c:752
   });
 }
 
-__global__ void __launch_bounds__(BX* BY) k_axpy(
-    Grid g, const double* __restrict__ s, const double* __restrict__ z,
-    const uint8_t* __restrict__ fluid, double* __restrict__ p, double* __restrict__ r,
-    double* partials, DevScalars* sc, double tol) {
+// ---- p += alpha s ; r -= alpha z ; ||r||inf ---------------------------------------------
+__global__ void __launch_bounds__(TT) k_axpy(
+    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ s,
+    const double* __restrict__ z, const uint8_t* __restrict__ fluid, double* __restrict__ p,
+    double* __restrict__ r, double* partials, DevScalars* sc, double tol) {
   if (sc->done) return;
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
   const double alpha = sc->alpha;
   double m = 0.0;
-  if (x < g.nx && y < g.ny) {
-    const size_t c = gidx(g, x, y);
-    if (fluid[c]) {
-      p[c] = p[c] + s[c] * alpha;                            // fmadd(s, alpha, p)  main.c:753
-      const double rn = r[c] + z[c] * -alpha;                // fmadd(z, -alpha, r) main.c:754
-      r[c] = rn;
-      m = fabs(rn);
+  for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
+    if (!live) return;
+    size_t c = gidx(g, x0, y0);
+    for (int y = y0; y < y1; ++y, c += g.pitch) {
+      const unsigned mc = ldmask(fluid + c);
+      if (!mc) continue;
+      const D4 sv = ld4(s + c), zv = ld4(z + c);
+      D4 pv = ld4(p + c), rv = ld4(r + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!mbit(mc, k)) continue;
+        pv.v[k] = pv.v[k] + sv.v[k] * alpha;                 // fmadd(s, alpha, p)  main.c:753
+        rv.v[k] = rv.v[k] + zv.v[k] * -alpha;                // fmadd(z, -alpha, r) main.c:754
+        const double a = fabs(rv.v[k]);
+        if (a > m) m = a;                                    // NaN-dropping, main.c:659-662
+      }
+      st4(p + c, pv);
+      st4(r + c, rv);
     }
-  }
-  // NaN-dropping max like `a > maximum` (main.c:659-662)
-  m = (m > 0.0) ? m : 0.0;
+  });
   const double bmax = block_reduce<true>(m);
   grid_reduce_last_block<true>(bmax, partials, &sc->ctr[CTR_NORM], [&](double total) {
     sc->resid = total;
@@ -83,22 +225,37 @@ __global__ void __launch_bounds__(BX* BY) k_axpy(
   });
 }
 
-__global__ void __launch_bounds__(BX* BY) k_update_search(
-    Grid g, const double* __restrict__ z, const uint8_t* __restrict__ fluid,
-    double* __restrict__ s, const DevScalars* sc) {
+// ---- s = z + beta s -------------------------------------------------------------------
+__global__ void __launch_bounds__(TT) k_update_search(
+    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ z,
+    const uint8_t* __restrict__ fluid, double* __restrict__ s, const DevScalars* sc) {
   if (sc->done) return;
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
-  if (x >= g.nx || y >= g.ny) return;
-  const size_t c = gidx(g, x, y);
-  if (fluid[c]) s[c] = z[c] + sc->beta * s[c];               // main.c:673
+  const double beta = sc->beta;
+  for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
+    if (!live) return;
+    size_t c = gidx(g, x0, y0);
+    for (int y = y0; y < y1; ++y, c += g.pitch) {
+      const unsigned mc = ldmask(fluid + c);
+      if (!mc) continue;
+      const D4 zv = ld4(z + c);
+      D4 sv = ld4(s + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (mbit(mc, k)) sv.v[k] = zv.v[k] + beta * sv.v[k];  // main.c:673
+      st4(s + c, sv);
+    }
+  });
 }
 
-__global__ void __launch_bounds__(BX* BY) k_copy_search(Grid g, const double* __restrict__ z,
-                                                        double* __restrict__ s) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
-  if (x >= g.nx || y >= g.ny) return;
-  const size_t c = gidx(g, x, y);
-  s[c] = z[c];                                               // memcpy(s, z) main.c:746
+// s = z on the active tiles (memcpy(s, z), main.c:746)
+__global__ void __launch_bounds__(TT) k_copy_search(Grid g, const uint8_t* __restrict__ active,
+                                                    const double* __restrict__ z,
+                                                    double* __restrict__ s) {
+  for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
+    if (!live) return;
+    size_t c = gidx(g, x0, y0);
+    for (int y = y0; y < y1; ++y, c += g.pitch) st4(s + c, ld4(z + c));
+  });
 }
 
 __global__ void k_pcg_reset(DevScalars* sc) {
@@ -115,10 +272,10 @@ __device__ __forceinline__ double rb_e_red(const int8_t* __restrict__ adiag, siz
   return a != 0.0 ? a : 1.0;
 }
 
-__global__ void __launch_bounds__(BX* BY) k_rb_build(
+__global__ void __launch_bounds__(256) k_rb_build(
     Grid g, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
     double* __restrict__ precon) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if (x < 1 || y < 1 || x >= g.nx - 1 || y >= g.ny - 1) return;
   const size_t c = gidx(g, x, y);
   if (!fluid[c]) return;
@@ -135,102 +292,185 @@ __global__ void __launch_bounds__(BX* BY) k_rb_build(
   precon[c] = 1.0 / sqrt(e);
 }
 
-// q = L^-1 r.  Red: q = r*pc.  Black: q = (r + sum pc_nb * q_nb) * pc with q_nb = r_nb*pc_nb
-// recomputed on the fly (identical bits to the stored value).
-__global__ void __launch_bounds__(BX* BY) k_rb_forward(
-    Grid g, const double* __restrict__ r, const uint8_t* __restrict__ fluid,
-    const double* __restrict__ precon, double* __restrict__ q, const DevScalars* sc) {
-  if (sc->done) return;
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
-  if (x < 1 || y < 1 || x >= g.nx - 1 || y >= g.ny - 1) return;
-  const size_t c = gidx(g, x, y);
-  if (!fluid[c]) return;
-  double t = r[c];
-  if ((x + y) & 1) {
-    const long off[4] = {-1, 1, -(long)g.pitch, (long)g.pitch};
+// q = L^-1 r.  Red: q = r*pc.  Black: q = (r + sum_nb pc_nb*(r_nb*pc_nb)) * pc.  The window
+// operand is W = pc*(r*pc), i.e. pc_nb*q_nb of a red neighbour, recomputed on the fly with
+// the same two roundings as the stored q would have.
+struct RbForward {
+  const double* __restrict__ r;
+  const double* __restrict__ pc;
+  double* __restrict__ q;
+  D4 rr, pp, ru, pu, out;          // r, pc of the centre row / of the row above
+  __device__ __forceinline__ D4 operand(size_t c, int slot) {
+    const D4 a = ld4(r + c), b = ld4(pc + c);
+    if (slot == SLOT_CENTER) { rr = a; pp = b; }
+    if (slot == SLOT_UP) { ru = a; pu = b; }
+    D4 w;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const size_t nb = c + off[k];
-      if (fluid[nb]) { const double pn = precon[nb]; t = t + pn * (r[nb] * pn); }
-    }
+    for (int k = 0; k < 4; ++k) w.v[k] = b.v[k] * (a.v[k] * b.v[k]);
+    return w;
   }
-  q[c] = t * precon[c];
+  __device__ __forceinline__ double operand1(size_t c) const { const double b = pc[c]; return b * (r[c] * b); }
+  __device__ __forceinline__ void rotate() { rr = ru; pp = pu; }
+  __device__ __forceinline__ void begin_row(size_t, unsigned) {
+    out.v[0] = out.v[1] = out.v[2] = out.v[3] = 0.0;
+  }
+  __device__ __forceinline__ void cell(size_t, int k, double, double l, bool fl, double rt, bool fr,
+                                       double d, bool fd, double u, bool fu, int x, int y) {
+    double t = rr.v[k];
+    if ((x + y) & 1) {
+      if (fl) t = t + l;
+      if (fr) t = t + rt;
+      if (fd) t = t + d;
+      if (fu) t = t + u;
+    }
+    out.v[k] = t * pp.v[k];
+  }
+  __device__ __forceinline__ void end_row(size_t c, unsigned) { st4(q + c, out); }
+};
+
+__global__ void __launch_bounds__(TT) k_rb_forward(
+    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ r,
+    const uint8_t* __restrict__ fluid, const double* __restrict__ precon, double* __restrict__ q,
+    const DevScalars* sc) {
+  if (sc->done) return;
+  RbForward op{r, precon, q, {}, {}, {}, {}, {}};
+  for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
+    stencil_tile(g, fluid, x0, y0, y1, live, op);
+  });
 }
 
-// z = L^-T q.  Black: z = q*pc.  Red: z = (q + sum pc * z_nb) * pc with z_nb = q_nb*pc_nb.
-// Fused with the z.r reduction that follows every preconditioner application
-// (main.c:748, 762) and the beta / sigma update (main.c:763-765).
-__global__ void __launch_bounds__(BX* BY) k_rb_backward(
-    Grid g, const double* __restrict__ q, const double* __restrict__ r,
-    const uint8_t* __restrict__ fluid, const double* __restrict__ precon,
-    double* __restrict__ z, double* partials, DevScalars* sc, int init) {
-  if (sc->done) return;
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
-  double prod = 0.0;
-  if (x >= 1 && y >= 1 && x < g.nx - 1 && y < g.ny - 1) {
-    const size_t c = gidx(g, x, y);
-    if (fluid[c]) {
-      const double pc = precon[c];
-      double t = q[c];
-      if (((x + y) & 1) == 0) {
-        const long off[4] = {-1, 1, -(long)g.pitch, (long)g.pitch};
+// z = L^-T q.  Black: z = q*pc.  Red: z = (q + sum_nb pc*(q_nb*pc_nb)) * pc; window operand
+// W = q*pc (z of a black neighbour).  Fused with the z.r reduction that follows every
+// preconditioner application (main.c:748, 762) and the beta / sigma update (main.c:763-765).
+struct RbBackward {
+  const double* __restrict__ q;
+  const double* __restrict__ pc;
+  const double* __restrict__ r;
+  double* __restrict__ z;
+  double acc;
+  D4 qq, pp, qu, pu, rr, out;      // q, pc of the centre row / of the row above; r of the centre
+  __device__ __forceinline__ D4 operand(size_t c, int slot) {
+    const D4 a = ld4(q + c), b = ld4(pc + c);
+    if (slot == SLOT_CENTER) { qq = a; pp = b; }
+    if (slot == SLOT_UP) { qu = a; pu = b; }
+    D4 w;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const size_t nb = c + off[k];
-          if (fluid[nb]) t = t + pc * (q[nb] * precon[nb]);
-        }
-      }
-      const double zc = t * pc;
-      z[c] = zc;
-      prod = zc * r[c];
-    }
+    for (int k = 0; k < 4; ++k) w.v[k] = a.v[k] * b.v[k];
+    return w;
   }
-  const double bsum = block_reduce<false>(prod);
+  __device__ __forceinline__ double operand1(size_t c) const { return q[c] * pc[c]; }
+  __device__ __forceinline__ void rotate() { qq = qu; pp = pu; }
+  __device__ __forceinline__ void begin_row(size_t c, unsigned) {
+    rr = ld4(r + c);
+    out.v[0] = out.v[1] = out.v[2] = out.v[3] = 0.0;
+  }
+  __device__ __forceinline__ void cell(size_t, int k, double wc, double l, bool fl, double rt, bool fr,
+                                       double d, bool fd, double u, bool fu, int x, int y) {
+    double zc;
+    if ((x + y) & 1) {
+      zc = wc;                                               // black: q*pc
+    } else {
+      const double p = pp.v[k];
+      double t = qq.v[k];
+      if (fl) t = t + p * l;
+      if (fr) t = t + p * rt;
+      if (fd) t = t + p * d;
+      if (fu) t = t + p * u;
+      zc = t * p;
+    }
+    out.v[k] = zc;
+    acc += zc * rr.v[k];
+  }
+  __device__ __forceinline__ void end_row(size_t c, unsigned) { st4(z + c, out); }
+};
+
+__global__ void __launch_bounds__(TT) k_rb_backward(
+    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ q,
+    const double* __restrict__ r, const uint8_t* __restrict__ fluid,
+    const double* __restrict__ precon, double* __restrict__ z, double* partials, DevScalars* sc,
+    int init) {
+  if (sc->done) return;
+  RbBackward op{q, precon, r, z, 0.0, {}, {}, {}, {}, {}, {}};
+  for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
+    stencil_tile(g, fluid, x0, y0, y1, live, op);
+  });
+  const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZR], [&](double total) {
     if (init) { sc->sigma = total; }                         // main.c:748
     else { sc->beta = total / sc->sigma; sc->sigma = total; }  // main.c:762-765
   });
 }
 
+// persistent grid: resident blocks per SM (occupancy of that kernel) x SM count, capped by
+// the number of tiles
+template <class K>
+int pcg_blocks(const Ctx& c, K kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TT, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 4;
+  const Tiles T = tiles_of(c.g);
+  const long want = (long)c.sm_count * per_sm;
+  return (int)(T.n < want ? T.n : want);
+}
+
 }  // namespace
 
+void launch_tile_flags(Ctx& c) {
+  ProfScope ps(c, KC_MISC);
+  cudaMemsetAsync(&c.sc->active_tiles, 0, sizeof(unsigned int), c.stream);
+  k_tile_flags<<<pcg_blocks(c, k_tile_flags), TT, 0, c.stream>>>(c.g, c.count, c.tile_active, c.sc);
+  c.launches += 1;
+}
+
 void launch_pcg_reset(Ctx& c) {
+  ProfScope ps(c, KC_MISC);
   k_pcg_reset<<<1, 1, 0, c.stream>>>(c.sc);
   c.launches += 1;
 }
 
 void launch_apply_a(Ctx& c, bool) {
-  k_apply_a<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(c.g, c.s, c.count, c.adiag, c.z,
-                                                        c.partials, c.sc);
+  ProfScope ps(c, KC_APPLY_A);
+  k_apply_a<<<pcg_blocks(c, k_apply_a), TT, 0, c.stream>>>(c.g, c.tile_active, c.s, c.count, c.adiag, c.z,
+                                                c.partials, c.sc);
   c.launches += 1;
 }
 
 void launch_axpy(Ctx& c, double tol) {
-  k_axpy<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(c.g, c.s, c.z, c.count, c.p, c.r,
-                                                     c.partials, c.sc, tol);
+  ProfScope ps(c, KC_AXPY);
+  k_axpy<<<pcg_blocks(c, k_axpy), TT, 0, c.stream>>>(c.g, c.tile_active, c.s, c.z, c.count, c.p, c.r,
+                                             c.partials, c.sc, tol);
   c.launches += 1;
 }
 
 void launch_update_search(Ctx& c) {
-  k_update_search<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(c.g, c.z, c.count, c.s, c.sc);
+  ProfScope ps(c, KC_UPDATE_SEARCH);
+  k_update_search<<<pcg_blocks(c, k_update_search), TT, 0, c.stream>>>(c.g, c.tile_active, c.z, c.count, c.s, c.sc);
   c.launches += 1;
 }
 
 void launch_copy_search(Ctx& c) {
-  k_copy_search<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(c.g, c.z, c.s);
+  ProfScope ps(c, KC_MISC);
+  k_copy_search<<<pcg_blocks(c, k_copy_search), TT, 0, c.stream>>>(c.g, c.tile_active, c.z, c.s);
   c.launches += 1;
 }
 
 void launch_rb_build(Ctx& c) {
-  k_rb_build<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(c.g, c.count, c.adiag, c.precon);
+  ProfScope ps(c, KC_PRECON_BUILD);
+  k_rb_build<<<dim3((c.g.nx + 31) / 32, (c.g.ny + 7) / 8), dim3(32, 8), 0, c.stream>>>(
+      c.g, c.count, c.adiag, c.precon);
   c.launches += 1;
 }
 
 void launch_rb_apply(Ctx& c, bool init) {
-  k_rb_forward<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(c.g, c.r, c.count, c.precon, c.q, c.sc);
-  k_rb_backward<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(c.g, c.q, c.r, c.count, c.precon,
-                                                            c.z, c.partials, c.sc, init ? 1 : 0);
+  ProfScope ps(c, KC_PRECON_APPLY);
+  k_rb_forward<<<pcg_blocks(c, k_rb_forward), TT, 0, c.stream>>>(c.g, c.tile_active, c.r, c.count, c.precon,
+                                                   c.q, c.sc);
+  k_rb_backward<<<pcg_blocks(c, k_rb_backward), TT, 0, c.stream>>>(c.g, c.tile_active, c.q, c.r, c.count,
+                                                    c.precon, c.z, c.partials, c.sc, init ? 1 : 0);
   c.launches += 2;
 }
+
+int pcg_tile_count(const Grid& g) { return tiles_of(g).n; }
+int pcg_tile_cells() { return TW * TH; }
 
 }  // namespace euler

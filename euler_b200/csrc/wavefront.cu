@@ -188,6 +188,7 @@ static void reset_wavefront(Ctx& c) {
 }
 
 void launch_ic0_build(Ctx& c) {
+  ProfScope ps(c, KC_PRECON_BUILD);
   reset_wavefront(c);
   k_ic0_sweep<WF_BUILD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, nullptr, nullptr, nullptr, c.wf_progress,
@@ -196,6 +197,7 @@ void launch_ic0_build(Ctx& c) {
 }
 
 void launch_ic0_apply(Ctx& c, bool init) {
+  ProfScope ps(c, KC_PRECON_APPLY);
   reset_wavefront(c);
   k_ic0_sweep<WF_FORWARD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, c.r, c.q, nullptr, c.wf_progress, &c.sc->ticket[1],

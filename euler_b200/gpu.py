@@ -46,7 +46,9 @@ class Stats(C.Structure):
                 ("n_markers", C.c_uint64), ("source_exhausted", C.c_int),
                 ("rng_state", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_bytes", C.c_uint64),
-                ("ms_markers", C.c_double), ("ms_grid", C.c_double), ("ms_project", C.c_double)]
+                ("ms_markers", C.c_double), ("ms_grid", C.c_double), ("ms_project", C.c_double),
+                ("active_cells", C.c_uint64),
+                ("kernel_ms", C.c_double * 16), ("kernel_count", C.c_uint64 * 16)]
 
 
 class EulerGpuError(RuntimeError):
@@ -73,6 +75,9 @@ _L.euler_gpu_set_source_exhausted.argtypes = [_H, C.c_int]
 _L.euler_gpu_stats.argtypes = [_H, C.POINTER(Stats)]
 _L.euler_gpu_set_profiling.argtypes = [_H, C.c_int]
 _L.euler_gpu_synchronize.argtypes = [_H]
+_L.euler_gpu_reset_profile.argtypes = [_H]
+_L.euler_gpu_kernel_class_name.restype = C.c_char_p
+_L.euler_gpu_kernel_class_name.argtypes = [C.c_int]
 _L.euler_gpu_stream.restype = C.c_void_p
 _L.euler_gpu_stream.argtypes = [_H]
 _L.euler_gpu_pcg_iterations.argtypes = [_H, C.c_int]
@@ -148,6 +153,18 @@ class EulerGpu:
     def pcg_iterations(self, n): _ck(_L.euler_gpu_pcg_iterations(self._h, n))
     def synchronize(self): _ck(_L.euler_gpu_synchronize(self._h))
     def set_profiling(self, on): _ck(_L.euler_gpu_set_profiling(self._h, 1 if on else 0))
+    def reset_profile(self): _ck(_L.euler_gpu_reset_profile(self._h))
+
+    def kernel_profile(self):
+        """{class name: (total ms, timed launch groups)} accumulated while profiling was on."""
+        st = self.stats()
+        out = {}
+        for i in range(16):
+            name = _L.euler_gpu_kernel_class_name(i)
+            if name and st.kernel_count[i]:
+                out[name.decode()] = (float(st.kernel_ms[i]), int(st.kernel_count[i]))
+        return out
+
     def set_rng_state(self, s): _ck(_L.euler_gpu_set_rng_state(self._h, s))
     def set_source_exhausted(self, e): _ck(_L.euler_gpu_set_source_exhausted(self._h, 1 if e else 0))
 

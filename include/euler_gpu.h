@@ -127,6 +127,8 @@ typedef struct euler_params {
   int   global_ny;
 } euler_params;
 
+#define EULER_KERNEL_CLASSES 16
+
 typedef struct euler_stats {
   uint64_t frames, substeps;        /* since create */
   uint64_t solves, solves_skipped;  /* project() calls that ran PCG / hit all_zero (main.c:742) */
@@ -141,6 +143,12 @@ typedef struct euler_stats {
   uint64_t device_bytes;            /* device memory owned by the handle */
   double   ms_markers, ms_grid, ms_project;  /* device time per stage group, summed, only
                                                 when profiling was enabled */
+  /* per kernel class (euler_gpu_kernel_class_name), only when profiling was enabled:
+   * summed CUDA-event time and number of timed launches groups */
+  uint64_t active_cells;            /* cells in PCG tiles that contain fluid (last solve): the
+                                       cells the PCG kernels actually stream */
+  double   kernel_ms[EULER_KERNEL_CLASSES];
+  uint64_t kernel_count[EULER_KERNEL_CLASSES];
 } euler_stats;
 
 typedef struct euler_gpu euler_gpu;
@@ -182,6 +190,10 @@ int euler_gpu_set_source_exhausted(euler_gpu *h, int exhausted);
 int euler_gpu_stats(euler_gpu *h, euler_stats *out);
 /* Toggle per-stage-group CUDA-event timing (adds synchronisation; off by default). */
 int euler_gpu_set_profiling(euler_gpu *h, int enabled);
+/* Name of kernel class i (0 <= i < EULER_KERNEL_CLASSES), or NULL. */
+const char *euler_gpu_kernel_class_name(int i);
+/* Zero the profiling accumulators. */
+int euler_gpu_reset_profile(euler_gpu *h);
 int euler_gpu_synchronize(euler_gpu *h);
 /* The CUDA stream (cudaStream_t) the handle enqueues on, for event timing by the caller. */
 void *euler_gpu_stream(euler_gpu *h);
