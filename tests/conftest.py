@@ -1,0 +1,44 @@
+"""pytest configuration: `-m gpu` tests need a B200 (they call the CUDA library through its
+C-ABI and fail loudly if it is missing); everything else runs on CPU."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SCENARIOS = ["basic", "block", "filter", "waterfall", "weird-edges"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def known_answers():
+    with open(os.path.join(GOLDEN, "known_answers.json")) as f:
+        return json.load(f)
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.float32:
+        return a.view(np.uint32)
+    if a.dtype == np.float64:
+        return a.view(np.uint64)
+    return a
+
+
+def same_bits(a, b):
+    """Bit-for-bit equality (NaNs with equal payload compare equal; +0 != -0)."""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(bits(a), bits(b))
+
+
+def load_state(name):
+    """Reference state dumped by tests/golden/make_golden.py."""
+    return np.load(os.path.join(GOLDEN, "state_%s_f10.npz" % name))

