@@ -239,6 +239,7 @@ int euler_gpu_default_params(euler_params* p) {
   p->tol = (double)1e-6f;                                    // main.c:736
   p->precon = EULER_PRECON_IC0_WAVEFRONT;
   p->marker_mode = EULER_MARKERS_REFERENCE;
+  p->dot_mode = EULER_DOT_TREE;
   p->rng_state = 0x9bd185c449534b91ull;                      // main.c:204
   p->device = 0; p->stream = nullptr; p->pcg_check_every = 8;
   p->row0 = 0; p->global_ny = 0;
@@ -304,6 +305,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.lim.v_x = nextafterf((float)(nx - 1), 0.f);              // V is X x (Y-1)
   c.lim.v_y = nextafterf((float)(ny - 2), 0.f);
   c.h = prm.h; c.rho = prm.rho; c.gravity = prm.gravity;
+  c.dot_mode = prm.dot_mode ? 1 : 0;
   c.max_markers = max_markers;
 
 #define TRY(x) do { int rc_ = (x); if (rc_) { euler_gpu_destroy(h); return rc_; } } while (0)

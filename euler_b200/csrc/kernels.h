@@ -32,6 +32,7 @@ struct Ctx {
   int sm_count;
   // constants (reference main.c:58-60, 735-736, 838)
   float h, rho, gravity;
+  int dot_mode;                   // 0 tree reduction, 1 reference-order sequential sum
   // static masks
   uint8_t *solid, *source, *sink;
   // dynamic cell classification: marker counts now / previous sub-step (main.c:96-97)
@@ -109,6 +110,7 @@ void launch_update_search(Ctx& c);                           // s = z + beta s
 void launch_pcg_reset(Ctx& c);                               // iters=0, done=0
 void launch_tile_flags(Ctx& c);                              // per-tile fluid flags from count
 int pcg_tile_count(const Grid& g);
+void launch_dot_zr_exact(Ctx& c, bool init);                 // no-op unless dot_mode
 int pcg_tile_cells();
 
 }  // namespace euler

@@ -176,7 +176,7 @@ struct ApplyA {
 __global__ void __launch_bounds__(TT) k_apply_a(
     Grid g, const uint8_t* __restrict__ active, const double* __restrict__ s,
     const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ z,
-    double* partials, DevScalars* sc) {
+    double* partials, DevScalars* sc, int exact) {
   if (sc->done) return;
   ApplyA op{s, adiag, z, 0.0, 0u, {}};
   for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(TT) k_apply_a(
   });
   const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZS], [&](double total) {
+    if (exact) return;                                       // k_dot_seq supplies z.s instead
     sc->zs = total;
     sc->alpha = sc->sigma / total;                           // main.c:752
   });
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(TT) k_rb_backward(
     Grid g, const uint8_t* __restrict__ active, const double* __restrict__ q,
     const double* __restrict__ r, const uint8_t* __restrict__ fluid,
     const double* __restrict__ precon, double* __restrict__ z, double* partials, DevScalars* sc,
-    int init) {
+    int init, int exact) {
   if (sc->done) return;
   RbBackward op{q, precon, r, z, 0.0, {}, {}, {}, {}, {}, {}};
   for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
@@ -396,9 +397,76 @@ __global__ void __launch_bounds__(TT) k_rb_backward(
   });
   const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZR], [&](double total) {
+    if (exact) return;
     if (init) { sc->sigma = total; }                         // main.c:748
     else { sc->beta = total / sc->sigma; sc->sigma = total; }  // main.c:762-765
   });
+}
+
+// ---- reference-order dot product ---------------------------------------------------------
+// dot() of main.c:629-639 sums a[y][x]*b[y][x] over fluid cells strictly in row-major order.
+// fp64 addition is not associative, and the reference's solves are often unconverged at the
+// 100-iteration cap (SURVEY §7 hard part 2), where 1-ulp differences in alpha/beta are
+// amplified to ~1e-5 in p.  dot_mode = EULER_DOT_REFERENCE_ORDER reproduces the reference's
+// sum bit for bit: the block forms the products of one 512-cell row segment at a time in
+// shared memory (coalesced, double-buffered, skipping segments of tiles without fluid) and
+// ONE thread chains the additions in order.  Adding +0.0 for a non-fluid cell never changes
+// the running sum (it cannot be -0.0: it starts at +0.0).  Latency-bound by design:
+// ~one dependent DADD per cell of the active tiles.
+enum { DOT_ZS = 0, DOT_ZR_INIT = 1, DOT_ZR = 2 };
+
+__global__ void __launch_bounds__(256) k_dot_seq(
+    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ a,
+    const double* __restrict__ b, const uint8_t* __restrict__ fluid, DevScalars* sc, int what) {
+  if (sc->done) return;
+  __shared__ double buf[2][TW];
+  const Tiles T = tiles_of(g);
+  const long nseg = (long)g.ny * T.tx;
+  auto next_active = [&](long k) {
+    for (; k < nseg; ++k)
+      if (active[(int)((k / T.tx) / TH) * T.tx + (int)(k % T.tx)]) break;
+    return k;
+  };
+  auto products = [&](long k, double& p0, double& p1) {
+    const int y = (int)(k / T.tx), x = (int)(k % T.tx) * TW + threadIdx.x * 2;
+    p0 = p1 = 0.0;
+    if (x < g.pitch) {
+      const size_t c = gidx(g, x, y);
+      const double2 av = *reinterpret_cast<const double2*>(a + c);
+      const double2 bv = *reinterpret_cast<const double2*>(b + c);
+      const unsigned short m = *reinterpret_cast<const unsigned short*>(fluid + c);
+      if (m & 0x00ffu) p0 = av.x * bv.x;
+      if (m & 0xff00u) p1 = av.y * bv.y;
+    }
+  };
+  double total = 0.0;
+  long k = next_active(0);
+  int cur = 0;
+  if (k < nseg) {
+    double p0, p1;
+    products(k, p0, p1);
+    buf[0][2 * threadIdx.x] = p0; buf[0][2 * threadIdx.x + 1] = p1;
+  }
+  __syncthreads();
+  while (k < nseg) {
+    const long kn = next_active(k + 1);
+    double p0 = 0.0, p1 = 0.0;
+    if (kn < nseg) products(kn, p0, p1);                     // loads in flight during the chain
+    if (threadIdx.x == 0) {
+      const double* v = buf[cur];
+#pragma unroll 16
+      for (int i = 0; i < TW; ++i) total += v[i];
+    }
+    buf[cur ^ 1][2 * threadIdx.x] = p0; buf[cur ^ 1][2 * threadIdx.x + 1] = p1;
+    __syncthreads();
+    cur ^= 1;
+    k = kn;
+  }
+  if (threadIdx.x == 0) {
+    if (what == DOT_ZS) { sc->zs = total; sc->alpha = sc->sigma / total; }
+    else if (what == DOT_ZR_INIT) { sc->sigma = total; }
+    else { sc->beta = total / sc->sigma; sc->sigma = total; }
+  }
 }
 
 // persistent grid: resident blocks per SM (occupancy of that kernel) x SM count, capped by
@@ -431,8 +499,12 @@ void launch_pcg_reset(Ctx& c) {
 void launch_apply_a(Ctx& c, bool) {
   ProfScope ps(c, KC_APPLY_A);
   k_apply_a<<<pcg_blocks(c, k_apply_a), TT, 0, c.stream>>>(c.g, c.tile_active, c.s, c.count, c.adiag, c.z,
-                                                c.partials, c.sc);
+                                                c.partials, c.sc, c.dot_mode);
   c.launches += 1;
+  if (c.dot_mode) {
+    k_dot_seq<<<1, 256, 0, c.stream>>>(c.g, c.tile_active, c.z, c.s, c.count, c.sc, DOT_ZS);
+    c.launches += 1;
+  }
 }
 
 void launch_axpy(Ctx& c, double tol) {
@@ -461,13 +533,24 @@ void launch_rb_build(Ctx& c) {
   c.launches += 1;
 }
 
+void launch_dot_zr_exact(Ctx& c, bool init);
+
 void launch_rb_apply(Ctx& c, bool init) {
   ProfScope ps(c, KC_PRECON_APPLY);
   k_rb_forward<<<pcg_blocks(c, k_rb_forward), TT, 0, c.stream>>>(c.g, c.tile_active, c.r, c.count, c.precon,
                                                    c.q, c.sc);
   k_rb_backward<<<pcg_blocks(c, k_rb_backward), TT, 0, c.stream>>>(c.g, c.tile_active, c.q, c.r, c.count,
-                                                    c.precon, c.z, c.partials, c.sc, init ? 1 : 0);
+                                                    c.precon, c.z, c.partials, c.sc, init ? 1 : 0,
+                                                    c.dot_mode);
   c.launches += 2;
+  launch_dot_zr_exact(c, init);
+}
+
+void launch_dot_zr_exact(Ctx& c, bool init) {
+  if (!c.dot_mode) return;
+  k_dot_seq<<<1, 256, 0, c.stream>>>(c.g, c.tile_active, c.z, c.r, c.count, c.sc,
+                                     init ? DOT_ZR_INIT : DOT_ZR);
+  c.launches += 1;
 }
 
 int pcg_tile_count(const Grid& g) { return tiles_of(g).n; }

@@ -57,7 +57,8 @@ template <int MODE>
 __global__ void __launch_bounds__(32) k_ic0_sweep(
     Grid g, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
     double* precon, const double* __restrict__ in, double* out, const double* __restrict__ rvec,
-    unsigned int* progress, unsigned int* ticket, double* partials, DevScalars* sc, int init) {
+    unsigned int* progress, unsigned int* ticket, double* partials, DevScalars* sc, int init,
+    int exact) {
   if (MODE != WF_BUILD && sc->done) return;
   const int lane = threadIdx.x;
   const int n_strips = gridDim.x;
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(32) k_ic0_sweep(
   if (MODE == WF_BACKWARD) {
     acc = warp_sum(acc);
     grid_reduce_last_block<false>(acc, partials, &sc->ctr[3], [&](double total) {
+      if (exact) return;                                     // k_dot_seq supplies z.r instead
       if (init) { sc->sigma = total; }                       // main.c:748
       else { sc->beta = total / sc->sigma; sc->sigma = total; }   // main.c:762-765
     });
@@ -192,7 +194,7 @@ void launch_ic0_build(Ctx& c) {
   reset_wavefront(c);
   k_ic0_sweep<WF_BUILD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, nullptr, nullptr, nullptr, c.wf_progress,
-      &c.sc->ticket[0], c.partials, c.sc, 0);
+      &c.sc->ticket[0], c.partials, c.sc, 0, 0);
   c.launches += 1;
 }
 
@@ -201,12 +203,13 @@ void launch_ic0_apply(Ctx& c, bool init) {
   reset_wavefront(c);
   k_ic0_sweep<WF_FORWARD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, c.r, c.q, nullptr, c.wf_progress, &c.sc->ticket[1],
-      c.partials, c.sc, 0);
+      c.partials, c.sc, 0, 0);
   reset_wavefront(c);
   k_ic0_sweep<WF_BACKWARD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, c.q, c.z, c.r, c.wf_progress, &c.sc->ticket[2],
-      c.partials, c.sc, init ? 1 : 0);
+      c.partials, c.sc, init ? 1 : 0, c.dot_mode);
   c.launches += 2;
+  launch_dot_zr_exact(c, init);
 }
 
 }  // namespace euler

@@ -17,6 +17,7 @@ _L = C.CDLL(LIB_PATH)
 
 PRECON_IC0_WAVEFRONT, PRECON_REDBLACK = 0, 1
 MARKERS_REFERENCE, MARKERS_FAST = 0, 1
+DOT_TREE, DOT_REFERENCE_ORDER = 0, 1
 (F_U, F_V, F_UTMP, F_VTMP, F_SOLID, F_SOURCE, F_SINK, F_COUNT, F_PREV_COUNT, F_MARKERS,
  F_PRECON, F_Q, F_ADIAG, F_P, F_R, F_Z, F_S) = range(17)
 (S_ADVECT_MARKERS, S_REFRESH_COUNTS, S_SOURCES, S_EXTRAPOLATE, S_ADVECT_VELOCITY, S_PROJECT,
@@ -32,7 +33,7 @@ class Params(C.Structure):
     _fields_ = [("h", C.c_float), ("rho", C.c_float), ("gravity", C.c_float),
                 ("frame_time", C.c_float), ("max_substeps", C.c_int), ("cfl_distance", C.c_float),
                 ("max_iterations", C.c_int), ("tol", C.c_double),
-                ("precon", C.c_int), ("marker_mode", C.c_int),
+                ("precon", C.c_int), ("marker_mode", C.c_int), ("dot_mode", C.c_int),
                 ("rng_state", C.c_uint64),
                 ("device", C.c_int), ("stream", C.c_void_p), ("pcg_check_every", C.c_int),
                 ("row0", C.c_int), ("global_ny", C.c_int)]

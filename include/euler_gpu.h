@@ -52,6 +52,17 @@ enum euler_precon {
                                      tolerance, different (fully parallel) factor. */
 };
 
+/* How the PCG dot products (dot(), main.c:629-639) are summed. */
+enum euler_dot_mode {
+  EULER_DOT_TREE            = 0, /* parallel tree reduction (deterministic, fastest) */
+  EULER_DOT_REFERENCE_ORDER = 1  /* the reference's sequential row-major sum, bit for bit.  With
+                                    the IC(0) wavefront this makes the whole solve — alpha,
+                                    beta, p, u, v — bit-identical to the reference's, even where
+                                    the reference stops unconverged at its iteration cap and
+                                    1-ulp differences would otherwise be amplified.  Latency-
+                                    bound (one dependent add per cell). */
+};
+
 /* How the marker array is kept. */
 enum euler_marker_mode {
   EULER_MARKERS_REFERENCE = 0, /* bit-identical ARRAY, not just multiset: reference swap-delete
@@ -114,6 +125,7 @@ typedef struct euler_params {
   double tol;            /* (double)1e-6f, absolute, on ||r||inf */
   int    precon;         /* enum euler_precon; default IC0_WAVEFRONT */
   int    marker_mode;    /* enum euler_marker_mode; default REFERENCE */
+  int    dot_mode;       /* enum euler_dot_mode; default TREE */
   /* source RNG: state of randf()'s xorshift64* stream (main.c:204) AFTER the host seeded
    * the initial markers; default = the reference seed 0x9bd185c449534b91 */
   uint64_t rng_state;

@@ -9,13 +9,13 @@ from euler_b200 import Scenario, shipped_text, resample, synthetic
 pytestmark = pytest.mark.gpu
 
 
-def _pair(text, nx, ny, precon, leak, **kw):
+def _pair(text, nx, ny, precon, leak, dot_mode=0, **kw):
     from euler_b200 import gpu as G
     from oracle.oracle import Oracle
     o = Oracle(nx, ny, text)
     o.c.precon_mode = precon
     o.c.quirk_marker_dt_leak = leak
-    g = G.EulerGpu.from_scenario(Scenario(text, nx, ny), precon=precon,
+    g = G.EulerGpu.from_scenario(Scenario(text, nx, ny), precon=precon, dot_mode=dot_mode,
                                  marker_mode=G.MARKERS_REFERENCE if leak else G.MARKERS_FAST, **kw)
     return o, g, G
 
@@ -33,6 +33,19 @@ def test_frames_ic0_wavefront_bit_exact_classification(name):
     assert same_bits(g.get(G.F_MARKERS), o.markers)
     for fld, ref in ((G.F_U, o.u), (G.F_V, o.v)):
         assert float(np.abs(g.get(fld) - ref).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    g.close()
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_frames_fully_bit_exact_with_reference_order_dots(name):
+    """IC(0) wavefront + reference-order dot products: EVERYTHING is bit-identical to the CPU
+    over 40 frames — counts, marker array, u, v, precon, iteration totals."""
+    o, g, G = _pair(shipped_text(name), 100, 40, 0, 0, dot_mode=1)
+    for f in range(40):
+        assert o.step_frame() == g.step_frame()
+    assert same_bits(g.get(G.F_COUNT), o.count) and same_bits(g.get(G.F_MARKERS), o.markers)
+    assert same_bits(g.get(G.F_U), o.u) and same_bits(g.get(G.F_V), o.v)
+    assert same_bits(g.get(G.F_PRECON), o.precon)
     st = g.stats()
     assert st.pcg_iterations == o.c.total_iterations and st.solves == o.c.total_solves
     g.close()
@@ -77,10 +90,12 @@ def test_red_black_converges_to_same_tolerance_as_ic0():
 
 def test_1024_ic0_wavefront_one_substep_vs_oracle():
     """BASELINE config[1]: block scenario upscaled to 1024^2, IC(0) wavefront mode.  The
-    reference hits its 100-iteration cap here; iterates still agree to 1e-9 relative."""
+    reference hits its 100-iteration cap here (||r||inf ~ 10 at exit): unconverged CG amplifies
+    the 1e-16 differences of a tree-reduced dot product to ~5e-6 in p (and |p|*1e-5 in u, v), so
+    this configuration runs with reference-order dot products and must be BIT-exact."""
     n = 1024
     text = synthetic("basic-fill", n, n)
-    o, g, G = _pair(text, n, n, 0, 0)
+    o, g, G = _pair(text, n, n, 0, 0, dot_mode=1)
     dt = o.calculate_timestep(0.1)
     assert g.calculate_timestep(0.1) == dt
     o.substep(dt); g.substep(dt)
@@ -89,10 +104,15 @@ def test_1024_ic0_wavefront_one_substep_vs_oracle():
     assert same_bits(g.get(G.F_COUNT), o.count) and same_bits(g.get(G.F_MARKERS), o.markers)
     fl = o.count != 0
     p = g.get(G.F_P)
-    assert float(np.abs(p[fl] - o.p[fl]).max()) <= 1e-9 * float(np.abs(o.p[fl]).max())
-    for fld, ref in ((G.F_U, o.u), (G.F_V, o.v)):
-        assert float(np.abs(g.get(fld) - ref).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    assert same_bits(p[fl], o.p[fl])
+    assert same_bits(g.get(G.F_U), o.u) and same_bits(g.get(G.F_V), o.v)
     g.close()
+    # the same sub-step with tree-reduced dots stays within the stated 1e-5 on pressure
+    o2, g2, G = _pair(text, n, n, 0, 0, dot_mode=0)
+    o2.substep(dt); g2.substep(dt)
+    p2 = g2.get(G.F_P)
+    assert float(np.abs(p2[fl] - o2.p[fl]).max()) <= 1e-5 * float(np.abs(o2.p[fl]).max())
+    g2.close()
 
 
 def test_4096_properties():
