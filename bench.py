@@ -48,6 +48,7 @@ ALG_BYTES_PER_CELL = {
     "maxsq": 8.0,
 }
 ALG_BYTES_PER_MARKER = {"advect_markers": 16.0}
+PCG_KERNELS = ("apply_a", "axpy_norm", "precon_apply", "update_search")
 
 
 def peaks():
@@ -178,6 +179,7 @@ def run_gpu(args):
     launches = int(st1.kernel_launches - st0.kernel_launches)
     n_markers = int(st1.n_markers)
     dev_bytes = int(st1.device_bytes)
+    active_cells = int(st1.active_cells)
     sim.close()
     del sim
 
@@ -213,7 +215,11 @@ def run_gpu(args):
         roof = None
         kernels = {}
         for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-            if name in ALG_BYTES_PER_CELL:
+            if name in PCG_KERNELS:
+                # PCG kernels stream only the tiles that contain fluid (like the reference,
+                # which touches only is_fluid cells): units = cells of those tiles
+                b = ALG_BYTES_PER_CELL[name] * active_cells
+            elif name in ALG_BYTES_PER_CELL:
                 b = ALG_BYTES_PER_CELL[name] * cells
             elif name in ALG_BYTES_PER_MARKER:
                 b = ALG_BYTES_PER_MARKER[name] * n_markers
@@ -227,7 +233,9 @@ def run_gpu(args):
             k = kernels[dom[0]]
             roof = {"kernel": dom[0], "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": k["frac"], "traffic": None, "peak_source": peak_src,
-                    "alg_bytes_per_launch": ALG_BYTES_PER_CELL[dom[0]] * cells,
+                    "alg_bytes_per_launch": ALG_BYTES_PER_CELL[dom[0]] * (active_cells if dom[0] in PCG_KERNELS else cells),
+                    "units_per_launch": active_cells if dom[0] in PCG_KERNELS else cells,
+                    "bytes_per_unit": ALG_BYTES_PER_CELL[dom[0]],
                     "ms_per_launch": k["ms_avg"], "share_of_step": k["share"]}
         value = cells * args.steps * world / (ms_max * 1e-3)
         line = {
@@ -238,7 +246,7 @@ def run_gpu(args):
             "config": {"workload": "%s %dx%d per GPU, one sub-step of sim_step per step, PCG cap 100 "
                                    "(reference main.c:735), %s preconditioner, fp64 PCG vectors"
                                    % (args.scenario, n, n, "red-black IC(0)" if args.precon == "rb" else "IC(0) wavefront"),
-                       "grid": [n, n], "markers": n_markers,
+                       "grid": [n, n], "markers": n_markers, "active_cells": active_cells,
                        "parallelism": "single GPU" if world == 1 else "independent replicas x%d" % world,
                        "l2_policy": "inputs >> L2: every plane is %.0f MB..%.0f MB vs 126 MB L2, no flush needed"
                                     % (cells / 1e6, cells * 8 / 1e6),

@@ -1,0 +1,227 @@
+/* euler_b200/host/main.c — the host program: CLI, scenario loading, step/render loop.
+ *
+ * Same user-facing behaviour as the reference's main() (main.c:982-1042): one positional
+ * scenario file in the reference's format, keys p (pause) / f (advance one frame while
+ * paused) / q (quit), 10 frames per second, 0.1 s of simulated time per frame, ASCII picture
+ * of the marker-count plane.  The simulation itself — everything the reference does inside
+ * sim_step() — runs on the GPU through the C-ABI of libeuler_gpu.so (include/euler_gpu.h),
+ * which this program binds at run time with dlopen; rendering stays on the host and needs
+ * only the uint8 count plane per drawn frame.
+ *
+ * Additions over the reference CLI (it cannot run without a tty, main.c:1005-1007):
+ *   --headless          no tty, no pacing; prints one JSON line of statistics at the end
+ *   --frames N          stop after N frames (default: run until 'q'; 100 in --headless)
+ *   --grid WxH          grid size (default 100x40 as the reference, main.c:22-25); the
+ *                       scenario text is resampled (nearest neighbour) when it differs
+ *   --synthetic NAME    built-in scenario instead of a file: basic-fill | full
+ *   --precon ic0|rb     reference-faithful IC(0) wavefront (default) | red-black IC(0)
+ *   --markers ref|fast  reference marker order & dt carry-over (default) | per-marker dt
+ *   --exact-dot         reference-order dot products (bit-identical solve)
+ *   --device D          CUDA device
+ *   --print             in --headless: print the final picture (plain ASCII)
+ *   --rainbow           accepted for CLI compatibility; colour transport is not on the GPU
+ *                       path yet, the picture is drawn in blue
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <dlfcn.h>
+#include <inttypes.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "euler_gpu.h"
+#include "render.h"
+#include "scenario.h"
+
+typedef struct api {
+  void *dl;
+  int (*default_params)(euler_params *);
+  int (*create)(euler_gpu **, int, int, const uint8_t *, const uint8_t *, const uint8_t *,
+                const float *, size_t, const euler_params *);
+  int (*destroy)(euler_gpu *);
+  int (*step_frame)(euler_gpu *, int *);
+  int (*read_marker_count)(euler_gpu *, uint8_t *);
+  int (*stats)(euler_gpu *, euler_stats *);
+  const char *(*last_error)(void);
+} api;
+
+static int bind_api(api *a, const char *argv0) {
+  const char *env = getenv("EULER_GPU_LIB");
+  char path[4096];
+  const char *cands[4]; int n = 0;
+  if (env) cands[n++] = env;
+  /* next to the executable: <root>/bin/euler-gpu -> <root>/euler_b200/lib/libeuler_gpu.so */
+  const char *slash = strrchr(argv0, '/');
+  if (slash) {
+    snprintf(path, sizeof path, "%.*s/../euler_b200/lib/libeuler_gpu.so", (int)(slash - argv0), argv0);
+    cands[n++] = path;
+  }
+  cands[n++] = "euler_b200/lib/libeuler_gpu.so";
+  cands[n++] = "libeuler_gpu.so";
+  for (int i = 0; i < n && !a->dl; ++i) a->dl = dlopen(cands[i], RTLD_NOW | RTLD_LOCAL);
+  if (!a->dl) { fprintf(stderr, "cannot load libeuler_gpu.so: %s\n", dlerror()); return -1; }
+#define BIND(field, sym) do { *(void **)(&a->field) = dlsym(a->dl, sym); \
+    if (!a->field) { fprintf(stderr, "libeuler_gpu.so lacks %s\n", sym); return -1; } } while (0)
+  BIND(default_params, "euler_gpu_default_params");
+  BIND(create, "euler_gpu_create");
+  BIND(destroy, "euler_gpu_destroy");
+  BIND(step_frame, "euler_gpu_step_frame");
+  BIND(read_marker_count, "euler_gpu_read_marker_count");
+  BIND(stats, "euler_gpu_stats");
+  BIND(last_error, "euler_gpu_last_error");
+#undef BIND
+  return 0;
+}
+
+static uint64_t fnv1a(const uint8_t *p, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+static void usage(const char *argv0) {
+  fprintf(stderr,
+          "usage: %s [--rainbow] [--headless] [--frames N] [--grid WxH] [--synthetic NAME]\n"
+          "       [--precon ic0|rb] [--markers ref|fast] [--exact-dot] [--device D] [--print] <scenario>\n",
+          argv0);
+}
+
+int main(int argc, char **argv) {
+  const char *file = NULL, *synthetic = NULL;
+  int headless = 0, frames = -1, nx = 100, ny = 40, do_print = 0;
+  api a; memset(&a, 0, sizeof a);
+  if (bind_api(&a, argv[0])) return 1;
+  euler_params prm;
+  a.default_params(&prm);
+
+  for (int i = 1; i < argc; ++i) {
+    const char *s = argv[i];
+    if (!strcmp(s, "--rainbow")) fprintf(stderr, "note: --rainbow is not on the GPU path yet; drawing in blue\n");
+    else if (!strcmp(s, "--headless")) headless = 1;
+    else if (!strcmp(s, "--print")) do_print = 1;
+    else if (!strcmp(s, "--exact-dot")) prm.dot_mode = EULER_DOT_REFERENCE_ORDER;
+    else if (!strcmp(s, "--frames") && i + 1 < argc) frames = atoi(argv[++i]);
+    else if (!strcmp(s, "--device") && i + 1 < argc) prm.device = atoi(argv[++i]);
+    else if (!strcmp(s, "--synthetic") && i + 1 < argc) synthetic = argv[++i];
+    else if (!strcmp(s, "--grid") && i + 1 < argc) {
+      if (sscanf(argv[++i], "%dx%d", &nx, &ny) != 2 || nx < 4 || ny < 4) { usage(argv[0]); return 1; }
+    } else if (!strcmp(s, "--precon") && i + 1 < argc) {
+      const char *v = argv[++i];
+      if (!strcmp(v, "ic0")) prm.precon = EULER_PRECON_IC0_WAVEFRONT;
+      else if (!strcmp(v, "rb")) prm.precon = EULER_PRECON_REDBLACK;
+      else { usage(argv[0]); return 1; }
+    } else if (!strcmp(s, "--markers") && i + 1 < argc) {
+      const char *v = argv[++i];
+      if (!strcmp(v, "ref")) prm.marker_mode = EULER_MARKERS_REFERENCE;
+      else if (!strcmp(v, "fast")) prm.marker_mode = EULER_MARKERS_FAST;
+      else { usage(argv[0]); return 1; }
+    } else if (s[0] == '-' && s[1] == '-') {
+      fprintf(stderr, "Unrecognized input: %s\n", s);        /* as main.c:995 */
+      return 1;
+    } else file = s;
+  }
+  if (!file && !synthetic) { usage(argv[0]); return 1; }    /* as main.c:986-989 */
+  if (headless && frames < 0) frames = 100;
+
+  /* scenario text -> masks + seeded markers (host, reference format and RNG stream) */
+  euler_scenario scn;
+  int rc;
+  if (synthetic) {
+    long len = 0;
+    char *text = euler_scenario_synthetic(synthetic, nx, ny, &len);
+    if (!text) { fprintf(stderr, "unknown synthetic scenario %s\n", synthetic); return 1; }
+    rc = euler_scenario_from_text(&scn, text, len, nx, ny);
+    free(text);
+  } else if (nx == 100 && ny == 40) {
+    rc = euler_scenario_load(&scn, file, nx, ny);
+  } else {
+    FILE *f = fopen(file, "rb");
+    rc = -2;
+    if (f) {
+      fseek(f, 0, SEEK_END); long len = ftell(f); fseek(f, 0, SEEK_SET);
+      char *raw = malloc((size_t)len + 1);
+      if (raw && (len == 0 || fread(raw, (size_t)len, 1, f) == 1)) {
+        long rlen = 0;
+        char *text = euler_scenario_resample(raw, len, nx - 2, ny - 2, &rlen);
+        rc = text ? euler_scenario_from_text(&scn, text, rlen, nx, ny) : -1;
+        free(text);
+      }
+      free(raw); fclose(f);
+    }
+  }
+  if (rc) { fprintf(stderr, "Could not load %s!\n", file ? file : synthetic); return 1; }  /* main.c:213 */
+
+  prm.rng_state = scn.rng_state;
+  euler_gpu *sim = NULL;
+  if (a.create(&sim, nx, ny, scn.solid, scn.source, scn.sink, scn.markers, scn.n_markers, &prm)) {
+    fprintf(stderr, "euler_gpu_create: %s\n", a.last_error());
+    return 1;
+  }
+  uint8_t *count = malloc((size_t)nx * ny);
+  if (!count) return 1;
+
+  long long substeps_total = 0;
+  euler_time t0 = euler_now();
+  if (headless) {
+    for (int f = 0; f < frames; ++f) {
+      int sub = 0;
+      if (a.step_frame(sim, &sub)) { fprintf(stderr, "step: %s\n", a.last_error()); return 1; }
+      substeps_total += sub;
+    }
+    if (a.read_marker_count(sim, count)) { fprintf(stderr, "read: %s\n", a.last_error()); return 1; }
+  } else {
+    euler_screen scr; memset(&scr, 0, sizeof scr);
+    if (euler_tty_window_size(&scr.rows, &scr.cols) == -1) {
+      fprintf(stderr, "stdout is not a terminal: use --headless\n");
+      return 1;
+    }
+    euler_tty_raw_mode();
+    euler_tty_clear();
+    a.read_marker_count(sim, count);
+    euler_draw(&scr, nx, ny, scn.solid, scn.sink, count);
+    int pause = 0, pending = 0, done = 0, f = 0;
+    euler_time start = euler_now();
+    while (!done && (frames < 0 || f < frames)) {
+      const char key = euler_tty_read_key();                 /* main.c:961-980 */
+      if (key == 'p') pause = !pause;
+      else if (key == 'f') pending++;
+      else if (key == 'q') { done = 1; break; }
+      if (!pause || pending) {                               /* main.c:844-846, 896-898 */
+        int sub = 0;
+        if (a.step_frame(sim, &sub)) { euler_tty_restore(); fprintf(stderr, "step: %s\n", a.last_error()); return 1; }
+        substeps_total += sub; f++;
+        if (pending) pending--;
+      }
+      start = euler_wait_until(start, 100000000ll);          /* 10 fps, main.c:1036 */
+      euler_tty_window_size(&scr.rows, &scr.cols);
+      a.read_marker_count(sim, count);
+      euler_draw(&scr, nx, ny, scn.solid, scn.sink, count);
+    }
+    euler_tty_clear();
+    euler_tty_restore();
+    euler_screen_free(&scr);
+    frames = f;
+  }
+  const double secs = (double)(euler_now().ns - t0.ns) * 1e-9;
+
+  euler_stats st;
+  a.stats(sim, &st);
+  if (do_print) {
+    size_t cap = (size_t)(nx + 1) * ny + 1;
+    char *pic = malloc(cap);
+    if (pic) { euler_draw_plain(pic, cap, nx, ny, 200, 60, scn.solid, scn.sink, count); fputs(pic, stdout); free(pic); }
+  }
+  if (headless) {
+    printf("{\"grid\": [%d, %d], \"frames\": %d, \"substeps\": %lld, \"seconds\": %.6f, "
+           "\"cell_updates_per_s\": %.6e, \"pcg_iterations\": %" PRIu64 ", \"pcg_iters_per_s\": %.6e, "
+           "\"solves\": %" PRIu64 ", \"solves_skipped\": %" PRIu64 ", \"markers\": %" PRIu64 ", "
+           "\"fnv_count\": \"%016" PRIx64 "\", \"rng_state\": \"%016" PRIx64 "\", \"kernel_launches\": %" PRIu64 "}\n",
+           nx, ny, frames, substeps_total, secs, (double)nx * ny * (double)substeps_total / secs,
+           st.pcg_iterations, (double)st.pcg_iterations / secs, st.solves, st.solves_skipped,
+           st.n_markers, fnv1a(count, (size_t)nx * ny), st.rng_state, st.kernel_launches);
+  }
+  free(count);
+  a.destroy(sim);
+  euler_scenario_free(&scn);
+  return 0;
+}

@@ -137,3 +137,23 @@ def test_4096_properties():
     assert float(p[cnt != 0].min()) >= 0.0
     assert np.isfinite(u).all() and np.isfinite(v).all()
     g.close()
+
+
+def test_host_program_headless_matches_golden(known_answers, tmp_path):
+    """bin/euler-gpu (the C host: parser, seeding, loop) run headless on the shipped scenarios
+    reproduces the reference's known-answer hashes of the count plane."""
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "bin", "euler-gpu")
+    assert os.path.exists(exe), "run `make host`"
+    for name, frames in (("block", 10), ("block", 50), ("basic", 50), ("weird-edges", 50), ("waterfall", 10)):
+        path = tmp_path / (name + ".txt")
+        path.write_bytes(shipped_text(name))
+        out = subprocess.run([exe, "--headless", "--frames", str(frames), "--exact-dot", str(path)],
+                             check=True, capture_output=True, text=True, cwd=ROOT).stdout
+        res = json.loads(out.strip().splitlines()[-1])
+        want = known_answers["%s@100x40/f%d" % (name, frames)]
+        assert res["fnv_count"] == want["fnv_count"], (name, frames)
+        assert res["markers"] == want["markers"] and res["rng_state"] == want["rng_state"]
