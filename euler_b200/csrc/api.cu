@@ -152,6 +152,9 @@ int run_project(euler_gpu* h, float dt) {
   launch_tile_flags(c);
   int rc = pull_scalars(h);
   if (rc) return rc;
+  if (h->host_sc->marker_overflow)
+    return fail(EULER_E_UNSUPPORTED, "reference marker mode: more than %zu rewinding markers in one "
+                "sub-step; use EULER_MARKERS_FAST", c.cand_cap);
   h->last_iterations = 0;
   if (!h->host_sc->nonzero_rhs) {
     h->solves_skipped++;                                    // all_zero(r), main.c:742
@@ -336,6 +339,15 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.n_segments = (max_markers + 1023) / 1024;
   TRY(alloc_array(h, &c.seg_count, c.n_segments));
   TRY(alloc_array(h, &c.seg_offset, c.n_segments));
+  if (prm.marker_mode == EULER_MARKERS_REFERENCE) {
+    // rewinding markers are rare (they crossed a cell edge and then hit a wall in the same
+    // sub-step); 1/16 of the marker capacity, at least 64k records
+    c.cand_cap = max_markers / 16 > 65536 ? max_markers / 16 : 65536;
+    unsigned char* raw = nullptr;
+    TRY(alloc_array(h, &raw, c.cand_cap * marker_candidate_bytes()));
+    c.cand = raw;
+    TRY(alloc_array(h, &c.cand_dt, c.cand_cap));
+  }
   const size_t nblk2d = (size_t)((nx + 31) / 32) * (size_t)((ny + 7) / 8);
   c.n_strips = (ny - 2 + 31) / 32;
   c.n_partials = 65536 > (size_t)c.n_strips ? 65536 : (size_t)c.n_strips;

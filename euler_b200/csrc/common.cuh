@@ -52,7 +52,8 @@ struct DevScalars {
   unsigned int ticket[4];
   // faithful marker mode (dt carry-over): number of candidate markers, first fired index
   unsigned long long n_candidates;
-  unsigned int active_tiles, pad2;
+  unsigned int active_tiles;
+  int marker_overflow;            // more rewinding markers than the candidate list holds
   unsigned long long first_fired;
 };
 

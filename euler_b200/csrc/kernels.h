@@ -46,7 +46,9 @@ struct Ctx {
   // compaction scratch
   unsigned int* seg_count;        // per 1024-marker segment
   unsigned int* seg_offset;
-  unsigned long long* del_list;   // ordered indices of deleted markers
+  void* cand;                     // reference marker mode: ordered rewind records
+  float* cand_dt;                 //   and dt after each of them
+  size_t cand_cap;
   size_t n_segments;
   // source cells, row-major (static)
   unsigned int* source_cells;
@@ -97,6 +99,7 @@ void launch_advect_markers(Ctx& c, float dt, int mode);      // in: markers, out
 void launch_refresh_counts(Ctx& c);                          // prev<-cur, re-bin, delete in sink/solid
 void launch_sources(Ctx& c);                                 // update_fluid_sources
 void init_rng_jump_table(unsigned long long* host_table /* 64*64 */);
+size_t marker_candidate_bytes();
 
 // ---- pressure solve (pcg_kernels.cu, wavefront.cu)
 void launch_ic0_build(Ctx& c);                               // E^-1, wavefront (once per project)

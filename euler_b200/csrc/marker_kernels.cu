@@ -30,13 +30,22 @@ __device__ __forceinline__ float time_until(float from, float to, float vel) {
   return fabsf(vel) > 0.f ? (to - from) / vel : FLT_MAX;     // main.c:451-457
 }
 
+// A rewind (main.c:500-501 / 517-518) seen while walking one marker: it fires iff the
+// crossing time t_hit is still < the marker's remaining dt, and then takes t_prev off dt.
+struct HitRec {
+  int n;
+  float t_hit[2], t_prev[2];      // a component can be blocked only once -> at most 2 hits
+};
+
 // One marker, RK1 with the reference's grid-line walk (main.c:466-535).
+template <bool RECORD>
 __device__ __forceinline__ float2 walk_marker(const Grid& g, const InterpLimits& lim,
                                               const float* __restrict__ u,
                                               const float* __restrict__ v,
                                               const uint8_t* __restrict__ fluid,
                                               const uint8_t* __restrict__ solid, float h,
-                                              float2 pos, float dt) {
+                                              float2 pos, float dt, HitRec* rec = nullptr) {
+  if (RECORD) rec->n = 0;
   float px = pos.x, py = pos.y;
   // velocity_at, main.c:440-449
   float vx = interpolate<FACE_U>(u, fluid, g, lim, px / h - 1.f, py / h - 0.5f);
@@ -60,6 +69,7 @@ __device__ __forceinline__ float2 walk_marker(const Grid& g, const InterpLimits&
     if (tx < ty) {
       const int sx = min(max(line_x + off_x, 0), g.nx - 1), sy = min(max(cy, 0), g.ny - 1);
       if (solid[gidx(g, sx, sy)]) {
+        if (RECORD && rec->n < 2) { rec->t_hit[rec->n] = t_next; rec->t_prev[rec->n] = t_prev; rec->n++; }
         px = px + t_prev * vx; py = py + t_prev * vy;        // rewind, main.c:500
         dt -= t_prev;
         t_next = 0.f;
@@ -75,6 +85,7 @@ __device__ __forceinline__ float2 walk_marker(const Grid& g, const InterpLimits&
     } else {
       const int sx = min(max(cx, 0), g.nx - 1), sy = min(max(line_y + off_y, 0), g.ny - 1);
       if (solid[gidx(g, sx, sy)]) {
+        if (RECORD && rec->n < 2) { rec->t_hit[rec->n] = t_next; rec->t_prev[rec->n] = t_prev; rec->n++; }
         px = px + t_prev * vx; py = py + t_prev * vy;        // main.c:517
         dt -= t_prev;
         t_next = 0.f;
@@ -102,7 +113,183 @@ __global__ void __launch_bounds__(MTHREADS) k_advect_markers(
   const size_t n = sc->n_markers;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
-    dst[i] = walk_marker(g, lim, u, v, fluid, solid, h, src[i], dt);
+    dst[i] = walk_marker<false>(g, lim, u, v, fluid, solid, h, src[i], dt);
+  }
+}
+
+// ---- reference marker mode: the `dt -= t_prev` carry-over (main.c:464, 501, 518) ---------
+// In the reference `dt` is advect_markers' PARAMETER, so what one marker's rewind takes off
+// it is also missing for every later marker of the array.  A walk with a smaller dt is a
+// prefix of the walk with a larger one, so:
+//   pass 1  every marker walks with the full dt0; markers whose rewind had t_prev > 0
+//           ("candidates", rare: they crossed a cell edge and then hit a wall) are counted
+//           per 1024-marker segment;
+//   pass 2  ordered list of the candidates with their (t_hit, t_prev) records;
+//   pass 3  ONE thread replays the reference's sequential bookkeeping over that short list:
+//           which rewinds still fire under the shrinking dt, and dt after each candidate;
+//   pass 4  every marker behind the first fired rewind re-walks with the dt it really had.
+// All fp32 operations (dt - t_prev, t_hit < dt) happen in the reference's order, so the
+// result is bit-identical to the sequential loop.
+struct Candidate {
+  unsigned int index;
+  int n;
+  float t_hit[2], t_prev[2];
+};
+
+__device__ __forceinline__ bool leaks(const HitRec& r) {
+  return (r.n > 0 && r.t_prev[0] > 0.f) || (r.n > 1 && r.t_prev[1] > 0.f);
+}
+
+__global__ void __launch_bounds__(MTHREADS) k_advect_markers_ref(
+    Grid g, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
+    const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid, float h,
+    const float2* __restrict__ src, float2* __restrict__ dst, unsigned int* __restrict__ seg_count,
+    DevScalars* sc, float dt) {
+  const size_t n = sc->n_markers;
+  const size_t nseg = (n + SEG - 1) / SEG;
+  __shared__ int sh[MTHREADS / 32];
+  for (size_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < SEG / MTHREADS; ++k) {
+      const size_t i = seg * SEG + (size_t)k * MTHREADS + threadIdx.x;
+      if (i < n) {
+        HitRec rec;
+        dst[i] = walk_marker<true>(g, lim, u, v, fluid, solid, h, src[i], dt, &rec);
+        mine += leaks(rec) ? 1 : 0;
+      }
+    }
+    int w = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(EULER_FULL_MASK, w, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+#pragma unroll
+      for (int k = 0; k < MTHREADS / 32; ++k) t += sh[k];
+      seg_count[seg] = (unsigned int)t;
+      if (t) atomicAdd(&sc->n_candidates, (unsigned long long)t);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(MTHREADS) k_list_candidates(
+    Grid g, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
+    const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid, float h,
+    const float2* __restrict__ src, const unsigned int* __restrict__ seg_count,
+    const unsigned int* __restrict__ seg_offset, Candidate* __restrict__ cand, size_t cand_cap,
+    const DevScalars* sc, float dt) {
+  if (sc->n_candidates == 0 || sc->n_candidates > cand_cap) return;
+  const size_t n = sc->n_markers;
+  const size_t nseg = (n + SEG - 1) / SEG;
+  __shared__ unsigned int warp_tot[MTHREADS / 32];
+  for (size_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    if (seg_count[seg] == 0) continue;
+    const unsigned int base = seg_offset[seg];
+    HitRec rec[SEG / MTHREADS];
+    bool is[SEG / MTHREADS];
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < SEG / MTHREADS; ++k) {
+      const size_t i = seg * SEG + (size_t)threadIdx.x * (SEG / MTHREADS) + k;
+      is[k] = false;
+      if (i < n) {
+        walk_marker<true>(g, lim, u, v, fluid, solid, h, src[i], dt, &rec[k]);
+        is[k] = leaks(rec[k]);
+      }
+      mine += is[k];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(EULER_FULL_MASK, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned int woff = 0;
+    for (int wv = 0; wv < (threadIdx.x >> 5); ++wv) woff += warp_tot[wv];
+    unsigned int rank = base + woff + incl - mine;
+#pragma unroll
+    for (int k = 0; k < SEG / MTHREADS; ++k) {
+      if (is[k]) {
+        Candidate c;
+        c.index = (unsigned int)(seg * SEG + (size_t)threadIdx.x * (SEG / MTHREADS) + k);
+        c.n = rec[k].n;
+        c.t_hit[0] = rec[k].t_hit[0]; c.t_hit[1] = rec[k].t_hit[1];
+        c.t_prev[0] = rec[k].t_prev[0]; c.t_prev[1] = rec[k].t_prev[1];
+        cand[rank++] = c;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// The reference's sequential bookkeeping, replayed over the candidates only.
+// dt_after[k] = value of `dt` after candidate k was processed; first_fired = index of the
+// first candidate that actually changed dt (markers up to and including it keep dt0).
+__global__ void __launch_bounds__(32) k_resolve_dt(const Candidate* __restrict__ cand,
+                                                   float* __restrict__ dt_after, size_t cand_cap,
+                                                   DevScalars* sc, float dt0) {
+  // one warp: lanes fetch 32 records at a time (coalesced), then every lane replays them in
+  // order from warp broadcasts, so the sequential chain never waits on global memory
+  const unsigned long long nc = sc->n_candidates;
+  const int lane = threadIdx.x;
+  unsigned long long first = ~0ull;
+  if (nc > cand_cap) { if (lane == 0) { sc->marker_overflow = 1; sc->first_fired = ~0ull; } return; }
+  float run = dt0;
+  for (unsigned long long base = 0; base < nc; base += 32) {
+    Candidate mine;
+    mine.index = 0; mine.n = 0;
+    mine.t_hit[0] = mine.t_hit[1] = mine.t_prev[0] = mine.t_prev[1] = 0.f;
+    if (base + lane < nc) mine = cand[base + lane];
+    float my_after = 0.f;
+    const int cnt = (int)((nc - base) < 32 ? (nc - base) : 32);
+    for (int j = 0; j < cnt; ++j) {
+      const int n = __shfl_sync(EULER_FULL_MASK, mine.n, j);
+      const float h0 = __shfl_sync(EULER_FULL_MASK, mine.t_hit[0], j);
+      const float h1 = __shfl_sync(EULER_FULL_MASK, mine.t_hit[1], j);
+      const float p0 = __shfl_sync(EULER_FULL_MASK, mine.t_prev[0], j);
+      const float p1 = __shfl_sync(EULER_FULL_MASK, mine.t_prev[1], j);
+      const unsigned int idx = __shfl_sync(EULER_FULL_MASK, mine.index, j);
+      float d = run;
+      if (n > 0 && h0 < d) {                                  // `while (t_near < dt)` ... `dt -= t_prev`
+        d -= p0;
+        if (n > 1 && h1 < d) d -= p1;
+      }
+      if (d != run && first == ~0ull) first = idx;
+      run = d;
+      if (lane == j) my_after = run;
+    }
+    if (base + lane < nc) dt_after[base + lane] = my_after;
+  }
+  if (lane == 0) sc->first_fired = first;
+}
+
+__global__ void __launch_bounds__(MTHREADS) k_advect_fixup(
+    Grid g, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
+    const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid, float h,
+    const float2* __restrict__ src, float2* __restrict__ dst,
+    const unsigned int* __restrict__ seg_count, const unsigned int* __restrict__ seg_offset,
+    const Candidate* __restrict__ cand, const float* __restrict__ dt_after, DevScalars* sc,
+    float dt0) {
+  const unsigned long long first = sc->first_fired;
+  if (sc->n_candidates == 0 || first == ~0ull) return;
+  const size_t n = sc->n_markers;
+  const size_t nseg = (n + SEG - 1) / SEG;
+  for (size_t seg = first / SEG + blockIdx.x; seg < nseg; seg += gridDim.x) {
+    const unsigned int off = seg_offset[seg], cnt = seg_count[seg];
+    const float dt_start = off == 0 ? dt0 : dt_after[off - 1];
+#pragma unroll
+    for (int k = 0; k < SEG / MTHREADS; ++k) {
+      const size_t i = seg * SEG + (size_t)k * MTHREADS + threadIdx.x;
+      if (i >= n || i <= first) continue;
+      float dt = dt_start;
+      for (unsigned int j = 0; j < cnt && cand[off + j].index < i; ++j) dt = dt_after[off + j];
+      if (dt != dt0) dst[i] = walk_marker<false>(g, lim, u, v, fluid, solid, h, src[i], dt);
+    }
   }
 }
 
@@ -160,8 +347,8 @@ __global__ void __launch_bounds__(MTHREADS) k_bin_markers(
 // Exclusive scan of seg_count (single block, 1024 threads, contiguous chunk per thread).
 __global__ void __launch_bounds__(1024) k_seg_scan(const unsigned int* __restrict__ seg_count,
                                                    unsigned int* __restrict__ seg_offset,
-                                                   const DevScalars* sc) {
-  if (sc->n_deleted == 0) return;
+                                                   const DevScalars* sc, int for_candidates) {
+  if ((for_candidates ? sc->n_candidates : sc->n_deleted) == 0) return;
   const size_t n = sc->n_markers;
   const size_t nseg = (n + SEG - 1) / SEG;
   const size_t per = (nseg + 1023) / 1024;
@@ -401,14 +588,32 @@ void init_rng_jump_table(unsigned long long* t) {
   }
 }
 
-void launch_advect_markers(Ctx& c, float dt, int /*mode*/) {
+void launch_advect_markers(Ctx& c, float dt, int mode) {
   ProfScope ps(c, KC_ADVECT_MARKERS);
   const int blocks = c.sm_count * 8;
-  k_advect_markers<<<blocks, MTHREADS, 0, c.stream>>>(c.g, c.lim, c.u, c.v, c.count, c.solid,
-                                                      c.h, c.markers, c.markers_alt, c.sc, dt);
-  c.launches += 1;
+  if (mode == 1) {          // EULER_MARKERS_FAST: every marker gets the full dt
+    k_advect_markers<<<blocks, MTHREADS, 0, c.stream>>>(c.g, c.lim, c.u, c.v, c.count, c.solid,
+                                                        c.h, c.markers, c.markers_alt, c.sc, dt);
+    c.launches += 1;
+  } else {                  // EULER_MARKERS_REFERENCE: reproduce the dt carry-over
+    Candidate* cand = reinterpret_cast<Candidate*>(c.cand);
+    cudaMemsetAsync(&c.sc->n_candidates, 0, sizeof(unsigned long long), c.stream);
+    k_advect_markers_ref<<<blocks, MTHREADS, 0, c.stream>>>(
+        c.g, c.lim, c.u, c.v, c.count, c.solid, c.h, c.markers, c.markers_alt, c.seg_count, c.sc, dt);
+    k_seg_scan<<<1, 1024, 0, c.stream>>>(c.seg_count, c.seg_offset, c.sc, 1);
+    k_list_candidates<<<blocks, MTHREADS, 0, c.stream>>>(
+        c.g, c.lim, c.u, c.v, c.count, c.solid, c.h, c.markers, c.seg_count, c.seg_offset, cand,
+        c.cand_cap, c.sc, dt);
+    k_resolve_dt<<<1, 32, 0, c.stream>>>(cand, c.cand_dt, c.cand_cap, c.sc, dt);
+    k_advect_fixup<<<blocks, MTHREADS, 0, c.stream>>>(
+        c.g, c.lim, c.u, c.v, c.count, c.solid, c.h, c.markers, c.markers_alt, c.seg_count,
+        c.seg_offset, cand, c.cand_dt, c.sc, dt);
+    c.launches += 5;
+  }
   float2* t = c.markers; c.markers = c.markers_alt; c.markers_alt = t;
 }
+
+size_t marker_candidate_bytes() { return sizeof(Candidate); }
 
 void launch_refresh_counts(Ctx& c) {
   ProfScope ps(c, KC_REFRESH_COUNTS);
@@ -417,7 +622,7 @@ void launch_refresh_counts(Ctx& c) {
   const int blocks = c.sm_count * 8;
   k_bin_markers<<<blocks, MTHREADS, 0, c.stream>>>(c.g, c.h, c.markers, c.sink, c.solid,
                                                    c.count32, c.seg_count, c.sc);
-  k_seg_scan<<<1, 1024, 0, c.stream>>>(c.seg_count, c.seg_offset, c.sc);
+  k_seg_scan<<<1, 1024, 0, c.stream>>>(c.seg_count, c.seg_offset, c.sc, 0);
   unsigned int* del_list = reinterpret_cast<unsigned int*>(c.markers_alt);
   k_list_deleted<<<blocks, MTHREADS, 0, c.stream>>>(c.g, c.h, c.markers, c.sink, c.solid,
                                                     c.seg_count, c.seg_offset, del_list, c.sc);

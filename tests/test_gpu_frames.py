@@ -157,3 +157,35 @@ def test_host_program_headless_matches_golden(known_answers, tmp_path):
         want = known_answers["%s@100x40/f%d" % (name, frames)]
         assert res["fnv_count"] == want["fnv_count"], (name, frames)
         assert res["markers"] == want["markers"] and res["rng_state"] == want["rng_state"]
+
+
+@pytest.mark.parametrize("name,frames", [("filter", 60), ("waterfall", 80), ("block", 30)])
+def test_reference_marker_mode_reproduces_dt_carry_over(name, frames):
+    """EULER_MARKERS_REFERENCE: the `dt -= t_prev` carry-over between successive markers
+    (main.c:464,501,518) is reproduced — with reference-order dots the run stays bit-identical
+    to the oracle (quirk ON) well past the frame where the quirk first fires (filter: 29,
+    waterfall: 46)."""
+    o, g, G = _pair(shipped_text(name), 100, 40, 0, 1, dot_mode=1)
+    for f in range(frames):
+        assert o.step_frame() == g.step_frame()
+        assert same_bits(g.get(G.F_COUNT), o.count), "frame %d" % (f + 1)
+    assert same_bits(g.get(G.F_MARKERS), o.markers)
+    assert same_bits(g.get(G.F_U), o.u) and same_bits(g.get(G.F_V), o.v)
+    g.close()
+
+
+def test_known_answers_through_gpu(known_answers):
+    """The reference's own known answers (tests/golden/known_answers.json, frame 50) straight
+    from the GPU in its default-faithful configuration."""
+    from oracle.oracle import fnv1a
+    from euler_b200 import gpu as G
+    for name in SCENARIOS:
+        g = G.EulerGpu.from_scenario(Scenario(shipped_text(name), 100, 40), dot_mode=1)
+        for _ in range(50):
+            g.step_frame()
+        want = known_answers["%s@100x40/f50" % name]
+        st = g.stats()
+        assert "%016x" % fnv1a(g.get(G.F_COUNT)) == want["fnv_count"], name
+        assert int(st.n_markers) == want["markers"] and "%016x" % st.rng_state == want["rng_state"]
+        assert abs(float(np.abs(g.get(G.F_U).astype(np.float64)).sum()) - want["sum_abs_u"]) < 1e-9
+        g.close()

@@ -249,3 +249,33 @@ def test_error_behaviour():
         g.set(G.F_MARKERS, np.zeros((4 * 64 + 1, 2), np.float32))
     assert g.step_frame() == 1 and g.stats().solves_skipped == 1      # empty grid: b == 0
     g.close()
+
+
+def test_advect_markers_reference_mode_stage():
+    """advect_markers with the dt carry-over, as a single stage from a state where it fires:
+    markers pushed diagonally into a floor so that many rewinds have t_prev > 0."""
+    from euler_b200 import gpu as G
+    from oracle.oracle import Oracle
+    nx, ny = 64, 40
+    rows = [" " * 62] * 30 + ["X" * 62] * 8
+    text = "\n".join(rows) + "\n"
+    o = Oracle(nx, ny, text)
+    g = G.EulerGpu.from_scenario(Scenario(text, nx, ny), marker_mode=G.MARKERS_REFERENCE)
+    rng = np.random.default_rng(21)
+    n = 6000
+    m = np.stack([rng.uniform(2.0, nx - 2.0, n), rng.uniform(9.02, 9.6, n)], 1).astype(np.float32)
+    cnt = np.zeros((ny, nx), np.uint8); cnt[9:12, 1:-1] = 4
+    o.count[:] = cnt; g.set(G.F_COUNT, cnt)
+    o.u[:] = rng.uniform(1.0, 3.0, (ny, nx)).astype(np.float32)
+    o.v[:] = rng.uniform(-3.0, -1.0, (ny, nx)).astype(np.float32)
+    g.set(G.F_U, o.u); g.set(G.F_V, o.v)
+    o.set_markers(m); g.set(G.F_MARKERS, m)
+    o.advect_markers(0.3); g.run_stage(G.S_ADVECT_MARKERS, 0.3)
+    got = g.get(G.F_MARKERS)
+    assert same_bits(got, o.markers)
+    # and it really differs from the per-marker-dt result
+    o2 = Oracle(nx, ny, text); o2.c.quirk_marker_dt_leak = 0
+    o2.count[:] = cnt; o2.u[:] = o.u; o2.v[:] = o.v; o2.set_markers(m)
+    o2.advect_markers(0.3)
+    assert not same_bits(o2.markers, o.markers)
+    g.close()
