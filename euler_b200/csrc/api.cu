@@ -309,6 +309,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.lim.v_y = nextafterf((float)(ny - 2), 0.f);
   c.h = prm.h; c.rho = prm.rho; c.gravity = prm.gravity;
   c.dot_mode = prm.dot_mode ? 1 : 0;
+  c.use_pipe = prm.stencil_variant == 0 ? 1 : 0;
   c.max_markers = max_markers;
 
 #define TRY(x) do { int rc_ = (x); if (rc_) { euler_gpu_destroy(h); return rc_; } } while (0)
@@ -353,6 +354,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.n_partials = 65536 > (size_t)c.n_strips ? 65536 : (size_t)c.n_strips;
   (void)nblk2d;
   TRY(alloc_array(h, &c.tile_active, (size_t)pcg_tile_count(c.g)));
+  TRY(alloc_array(h, &c.tile_list, (size_t)pcg_tile_count(c.g)));
   TRY(alloc_array(h, &c.partials, c.n_partials));
   TRY(alloc_array(h, &c.wf_progress, (size_t)c.n_strips));
   TRY(alloc_array(h, &c.sc, 1));

@@ -33,6 +33,7 @@ struct Ctx {
   // constants (reference main.c:58-60, 735-736, 838)
   float h, rho, gravity;
   int dot_mode;                   // 0 tree reduction, 1 reference-order sequential sum
+  int use_pipe;                   // stencil kernels: 1 TMA row pipeline, 0 register window
   // static masks
   uint8_t *solid, *source, *sink;
   // dynamic cell classification: marker counts now / previous sub-step (main.c:96-97)
@@ -58,6 +59,7 @@ struct Ctx {
   int8_t* adiag;
   double *precon, *q, *p, *r, *z, *s;
   uint8_t* tile_active;           // per PCG tile: contains fluid (pcg_kernels.cu)
+  int* tile_list;                 // ordered compact list of those tiles
   double* partials;               // grid-reduction scratch
   size_t n_partials;
   unsigned int* wf_progress;      // wavefront strip progress flags

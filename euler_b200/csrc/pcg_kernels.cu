@@ -10,7 +10,7 @@
 // The reference-faithful natural-order IC(0) lives in wavefront.cu.
 //
 // Execution shape (all kernels here): a PERSISTENT grid of sm_count x PCG_BLOCKS_PER_SM blocks
-// walks the grid in tiles of TW x TH = 512 x 16 cells.  A thread owns 4 consecutive x (one
+// walks the grid in tiles of TW x TH = 512 x 32 cells.  A thread owns 4 consecutive x (one
 // uchar4 / two double2 loads per plane and row, 16 B-aligned, fully coalesced) and marches
 // up the TH rows of the tile keeping a three-row window of the stencil operand in
 // REGISTERS, so every operand row is loaded from HBM/L2 once per tile (plus one halo row
@@ -29,12 +29,13 @@
 // every element-wise result bit-identical to the CPU's; only the order of the dot-product
 // sums differs.
 #include "kernels.h"
+#include "pcg_pipe.cuh"
 
 namespace euler {
 
 namespace {
 
-constexpr int TW = 512, TH = 16, TT = 128;     // tile width/height in cells, threads per block
+constexpr int TW = 512, TH = 32, TT = 128;     // tile width/height in cells, threads per block
 enum { CTR_ZS = 0, CTR_NORM = 1, CTR_ZR = 2 };
 
 struct Tiles { int tx, ty, n; };
@@ -45,6 +46,8 @@ __host__ __device__ inline Tiles tiles_of(const Grid& g) {
   t.n = t.tx * t.ty;
   return t;
 }
+
+struct TileList { const int* __restrict__ list; const unsigned int* __restrict__ count; };
 
 struct D4 { double v[4]; };
 
@@ -74,11 +77,33 @@ __global__ void __launch_bounds__(TT) k_tile_flags(Grid g, const uint8_t* __rest
     if (x0 < g.pitch)
       for (int y = y0; y < y1; ++y) any |= ldmask(fluid + gidx(g, x0, y));
     const int has = __syncthreads_or(any != 0);
-    if (threadIdx.x == 0) {
-      active[tile] = has ? 1 : 0;
-      if (has) atomicAdd(&sc->active_tiles, 1u);
-    }
+    if (threadIdx.x == 0) active[tile] = has ? 1 : 0;
   }
+}
+
+// Ordered, compact list of the tiles that contain fluid (single block): the persistent
+// kernels walk list[blockIdx.x + i*gridDim.x], which balances the blocks to within one tile
+// whatever the shape of the fluid region.
+__global__ void __launch_bounds__(1024) k_tile_compact(Grid g, const uint8_t* __restrict__ active,
+                                                       int* __restrict__ list, DevScalars* sc) {
+  const Tiles T = tiles_of(g);
+  __shared__ int sh[1024];
+  const int per = (T.n + 1023) / 1024;
+  const int lo = min(T.n, per * (int)threadIdx.x), hi = min(T.n, lo + per);
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) cnt += active[i] ? 1 : 0;
+  sh[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int v = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = sh[threadIdx.x] - cnt;
+  for (int i = lo; i < hi; ++i)
+    if (active[i]) list[run++] = i;
+  if (threadIdx.x == 1023) sc->active_tiles = (unsigned int)sh[1023];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -131,11 +156,11 @@ __device__ __forceinline__ void stencil_tile(const Grid& g, const uint8_t* __res
 }
 
 template <class Body>
-__device__ __forceinline__ void for_each_tile(const Grid& g, const uint8_t* __restrict__ active,
-                                              Body body) {
+__device__ __forceinline__ void for_each_tile(const Grid& g, const TileList& tl, Body body) {
   const Tiles T = tiles_of(g);
-  for (int tile = blockIdx.x; tile < T.n; tile += gridDim.x) {
-    if (!active[tile]) continue;
+  const int n = (int)*tl.count;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int tile = tl.list[i];
     const int x0 = (tile % T.tx) * TW + threadIdx.x * 4, y0 = (tile / T.tx) * TH;
     // threads past the row end keep participating in the shuffles with a clamped, harmless
     // address (their mask is the zero padding / they are never asked for a valid neighbour)
@@ -174,7 +199,7 @@ struct ApplyA {
 };
 
 __global__ void __launch_bounds__(TT) k_apply_a(
-    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ s,
+    Grid g, TileList active, const double* __restrict__ s,
     const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ z,
     double* partials, DevScalars* sc, int exact) {
   if (sc->done) return;
@@ -192,7 +217,7 @@ __global__ void __launch_bounds__(TT) k_apply_a(
 
 // ---- p += alpha s ; r -= alpha z ; ||r||inf ---------------------------------------------
 __global__ void __launch_bounds__(TT) k_axpy(
-    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ s,
+    Grid g, TileList active, const double* __restrict__ s,
     const double* __restrict__ z, const uint8_t* __restrict__ fluid, double* __restrict__ p,
     double* __restrict__ r, double* partials, DevScalars* sc, double tol) {
   if (sc->done) return;
@@ -228,7 +253,7 @@ __global__ void __launch_bounds__(TT) k_axpy(
 
 // ---- s = z + beta s -------------------------------------------------------------------
 __global__ void __launch_bounds__(TT) k_update_search(
-    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ z,
+    Grid g, TileList active, const double* __restrict__ z,
     const uint8_t* __restrict__ fluid, double* __restrict__ s, const DevScalars* sc) {
   if (sc->done) return;
   const double beta = sc->beta;
@@ -249,7 +274,7 @@ __global__ void __launch_bounds__(TT) k_update_search(
 }
 
 // s = z on the active tiles (memcpy(s, z), main.c:746)
-__global__ void __launch_bounds__(TT) k_copy_search(Grid g, const uint8_t* __restrict__ active,
+__global__ void __launch_bounds__(TT) k_copy_search(Grid g, TileList active,
                                                     const double* __restrict__ z,
                                                     double* __restrict__ s) {
   for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
@@ -330,7 +355,7 @@ struct RbForward {
 };
 
 __global__ void __launch_bounds__(TT) k_rb_forward(
-    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ r,
+    Grid g, TileList active, const double* __restrict__ r,
     const uint8_t* __restrict__ fluid, const double* __restrict__ precon, double* __restrict__ q,
     const DevScalars* sc) {
   if (sc->done) return;
@@ -386,7 +411,7 @@ struct RbBackward {
 };
 
 __global__ void __launch_bounds__(TT) k_rb_backward(
-    Grid g, const uint8_t* __restrict__ active, const double* __restrict__ q,
+    Grid g, TileList active, const double* __restrict__ q,
     const double* __restrict__ r, const uint8_t* __restrict__ fluid,
     const double* __restrict__ precon, double* __restrict__ z, double* partials, DevScalars* sc,
     int init, int exact) {
@@ -469,13 +494,192 @@ __global__ void __launch_bounds__(256) k_dot_seq(
   }
 }
 
+// =========================================================================================
+// TMA-fed variants of the three stencil kernels (pcg_pipe.cuh): same arithmetic, same
+// results bit for bit, operands staged through a shared-memory ring by the bulk-copy engine.
+// =========================================================================================
+static_assert(pipe::TW == TW && pipe::TT == TT, "pipe tiling must match");
+
+__device__ __forceinline__ unsigned lds_mask4(const uint8_t* p) {       // 4-aligned
+  return *reinterpret_cast<const unsigned*>(p);
+}
+__device__ __forceinline__ D4 lds4(const double* p) {                   // 16 B aligned
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  D4 r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  return r;
+}
+
+struct ApplyAPipe {
+  // planes: d0 = s ; b0 = fluid, b1 = adiag
+  const Grid g;
+  double* __restrict__ z;
+  double acc;
+  __device__ __forceinline__ void row(const pipe::RowView<1, 2>& dn, const pipe::RowView<1, 2>& ce,
+                                      const pipe::RowView<1, 2>& up, int t4, int x, int y, bool live) {
+    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    if (!mc) return;
+    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
+    const unsigned am = lds_mask4(ce.b[1] + t4);
+    const D4 sc = lds4(ce.d[0] + t4), sd = lds4(dn.d[0] + t4), su = lds4(up.d[0] + t4);
+    const double sl = ce.d[0][t4 - 1], sr = ce.d[0][t4 + 4];
+    D4 out;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      out.v[k] = 0.0;
+      if (!mbit(mc, k)) continue;
+      // main.c:683-687: a_diag*s - right - up - left - down, each only towards fluid
+      double o = (double)(int)(signed char)((am >> (8 * k)) & 0xffu) * sc.v[k];
+      const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
+      const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
+      o -= r_ok ? (k == 3 ? sr : sc.v[k + 1]) : 0.0;
+      o -= mbit(mu, k) ? su.v[k] : 0.0;
+      o -= l_ok ? (k == 0 ? sl : sc.v[k - 1]) : 0.0;
+      o -= mbit(md, k) ? sd.v[k] : 0.0;
+      out.v[k] = o;
+      acc += o * sc.v[k];
+    }
+    st4(z + gidx(g, x, y), out);
+  }
+};
+
+template <int NS>
+__global__ void __launch_bounds__(TT) k_apply_a_pipe(
+    Grid g, TileList active, const double* __restrict__ s,
+    const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ z,
+    double* partials, DevScalars* sc, int exact) {
+  if (sc->done) return;
+  ApplyAPipe op{g, z, 0.0};
+  pipe::Planes<1, 2> in;
+  in.d[0] = s; in.b[0] = fluid; in.b[1] = reinterpret_cast<const uint8_t*>(adiag);
+  pipe::run<1, 2, NS, TH>(g, active.list, (int)*active.count, in, op);
+  const double bsum = block_reduce<false>(op.acc);
+  grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZS], [&](double total) {
+    if (exact) return;
+    sc->zs = total;
+    sc->alpha = sc->sigma / total;                           // main.c:752
+  });
+}
+
+struct RbForwardPipe {
+  // planes: d0 = r, d1 = pc ; b0 = fluid
+  const Grid g;
+  double* __restrict__ q;
+  __device__ __forceinline__ static double w(double r, double p) { return p * (r * p); }
+  __device__ __forceinline__ void row(const pipe::RowView<2, 1>& dn, const pipe::RowView<2, 1>& ce,
+                                      const pipe::RowView<2, 1>& up, int t4, int x, int y, bool live) {
+    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    if (!mc) return;
+    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
+    const D4 rc = lds4(ce.d[0] + t4), pc = lds4(ce.d[1] + t4);
+    const D4 rd = lds4(dn.d[0] + t4), pd = lds4(dn.d[1] + t4);
+    const D4 ru = lds4(up.d[0] + t4), pu = lds4(up.d[1] + t4);
+    const double wl = w(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), wr = w(ce.d[0][t4 + 4], ce.d[1][t4 + 4]);
+    D4 out;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      out.v[k] = 0.0;
+      if (!mbit(mc, k)) continue;
+      double t = rc.v[k];
+      if ((x + k + y) & 1) {                                 // black: + sum over red neighbours
+        const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
+        const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
+        if (l_ok) t = t + (k == 0 ? wl : w(rc.v[k - 1], pc.v[k - 1]));
+        if (r_ok) t = t + (k == 3 ? wr : w(rc.v[k + 1], pc.v[k + 1]));
+        if (mbit(md, k)) t = t + w(rd.v[k], pd.v[k]);
+        if (mbit(mu, k)) t = t + w(ru.v[k], pu.v[k]);
+      }
+      out.v[k] = t * pc.v[k];
+    }
+    st4(q + gidx(g, x, y), out);
+  }
+};
+
+template <int NS>
+__global__ void __launch_bounds__(TT) k_rb_forward_pipe(
+    Grid g, TileList active, const double* __restrict__ r,
+    const uint8_t* __restrict__ fluid, const double* __restrict__ precon, double* __restrict__ q,
+    const DevScalars* sc) {
+  if (sc->done) return;
+  RbForwardPipe op{g, q};
+  pipe::Planes<2, 1> in;
+  in.d[0] = r; in.d[1] = precon; in.b[0] = fluid;
+  pipe::run<2, 1, NS, TH>(g, active.list, (int)*active.count, in, op);
+}
+
+struct RbBackwardPipe {
+  // planes: d0 = q, d1 = pc, d2 = r ; b0 = fluid
+  const Grid g;
+  double* __restrict__ z;
+  double acc;
+  __device__ __forceinline__ void row(const pipe::RowView<3, 1>& dn, const pipe::RowView<3, 1>& ce,
+                                      const pipe::RowView<3, 1>& up, int t4, int x, int y, bool live) {
+    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    if (!mc) return;
+    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
+    const D4 qc = lds4(ce.d[0] + t4), pc = lds4(ce.d[1] + t4), rc = lds4(ce.d[2] + t4);
+    const D4 qd = lds4(dn.d[0] + t4), pd = lds4(dn.d[1] + t4);
+    const D4 qu = lds4(up.d[0] + t4), pu = lds4(up.d[1] + t4);
+    const double zl = ce.d[0][t4 - 1] * ce.d[1][t4 - 1], zr = ce.d[0][t4 + 4] * ce.d[1][t4 + 4];
+    D4 out;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      out.v[k] = 0.0;
+      if (!mbit(mc, k)) continue;
+      double zc;
+      const double p = pc.v[k];
+      if ((x + k + y) & 1) {
+        zc = qc.v[k] * p;                                    // black: q*pc
+      } else {
+        const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
+        const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
+        double t = qc.v[k];
+        if (l_ok) t = t + p * (k == 0 ? zl : qc.v[k - 1] * pc.v[k - 1]);
+        if (r_ok) t = t + p * (k == 3 ? zr : qc.v[k + 1] * pc.v[k + 1]);
+        if (mbit(md, k)) t = t + p * (qd.v[k] * pd.v[k]);
+        if (mbit(mu, k)) t = t + p * (qu.v[k] * pu.v[k]);
+        zc = t * p;
+      }
+      out.v[k] = zc;
+      acc += zc * rc.v[k];
+    }
+    st4(z + gidx(g, x, y), out);
+  }
+};
+
+template <int NS>
+__global__ void __launch_bounds__(TT) k_rb_backward_pipe(
+    Grid g, TileList active, const double* __restrict__ q,
+    const double* __restrict__ r, const uint8_t* __restrict__ fluid,
+    const double* __restrict__ precon, double* __restrict__ z, double* partials, DevScalars* sc,
+    int init, int exact) {
+  if (sc->done) return;
+  RbBackwardPipe op{g, z, 0.0};
+  pipe::Planes<3, 1> in;
+  in.d[0] = q; in.d[1] = precon; in.d[2] = r; in.b[0] = fluid;
+  pipe::run<3, 1, NS, TH>(g, active.list, (int)*active.count, in, op);
+  const double bsum = block_reduce<false>(op.acc);
+  grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZR], [&](double total) {
+    if (exact) return;
+    if (init) { sc->sigma = total; }                         // main.c:748
+    else { sc->beta = total / sc->sigma; sc->sigma = total; }  // main.c:762-765
+  });
+}
+
+constexpr int NS_A = 8, NS_F = 6, NS_B = 5;
+
 // persistent grid: resident blocks per SM (occupancy of that kernel) x SM count, capped by
 // the number of tiles
 template <class K>
-int pcg_blocks(const Ctx& c, K kernel) {
+int pcg_blocks(const Ctx& c, K kernel, int smem = 0) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TT, 0) != cudaSuccess || per_sm < 1)
-    per_sm = 4;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TT, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
   const Tiles T = tiles_of(c.g);
   const long want = (long)c.sm_count * per_sm;
   return (int)(T.n < want ? T.n : want);
@@ -485,9 +689,11 @@ int pcg_blocks(const Ctx& c, K kernel) {
 
 void launch_tile_flags(Ctx& c) {
   ProfScope ps(c, KC_MISC);
-  cudaMemsetAsync(&c.sc->active_tiles, 0, sizeof(unsigned int), c.stream);
-  k_tile_flags<<<pcg_blocks(c, k_tile_flags), TT, 0, c.stream>>>(c.g, c.count, c.tile_active, c.sc);
-  c.launches += 1;
+  const Tiles T = tiles_of(c.g);
+  const int nb = T.n < c.sm_count * 16 ? T.n : c.sm_count * 16;
+  k_tile_flags<<<nb, TT, 0, c.stream>>>(c.g, c.count, c.tile_active, c.sc);
+  k_tile_compact<<<1, 1024, 0, c.stream>>>(c.g, c.tile_active, c.tile_list, c.sc);
+  c.launches += 2;
 }
 
 void launch_pcg_reset(Ctx& c) {
@@ -498,8 +704,14 @@ void launch_pcg_reset(Ctx& c) {
 
 void launch_apply_a(Ctx& c, bool) {
   ProfScope ps(c, KC_APPLY_A);
-  k_apply_a<<<pcg_blocks(c, k_apply_a), TT, 0, c.stream>>>(c.g, c.tile_active, c.s, c.count, c.adiag, c.z,
-                                                c.partials, c.sc, c.dot_mode);
+  if (c.use_pipe) {
+    constexpr int smem = pipe::smem_bytes<1, 2, NS_A>();
+    k_apply_a_pipe<NS_A><<<pcg_blocks(c, k_apply_a_pipe<NS_A>, smem), TT, smem, c.stream>>>(
+        c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.s, c.count, c.adiag, c.z, c.partials, c.sc, c.dot_mode);
+  } else {
+    k_apply_a<<<pcg_blocks(c, k_apply_a), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.s, c.count, c.adiag, c.z,
+                                                  c.partials, c.sc, c.dot_mode);
+  }
   c.launches += 1;
   if (c.dot_mode) {
     k_dot_seq<<<1, 256, 0, c.stream>>>(c.g, c.tile_active, c.z, c.s, c.count, c.sc, DOT_ZS);
@@ -509,20 +721,20 @@ void launch_apply_a(Ctx& c, bool) {
 
 void launch_axpy(Ctx& c, double tol) {
   ProfScope ps(c, KC_AXPY);
-  k_axpy<<<pcg_blocks(c, k_axpy), TT, 0, c.stream>>>(c.g, c.tile_active, c.s, c.z, c.count, c.p, c.r,
+  k_axpy<<<pcg_blocks(c, k_axpy), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.s, c.z, c.count, c.p, c.r,
                                              c.partials, c.sc, tol);
   c.launches += 1;
 }
 
 void launch_update_search(Ctx& c) {
   ProfScope ps(c, KC_UPDATE_SEARCH);
-  k_update_search<<<pcg_blocks(c, k_update_search), TT, 0, c.stream>>>(c.g, c.tile_active, c.z, c.count, c.s, c.sc);
+  k_update_search<<<pcg_blocks(c, k_update_search), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.z, c.count, c.s, c.sc);
   c.launches += 1;
 }
 
 void launch_copy_search(Ctx& c) {
   ProfScope ps(c, KC_MISC);
-  k_copy_search<<<pcg_blocks(c, k_copy_search), TT, 0, c.stream>>>(c.g, c.tile_active, c.z, c.s);
+  k_copy_search<<<pcg_blocks(c, k_copy_search), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.z, c.s);
   c.launches += 1;
 }
 
@@ -537,11 +749,20 @@ void launch_dot_zr_exact(Ctx& c, bool init);
 
 void launch_rb_apply(Ctx& c, bool init) {
   ProfScope ps(c, KC_PRECON_APPLY);
-  k_rb_forward<<<pcg_blocks(c, k_rb_forward), TT, 0, c.stream>>>(c.g, c.tile_active, c.r, c.count, c.precon,
-                                                   c.q, c.sc);
-  k_rb_backward<<<pcg_blocks(c, k_rb_backward), TT, 0, c.stream>>>(c.g, c.tile_active, c.q, c.r, c.count,
-                                                    c.precon, c.z, c.partials, c.sc, init ? 1 : 0,
-                                                    c.dot_mode);
+  if (c.use_pipe) {
+    constexpr int sf = pipe::smem_bytes<2, 1, NS_F>(), sb = pipe::smem_bytes<3, 1, NS_B>();
+    k_rb_forward_pipe<NS_F><<<pcg_blocks(c, k_rb_forward_pipe<NS_F>, sf), TT, sf, c.stream>>>(
+        c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.r, c.count, c.precon, c.q, c.sc);
+    k_rb_backward_pipe<NS_B><<<pcg_blocks(c, k_rb_backward_pipe<NS_B>, sb), TT, sb, c.stream>>>(
+        c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.q, c.r, c.count, c.precon, c.z, c.partials, c.sc, init ? 1 : 0,
+        c.dot_mode);
+  } else {
+    k_rb_forward<<<pcg_blocks(c, k_rb_forward), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.r, c.count, c.precon,
+                                                     c.q, c.sc);
+    k_rb_backward<<<pcg_blocks(c, k_rb_backward), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.q, c.r, c.count,
+                                                      c.precon, c.z, c.partials, c.sc, init ? 1 : 0,
+                                                      c.dot_mode);
+  }
   c.launches += 2;
   launch_dot_zr_exact(c, init);
 }

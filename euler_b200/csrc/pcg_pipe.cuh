@@ -1,0 +1,203 @@
+// euler_b200/csrc/pcg_pipe.cuh — TMA-fed row pipeline for the 5-point stencil kernels of the
+// pressure solve (apply_a, red-black forward/backward).
+//
+// Why: with a register window the loads of the next row are consumed almost immediately, so
+// the bytes in flight are bounded by registers x occupancy and the kernels sat at ~45 % of
+// HBM bandwidth (profiles/r01a_*).  Here the bulk-copy engine keeps the memory system busy
+// independently of the SM's registers:
+//
+//   * a persistent block walks its 512 x TH tiles row by row; every input-plane row segment of
+//     a tile (with its halo columns) is ONE contiguous, 16 B-aligned range, fetched with
+//     `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` (SASS: UBLKCP) into a
+//     ring of NS shared-memory stages;
+//   * `full[stage]` mbarriers carry the transaction bytes; `empty[stage]` mbarriers are
+//     arrived on by the 4 consumer warps when a row is no longer needed (a row lives for
+//     three output rows: as up-, centre- and down-neighbour);
+//   * one elected thread issues the copies NS-3 rows ahead of the row being computed and keeps
+//     going across tile boundaries, so the pipeline never drains inside a launch;
+//   * consumers read centre/left/right/up/down straight from shared memory (no shuffles, no
+//     edge-lane special case) and store results with 16 B vector stores.
+#pragma once
+#include "common.cuh"
+
+namespace euler {
+namespace pipe {
+
+constexpr int TW = 512, TT = 128;            // tile width in cells, threads per block
+constexpr int HX8 = 2;                       // halo columns of an fp64 plane (16 B)
+constexpr int HX1 = 16;                      // halo columns of a u8 plane (16 B)
+constexpr int ROW8 = (TW + 2 * HX8) * 8;     // bytes of one fp64 row segment in smem
+constexpr int ROW1 = (TW + 2 * HX1);         // bytes of one u8 row segment in smem
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  while (!mbar_try_wait(b, parity)) {}
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+struct Tiles { int tx, ty, n; };
+__host__ __device__ inline Tiles tiles_of(const Grid& g, int th) {
+  Tiles t;
+  t.tx = (g.pitch + TW - 1) / TW;
+  t.ty = (g.ny + th - 1) / th;
+  t.n = t.tx * t.ty;
+  return t;
+}
+
+// Enumerates the rows (jobs) a block has to load: for every tile of the compact active-tile
+// list assigned to it (positions blockIdx.x, +gridDim.x, ...), rows y0-1 .. y1 inclusive.
+struct JobIter {
+  int pos, yy, x0, y0, y1, w;      // pos = position in the compact list of active tiles
+  bool valid;
+  __device__ __forceinline__ void seek(const Grid& g, const Tiles& T, int th,
+                                       const int* __restrict__ list, int n) {
+    valid = pos < n;
+    if (valid) {
+      const int tile = list[pos];
+      x0 = (tile % T.tx) * TW;
+      y0 = (tile / T.tx) * th;
+      y1 = min(y0 + th, g.ny);
+      w = min(TW, g.pitch - x0);
+      yy = y0 - 1;
+    }
+  }
+  __device__ __forceinline__ void start(const Grid& g, const Tiles& T, int th,
+                                        const int* __restrict__ list, int n) {
+    pos = blockIdx.x;
+    seek(g, T, th, list, n);
+  }
+  __device__ __forceinline__ void next(const Grid& g, const Tiles& T, int th,
+                                       const int* __restrict__ list, int n) {
+    if (yy < y1) { ++yy; return; }
+    pos += gridDim.x;
+    seek(g, T, th, list, n);
+  }
+};
+
+// One stage of the ring, as seen by the consumers: pointers are biased so that index i is tile
+// column i (fp64 planes valid for i in [-2, TW+2), u8 planes for i in [-16, TW+16)).
+template <int ND, int NB>
+struct RowView {
+  const double* d[ND];
+  const uint8_t* b[NB];
+};
+
+template <int ND, int NB>
+struct Layout {
+  static constexpr int stage_bytes = ND * ROW8 + NB * ROW1;
+  __device__ static __forceinline__ RowView<ND, NB> view(unsigned char* stage) {
+    RowView<ND, NB> v;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) v.d[i] = reinterpret_cast<const double*>(stage + i * ROW8) + HX8;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) v.b[i] = stage + ND * ROW8 + i * ROW1 + HX1;
+    return v;
+  }
+};
+
+template <int ND, int NB>
+struct Planes {
+  const double* d[ND];
+  const uint8_t* b[NB];
+};
+
+// The pipeline driver.  `Op::row(dn, ce, up, t4, x, y, live)` is called by every thread for
+// each output row of each active tile of the block: t4 = 4*threadIdx.x is the tile column of
+// the thread's first cell, x its global column; `live` is false for threads past the row end.
+template <int ND, int NB, int NS, int TH, class Op>
+__device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list, int n_active,
+                                    const Planes<ND, NB>& in, Op& op) {
+  using L = Layout<ND, NB>;
+  constexpr int PF = NS - 3;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* stages = smem_raw;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NS * L::stage_bytes);
+  uint64_t* empty = full + NS;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, TT / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const Tiles T = tiles_of(g, TH);
+  JobIter cons, prod;
+  cons.start(g, T, TH, list, n_active);
+  prod = cons;
+  int issued = 0;
+
+  auto issue = [&]() {          // thread 0 only
+    const int s = issued % NS, use = issued / NS;
+    mbar_wait(empty + s, (use & 1) ^ 1);
+    unsigned char* st = stages + s * L::stage_bytes;
+    const uint32_t b8 = (uint32_t)(prod.w + 2 * HX8) * 8u, b1 = (uint32_t)(prod.w + 2 * HX1);
+    mbar_expect_tx(full + s, ND * b8 + NB * b1);
+    const long row = (long)prod.yy * g.pitch + prod.x0;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) bulk_g2s(st + i * ROW8, in.d[i] + row - HX8, b8, full + s);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) bulk_g2s(st + ND * ROW8 + i * ROW1, in.b[i] + row - HX1, b1, full + s);
+    ++issued;
+    prod.next(g, T, TH, list, n_active);
+  };
+
+  for (int j = 0; cons.valid; ++j) {
+    if (threadIdx.x == 0)
+      while (prod.valid && issued <= j + PF) issue();
+    mbar_wait(full + (j % NS), (j / NS) & 1);
+    if (cons.yy >= cons.y0 + 1) {
+      const RowView<ND, NB> up = L::view(stages + (j % NS) * L::stage_bytes);
+      const RowView<ND, NB> ce = L::view(stages + ((j + NS - 1) % NS) * L::stage_bytes);
+      const RowView<ND, NB> dn = L::view(stages + ((j + NS - 2) % NS) * L::stage_bytes);
+      const int t4 = threadIdx.x * 4;
+      op.row(dn, ce, up, t4, cons.x0 + t4, cons.yy - 1, t4 < cons.w);
+      // the row two behind is done with; at the end of a tile so are the last two
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(empty + ((j + NS - 2) % NS));
+        if (cons.yy == cons.y1) {
+          mbar_arrive(empty + ((j + NS - 1) % NS));
+          mbar_arrive(empty + (j % NS));
+        }
+      }
+    }
+    cons.next(g, T, TH, list, n_active);
+  }
+}
+
+template <int ND, int NB, int NS>
+constexpr int smem_bytes() { return NS * Layout<ND, NB>::stage_bytes + 2 * NS * 8; }
+
+}  // namespace pipe
+}  // namespace euler

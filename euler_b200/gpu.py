@@ -35,7 +35,7 @@ class Params(C.Structure):
                 ("max_iterations", C.c_int), ("tol", C.c_double),
                 ("precon", C.c_int), ("marker_mode", C.c_int), ("dot_mode", C.c_int),
                 ("rng_state", C.c_uint64),
-                ("device", C.c_int), ("stream", C.c_void_p), ("pcg_check_every", C.c_int),
+                ("device", C.c_int), ("stream", C.c_void_p), ("pcg_check_every", C.c_int), ("stencil_variant", C.c_int),
                 ("row0", C.c_int), ("global_ny", C.c_int)]
 
 

@@ -133,6 +133,8 @@ typedef struct euler_params {
   int   device;          /* CUDA device ordinal; default 0 */
   void *stream;          /* cudaStream_t to enqueue on; NULL = the library creates one */
   int   pcg_check_every; /* iterations enqueued between convergence polls; default 8 */
+  int   stencil_variant; /* PCG stencil kernels: 0 = TMA bulk-copy row pipeline (default),
+                            1 = register sliding window (kept for A/B measurements) */
   /* row-slab decomposition: this handle owns global rows [row0, row0+ny) of a
    * grid that is global_ny rows tall; 0/0 = not decomposed.  See euler_gpu_comm_init. */
   int   row0;
