@@ -13,7 +13,7 @@ CSRC     := euler_b200/csrc
 LIBDIR   := euler_b200/lib
 OBJDIR   := build/obj
 CU_SRCS  := $(CSRC)/api.cu $(CSRC)/grid_kernels.cu $(CSRC)/marker_kernels.cu \
-            $(CSRC)/pcg_kernels.cu $(CSRC)/wavefront.cu
+            $(CSRC)/pcg_kernels.cu $(CSRC)/wavefront.cu $(CSRC)/comm.cu
 CU_OBJS  := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 HDRS     := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/euler_gpu.h
 HOST     := euler_b200/host

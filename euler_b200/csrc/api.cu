@@ -11,6 +11,7 @@
 
 #include <vector>
 
+#include "comm.h"
 #include "kernels.h"
 
 using namespace euler;
@@ -37,10 +38,17 @@ int fail(int code, const char* fmt, ...) {
 
 }  // namespace
 
+constexpr int SLAB_HALO = 4;     // halo rows kept on each side of the owned rows
+
 struct euler_gpu {
   Ctx c;
   euler_params prm;
-  int nx, ny;
+  int nx, ny;                    // GLOBAL grid size
+  bool slab;                     // row-slab decomposition configured (params.slab_rows > 0)
+  int row0, rows, lo;            // first owned global row, owned rows, first stored global row
+  Comm cm;
+  bool comm_ready;
+  unsigned long long* n_keep;    // device scratch of the marker partition
   bool own_stream;
   std::vector<void*> allocs;     // raw cudaMalloc pointers
   DevScalars* host_sc;           // pinned mirror
@@ -115,9 +123,11 @@ FieldInfo field_info(euler_gpu* h, int f) {
   }
 }
 
+// host arrays always have the GLOBAL shape [ny][nx]; the handle takes the rows it stores
 int upload_plane(euler_gpu* h, void* dst, const void* src, size_t elem) {
   const Grid& g = h->c.g;
-  CU(cudaMemcpy2DAsync(dst, g.pitch * elem, src, (size_t)g.nx * elem, (size_t)g.nx * elem, g.ny,
+  const char* from = reinterpret_cast<const char*>(src) + (size_t)h->lo * g.nx * elem;
+  CU(cudaMemcpy2DAsync(dst, g.pitch * elem, from, (size_t)g.nx * elem, (size_t)g.nx * elem, g.ny,
                        cudaMemcpyHostToDevice, h->c.stream));
   return 0;
 }
@@ -213,8 +223,141 @@ int run_substep(euler_gpu* h, float dt) {
   return 0;
 }
 
+// ---- row-slab mode: same stages, plus the exchange steps ---------------------
+#define CM(call) do { if ((call)) return fail(EULER_E_COMM, "%s: %s", #call, comm_last_error()); } while (0)
+
+int dist_precon_apply(euler_gpu* h, bool init) {
+  Ctx& c = h->c;
+  CM(comm_halo(c, h->cm, c.r, 8, 1));               // forward reads r (and pc) of the row above/below
+  launch_rb_forward(c);
+  CM(comm_halo(c, h->cm, c.q, 8, 1));               // backward reads q of the row above/below
+  launch_rb_backward(c, init);
+  CM(comm_gather_scalars(c, h->cm, c.sc->part));    // {z.r partial, ||r||inf partial}
+  launch_dist_beta(c, h->cm.gather, h->cm.nranks, init, h->prm.tol);
+  return 0;
+}
+
+int dist_iteration(euler_gpu* h) {
+  Ctx& c = h->c;
+  CM(comm_halo(c, h->cm, c.s, 8, 1));               // apply_a reads s[y+-1], main.c:685-687
+  launch_apply_a(c, true);
+  CM(comm_gather_scalars(c, h->cm, c.sc->part));    // {z.s partial}
+  launch_dist_alpha(c, h->cm.gather, h->cm.nranks);
+  launch_axpy(c, h->prm.tol);
+  int rc = dist_precon_apply(h, false);
+  if (rc) return rc;
+  launch_update_search(c);
+  return 0;
+}
+
+int run_project_dist(euler_gpu* h, float dt) {
+  Ctx& c = h->c;
+  launch_build_rhs(c, dt);
+  launch_tile_flags(c);
+  CM(comm_allreduce_max_i32(c, h->cm, &c.sc->nonzero_rhs, 1));   // all_zero(r) over the whole grid
+  int rc = pull_scalars(h);
+  if (rc) return rc;
+  h->last_iterations = 0;
+  if (!h->host_sc->nonzero_rhs) {
+    h->solves_skipped++;
+  } else {
+    h->solves++;
+    launch_pcg_reset(c);
+    launch_rb_build(c);
+    rc = dist_precon_apply(h, true);
+    if (rc) return rc;
+    launch_copy_search(c);
+    int remaining = h->prm.max_iterations;
+    const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
+    while (remaining > 0) {
+      const int chunk = remaining < every ? remaining : every;
+      for (int i = 0; i < chunk; ++i) { rc = dist_iteration(h); if (rc) return rc; }
+      remaining -= chunk;
+      rc = pull_scalars(h);
+      if (rc) return rc;
+      if (h->host_sc->done) break;
+    }
+    h->last_iterations = h->host_sc->iters;
+    h->last_residual = h->host_sc->resid;
+    h->pcg_iterations += (uint64_t)h->host_sc->iters;
+  }
+  CM(comm_halo_up_only(c, h->cm, c.p, 8));           // p[y+1] of the last owned row, main.c:800
+  launch_pressure_update(c, dt);
+  CM(comm_halo(c, h->cm, c.u, 4, SLAB_HALO));
+  CM(comm_halo(c, h->cm, c.v, 4, SLAB_HALO));
+  CM(comm_allreduce_max_u32(c, h->cm, &c.sc->max_u2_bits, 2));   // next calculate_timestep
+  h->max_valid = true;
+  return check_launch("project");
+}
+
+// markers that crossed into a neighbouring slab (displacement < 1 cell per sub-step)
+int migrate_markers(euler_gpu* h) {
+  Ctx& c = h->c;
+  Comm& cm = h->cm;
+  launch_partition_markers(c, h->row0, h->row0 + h->rows, cm.send_dn, cm.send_up, cm.send_cap, h->n_keep);
+  // counts first: what I send down/up, what the neighbours send me
+  CU(cudaMemsetAsync(cm.mig, 0, 2 * sizeof(unsigned long long), c.stream));
+  CM(comm_exchange(c, cm, &c.sc->n_send_dn, 8, &cm.mig[0], 8, &c.sc->n_send_up, 8, &cm.mig[1], 8));
+  unsigned long long host[5];
+  CU(cudaMemcpyAsync(&host[0], &c.sc->n_send_dn, 16, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaMemcpyAsync(&host[2], cm.mig, 16, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaMemcpyAsync(&host[4], h->n_keep, 8, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  const unsigned long long to_dn = host[0], to_up = host[1], from_dn = host[2], from_up = host[3], keep = host[4];
+  if (to_dn > cm.send_cap || to_up > cm.send_cap)
+    return fail(EULER_E_UNSUPPORTED, "more than %zu markers cross a slab boundary in one sub-step", cm.send_cap);
+  if (keep + from_dn + from_up > c.max_markers)
+    return fail(EULER_E_UNSUPPORTED, "slab marker capacity exceeded");
+  CM(comm_exchange(c, cm, cm.send_dn, (size_t)to_dn * 8, c.markers + keep, (size_t)from_dn * 8,
+                   cm.send_up, (size_t)to_up * 8, c.markers + keep + from_dn, (size_t)from_up * 8));
+  const unsigned long long n_new = keep + from_dn + from_up;
+  CU(cudaMemcpyAsync(&c.sc->n_markers, &n_new, 8, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaStreamSynchronize(c.stream));               // n_new is a stack variable
+  return 0;
+}
+
+int run_substep_dist(euler_gpu* h, float dt) {
+  Ctx& c = h->c;
+  h->last_dt = dt;
+  prof_mark(h, 0);
+  launch_advect_markers(c, dt, EULER_MARKERS_FAST);
+  int rc = migrate_markers(h);
+  if (rc) return rc;
+  launch_refresh_counts(c);
+  if (c.n_source_cells_global) {
+    launch_sources_count(c);
+    CM(comm_gather_scalars(c, h->cm, c.sc->part));
+    launch_sources_prep(c, h->cm.gather, h->cm.rank, h->cm.nranks);
+    launch_sources(c);
+  }
+  CM(comm_halo(c, h->cm, c.count, 1, SLAB_HALO));    // classification of the neighbours' edge rows
+  prof_mark(h, 1);
+  launch_extrapolate(c);
+  { float* t = c.u; c.u = c.uext; c.uext = t; t = c.v; c.v = c.vext; c.vext = t; }
+  launch_advect_velocity(c, dt);
+  prof_mark(h, 2);
+  rc = run_project_dist(h, dt);
+  if (rc) return rc;
+  prof_mark(h, 3);
+  h->substeps++;
+  if (h->profiling) {
+    CU(cudaEventSynchronize(h->ev[3]));
+    CU(cudaStreamSynchronize(c.stream));
+    prof_collect(c);
+    float a = 0, b = 0, d = 0;
+    cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&d, h->ev[2], h->ev[3]);
+    h->ms_markers += a; h->ms_grid += b; h->ms_project += d;
+  }
+  return 0;
+}
+
 int compute_dt(euler_gpu* h, float frame_time, float* dt) {
-  if (!h->max_valid) launch_maxsq(h->c);
+  if (!h->max_valid) {
+    launch_maxsq(h->c);
+    if (h->slab) CM(comm_allreduce_max_u32(h->c, h->cm, &h->c.sc->max_u2_bits, 2));
+  }
   h->max_valid = true;
   launch_timestep(h->c, frame_time, h->prm.cfl_distance);
   int rc = pull_scalars(h);
@@ -245,7 +388,7 @@ int euler_gpu_default_params(euler_params* p) {
   p->dot_mode = EULER_DOT_TREE;
   p->rng_state = 0x9bd185c449534b91ull;                      // main.c:204
   p->device = 0; p->stream = nullptr; p->pcg_check_every = 8;
-  p->row0 = 0; p->global_ny = 0;
+  p->slab_row0 = 0; p->slab_rows = 0;
   return 0;
 }
 
@@ -253,6 +396,7 @@ int euler_gpu_destroy(euler_gpu* h) {
   if (!h) return 0;
   cudaSetDevice(h->prm.device);
   if (h->c.stream) cudaStreamSynchronize(h->c.stream);
+  if (h->comm_ready) comm_destroy(&h->cm);
   for (void* p : h->allocs) cudaFree(p);
   if (h->host_sc) cudaFreeHost(h->host_sc);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -273,11 +417,26 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   if (nx < 4 || ny < 4) return fail(EULER_E_INVALID, "grid %dx%d too small (min 4x4)", nx, ny);
   if (!solid || !source || !sink) return fail(EULER_E_INVALID, "mask planes must not be NULL");
   if (n_markers && !markers_xy) return fail(EULER_E_INVALID, "markers is NULL");
-  const size_t max_markers = 4 * (size_t)nx * ny;            // MAX_MARKER_COUNT, main.c:92
-  if (n_markers > max_markers) return fail(EULER_E_INVALID, "too many markers");
-  if (max_markers >= 0xFFFFFFFFull) return fail(EULER_E_UNSUPPORTED, "grid too large");
+  const size_t max_markers_global = 4 * (size_t)nx * ny;     // MAX_MARKER_COUNT, main.c:92
+  if (n_markers > max_markers_global) return fail(EULER_E_INVALID, "too many markers");
+  if (max_markers_global >= 0xFFFFFFFFull) return fail(EULER_E_UNSUPPORTED, "grid too large");
   euler_params prm;
   if (params) prm = *params; else euler_gpu_default_params(&prm);
+  const bool slab = prm.slab_rows > 0;
+  if (slab) {
+    if (prm.slab_row0 < 0 || prm.slab_row0 + prm.slab_rows > ny || prm.slab_rows < 2 * SLAB_HALO)
+      return fail(EULER_E_INVALID, "slab rows [%d,%d) invalid for ny=%d (min %d rows per slab)",
+                  prm.slab_row0, prm.slab_row0 + prm.slab_rows, ny, 2 * SLAB_HALO);
+    if (prm.precon != EULER_PRECON_REDBLACK || prm.marker_mode != EULER_MARKERS_FAST || prm.dot_mode != EULER_DOT_TREE)
+      return fail(EULER_E_UNSUPPORTED, "row slabs need precon=REDBLACK, marker_mode=FAST, dot_mode=TREE "
+                  "(the IC(0) wavefront and the reference orders are sequential across the whole grid)");
+  }
+  const int row0 = slab ? prm.slab_row0 : 0, rows = slab ? prm.slab_rows : ny;
+  const int lo = row0 - SLAB_HALO > 0 ? row0 - SLAB_HALO : 0;
+  const int hi = row0 + rows + SLAB_HALO < ny ? row0 + rows + SLAB_HALO : ny;
+  const int ny_loc = slab ? hi - lo : ny;
+  // local capacity: every stored row full, plus what may arrive from the neighbours
+  const size_t max_markers = 4 * (size_t)nx * ny_loc;
   if (prm.precon != EULER_PRECON_IC0_WAVEFRONT && prm.precon != EULER_PRECON_REDBLACK)
     return fail(EULER_E_INVALID, "unknown preconditioner %d", prm.precon);
   if (prm.marker_mode != EULER_MARKERS_REFERENCE && prm.marker_mode != EULER_MARKERS_FAST)
@@ -294,15 +453,20 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   euler_gpu* h = new euler_gpu();
   memset(&h->c, 0, sizeof h->c);
   h->prm = prm; h->nx = nx; h->ny = ny;
+  h->slab = slab; h->row0 = row0; h->rows = rows; h->lo = slab ? lo : 0;
+  memset(&h->cm, 0, sizeof h->cm); h->comm_ready = false; h->n_keep = nullptr;
   h->host_sc = nullptr; h->device_bytes = 0; h->max_valid = false;
   h->frames = h->substeps = h->solves = h->solves_skipped = h->pcg_iterations = 0;
   h->last_iterations = 0; h->last_residual = 0; h->last_dt = 0; h->profiling = false;
   h->ms_markers = h->ms_grid = h->ms_project = 0;
   for (int i = 0; i < 4; ++i) h->ev[i] = nullptr;
   Ctx& c = h->c;
-  c.g.nx = nx; c.g.ny = ny;
+  c.g.nx = nx; c.g.ny = ny_loc;
   c.g.pitch = (nx + PITCH_ALIGN - 1) / PITCH_ALIGN * PITCH_ALIGN;
-  c.g.row0 = 0; c.g.gny = ny;
+  c.g.yoff = h->lo; c.g.gny = ny;
+  c.own0 = row0 - h->lo; c.own1 = c.own0 + rows;
+  c.distributed = 0;
+  c.max_markers_global = max_markers_global;
   c.lim.u_x = nextafterf((float)(nx - 2), 0.f);              // main.c:339-340, U is (X-1) x Y
   c.lim.u_y = nextafterf((float)(ny - 1), 0.f);
   c.lim.v_x = nextafterf((float)(nx - 1), 0.f);              // V is X x (Y-1)
@@ -350,7 +514,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
     TRY(alloc_array(h, &c.cand_dt, c.cand_cap));
   }
   const size_t nblk2d = (size_t)((nx + 31) / 32) * (size_t)((ny + 7) / 8);
-  c.n_strips = (ny - 2 + 31) / 32;
+  c.n_strips = (ny_loc - 2 + 31) / 32;
   c.n_partials = 65536 > (size_t)c.n_strips ? 65536 : (size_t)c.n_strips;
   (void)nblk2d;
   TRY(alloc_array(h, &c.tile_active, (size_t)pcg_tile_count(c.g)));
@@ -363,15 +527,30 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   TRY(upload_plane(h, c.solid, solid, 1));
   TRY(upload_plane(h, c.source, source, 1));
   TRY(upload_plane(h, c.sink, sink, 1));
+  std::vector<float> mine;
+  if (slab) {                    // keep the markers whose cell row this slab owns
+    for (size_t i = 0; i < n_markers; ++i) {
+      const int gy = (int)floorf(markers_xy[2 * i + 1] / prm.h);
+      if (gy >= row0 && gy < row0 + rows) { mine.push_back(markers_xy[2 * i]); mine.push_back(markers_xy[2 * i + 1]); }
+    }
+    markers_xy = mine.data();
+    n_markers = mine.size() / 2;
+    if (n_markers > max_markers) { euler_gpu_destroy(h); return fail(EULER_E_INVALID, "too many markers in slab"); }
+  }
   if (n_markers)
     TRYCU(cudaMemcpyAsync(c.markers, markers_xy, n_markers * sizeof(float2), cudaMemcpyHostToDevice, c.stream));
 
   // static row-major list of source cells (main.c:284-286 visits them in this order)
   std::vector<unsigned int> cells;
+  size_t n_src_global = 0;
   for (int y = 0; y < ny; ++y)
     for (int x = 0; x < nx; ++x)
-      if (source[(size_t)y * nx + x]) cells.push_back((unsigned int)((size_t)y * c.g.pitch + x));
+      if (source[(size_t)y * nx + x]) {
+        n_src_global++;
+        if (y >= row0 && y < row0 + rows) cells.push_back((unsigned int)((size_t)(y - h->lo) * c.g.pitch + x));
+      }
   c.n_source_cells = cells.size();
+  c.n_source_cells_global = n_src_global;
   TRY(alloc_array(h, &c.source_cells, cells.size()));
   if (!cells.empty())
     TRYCU(cudaMemcpyAsync(c.source_cells, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice, c.stream));
@@ -386,6 +565,11 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   TRYCU(cudaStreamSynchronize(c.stream));   // host vectors above go out of scope
 
   launch_refresh_counts(c);                                  // sim_init, main.c:268
+  if (slab) {
+    // halo rows of the initial count plane: counted from the host's copy of the markers
+    // (before any communicator exists); afterwards they are refreshed by halo exchange
+    TRY(alloc_array(h, &h->n_keep, 1));
+  }
   TRY(check_launch("create"));
   TRYCU(cudaStreamSynchronize(c.stream));
 #undef TRY
@@ -397,16 +581,20 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
 #define ENTER(h)                                                   \
   if (!(h)) return fail(EULER_E_INVALID, "handle is NULL");        \
   CU(cudaSetDevice((h)->prm.device))
+#define NEED_COMM(h) \
+  if ((h)->slab && !(h)->comm_ready) return fail(EULER_E_COMM, "slab handle: call euler_gpu_comm_init first")
 
 int euler_gpu_calculate_timestep(euler_gpu* h, float frame_time, float* dt) {
   ENTER(h);
+  NEED_COMM(h);
   if (!dt) return fail(EULER_E_INVALID, "dt is NULL");
   return compute_dt(h, frame_time, dt);
 }
 
 int euler_gpu_substep(euler_gpu* h, float dt) {
   ENTER(h);
-  int rc = run_substep(h, dt);
+  NEED_COMM(h);
+  int rc = h->slab ? run_substep_dist(h, dt) : run_substep(h, dt);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->c.stream));
   return 0;
@@ -414,6 +602,7 @@ int euler_gpu_substep(euler_gpu* h, float dt) {
 
 int euler_gpu_step_frame(euler_gpu* h, int* substeps) {
   ENTER(h);
+  NEED_COMM(h);
   float frame_time = h->prm.frame_time;                      // main.c:849-851
   int step = 0;
   for (; frame_time > 0.f && step < h->prm.max_substeps; ++step) {
@@ -421,7 +610,7 @@ int euler_gpu_step_frame(euler_gpu* h, int* substeps) {
     int rc = compute_dt(h, frame_time, &dt);
     if (rc) return rc;
     frame_time -= dt;
-    rc = run_substep(h, dt);
+    rc = h->slab ? run_substep_dist(h, dt) : run_substep(h, dt);
     if (rc) return rc;
   }
   h->frames++;
@@ -432,6 +621,7 @@ int euler_gpu_step_frame(euler_gpu* h, int* substeps) {
 
 int euler_gpu_run_stage(euler_gpu* h, int stage, float dt) {
   ENTER(h);
+  if (h->slab) return fail(EULER_E_UNSUPPORTED, "run_stage is a single-GPU parity hook");
   Ctx& c = h->c;
   switch (stage) {
     case EULER_S_ADVECT_MARKERS: launch_advect_markers(c, dt, h->prm.marker_mode); break;
@@ -493,10 +683,13 @@ int euler_gpu_get(euler_gpu* h, int field, void* dst, size_t bytes) {
   }
   FieldInfo fi = field_info(h, field);
   if (!fi.ptr) return fail(EULER_E_INVALID, "unknown field %d", field);
-  const size_t want = (size_t)g.nx * g.ny * fi.elem;
+  const size_t want = (size_t)g.nx * h->ny * fi.elem;
   if (bytes != want) return fail(EULER_E_INVALID, "field %d: %zu bytes given, %zu needed", field, bytes, want);
-  CU(cudaMemcpy2DAsync(dst, (size_t)g.nx * fi.elem, fi.ptr, g.pitch * fi.elem, (size_t)g.nx * fi.elem,
-                       g.ny, cudaMemcpyDeviceToHost, h->c.stream));
+  // slab mode: only the rows this handle OWNS are written (at their global position)
+  char* to = reinterpret_cast<char*>(dst) + (size_t)h->row0 * g.nx * fi.elem;
+  const char* from = reinterpret_cast<const char*>(fi.ptr) + (size_t)h->c.own0 * g.pitch * fi.elem;
+  CU(cudaMemcpy2DAsync(to, (size_t)g.nx * fi.elem, from, g.pitch * fi.elem, (size_t)g.nx * fi.elem,
+                       h->rows, cudaMemcpyDeviceToHost, h->c.stream));
   CU(cudaStreamSynchronize(h->c.stream));
   return 0;
 }
@@ -508,6 +701,7 @@ int euler_gpu_set(euler_gpu* h, int field, const void* src, size_t bytes) {
   if (field == EULER_F_MARKERS) {
     if (bytes % sizeof(float2)) return fail(EULER_E_INVALID, "markers: size not a multiple of 8");
     const size_t n = bytes / sizeof(float2);
+    if (h->slab) return fail(EULER_E_UNSUPPORTED, "set(MARKERS) on a slab handle");
     if (n > h->c.max_markers) return fail(EULER_E_INVALID, "markers: %zu > max %zu", n, h->c.max_markers);
     if (n) CU(cudaMemcpyAsync(h->c.markers, src, bytes, cudaMemcpyHostToDevice, h->c.stream));
     unsigned long long nn = n;
@@ -518,7 +712,7 @@ int euler_gpu_set(euler_gpu* h, int field, const void* src, size_t bytes) {
   if (field == EULER_F_SOURCE) return fail(EULER_E_UNSUPPORTED, "source plane is fixed at create()");
   FieldInfo fi = field_info(h, field);
   if (!fi.ptr) return fail(EULER_E_INVALID, "unknown field %d", field);
-  const size_t want = (size_t)g.nx * g.ny * fi.elem;
+  const size_t want = (size_t)g.nx * h->ny * fi.elem;
   if (bytes != want) return fail(EULER_E_INVALID, "field %d: %zu bytes given, %zu needed", field, bytes, want);
   int rc = upload_plane(h, fi.ptr, src, fi.elem);
   if (rc) return rc;
@@ -603,11 +797,44 @@ int euler_gpu_synchronize(euler_gpu* h) {
 
 void* euler_gpu_stream(euler_gpu* h) { return h ? (void*)h->c.stream : nullptr; }
 
-int euler_gpu_comm_unique_id(void*) {
-  return fail(EULER_E_UNSUPPORTED, "multi-GPU slabs are not built into this library yet");
+int euler_gpu_comm_unique_id(void* unique_id_128) {
+  if (!unique_id_128) return fail(EULER_E_INVALID, "unique_id is NULL");
+  if (comm_unique_id(unique_id_128)) return fail(EULER_E_COMM, "%s", comm_last_error());
+  return 0;
 }
-int euler_gpu_comm_init(euler_gpu*, int, int, const void*) {
-  return fail(EULER_E_UNSUPPORTED, "multi-GPU slabs are not built into this library yet");
+
+int euler_gpu_comm_init(euler_gpu* h, int rank, int n_ranks, const void* unique_id_128) {
+  ENTER(h);
+  if (!h->slab) return fail(EULER_E_INVALID, "handle was not created with slab_rows > 0");
+  if (!unique_id_128 || rank < 0 || rank >= n_ranks) return fail(EULER_E_INVALID, "bad rank/id");
+  if (comm_init(&h->cm, rank, n_ranks, unique_id_128)) return fail(EULER_E_COMM, "%s", comm_last_error());
+  Ctx& c = h->c;
+  void* raw = nullptr;
+  CU(cudaMalloc(&raw, sizeof(double) * GATHER_SLOTS * n_ranks)); h->allocs.push_back(raw);
+  h->cm.gather = (double*)raw;
+  CU(cudaMalloc(&raw, 2 * sizeof(unsigned long long))); h->allocs.push_back(raw);
+  h->cm.mig = (unsigned long long*)raw;
+  h->cm.send_cap = 32 * (size_t)h->nx;              // markers crossing one boundary per sub-step
+  CU(cudaMalloc(&raw, h->cm.send_cap * 8)); h->allocs.push_back(raw); h->cm.send_dn = (float2*)raw;
+  CU(cudaMalloc(&raw, h->cm.send_cap * 8)); h->allocs.push_back(raw); h->cm.send_up = (float2*)raw;
+  h->device_bytes += 2 * h->cm.send_cap * 8;
+  c.distributed = 1;
+  h->comm_ready = true;
+  // halo rows of the initial classification (create() binned only the owned markers)
+  CM(comm_halo(c, h->cm, c.count, 1, SLAB_HALO));
+  CU(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int euler_gpu_slab_partition(int global_ny, int n_ranks, int rank, int* row0, int* rows) {
+  if (global_ny < 1 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !row0 || !rows)
+    return fail(EULER_E_INVALID, "bad slab partition arguments");
+  // contiguous, balanced to within one row; multiples of nothing in particular: rows are
+  // independent units (x is the fast axis, main.c:64)
+  const int base = global_ny / n_ranks, extra = global_ny % n_ranks;
+  *rows = base + (rank < extra ? 1 : 0);
+  *row0 = rank * base + (rank < extra ? rank : extra);
+  return 0;
 }
 
 }  // extern "C"

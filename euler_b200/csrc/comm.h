@@ -1,0 +1,41 @@
+// euler_b200/csrc/comm.h — row-slab decomposition plumbing: NCCL over
+// NVLink/NVSwitch, one process per GPU.  NCCL is bound at run time with dlopen (the library
+// has no link-time dependency on it; inside a torch process the already-loaded libnccl is
+// reused).  Everything here is enqueued on the handle's stream; nothing synchronises.
+#pragma once
+#include <stddef.h>
+
+#include "kernels.h"
+
+namespace euler {
+
+struct Comm {
+  void* nccl;          // ncclComm_t
+  int rank, nranks;
+  double* gather;      // device: nranks * GATHER_SLOTS doubles
+  unsigned long long* mig;   // device scratch for marker migration counts
+  float2 *send_dn, *send_up; // device staging for migrating markers
+  size_t send_cap;
+};
+constexpr int GATHER_SLOTS = 4;
+
+const char* comm_last_error();
+int comm_load();                                                  // dlopen + dlsym; 0 ok
+int comm_unique_id(void* out128);
+int comm_init(Comm* cm, int rank, int nranks, const void* uid128);
+void comm_destroy(Comm* cm);
+
+// halo rows of a plane: `depth` rows below own0 and above own1 are refreshed from the
+// neighbouring slabs' owned rows (byte-wise, any element size)
+int comm_halo(Ctx& c, Comm& cm, void* plane, size_t elem, int depth);
+// only the row above own1 (one-directional: p[y+1] of the pressure update)
+int comm_halo_up_only(Ctx& c, Comm& cm, void* plane, size_t elem);
+// all-gather of GATHER_SLOTS doubles per rank starting at `src` (device) into cm.gather
+int comm_gather_scalars(Ctx& c, Comm& cm, const double* src);
+int comm_allreduce_max_u32(Ctx& c, Comm& cm, unsigned int* buf, size_t n);
+int comm_allreduce_max_i32(Ctx& c, Comm& cm, int* buf, size_t n);
+// point-to-point with both neighbours in one group; pointers may be null when count is 0
+int comm_exchange(Ctx& c, Comm& cm, const void* to_dn, size_t n_to_dn, void* from_dn, size_t n_from_dn,
+                  const void* to_up, size_t n_to_up, void* from_up, size_t n_from_up);
+
+}  // namespace euler

@@ -20,11 +20,16 @@ constexpr int PITCH_ALIGN = 32;
 
 enum FaceType { CELL_P = 0, FACE_U = 1, FACE_V = 2 };   // reference celltype_t, main.c:46-50
 
+// A (view of a) grid.  Single GPU: ny == gny, yoff == 0.  Row-slab decomposition: the handle
+// stores rows [yoff, yoff+ny) of a grid that is gny rows tall (owned rows plus halo rows), and
+// the PCG kernels get a view of the owned rows only (pointers advanced, yoff adjusted).
+// Wherever a GLOBAL row matters — sample positions, border clamps, red/black parity, validity
+// of the last V row — kernels use y + yoff and gny.
 struct Grid {
-  int nx, ny;      // rows stored by this handle (== global size when not slab-decomposed)
+  int nx, ny;      // columns, rows in this view
   int pitch;       // elements per row
-  int row0;        // global index of local row 0
-  int gny;         // global ny
+  int yoff;        // global row index of row 0 of this view
+  int gny;         // global number of rows
 };
 
 __host__ __device__ __forceinline__ size_t gidx(const Grid& g, int x, int y) {
@@ -55,6 +60,11 @@ struct DevScalars {
   unsigned int active_tiles;
   int marker_overflow;            // more rewinding markers than the candidate list holds
   unsigned long long first_fired;
+  // row-slab decomposition: this rank's contributions to the per-iteration all-gather
+  // {dot-product partial, ||r||inf partial, source cells needing a marker, marker count}
+  double part[4];
+  unsigned long long n_send_dn, n_send_up;   // markers leaving towards the lower/upper slab
+  unsigned long long src_base, n_markers_global;
 };
 
 #define EULER_FULL_MASK 0xffffffffu

@@ -45,7 +45,10 @@ __device__ __forceinline__ float interpolate(const float* __restrict__ q,
   iy = iy < 0.f ? 0.f : (iy > hy ? hy : iy);
   const float wx = truncf(ix), wy = truncf(iy);
   const float fx = ix - wx, fy = iy - wy;                    // == modff for finite input
-  const int bx = (int)wx, by = (int)wy;
+  const int bx = (int)wx;
+  // global row -> row of this view; clamped into the guard band so that a sample outside the
+  // locally stored rows (cannot happen for a marker/face the view owns) stays memory-safe
+  const int by = min(max((int)wy - g.yoff, -(GUARD_ROWS - 1)), g.ny + GUARD_ROWS - 3);
 
   const bool ok00 = face_has<TYPE>(fluid, g, bx, by);
   const bool ok10 = face_has<TYPE>(fluid, g, bx + 1, by);

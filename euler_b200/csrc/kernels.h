@@ -25,7 +25,8 @@ struct Prof {
 
 struct Ctx {
   Prof prof;
-  Grid g;
+  Grid g;                         // all locally stored rows
+  int own0, own1;                 // rows of g this handle owns (== 0, g.ny when not decomposed)
   InterpLimits lim;
   cudaStream_t stream;
   unsigned long long launches;
@@ -34,6 +35,7 @@ struct Ctx {
   float h, rho, gravity;
   int dot_mode;                   // 0 tree reduction, 1 reference-order sequential sum
   int use_pipe;                   // stencil kernels: 1 TMA row pipeline, 0 register window
+  int distributed;                // row-slab mode: reductions are finished across ranks (comm.cu)
   // static masks
   uint8_t *solid, *source, *sink;
   // dynamic cell classification: marker counts now / previous sub-step (main.c:96-97)
@@ -43,7 +45,8 @@ struct Ctx {
   float *u, *v, *utmp, *vtmp, *uext, *vext;
   // markers (main.c:92-95): ping-pong AoS float2 arrays
   float2 *markers, *markers_alt;
-  size_t max_markers;
+  size_t max_markers;             // capacity of the local arrays
+  size_t max_markers_global;      // MAX_MARKER_COUNT of the whole grid (main.c:92)
   // compaction scratch
   unsigned int* seg_count;        // per 1024-marker segment
   unsigned int* seg_offset;
@@ -54,6 +57,7 @@ struct Ctx {
   // source cells, row-major (static)
   unsigned int* source_cells;
   size_t n_source_cells;
+  size_t n_source_cells_global;
   unsigned long long* rng_jump;   // 64 x 64 columns of T^(2^j), xorshift64 transition
   // pressure solve
   int8_t* adiag;
@@ -100,6 +104,10 @@ void launch_pressure_update(Ctx& c, float dt);               // p,utmp,vtmp -> u
 void launch_advect_markers(Ctx& c, float dt, int mode);      // in: markers, out: markers (swapped inside)
 void launch_refresh_counts(Ctx& c);                          // prev<-cur, re-bin, delete in sink/solid
 void launch_sources(Ctx& c);                                 // update_fluid_sources
+void launch_sources_count(Ctx& c);
+void launch_sources_prep(Ctx& c, const double* gathered, int rank, int nranks);
+void launch_partition_markers(Ctx& c, int own_lo_global, int own_hi_global, float2* send_dn,
+                              float2* send_up, size_t send_cap, unsigned long long* n_keep);
 void init_rng_jump_table(unsigned long long* host_table /* 64*64 */);
 size_t marker_candidate_bytes();
 
@@ -108,6 +116,10 @@ void launch_ic0_build(Ctx& c);                               // E^-1, wavefront 
 void launch_ic0_apply(Ctx& c, bool init);                    // z = M^-1 r (+ z.r, sigma/beta)
 void launch_rb_build(Ctx& c);                                // red-black E^-1
 void launch_rb_apply(Ctx& c, bool init);                     // z = M^-1 r (+ z.r, sigma/beta)
+void launch_rb_forward(Ctx& c);                              //   q = L^-1 r
+void launch_rb_backward(Ctx& c, bool init);                  //   z = L^-T q (+ z.r)
+void launch_dist_alpha(Ctx& c, const double* gathered, int nranks);
+void launch_dist_beta(Ctx& c, const double* gathered, int nranks, bool init, double tol);
 void launch_copy_search(Ctx& c);                             // s = z
 void launch_apply_a(Ctx& c, bool with_alpha);                // z = A s (+ z.s, alpha)
 void launch_axpy(Ctx& c, double tol);                        // p += a s, r -= a z, ||r||inf

@@ -67,7 +67,7 @@ __device__ __forceinline__ float2 walk_marker(const Grid& g, const InterpLimits&
   float t_next = fminf(tx, ty);
   while (t_next < dt) {
     if (tx < ty) {
-      const int sx = min(max(line_x + off_x, 0), g.nx - 1), sy = min(max(cy, 0), g.ny - 1);
+      const int sx = min(max(line_x + off_x, 0), g.nx - 1), sy = min(max(cy - g.yoff, 0), g.ny - 1);
       if (solid[gidx(g, sx, sy)]) {
         if (RECORD && rec->n < 2) { rec->t_hit[rec->n] = t_next; rec->t_prev[rec->n] = t_prev; rec->n++; }
         px = px + t_prev * vx; py = py + t_prev * vy;        // rewind, main.c:500
@@ -83,7 +83,7 @@ __device__ __forceinline__ float2 walk_marker(const Grid& g, const InterpLimits&
         tx = time_until(px, gx, vx);
       }
     } else {
-      const int sx = min(max(cx, 0), g.nx - 1), sy = min(max(line_y + off_y, 0), g.ny - 1);
+      const int sx = min(max(cx, 0), g.nx - 1), sy = min(max(line_y + off_y - g.yoff, 0), g.ny - 1);
       if (solid[gidx(g, sx, sy)]) {
         if (RECORD && rec->n < 2) { rec->t_hit[rec->n] = t_next; rec->t_prev[rec->n] = t_prev; rec->n++; }
         px = px + t_prev * vx; py = py + t_prev * vy;        // main.c:517
@@ -301,7 +301,7 @@ __device__ __forceinline__ bool marker_cell(const Grid& g, float h, float2 p, si
   // the reference asserts 0 < x < X, 0 < y < Y (main.c:108, compiled out); clamp so a stray
   // marker lands in the sink ring and is deleted instead of indexing out of bounds
   cx = min(max(cx, 0), g.nx - 1);
-  cy = min(max(cy, 0), g.ny - 1);
+  cy = min(max(cy - g.yoff, 0), g.ny - 1);                  // global row -> stored row
   *cell = gidx(g, cx, cy);
   return true;
 }
@@ -485,6 +485,81 @@ __global__ void __launch_bounds__(256) k_fold_counts(Grid g, unsigned int* __res
   }
 }
 
+
+// ---- row-slab mode: markers that left the rows this rank owns -------------------------------
+// Displacement per sub-step is < 1 cell (CFL 0.75, main.c:838), so a marker can only move to
+// an adjacent slab.  Out-of-place three-way partition with warp-aggregated cursors: keepers
+// go to `keep`, leavers to the staging buffers that NCCL sends to the neighbours.
+__global__ void __launch_bounds__(MTHREADS) k_partition_markers(
+    float h, int own_lo, int own_hi, const float2* __restrict__ src, float2* __restrict__ keep,
+    float2* __restrict__ send_dn, float2* __restrict__ send_up, size_t send_cap, DevScalars* sc,
+    unsigned long long* n_keep) {
+  const size_t n = sc->n_markers;
+  const size_t per = (size_t)gridDim.x * blockDim.x;
+  const size_t rounds = (n + per - 1) / per;
+  const int lane = threadIdx.x & 31;
+  for (size_t rd = 0; rd < rounds; ++rd) {
+    const size_t i = rd * per + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    int cls = -1;                                     // 0 keep, 1 down, 2 up
+    float2 m = make_float2(0.f, 0.f);
+    if (i < n) {
+      m = src[i];
+      const int gy = (int)floorf(m.y / h);
+      cls = gy < own_lo ? 1 : (gy >= own_hi ? 2 : 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned bal = __ballot_sync(EULER_FULL_MASK, cls == k);
+      if (!bal) continue;
+      unsigned long long base = 0;
+      if (lane == __ffs(bal) - 1)
+        base = atomicAdd(k == 0 ? n_keep : (k == 1 ? &sc->n_send_dn : &sc->n_send_up),
+                         (unsigned long long)__popc(bal));
+      base = __shfl_sync(EULER_FULL_MASK, base, __ffs(bal) - 1);
+      if (cls == k) {
+        const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+        if (k == 0) keep[pos] = m;
+        else if (pos < send_cap) (k == 1 ? send_dn : send_up)[pos] = m;
+        else sc->marker_overflow = 1;
+      }
+    }
+  }
+}
+
+// source cells of this slab that need a marker (main.c:287), for the cross-rank prefix
+__global__ void __launch_bounds__(1024) k_sources_count(const unsigned int* __restrict__ cells,
+                                                        size_t ncells, const uint8_t* __restrict__ count,
+                                                        DevScalars* sc) {
+  int mine = 0;
+  for (size_t i = threadIdx.x; i < ncells; i += 1024) mine += count[cells[i]] < 4 ? 1 : 0;
+  __shared__ int sh[32];
+  int w = mine;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(EULER_FULL_MASK, w, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < 32; ++k) t += sh[k];
+    sc->part[2] = (double)t;
+    sc->part[3] = (double)sc->n_markers;
+  }
+}
+
+// fold the all-gathered {need, n_markers} pairs: my base rank in the global row-major order of
+// needy source cells, the global marker count and the global number of needy cells
+__global__ void k_sources_prep(DevScalars* sc, const double* __restrict__ gathered, int rank, int nranks) {
+  double base = 0.0, total = 0.0, nglob = 0.0;
+  for (int r = 0; r < nranks; ++r) {
+    if (r < rank) base += gathered[r * 4 + 2];
+    total += gathered[r * 4 + 2];
+    nglob += gathered[r * 4 + 3];
+  }
+  sc->src_base = (unsigned long long)base;
+  sc->n_markers_global = (unsigned long long)nglob;
+  sc->part[2] = total;
+}
+
 // ------------------------------------------------------------------- sources ----
 
 // xorshift64 state transition is linear over GF(2) (misc/rng.c:7-9); jump[j] holds the 64
@@ -515,12 +590,17 @@ __device__ __forceinline__ float rng_float(unsigned long long s) {
 // the stream (y jitter first: gcc evaluates v2f's second argument first, see oracle).
 __global__ void __launch_bounds__(1024) k_sources(
     Grid g, float h, const unsigned int* __restrict__ cells, size_t ncells,
-    uint8_t* __restrict__ count, float2* __restrict__ markers, size_t max_markers,
-    const unsigned long long* __restrict__ jump, DevScalars* sc) {
+    uint8_t* __restrict__ count, float2* __restrict__ markers, size_t max_markers_global,
+    const unsigned long long* __restrict__ jump, DevScalars* sc, int distributed) {
+  // single GPU: ranks start at 0 and the global marker count is the local one.  Slab mode:
+  // this slab's needy cells come after those of the slabs below it (row-major order), the
+  // MAX_MARKER_COUNT-1 latch (main.c:281,290) looks at the global count.
   const unsigned long long n0 = sc->n_markers;
-  const unsigned long long cap = max_markers - 1;            // main.c:281
-  const bool exhausted0 = sc->source_exhausted || n0 == cap;
-  const unsigned long long allow = exhausted0 ? 0 : cap - n0;
+  const unsigned long long nglob = distributed ? sc->n_markers_global : n0;
+  const unsigned long long rank0 = distributed ? sc->src_base : 0ull;
+  const unsigned long long cap = max_markers_global - 1;     // main.c:281
+  const bool exhausted0 = sc->source_exhausted || nglob == cap;
+  const unsigned long long allow = exhausted0 ? 0 : cap - nglob;
   const unsigned long long state0 = sc->rng_state;
   __shared__ unsigned int warp_tot[32];
   __shared__ unsigned long long carry_sh;
@@ -544,7 +624,8 @@ __global__ void __launch_bounds__(1024) k_sources(
       if (wv < wid) woff += t;
       total += t;
     }
-    const unsigned long long rank = carry_sh + woff + __popc(bal & ((1u << lane) - 1u));
+    const unsigned long long lrank = carry_sh + woff + __popc(bal & ((1u << lane) - 1u));
+    const unsigned long long rank = rank0 + lrank;
     if (need && rank < allow) {
       unsigned long long s = rng_jump(jump, state0, 2 * rank);
       s = rng_step(s);
@@ -552,7 +633,7 @@ __global__ void __launch_bounds__(1024) k_sources(
       s = rng_step(s);
       const float jx = rng_float(s);
       const int y = (int)(cell / (unsigned int)g.pitch), x = (int)(cell % (unsigned int)g.pitch);
-      markers[n0 + rank] = make_float2(h * (x + jx), h * (y + jy));   // main.c:288
+      markers[n0 + lrank] = make_float2(h * (x + jx), h * (y + g.yoff + jy));   // main.c:288
       count[cell] += 1;
     }
     __syncthreads();
@@ -560,10 +641,15 @@ __global__ void __launch_bounds__(1024) k_sources(
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const unsigned long long added = carry_sh < allow ? carry_sh : allow;
-    sc->n_markers = n0 + added;
-    sc->rng_state = rng_jump(jump, state0, 2 * added);
-    sc->source_exhausted = (exhausted0 || (n0 + added == cap)) ? 1 : 0;
+    // markers this slab appended: its needy cells whose global rank is below `allow`
+    unsigned long long mine = carry_sh;
+    if (rank0 >= allow) mine = 0;
+    else if (rank0 + mine > allow) mine = allow - rank0;
+    const unsigned long long need_all = distributed ? (unsigned long long)sc->part[2] : carry_sh;
+    const unsigned long long added_all = need_all < allow ? need_all : allow;
+    sc->n_markers = n0 + mine;
+    sc->rng_state = rng_jump(jump, state0, 2 * added_all);
+    sc->source_exhausted = (exhausted0 || (nglob + added_all == cap)) ? 1 : 0;
   }
 }
 
@@ -632,11 +718,33 @@ void launch_refresh_counts(Ctx& c) {
 }
 
 void launch_sources(Ctx& c) {
-  if (c.n_source_cells == 0) return;
+  if (c.n_source_cells_global == 0) return;
   ProfScope ps(c, KC_SOURCES);
   k_sources<<<1, 1024, 0, c.stream>>>(c.g, c.h, c.source_cells, c.n_source_cells, c.count,
-                                      c.markers, c.max_markers, c.rng_jump, c.sc);
+                                      c.markers, c.max_markers_global, c.rng_jump, c.sc,
+                                      c.distributed);
   c.launches += 1;
+}
+
+void launch_sources_count(Ctx& c) {
+  k_sources_count<<<1, 1024, 0, c.stream>>>(c.source_cells, c.n_source_cells, c.count, c.sc);
+  c.launches += 1;
+}
+void launch_sources_prep(Ctx& c, const double* gathered, int rank, int nranks) {
+  k_sources_prep<<<1, 1, 0, c.stream>>>(c.sc, gathered, rank, nranks);
+  c.launches += 1;
+}
+
+// three-way partition; keepers land in markers_alt, which becomes the marker array
+void launch_partition_markers(Ctx& c, int own_lo_global, int own_hi_global, float2* send_dn,
+                              float2* send_up, size_t send_cap, unsigned long long* n_keep) {
+  ProfScope ps(c, KC_REFRESH_COUNTS);
+  cudaMemsetAsync(&c.sc->n_send_dn, 0, 2 * sizeof(unsigned long long), c.stream);
+  cudaMemsetAsync(n_keep, 0, sizeof(unsigned long long), c.stream);
+  k_partition_markers<<<c.sm_count * 8, MTHREADS, 0, c.stream>>>(
+      c.h, own_lo_global, own_hi_global, c.markers, c.markers_alt, send_dn, send_up, send_cap, c.sc, n_keep);
+  c.launches += 1;
+  float2* t = c.markers; c.markers = c.markers_alt; c.markers_alt = t;
 }
 
 }  // namespace euler

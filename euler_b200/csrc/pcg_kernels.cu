@@ -146,7 +146,7 @@ __device__ __forceinline__ void stencil_tile(const Grid& g, const uint8_t* __res
         const bool fl = k == 0 ? (ml != 0) : mbit(mc, k - 1);
         const double r = k == 3 ? wr : wc.v[k + 1];
         const bool fr = k == 3 ? (mr != 0) : mbit(mc, k + 1);
-        op.cell(c, k, wc.v[k], l, fl, r, fr, wd.v[k], mbit(md, k), wu.v[k], mbit(mu, k), x0 + k, y);
+        op.cell(c, k, wc.v[k], l, fl, r, fr, wd.v[k], mbit(md, k), wu.v[k], mbit(mu, k), x0 + k, y + g.yoff);
       }
       op.end_row(c, mc);
     }
@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(TT) k_apply_a(
   });
   const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZS], [&](double total) {
+    if (exact == 2) { sc->part[0] = total; return; }         // slab mode: summed over ranks later
     if (exact) return;                                       // k_dot_seq supplies z.s instead
     sc->zs = total;
     sc->alpha = sc->sigma / total;                           // main.c:752
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(TT) k_apply_a(
 __global__ void __launch_bounds__(TT) k_axpy(
     Grid g, TileList active, const double* __restrict__ s,
     const double* __restrict__ z, const uint8_t* __restrict__ fluid, double* __restrict__ p,
-    double* __restrict__ r, double* partials, DevScalars* sc, double tol) {
+    double* __restrict__ r, double* partials, DevScalars* sc, double tol, int defer) {
   if (sc->done) return;
   const double alpha = sc->alpha;
   double m = 0.0;
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(TT) k_axpy(
   });
   const double bmax = block_reduce<true>(m);
   grid_reduce_last_block<true>(bmax, partials, &sc->ctr[CTR_NORM], [&](double total) {
+    if (defer) { sc->part[1] = total; return; }              // slab mode: max over ranks later
     sc->resid = total;
     sc->iters += 1;
     if (total <= tol) sc->done = 1;                          // main.c:756-758
@@ -302,10 +304,10 @@ __global__ void __launch_bounds__(256) k_rb_build(
     Grid g, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
     double* __restrict__ precon) {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if (x < 1 || y < 1 || x >= g.nx - 1 || y >= g.ny - 1) return;
+  if (x < 1 || y + g.yoff < 1 || x >= g.nx - 1 || y + g.yoff >= g.gny - 1 || y >= g.ny) return;
   const size_t c = gidx(g, x, y);
   if (!fluid[c]) return;
-  if (((x + y) & 1) == 0) { precon[c] = 1.0 / sqrt(rb_e_red(adiag, c)); return; }
+  if (((x + y + g.yoff) & 1) == 0) { precon[c] = 1.0 / sqrt(rb_e_red(adiag, c)); return; }
   const double a = (double)adiag[c];
   double e = a;
   const long off[4] = {-1, 1, -(long)g.pitch, (long)g.pitch};
@@ -422,6 +424,7 @@ __global__ void __launch_bounds__(TT) k_rb_backward(
   });
   const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZR], [&](double total) {
+    if (exact == 2) { sc->part[0] = total; return; }
     if (exact) return;
     if (init) { sc->sigma = total; }                         // main.c:748
     else { sc->beta = total / sc->sigma; sc->sigma = total; }  // main.c:762-765
@@ -556,6 +559,7 @@ __global__ void __launch_bounds__(TT) k_apply_a_pipe(
   pipe::run<1, 2, NS, TH>(g, active.list, (int)*active.count, in, op);
   const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZS], [&](double total) {
+    if (exact == 2) { sc->part[0] = total; return; }
     if (exact) return;
     sc->zs = total;
     sc->alpha = sc->sigma / total;                           // main.c:752
@@ -583,7 +587,7 @@ struct RbForwardPipe {
       out.v[k] = 0.0;
       if (!mbit(mc, k)) continue;
       double t = rc.v[k];
-      if ((x + k + y) & 1) {                                 // black: + sum over red neighbours
+      if ((x + k + y + g.yoff) & 1) {                        // black: + sum over red neighbours
         const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
         const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
         if (l_ok) t = t + (k == 0 ? wl : w(rc.v[k - 1], pc.v[k - 1]));
@@ -631,7 +635,7 @@ struct RbBackwardPipe {
       if (!mbit(mc, k)) continue;
       double zc;
       const double p = pc.v[k];
-      if ((x + k + y) & 1) {
+      if ((x + k + y + g.yoff) & 1) {
         zc = qc.v[k] * p;                                    // black: q*pc
       } else {
         const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
@@ -663,10 +667,35 @@ __global__ void __launch_bounds__(TT) k_rb_backward_pipe(
   pipe::run<3, 1, NS, TH>(g, active.list, (int)*active.count, in, op);
   const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZR], [&](double total) {
+    if (exact == 2) { sc->part[0] = total; return; }
     if (exact) return;
     if (init) { sc->sigma = total; }                         // main.c:748
     else { sc->beta = total / sc->sigma; sc->sigma = total; }  // main.c:762-765
   });
+}
+
+// ---- slab mode: fold the all-gathered partials (rank order => deterministic) --------------
+__global__ void k_dist_alpha(DevScalars* sc, const double* __restrict__ gathered, int nranks) {
+  if (sc->done) return;
+  double zs = 0.0;
+  for (int r = 0; r < nranks; ++r) zs += gathered[r * 4 + 0];
+  sc->zs = zs;
+  sc->alpha = sc->sigma / zs;                                // main.c:752
+}
+// after the preconditioner: z.r (sum) and, except for the initial application, ||r||inf (max)
+// of the axpy that preceded it — the stop test of main.c:756 is evaluated here, one stage
+// late: p and r are final either way, only the wasted z is different
+__global__ void k_dist_beta(DevScalars* sc, const double* __restrict__ gathered, int nranks, int init,
+                            double tol) {
+  if (sc->done) return;
+  double zr = 0.0, m = 0.0;
+  for (int r = 0; r < nranks; ++r) { zr += gathered[r * 4 + 0]; m = fmax(m, gathered[r * 4 + 1]); }
+  if (init) { sc->sigma = zr; return; }
+  sc->resid = m;
+  sc->iters += 1;
+  if (m <= tol) { sc->done = 1; return; }
+  sc->beta = zr / sc->sigma;
+  sc->sigma = zr;
 }
 
 constexpr int NS_A = 8, NS_F = 6, NS_B = 5;
@@ -687,12 +716,43 @@ int pcg_blocks(const Ctx& c, K kernel, int smem = 0) {
 
 }  // namespace
 
+// The PCG kernels work on the rows this handle OWNS: a view with advanced base pointers, so
+// that row -1 and row ny of the view are the halo rows received from the neighbouring slabs
+// (or guard rows of zeros on a single GPU).
+struct PV {
+  Grid g;
+  const uint8_t* fluid;
+  const int8_t* adiag;
+  double *s, *z, *r, *p, *q, *precon;
+};
+static PV pview(const Ctx& c) {
+  const size_t o = (size_t)c.own0 * c.g.pitch;
+  PV v;
+  v.g = c.g; v.g.ny = c.own1 - c.own0; v.g.yoff = c.g.yoff + c.own0;
+  v.fluid = c.count + o; v.adiag = c.adiag + o;
+  v.s = c.s + o; v.z = c.z + o; v.r = c.r + o; v.p = c.p + o; v.q = c.q + o; v.precon = c.precon + o;
+  return v;
+}
+static inline int dotflag(const Ctx& c) { return c.distributed ? 2 : c.dot_mode; }
+
+void launch_dot_zr_exact(Ctx& c, bool init);
+
+void launch_dist_alpha(Ctx& c, const double* gathered, int nranks) {
+  k_dist_alpha<<<1, 1, 0, c.stream>>>(c.sc, gathered, nranks);
+  c.launches += 1;
+}
+void launch_dist_beta(Ctx& c, const double* gathered, int nranks, bool init, double tol) {
+  k_dist_beta<<<1, 1, 0, c.stream>>>(c.sc, gathered, nranks, init ? 1 : 0, tol);
+  c.launches += 1;
+}
+
 void launch_tile_flags(Ctx& c) {
   ProfScope ps(c, KC_MISC);
-  const Tiles T = tiles_of(c.g);
+  const PV v = pview(c);
+  const Tiles T = tiles_of(v.g);
   const int nb = T.n < c.sm_count * 16 ? T.n : c.sm_count * 16;
-  k_tile_flags<<<nb, TT, 0, c.stream>>>(c.g, c.count, c.tile_active, c.sc);
-  k_tile_compact<<<1, 1024, 0, c.stream>>>(c.g, c.tile_active, c.tile_list, c.sc);
+  k_tile_flags<<<nb, TT, 0, c.stream>>>(v.g, v.fluid, c.tile_active, c.sc);
+  k_tile_compact<<<1, 1024, 0, c.stream>>>(v.g, c.tile_active, c.tile_list, c.sc);
   c.launches += 2;
 }
 
@@ -702,74 +762,93 @@ void launch_pcg_reset(Ctx& c) {
   c.launches += 1;
 }
 
+#define TL TileList{c.tile_list, &c.sc->active_tiles}
+
 void launch_apply_a(Ctx& c, bool) {
   ProfScope ps(c, KC_APPLY_A);
+  const PV v = pview(c);
   if (c.use_pipe) {
     constexpr int smem = pipe::smem_bytes<1, 2, NS_A>();
     k_apply_a_pipe<NS_A><<<pcg_blocks(c, k_apply_a_pipe<NS_A>, smem), TT, smem, c.stream>>>(
-        c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.s, c.count, c.adiag, c.z, c.partials, c.sc, c.dot_mode);
+        v.g, TL, v.s, v.fluid, v.adiag, v.z, c.partials, c.sc, dotflag(c));
   } else {
-    k_apply_a<<<pcg_blocks(c, k_apply_a), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.s, c.count, c.adiag, c.z,
-                                                  c.partials, c.sc, c.dot_mode);
+    k_apply_a<<<pcg_blocks(c, k_apply_a), TT, 0, c.stream>>>(v.g, TL, v.s, v.fluid, v.adiag, v.z,
+                                                             c.partials, c.sc, dotflag(c));
   }
   c.launches += 1;
-  if (c.dot_mode) {
-    k_dot_seq<<<1, 256, 0, c.stream>>>(c.g, c.tile_active, c.z, c.s, c.count, c.sc, DOT_ZS);
+  if (c.dot_mode && !c.distributed) {
+    k_dot_seq<<<1, 256, 0, c.stream>>>(v.g, c.tile_active, v.z, v.s, v.fluid, c.sc, DOT_ZS);
     c.launches += 1;
   }
 }
 
 void launch_axpy(Ctx& c, double tol) {
   ProfScope ps(c, KC_AXPY);
-  k_axpy<<<pcg_blocks(c, k_axpy), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.s, c.z, c.count, c.p, c.r,
-                                             c.partials, c.sc, tol);
+  const PV v = pview(c);
+  k_axpy<<<pcg_blocks(c, k_axpy), TT, 0, c.stream>>>(v.g, TL, v.s, v.z, v.fluid, v.p, v.r, c.partials,
+                                                     c.sc, tol, c.distributed ? 1 : 0);
   c.launches += 1;
 }
 
 void launch_update_search(Ctx& c) {
   ProfScope ps(c, KC_UPDATE_SEARCH);
-  k_update_search<<<pcg_blocks(c, k_update_search), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.z, c.count, c.s, c.sc);
+  const PV v = pview(c);
+  k_update_search<<<pcg_blocks(c, k_update_search), TT, 0, c.stream>>>(v.g, TL, v.z, v.fluid, v.s, c.sc);
   c.launches += 1;
 }
 
 void launch_copy_search(Ctx& c) {
   ProfScope ps(c, KC_MISC);
-  k_copy_search<<<pcg_blocks(c, k_copy_search), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.z, c.s);
+  const PV v = pview(c);
+  k_copy_search<<<pcg_blocks(c, k_copy_search), TT, 0, c.stream>>>(v.g, TL, v.z, v.s);
   c.launches += 1;
 }
 
 void launch_rb_build(Ctx& c) {
+  // over ALL locally stored rows: halo rows get their own (identical) factor, no exchange
   ProfScope ps(c, KC_PRECON_BUILD);
   k_rb_build<<<dim3((c.g.nx + 31) / 32, (c.g.ny + 7) / 8), dim3(32, 8), 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon);
   c.launches += 1;
 }
 
-void launch_dot_zr_exact(Ctx& c, bool init);
-
-void launch_rb_apply(Ctx& c, bool init) {
+void launch_rb_forward(Ctx& c) {
   ProfScope ps(c, KC_PRECON_APPLY);
+  const PV v = pview(c);
   if (c.use_pipe) {
-    constexpr int sf = pipe::smem_bytes<2, 1, NS_F>(), sb = pipe::smem_bytes<3, 1, NS_B>();
+    constexpr int sf = pipe::smem_bytes<2, 1, NS_F>();
     k_rb_forward_pipe<NS_F><<<pcg_blocks(c, k_rb_forward_pipe<NS_F>, sf), TT, sf, c.stream>>>(
-        c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.r, c.count, c.precon, c.q, c.sc);
-    k_rb_backward_pipe<NS_B><<<pcg_blocks(c, k_rb_backward_pipe<NS_B>, sb), TT, sb, c.stream>>>(
-        c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.q, c.r, c.count, c.precon, c.z, c.partials, c.sc, init ? 1 : 0,
-        c.dot_mode);
+        v.g, TL, v.r, v.fluid, v.precon, v.q, c.sc);
   } else {
-    k_rb_forward<<<pcg_blocks(c, k_rb_forward), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.r, c.count, c.precon,
-                                                     c.q, c.sc);
-    k_rb_backward<<<pcg_blocks(c, k_rb_backward), TT, 0, c.stream>>>(c.g, TileList{c.tile_list, &c.sc->active_tiles}, c.q, c.r, c.count,
-                                                      c.precon, c.z, c.partials, c.sc, init ? 1 : 0,
-                                                      c.dot_mode);
+    k_rb_forward<<<pcg_blocks(c, k_rb_forward), TT, 0, c.stream>>>(v.g, TL, v.r, v.fluid, v.precon, v.q, c.sc);
   }
-  c.launches += 2;
+  c.launches += 1;
+}
+
+void launch_rb_backward(Ctx& c, bool init) {
+  ProfScope ps(c, KC_PRECON_APPLY);
+  const PV v = pview(c);
+  if (c.use_pipe) {
+    constexpr int sb = pipe::smem_bytes<3, 1, NS_B>();
+    k_rb_backward_pipe<NS_B><<<pcg_blocks(c, k_rb_backward_pipe<NS_B>, sb), TT, sb, c.stream>>>(
+        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c));
+  } else {
+    k_rb_backward<<<pcg_blocks(c, k_rb_backward), TT, 0, c.stream>>>(
+        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c));
+  }
+  c.launches += 1;
   launch_dot_zr_exact(c, init);
 }
 
+void launch_rb_apply(Ctx& c, bool init) {
+  launch_rb_forward(c);
+  launch_rb_backward(c, init);
+}
+
 void launch_dot_zr_exact(Ctx& c, bool init) {
-  if (!c.dot_mode) return;
-  k_dot_seq<<<1, 256, 0, c.stream>>>(c.g, c.tile_active, c.z, c.r, c.count, c.sc,
+  if (!c.dot_mode || c.distributed) return;
+  const PV v = pview(c);
+  k_dot_seq<<<1, 256, 0, c.stream>>>(v.g, c.tile_active, v.z, v.r, v.fluid, c.sc,
                                      init ? DOT_ZR_INIT : DOT_ZR);
   c.launches += 1;
 }

@@ -36,7 +36,7 @@ class Params(C.Structure):
                 ("precon", C.c_int), ("marker_mode", C.c_int), ("dot_mode", C.c_int),
                 ("rng_state", C.c_uint64),
                 ("device", C.c_int), ("stream", C.c_void_p), ("pcg_check_every", C.c_int), ("stencil_variant", C.c_int),
-                ("row0", C.c_int), ("global_ny", C.c_int)]
+                ("slab_row0", C.c_int), ("slab_rows", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -84,6 +84,7 @@ _L.euler_gpu_stream.argtypes = [_H]
 _L.euler_gpu_pcg_iterations.argtypes = [_H, C.c_int]
 _L.euler_gpu_comm_unique_id.argtypes = [C.c_void_p]
 _L.euler_gpu_comm_init.argtypes = [_H, C.c_int, C.c_int, C.c_void_p]
+_L.euler_gpu_slab_partition.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
 
 
 def _ck(rc):
@@ -95,6 +96,19 @@ def default_params():
     p = Params()
     _ck(_L.euler_gpu_default_params(C.byref(p)))
     return p
+
+
+def slab_partition(global_ny, n_ranks, rank):
+    """(row0, rows) of `rank` in the balanced row-slab split (euler_gpu_slab_partition)."""
+    a, b = C.c_int(0), C.c_int(0)
+    _ck(_L.euler_gpu_slab_partition(global_ny, n_ranks, rank, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    _ck(_L.euler_gpu_comm_unique_id(buf))
+    return buf.raw
 
 
 def abi_version():
@@ -138,6 +152,10 @@ class EulerGpu:
 
     def __enter__(self): return self
     def __exit__(self, *a): self.close()
+
+    def comm_init(self, rank, n_ranks, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _ck(_L.euler_gpu_comm_init(self._h, rank, n_ranks, buf))
 
     def step_frame(self):
         n = C.c_int(0)

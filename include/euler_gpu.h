@@ -135,10 +135,13 @@ typedef struct euler_params {
   int   pcg_check_every; /* iterations enqueued between convergence polls; default 8 */
   int   stencil_variant; /* PCG stencil kernels: 0 = TMA bulk-copy row pipeline (default),
                             1 = register sliding window (kept for A/B measurements) */
-  /* row-slab decomposition: this handle owns global rows [row0, row0+ny) of a
-   * grid that is global_ny rows tall; 0/0 = not decomposed.  See euler_gpu_comm_init. */
-  int   row0;
-  int   global_ny;
+  /* row-slab decomposition: this handle owns global rows
+   * [slab_row0, slab_row0 + slab_rows) of the nx x ny grid passed to create(); slab_rows = 0
+   * means "not decomposed".  create() is given the GLOBAL planes and markers on every rank
+   * and keeps its slab (+4 halo rows); get()/read_marker_count() write only the owned rows of
+   * a global-shaped buffer.  Needs precon=REDBLACK, marker_mode=FAST.  See euler_gpu_comm_init. */
+  int   slab_row0;
+  int   slab_rows;
 } euler_params;
 
 #define EULER_KERNEL_CLASSES 16
@@ -221,6 +224,8 @@ int euler_gpu_pcg_iterations(euler_gpu *h, int iterations);
  * produced on rank 0 by euler_gpu_comm_unique_id and distributed by the caller (any side
  * channel: torch.distributed, MPI, a file).  Collective over all ranks. */
 int euler_gpu_comm_unique_id(void *unique_id_128);
+/* Balanced contiguous split of global_ny rows over n_ranks (pure host arithmetic). */
+int euler_gpu_slab_partition(int global_ny, int n_ranks, int rank, int *row0, int *rows);
 int euler_gpu_comm_init(euler_gpu *h, int rank, int n_ranks, const void *unique_id_128);
 
 const char *euler_gpu_last_error(void);

@@ -1,0 +1,71 @@
+"""world_size-2 gloo test (CPU) of the host-side multi-rank logic: the balanced row-slab
+partition every rank computes for itself must tile the grid, and the rank plumbing bench.py
+uses (broadcast of the 128-byte communicator id, max-over-ranks of the timing) must work."""
+import os
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from euler_b200 import gpu as G
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    res = []
+    for ny in (40, 41, 1024, 16384, 17):
+        r0, n = G.slab_partition(ny, world, rank)
+        t = torch.tensor([r0, n], dtype=torch.int64)
+        allt = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rows = [(int(a[0]), int(a[1])) for a in allt]
+        res.append((ny, rows))
+    # communicator id: rank 0 makes 128 bytes, everyone ends up with the same bytes
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.arange(128, dtype=torch.uint8)
+    dist.broadcast(uid, src=0)
+    # timing: max over ranks
+    t = torch.tensor([10.0 + rank], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        import json
+        with open(out, "w") as f:
+            json.dump({"parts": res, "uid_ok": bool((uid == torch.arange(128, dtype=torch.uint8)).all()),
+                       "tmax": float(t[0])}, f)
+    else:
+        assert bool((uid == torch.arange(128, dtype=torch.uint8)).all())
+    dist.destroy_process_group()
+
+
+def test_slab_partition_and_rank_plumbing_gloo(tmp_path):
+    import json
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "res.json")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    res = json.load(open(out))
+    assert res["uid_ok"] and res["tmax"] == 11.0
+    for ny, rows in res["parts"]:
+        assert rows[0][0] == 0 and rows[0][0] + rows[0][1] == rows[1][0]
+        assert rows[1][0] + rows[1][1] == ny and abs(rows[0][1] - rows[1][1]) <= 1
+
+
+def test_slab_partition_many_ranks():
+    from euler_b200 import gpu as G
+    for ny in (16384, 8192, 1000, 37):
+        for n in (1, 2, 4, 8):
+            nxt = 0
+            sizes = []
+            for r in range(n):
+                r0, k = G.slab_partition(ny, n, r)
+                assert r0 == nxt
+                nxt = r0 + k
+                sizes.append(k)
+            assert nxt == ny and max(sizes) - min(sizes) <= 1
+    with pytest.raises(G.EulerGpuError):
+        G.slab_partition(10, 2, 2)
