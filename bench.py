@@ -10,10 +10,11 @@ of reference sim_step() (main.c:851-894): calculate_timestep, marker advection +
 sources, extrapolation, semi-Lagrangian velocity advection + gravity + boundaries, and the
 pressure projection (PCG capped at the reference's 100 iterations).
 
-Workload at N=1: the 16384^2 synthetic "basic-fill" scenario (walled box,
-fluid block resting on the floor so the solve is active from the first sub-step), red-black
-IC(0) preconditioner, fp64 PCG vectors as in the reference.  At N>1 every rank runs one such
-grid (independent replicas, weak scaling) until slab decomposition lands — the line says so.
+Workload: the 16384^2 synthetic "basic-fill" scenario (walled box, fluid block
+resting on the floor so the solve is active from the first sub-step), red-black IC(0)
+preconditioner, fp64 PCG vectors as in the reference.  At N>1 the SAME grid is cut into N row
+slabs, one per GPU/process (strong scaling): NCCL halo exchange, cross-slab marker migration,
+PCG scalars reduced across ranks.
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref, built unmodified
 from /root/reference with its own -O3 -ffast-math flags) on the box's host cores: one thread,
@@ -137,10 +138,25 @@ def run_gpu(args):
 
     stream = torch.cuda.Stream()          # the handle enqueues on this stream; events are recorded on it
 
+    if world > 1 and args.precon != "rb":
+        raise SystemExit("row slabs need --precon rb")
+    # slabs balanced by work: the PCG streams only tiles with fluid, the grid stages every cell
+    weight = scn.fluid.sum(axis=1, dtype=np.uint64) * 50 + np.uint64(n)
+    row0, rows = G.slab_partition_weighted(weight, world, rank) if world > 1 else (0, 0)
+
     def make():
-        return G.EulerGpu.from_scenario(scn, precon=precon, marker_mode=G.MARKERS_FAST,
-                                        device=local, stream=stream.cuda_stream,
-                                        pcg_check_every=args.check_every)
+        sim = G.EulerGpu.from_scenario(scn, precon=precon, marker_mode=G.MARKERS_FAST,
+                                       device=local, stream=stream.cuda_stream,
+                                       pcg_check_every=args.check_every,
+                                       slab_row0=row0, slab_rows=rows)
+        if world > 1:
+            # communicator id made on rank 0, broadcast over torch.distributed (plumbing only)
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid = torch.tensor(list(G.comm_unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(uid, src=0)
+            sim.comm_init(rank, world, bytes(uid.cpu().tolist()))
+        return sim
 
     def barrier():
         torch.cuda.synchronize()
@@ -196,17 +212,17 @@ def run_gpu(args):
         sim.read_marker_count(count_host)
     sim.synchronize()
     t_e2e = time.perf_counter() - t0
-    h2d = (3 * cells + scn.markers.nbytes) / args.steps
-    d2h = float(cells)
+    h2d = (3 * cells + scn.markers.nbytes) / args.steps / world
+    d2h = float(cells) / world
     sim.close()
 
     t = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
-    it = torch.tensor([iters, launches], dtype=torch.float64, device="cuda")
+    it = torch.tensor([launches], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(it, op=dist.ReduceOp.SUM)
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
-    iters_all, launches_all = int(it[0]), int(it[1])
+    iters_all, launches_all = iters, int(it[0])      # one global solve: every rank counts the same iterations
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -237,24 +253,26 @@ def run_gpu(args):
                     "units_per_launch": active_cells if dom[0] in PCG_KERNELS else cells,
                     "bytes_per_unit": ALG_BYTES_PER_CELL[dom[0]],
                     "ms_per_launch": k["ms_avg"], "share_of_step": k["share"]}
-        value = cells * args.steps * world / (ms_max * 1e-3)
+        value = cells * args.steps / (ms_max * 1e-3)
         line = {
             "metric": "MAC cell-updates/s", "value": value, "unit": "cell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s %dx%d per GPU, one sub-step of sim_step per step, PCG cap 100 "
+            "config": {"workload": "%s %dx%d (whole grid), one sub-step of sim_step per step, PCG cap 100 "
                                    "(reference main.c:735), %s preconditioner, fp64 PCG vectors"
                                    % (args.scenario, n, n, "red-black IC(0)" if args.precon == "rb" else "IC(0) wavefront"),
                        "grid": [n, n], "markers": n_markers, "active_cells": active_cells,
-                       "parallelism": "single GPU" if world == 1 else "independent replicas x%d" % world,
+                       "parallelism": "single GPU" if world == 1 else
+                                      "%d row slabs balanced by fluid cells (rank 0: %d rows), NCCL halo exchange + marker migration" % (world, rows),
                        "l2_policy": "inputs >> L2: every plane is %.0f MB..%.0f MB vs 126 MB L2, no flush needed"
                                     % (cells / 1e6, cells * 8 / 1e6),
                        "device_bytes": dev_bytes, "host_setup_s": round(t_host, 2)},
             "pcg_iters_per_s": iters_all / (ms_max * 1e-3),
             "pcg_iterations": iters_all,
             "gpu_launches": launches_all,
-            "e2e": {"value": cells * args.steps * world / (e2e_ms_max * 1e-3), "unit": "cell-updates/s",
+            "e2e": {"value": cells * args.steps / (e2e_ms_max * 1e-3), "unit": "cell-updates/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "euler_gpu_create from host arrays + K sub-steps + per-step D2H of the count plane"},
             "roofline": roof,

@@ -826,6 +826,32 @@ int euler_gpu_comm_init(euler_gpu* h, int rank, int n_ranks, const void* unique_
   return 0;
 }
 
+int euler_gpu_slab_partition_weighted(const uint64_t* row_weight, int global_ny, int n_ranks, int rank,
+                                      int* row0, int* rows) {
+  if (!row_weight || global_ny < 1 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !row0 || !rows)
+    return fail(EULER_E_INVALID, "bad slab partition arguments");
+  const int min_rows = 2 * SLAB_HALO;
+  if (global_ny < n_ranks * min_rows) return fail(EULER_E_INVALID, "grid too short for %d slabs", n_ranks);
+  // boundary k sits where the running weight first reaches k/n of the total, then boundaries
+  // are pushed apart so that every slab keeps at least min_rows rows
+  std::vector<int> cut(n_ranks + 1, 0);
+  long double total = 0;
+  for (int y = 0; y < global_ny; ++y) total += (long double)row_weight[y];
+  cut[n_ranks] = global_ny;
+  long double run = 0;
+  int k = 1;
+  for (int y = 0; y < global_ny && k < n_ranks; ++y) {
+    run += (long double)row_weight[y];
+    while (k < n_ranks && run * n_ranks >= total * k) cut[k++] = y + 1;
+  }
+  for (; k < n_ranks; ++k) cut[k] = global_ny;
+  for (int i = 1; i < n_ranks; ++i) if (cut[i] < cut[i - 1] + min_rows) cut[i] = cut[i - 1] + min_rows;
+  for (int i = n_ranks - 1; i >= 1; --i) if (cut[i] > cut[i + 1] - min_rows) cut[i] = cut[i + 1] - min_rows;
+  *row0 = cut[rank];
+  *rows = cut[rank + 1] - cut[rank];
+  return 0;
+}
+
 int euler_gpu_slab_partition(int global_ny, int n_ranks, int rank, int* row0, int* rows) {
   if (global_ny < 1 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !row0 || !rows)
     return fail(EULER_E_INVALID, "bad slab partition arguments");

@@ -85,6 +85,7 @@ _L.euler_gpu_pcg_iterations.argtypes = [_H, C.c_int]
 _L.euler_gpu_comm_unique_id.argtypes = [C.c_void_p]
 _L.euler_gpu_comm_init.argtypes = [_H, C.c_int, C.c_int, C.c_void_p]
 _L.euler_gpu_slab_partition.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+_L.euler_gpu_slab_partition_weighted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
 
 
 def _ck(rc):
@@ -102,6 +103,13 @@ def slab_partition(global_ny, n_ranks, rank):
     """(row0, rows) of `rank` in the balanced row-slab split (euler_gpu_slab_partition)."""
     a, b = C.c_int(0), C.c_int(0)
     _ck(_L.euler_gpu_slab_partition(global_ny, n_ranks, rank, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def slab_partition_weighted(row_weight, n_ranks, rank):
+    w = np.ascontiguousarray(row_weight, dtype=np.uint64)
+    a, b = C.c_int(0), C.c_int(0)
+    _ck(_L.euler_gpu_slab_partition_weighted(w.ctypes.data, len(w), n_ranks, rank, C.byref(a), C.byref(b)))
     return a.value, b.value
 
 

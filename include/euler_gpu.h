@@ -226,6 +226,10 @@ int euler_gpu_pcg_iterations(euler_gpu *h, int iterations);
 int euler_gpu_comm_unique_id(void *unique_id_128);
 /* Balanced contiguous split of global_ny rows over n_ranks (pure host arithmetic). */
 int euler_gpu_slab_partition(int global_ny, int n_ranks, int rank, int *row0, int *rows);
+/* Same, but balancing the sum of row_weight[y] (e.g. fluid cells per row + a small constant:
+ * the PCG only streams tiles that contain fluid) instead of the row count. */
+int euler_gpu_slab_partition_weighted(const uint64_t *row_weight, int global_ny, int n_ranks,
+                                      int rank, int *row0, int *rows);
 int euler_gpu_comm_init(euler_gpu *h, int rank, int n_ranks, const void *unique_id_128);
 
 const char *euler_gpu_last_error(void);

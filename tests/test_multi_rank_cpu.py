@@ -69,3 +69,25 @@ def test_slab_partition_many_ranks():
             assert nxt == ny and max(sizes) - min(sizes) <= 1
     with pytest.raises(G.EulerGpuError):
         G.slab_partition(10, 2, 2)
+
+
+def test_weighted_slab_partition():
+    import numpy as np
+    from euler_b200 import gpu as G
+    ny = 4096
+    w = np.ones(ny, np.uint64)
+    w[: ny // 2] = 101                       # all the work in the lower half
+    for n in (2, 4, 8):
+        cuts, loads = [], []
+        nxt = 0
+        for r in range(n):
+            r0, k = G.slab_partition_weighted(w, n, r)
+            assert r0 == nxt and k >= 8
+            nxt = r0 + k
+            loads.append(int(w[r0:r0 + k].sum()))
+        assert nxt == ny
+        assert max(loads) <= 1.05 * (int(w.sum()) / n) + 101
+    # degenerate: no weight anywhere still tiles the grid with >= 8 rows per slab
+    z = np.zeros(64, np.uint64)
+    rows = [G.slab_partition_weighted(z, 4, r) for r in range(4)]
+    assert rows[0][0] == 0 and sum(k for _, k in rows) == 64 and all(k >= 8 for _, k in rows)
