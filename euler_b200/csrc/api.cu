@@ -228,9 +228,9 @@ int run_substep(euler_gpu* h, float dt) {
 
 int dist_precon_apply(euler_gpu* h, bool init) {
   Ctx& c = h->c;
-  CM(comm_halo(c, h->cm, c.r, 8, 1));               // forward reads r (and pc) of the row above/below
+  // no exchange: r is kept consistent on the halo rows by redundant updates (pcg_kernels.cu
+  // pview), q and z are recomputed there
   launch_rb_forward(c);
-  CM(comm_halo(c, h->cm, c.q, 8, 1));               // backward reads q of the row above/below
   launch_rb_backward(c, init);
   CM(comm_gather_scalars(c, h->cm, c.sc->part));    // {z.r partial, ||r||inf partial}
   launch_dist_beta(c, h->cm.gather, h->cm.nranks, init, h->prm.tol);
@@ -239,7 +239,7 @@ int dist_precon_apply(euler_gpu* h, bool init) {
 
 int dist_iteration(euler_gpu* h) {
   Ctx& c = h->c;
-  CM(comm_halo(c, h->cm, c.s, 8, 1));               // apply_a reads s[y+-1], main.c:685-687
+  CM(comm_halo(c, h->cm, c.s, 8, SLAB_HALO));        // the one exchange per iteration
   launch_apply_a(c, true);
   CM(comm_gather_scalars(c, h->cm, c.sc->part));    // {z.s partial}
   launch_dist_alpha(c, h->cm.gather, h->cm.nranks);
@@ -264,6 +264,7 @@ int run_project_dist(euler_gpu* h, float dt) {
     h->solves++;
     launch_pcg_reset(c);
     launch_rb_build(c);
+    CM(comm_halo(c, h->cm, c.r, 8, SLAB_HALO));      // b is only valid one row into the halo
     rc = dist_precon_apply(h, true);
     if (rc) return rc;
     launch_copy_search(c);
@@ -281,7 +282,8 @@ int run_project_dist(euler_gpu* h, float dt) {
     h->last_residual = h->host_sc->resid;
     h->pcg_iterations += (uint64_t)h->host_sc->iters;
   }
-  CM(comm_halo_up_only(c, h->cm, c.p, 8));           // p[y+1] of the last owned row, main.c:800
+  // p[y+1] of the last owned row (main.c:800) is already there: p was updated redundantly on
+  // the halo rows.  (When the solve was skipped p == 0 everywhere.)
   launch_pressure_update(c, dt);
   CM(comm_halo(c, h->cm, c.u, 4, SLAB_HALO));
   CM(comm_halo(c, h->cm, c.v, 4, SLAB_HALO));

@@ -175,6 +175,7 @@ struct ApplyA {
   const int8_t* __restrict__ adiag;
   double* __restrict__ z;
   double acc;
+  int a0, a1;                      // rows whose cells count towards the dot product
   unsigned am;
   D4 out;
   __device__ __forceinline__ D4 operand(size_t c, int) const { return ld4(s + c); }
@@ -185,7 +186,7 @@ struct ApplyA {
     out.v[0] = out.v[1] = out.v[2] = out.v[3] = 0.0;
   }
   __device__ __forceinline__ void cell(size_t, int k, double sc, double l, bool fl, double r, bool fr,
-                                       double d, bool fd, double u, bool fu, int, int) {
+                                       double d, bool fd, double u, bool fu, int, int gy) {
     // main.c:683-687: a_diag*s - right - up - left - down, each only towards fluid
     double o = (double)(int)(signed char)((am >> (8 * k)) & 0xffu) * sc;
     o -= fr ? r : 0.0;
@@ -193,7 +194,7 @@ struct ApplyA {
     o -= fl ? l : 0.0;
     o -= fd ? d : 0.0;
     out.v[k] = o;
-    acc += o * sc;
+    if (gy >= a0 && gy < a1) acc += o * sc;
   }
   __device__ __forceinline__ void end_row(size_t c, unsigned) { st4(z + c, out); }
 };
@@ -201,9 +202,9 @@ struct ApplyA {
 __global__ void __launch_bounds__(TT) k_apply_a(
     Grid g, TileList active, const double* __restrict__ s,
     const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ z,
-    double* partials, DevScalars* sc, int exact) {
+    double* partials, DevScalars* sc, int exact, int acc0, int acc1) {
   if (sc->done) return;
-  ApplyA op{s, adiag, z, 0.0, 0u, {}};
+  ApplyA op{s, adiag, z, 0.0, acc0 + g.yoff, acc1 + g.yoff, 0u, {}};
   for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
     stencil_tile(g, fluid, x0, y0, y1, live, op);
   });
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(TT) k_apply_a(
 __global__ void __launch_bounds__(TT) k_axpy(
     Grid g, TileList active, const double* __restrict__ s,
     const double* __restrict__ z, const uint8_t* __restrict__ fluid, double* __restrict__ p,
-    double* __restrict__ r, double* partials, DevScalars* sc, double tol, int defer) {
+    double* __restrict__ r, double* partials, DevScalars* sc, double tol, int defer, int acc0,
+    int acc1) {
   if (sc->done) return;
   const double alpha = sc->alpha;
   double m = 0.0;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(TT) k_axpy(
         pv.v[k] = pv.v[k] + sv.v[k] * alpha;                 // fmadd(s, alpha, p)  main.c:753
         rv.v[k] = rv.v[k] + zv.v[k] * -alpha;                // fmadd(z, -alpha, r) main.c:754
         const double a = fabs(rv.v[k]);
-        if (a > m) m = a;                                    // NaN-dropping, main.c:659-662
+        if (a > m && y >= acc0 && y < acc1) m = a;           // NaN-dropping, main.c:659-662
       }
       st4(p + c, pv);
       st4(r + c, rv);
@@ -376,6 +378,7 @@ struct RbBackward {
   const double* __restrict__ r;
   double* __restrict__ z;
   double acc;
+  int a0, a1;
   D4 qq, pp, qu, pu, rr, out;      // q, pc of the centre row / of the row above; r of the centre
   __device__ __forceinline__ D4 operand(size_t c, int slot) {
     const D4 a = ld4(q + c), b = ld4(pc + c);
@@ -407,7 +410,7 @@ struct RbBackward {
       zc = t * p;
     }
     out.v[k] = zc;
-    acc += zc * rr.v[k];
+    if (y >= a0 && y < a1) acc += zc * rr.v[k];
   }
   __device__ __forceinline__ void end_row(size_t c, unsigned) { st4(z + c, out); }
 };
@@ -416,9 +419,9 @@ __global__ void __launch_bounds__(TT) k_rb_backward(
     Grid g, TileList active, const double* __restrict__ q,
     const double* __restrict__ r, const uint8_t* __restrict__ fluid,
     const double* __restrict__ precon, double* __restrict__ z, double* partials, DevScalars* sc,
-    int init, int exact) {
+    int init, int exact, int acc0, int acc1) {
   if (sc->done) return;
-  RbBackward op{q, precon, r, z, 0.0, {}, {}, {}, {}, {}, {}};
+  RbBackward op{q, precon, r, z, 0.0, acc0 + g.yoff, acc1 + g.yoff, {}, {}, {}, {}, {}, {}};
   for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
     stencil_tile(g, fluid, x0, y0, y1, live, op);
   });
@@ -518,6 +521,7 @@ struct ApplyAPipe {
   const Grid g;
   double* __restrict__ z;
   double acc;
+  int a0, a1;
   __device__ __forceinline__ void row(const pipe::RowView<1, 2>& dn, const pipe::RowView<1, 2>& ce,
                                       const pipe::RowView<1, 2>& up, int t4, int x, int y, bool live) {
     const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
@@ -541,7 +545,7 @@ struct ApplyAPipe {
       o -= l_ok ? (k == 0 ? sl : sc.v[k - 1]) : 0.0;
       o -= mbit(md, k) ? sd.v[k] : 0.0;
       out.v[k] = o;
-      acc += o * sc.v[k];
+      if (y >= a0 && y < a1) acc += o * sc.v[k];
     }
     st4(z + gidx(g, x, y), out);
   }
@@ -551,9 +555,9 @@ template <int NS>
 __global__ void __launch_bounds__(TT) k_apply_a_pipe(
     Grid g, TileList active, const double* __restrict__ s,
     const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ z,
-    double* partials, DevScalars* sc, int exact) {
+    double* partials, DevScalars* sc, int exact, int acc0, int acc1) {
   if (sc->done) return;
-  ApplyAPipe op{g, z, 0.0};
+  ApplyAPipe op{g, z, 0.0, acc0, acc1};
   pipe::Planes<1, 2> in;
   in.d[0] = s; in.b[0] = fluid; in.b[1] = reinterpret_cast<const uint8_t*>(adiag);
   pipe::run<1, 2, NS, TH>(g, active.list, (int)*active.count, in, op);
@@ -618,6 +622,7 @@ struct RbBackwardPipe {
   const Grid g;
   double* __restrict__ z;
   double acc;
+  int a0, a1;
   __device__ __forceinline__ void row(const pipe::RowView<3, 1>& dn, const pipe::RowView<3, 1>& ce,
                                       const pipe::RowView<3, 1>& up, int t4, int x, int y, bool live) {
     const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
@@ -648,7 +653,7 @@ struct RbBackwardPipe {
         zc = t * p;
       }
       out.v[k] = zc;
-      acc += zc * rc.v[k];
+      if (y >= a0 && y < a1) acc += zc * rc.v[k];
     }
     st4(z + gidx(g, x, y), out);
   }
@@ -659,9 +664,9 @@ __global__ void __launch_bounds__(TT) k_rb_backward_pipe(
     Grid g, TileList active, const double* __restrict__ q,
     const double* __restrict__ r, const uint8_t* __restrict__ fluid,
     const double* __restrict__ precon, double* __restrict__ z, double* partials, DevScalars* sc,
-    int init, int exact) {
+    int init, int exact, int acc0, int acc1) {
   if (sc->done) return;
-  RbBackwardPipe op{g, z, 0.0};
+  RbBackwardPipe op{g, z, 0.0, acc0, acc1};
   pipe::Planes<3, 1> in;
   in.d[0] = q; in.d[1] = precon; in.d[2] = r; in.b[0] = fluid;
   pipe::run<3, 1, NS, TH>(g, active.list, (int)*active.count, in, op);
@@ -721,14 +726,24 @@ int pcg_blocks(const Ctx& c, K kernel, int smem = 0) {
 // (or guard rows of zeros on a single GPU).
 struct PV {
   Grid g;
+  int a0, a1;            // the OWNED rows, in view coordinates: only they enter reductions
   const uint8_t* fluid;
   const int8_t* adiag;
   double *s, *z, *r, *p, *q, *precon;
 };
+// Slab mode: the view is the owned rows +-PCG_EXT halo rows.  Every vector update is done
+// redundantly on those halo rows with the owner's exact arithmetic, so one exchange of s
+// (4 rows) per iteration keeps r, p, q, z consistent without exchanging them: validity
+// shrinks by one row per stencil (s: +-4 -> A s, r: +-3 -> q: +-2 -> z, new s: +-1).
+constexpr int PCG_EXT = 3;
 static PV pview(const Ctx& c) {
-  const size_t o = (size_t)c.own0 * c.g.pitch;
+  const int ext = c.distributed ? PCG_EXT : 0;
+  const int lo = c.own0 - ext > 0 ? c.own0 - ext : 0;
+  const int hi = c.own1 + ext < c.g.ny ? c.own1 + ext : c.g.ny;
+  const size_t o = (size_t)lo * c.g.pitch;
   PV v;
-  v.g = c.g; v.g.ny = c.own1 - c.own0; v.g.yoff = c.g.yoff + c.own0;
+  v.g = c.g; v.g.ny = hi - lo; v.g.yoff = c.g.yoff + lo;
+  v.a0 = c.own0 - lo; v.a1 = c.own1 - lo;
   v.fluid = c.count + o; v.adiag = c.adiag + o;
   v.s = c.s + o; v.z = c.z + o; v.r = c.r + o; v.p = c.p + o; v.q = c.q + o; v.precon = c.precon + o;
   return v;
@@ -770,10 +785,10 @@ void launch_apply_a(Ctx& c, bool) {
   if (c.use_pipe) {
     constexpr int smem = pipe::smem_bytes<1, 2, NS_A>();
     k_apply_a_pipe<NS_A><<<pcg_blocks(c, k_apply_a_pipe<NS_A>, smem), TT, smem, c.stream>>>(
-        v.g, TL, v.s, v.fluid, v.adiag, v.z, c.partials, c.sc, dotflag(c));
+        v.g, TL, v.s, v.fluid, v.adiag, v.z, c.partials, c.sc, dotflag(c), v.a0, v.a1);
   } else {
     k_apply_a<<<pcg_blocks(c, k_apply_a), TT, 0, c.stream>>>(v.g, TL, v.s, v.fluid, v.adiag, v.z,
-                                                             c.partials, c.sc, dotflag(c));
+                                                             c.partials, c.sc, dotflag(c), v.a0, v.a1);
   }
   c.launches += 1;
   if (c.dot_mode && !c.distributed) {
@@ -786,7 +801,7 @@ void launch_axpy(Ctx& c, double tol) {
   ProfScope ps(c, KC_AXPY);
   const PV v = pview(c);
   k_axpy<<<pcg_blocks(c, k_axpy), TT, 0, c.stream>>>(v.g, TL, v.s, v.z, v.fluid, v.p, v.r, c.partials,
-                                                     c.sc, tol, c.distributed ? 1 : 0);
+                                                     c.sc, tol, c.distributed ? 1 : 0, v.a0, v.a1);
   c.launches += 1;
 }
 
@@ -831,10 +846,10 @@ void launch_rb_backward(Ctx& c, bool init) {
   if (c.use_pipe) {
     constexpr int sb = pipe::smem_bytes<3, 1, NS_B>();
     k_rb_backward_pipe<NS_B><<<pcg_blocks(c, k_rb_backward_pipe<NS_B>, sb), TT, sb, c.stream>>>(
-        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c));
+        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c), v.a0, v.a1);
   } else {
     k_rb_backward<<<pcg_blocks(c, k_rb_backward), TT, 0, c.stream>>>(
-        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c));
+        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c), v.a0, v.a1);
   }
   c.launches += 1;
   launch_dot_zr_exact(c, init);
