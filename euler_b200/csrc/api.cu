@@ -174,12 +174,28 @@ int run_project(euler_gpu* h, float dt) {
     if (h->prm.precon == EULER_PRECON_REDBLACK) launch_rb_build(c);
     else launch_ic0_build(c);
     enqueue_precon_apply(h, true);                          // z = M^-1 r, sigma = z.r  (:744-748)
-    launch_copy_search(c);                                  // s = z                    (:746)
+    bool first = true;
+    if (!c.fused) launch_copy_search(c);                    // s = z                    (:746)
     int remaining = h->prm.max_iterations;
     const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
     while (remaining > 0) {
       const int chunk = remaining < every ? remaining : every;
-      for (int i = 0; i < chunk; ++i) enqueue_iteration(h);
+      for (int i = 0; i < chunk; ++i) {
+        if (c.fused) {
+          // c.z holds M^-1 r here; the fused kernels read it, leave A s in c.q ... and swap
+          launch_fused_search_apply(c, first);              // s = z (+ beta s), A s -> c.q, alpha
+          if (c.fused >= 2) {
+            launch_fused_axpy_forward(c, h->prm.tol);       // p, r, ||r||inf, q = L^-1 r
+          } else {
+            launch_axpy(c, h->prm.tol, true);               // p, r, ||r||inf (A s read from c.q)
+            launch_rb_forward(c);                           // q = L^-1 r -> c.q
+          }
+          launch_rb_backward(c, false);                     // z = L^-T q -> c.z, z.r, beta
+          first = false;
+        } else {
+          enqueue_iteration(h);
+        }
+      }
       remaining -= chunk;
       rc = pull_scalars(h);
       if (rc) return rc;
@@ -237,16 +253,23 @@ int dist_precon_apply(euler_gpu* h, bool init) {
   return 0;
 }
 
-int dist_iteration(euler_gpu* h) {
+int dist_iteration(euler_gpu* h, bool first) {
   Ctx& c = h->c;
-  CM(comm_halo(c, h->cm, c.s, 8, SLAB_HALO));        // the one exchange per iteration
-  launch_apply_a(c, true);
+  if (c.fused) {
+    // the one exchange per iteration: z = M^-1 r, 4 rows deep; s' = z + beta s is then formed
+    // redundantly on the halo rows (s itself was formed the same way one iteration earlier)
+    CM(comm_halo(c, h->cm, c.z, 8, SLAB_HALO));
+    launch_fused_search_apply(c, first);            // s', A s' -> c.q, z.s partial
+  } else {
+    CM(comm_halo(c, h->cm, c.s, 8, SLAB_HALO));
+    launch_apply_a(c, true);
+  }
   CM(comm_gather_scalars(c, h->cm, c.sc->part));    // {z.s partial}
   launch_dist_alpha(c, h->cm.gather, h->cm.nranks);
-  launch_axpy(c, h->prm.tol);
+  launch_axpy(c, h->prm.tol, c.fused != 0);
   int rc = dist_precon_apply(h, false);
   if (rc) return rc;
-  launch_update_search(c);
+  if (!c.fused) launch_update_search(c);
   return 0;
 }
 
@@ -267,12 +290,13 @@ int run_project_dist(euler_gpu* h, float dt) {
     CM(comm_halo(c, h->cm, c.r, 8, SLAB_HALO));      // b is only valid one row into the halo
     rc = dist_precon_apply(h, true);
     if (rc) return rc;
-    launch_copy_search(c);
+    if (!c.fused) launch_copy_search(c);
+    bool first = true;
     int remaining = h->prm.max_iterations;
     const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
     while (remaining > 0) {
       const int chunk = remaining < every ? remaining : every;
-      for (int i = 0; i < chunk; ++i) { rc = dist_iteration(h); if (rc) return rc; }
+      for (int i = 0; i < chunk; ++i) { rc = dist_iteration(h, first); if (rc) return rc; first = false; }
       remaining -= chunk;
       rc = pull_scalars(h);
       if (rc) return rc;
@@ -475,7 +499,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.lim.v_y = nextafterf((float)(ny - 2), 0.f);
   c.h = prm.h; c.rho = prm.rho; c.gravity = prm.gravity;
   c.dot_mode = prm.dot_mode ? 1 : 0;
-  c.use_pipe = prm.stencil_variant == 0 ? 1 : 0;
+  c.use_pipe = prm.stencil_variant != 1 ? 1 : 0;
   c.max_markers = max_markers;
 
 #define TRY(x) do { int rc_ = (x); if (rc_) { euler_gpu_destroy(h); return rc_; } } while (0)
@@ -501,6 +525,11 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   TRY(alloc_plane(h, &c.adiag));
   TRY(alloc_plane(h, &c.precon)); TRY(alloc_plane(h, &c.q)); TRY(alloc_plane(h, &c.p));
   TRY(alloc_plane(h, &c.r)); TRY(alloc_plane(h, &c.z)); TRY(alloc_plane(h, &c.s));
+  // stencil_variant 0: fused update_search+apply_a (default); 2: additionally axpy+forward fused
+  // (measured slower: profiles/r01 notes); 1: nothing fused, register-window stencils
+  c.fused = (prm.precon == EULER_PRECON_REDBLACK && prm.dot_mode == EULER_DOT_TREE && prm.stencil_variant != 1)
+                ? (prm.stencil_variant == 2 ? 2 : 1) : 0;
+  if (c.fused) { TRY(alloc_plane(h, &c.s2)); TRY(alloc_plane(h, &c.r2)); }
   TRY(alloc_array(h, &c.markers, max_markers));
   TRY(alloc_array(h, &c.markers_alt, max_markers));
   c.n_segments = (max_markers + 1023) / 1024;
@@ -787,7 +816,7 @@ const char* euler_gpu_kernel_class_name(int i) {
   static const char* names[KC__COUNT] = {
       "maxsq", "advect_markers", "refresh_counts", "sources", "extrapolate_bounds",
       "advect_velocity", "build_rhs", "precon_build", "precon_apply", "apply_a", "axpy_norm",
-      "update_search", "pressure_update", "misc"};
+      "update_search", "pressure_update", "misc", "fused_search_apply_a", "fused_axpy_forward"};
   return (i >= 0 && i < KC__COUNT) ? names[i] : nullptr;
 }
 

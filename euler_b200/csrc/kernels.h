@@ -11,7 +11,7 @@ namespace euler {
 enum KernelClass {
   KC_MAXSQ = 0, KC_ADVECT_MARKERS, KC_REFRESH_COUNTS, KC_SOURCES, KC_EXTRAPOLATE,
   KC_ADVECT_VELOCITY, KC_BUILD_RHS, KC_PRECON_BUILD, KC_PRECON_APPLY, KC_APPLY_A, KC_AXPY,
-  KC_UPDATE_SEARCH, KC_PRESSURE_UPDATE, KC_MISC, KC__COUNT
+  KC_UPDATE_SEARCH, KC_PRESSURE_UPDATE, KC_MISC, KC_FUSED_A, KC_FUSED_B, KC__COUNT
 };
 
 struct Prof {
@@ -62,6 +62,8 @@ struct Ctx {
   // pressure solve
   int8_t* adiag;
   double *precon, *q, *p, *r, *z, *s;
+  double *s2, *r2;                // twins of s and r for the fused red-black iteration
+  int fused;                      // red-black: two fused kernels per iteration
   uint8_t* tile_active;           // per PCG tile: contains fluid (pcg_kernels.cu)
   int* tile_list;                 // ordered compact list of those tiles
   double* partials;               // grid-reduction scratch
@@ -118,11 +120,13 @@ void launch_rb_build(Ctx& c);                                // red-black E^-1
 void launch_rb_apply(Ctx& c, bool init);                     // z = M^-1 r (+ z.r, sigma/beta)
 void launch_rb_forward(Ctx& c);                              //   q = L^-1 r
 void launch_rb_backward(Ctx& c, bool init);                  //   z = L^-T q (+ z.r)
+void launch_fused_search_apply(Ctx& c, bool init);            // s' = z + beta s ; A s' ; alpha
+void launch_fused_axpy_forward(Ctx& c, double tol);           // p, r', ||r'||inf, q = L^-1 r'
 void launch_dist_alpha(Ctx& c, const double* gathered, int nranks);
 void launch_dist_beta(Ctx& c, const double* gathered, int nranks, bool init, double tol);
 void launch_copy_search(Ctx& c);                             // s = z
 void launch_apply_a(Ctx& c, bool with_alpha);                // z = A s (+ z.s, alpha)
-void launch_axpy(Ctx& c, double tol);                        // p += a s, r -= a z, ||r||inf
+void launch_axpy(Ctx& c, double tol, bool as_in_q = false);  // p += a s, r -= a (A s), ||r||inf
 void launch_update_search(Ctx& c);                           // s = z + beta s
 void launch_pcg_reset(Ctx& c);                               // iters=0, done=0
 void launch_tile_flags(Ctx& c);                              // per-tile fluid flags from count

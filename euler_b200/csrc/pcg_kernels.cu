@@ -705,6 +705,180 @@ __global__ void k_dist_beta(DevScalars* sc, const double* __restrict__ gathered,
 
 constexpr int NS_A = 8, NS_F = 6, NS_B = 5;
 
+// =========================================================================================
+// Fused iteration for the red-black mode: TWO kernels per PCG iteration instead of five.
+//
+//   k_fused_search_apply   s' = z + beta s  (update_search, main.c:669-677)  and  A s'
+//                          (apply_a, main.c:679-691) + the z.s reduction and alpha:
+//                          34 B/cell instead of 24 + 18.
+//   k_fused_axpy_forward   p += alpha s', r' = r - alpha A s' (main.c:753-754), ||r'||inf
+//                          (:756) and q = L^-1 r' (first half of the red-black solve):
+//                          65 B/cell instead of 48 + 25.  The second half (k_rb_backward,
+//                          fused with z.r') follows; fusing it too would need r' on the
+//                          radius-2 diamond of every cell (tried: the recomputation makes the
+//                          kernel shared-memory/fp64 bound, profiles/r01 notes).
+//
+// Both recompute what a neighbour cell would have produced instead of reading it back from
+// HBM: s' and r' on the 5-point halo of a cell.  Each recomputed value
+// uses exactly the arithmetic of the unfused kernels, so results are bit-identical to them
+// (and to the CPU mirror in the oracle).  Because neighbours are re-derived from the OLD s / r,
+// the new s / r cannot be written in place: s and r ping-pong between two planes each.
+// =========================================================================================
+
+struct FusedSearchApply {
+  // planes: d0 = z (M^-1 r), d1 = s ; b0 = fluid, b1 = adiag
+  const Grid g;
+  double* __restrict__ s_new;
+  double* __restrict__ as;
+  double beta;
+  bool init;                      // first iteration: s' = z (memcpy(s, z), main.c:746)
+  double acc;
+  int a0, a1;
+  __device__ __forceinline__ double sn(double z, double s) const { return init ? z : z + beta * s; }
+  __device__ __forceinline__ void row(const pipe::RowView<2, 2>& dn, const pipe::RowView<2, 2>& ce,
+                                      const pipe::RowView<2, 2>& up, int t4, int x, int y, bool live) {
+    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    if (!mc) return;
+    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
+    const unsigned am = lds_mask4(ce.b[1] + t4);
+    const D4 zc = lds4(ce.d[0] + t4), sc = lds4(ce.d[1] + t4);
+    const D4 zd = lds4(dn.d[0] + t4), sd = lds4(dn.d[1] + t4);
+    const D4 zu = lds4(up.d[0] + t4), su = lds4(up.d[1] + t4);
+    const double nl = sn(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), nr = sn(ce.d[0][t4 + 4], ce.d[1][t4 + 4]);
+    D4 nc, out;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nc.v[k] = sn(zc.v[k], sc.v[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      out.v[k] = 0.0;
+      if (!mbit(mc, k)) { nc.v[k] = sc.v[k]; continue; }       // non-fluid: s untouched
+      double o = (double)(int)(signed char)((am >> (8 * k)) & 0xffu) * nc.v[k];
+      const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
+      const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
+      o -= r_ok ? (k == 3 ? nr : sn(zc.v[(k + 1) & 3], sc.v[(k + 1) & 3])) : 0.0;
+      o -= mbit(mu, k) ? sn(zu.v[k], su.v[k]) : 0.0;
+      o -= l_ok ? (k == 0 ? nl : sn(zc.v[(k + 3) & 3], sc.v[(k + 3) & 3])) : 0.0;
+      o -= mbit(md, k) ? sn(zd.v[k], sd.v[k]) : 0.0;
+      out.v[k] = o;
+      if (y >= a0 && y < a1) acc += o * nc.v[k];
+    }
+    const size_t c = gidx(g, x, y);
+    st4(s_new + c, nc);
+    st4(as + c, out);
+  }
+};
+
+template <int NS>
+__global__ void __launch_bounds__(TT) k_fused_search_apply(
+    Grid g, TileList active, const double* __restrict__ z, const double* __restrict__ s,
+    const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ s_new,
+    double* __restrict__ as, double* partials, DevScalars* sc, int init, int exact, int acc0, int acc1) {
+  if (sc->done) return;
+  FusedSearchApply op{g, s_new, as, sc->beta, init != 0, 0.0, acc0, acc1};
+  pipe::Planes<2, 2> in;
+  in.d[0] = z; in.d[1] = s; in.b[0] = fluid; in.b[1] = reinterpret_cast<const uint8_t*>(adiag);
+  pipe::run<2, 2, NS, TH>(g, active.list, (int)*active.count, in, op);
+  const double bsum = block_reduce<false>(op.acc);
+  grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZS], [&](double total) {
+    if (exact == 2) { sc->part[0] = total; return; }
+    sc->zs = total;
+    sc->alpha = sc->sigma / total;                           // main.c:752
+  });
+}
+
+struct FusedAxpyForward {
+  // planes: d0 = r, d1 = A s, d2 = pc ; b0 = fluid
+  const Grid g;
+  const double* __restrict__ s;
+  double* __restrict__ p;
+  double* __restrict__ r_new;
+  double* __restrict__ q;
+  double alpha;
+  double mx;
+  int a0, a1;
+  // s and p are plain element-wise operands (no halo): they bypass the TMA ring and are
+  // fetched one row ahead into registers instead
+  D4 s_next, p_next;
+  size_t c_next;
+  using RV = pipe::RowView<3, 1>;
+  __device__ __forceinline__ double rn(double r, double as) const {
+    return r + as * -alpha;                                  // fmadd(z, -alpha, r), main.c:754
+  }
+  // pc * (r' * pc): what a RED neighbour contributes to a black cell's forward solve
+  __device__ __forceinline__ double wred(double r, double as, double pc) const { return pc * (rn(r, as) * pc); }
+  __device__ __forceinline__ void row(const RV& dn, const RV& ce, const RV& up, int t4, int x, int y,
+                                      bool live) {
+    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    if (!mc) return;
+    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
+    const D4 rc = lds4(ce.d[0] + t4), ac = lds4(ce.d[1] + t4), pc = lds4(ce.d[2] + t4);
+    const D4 rd = lds4(dn.d[0] + t4), ad = lds4(dn.d[1] + t4), pd = lds4(dn.d[2] + t4);
+    const D4 ru = lds4(up.d[0] + t4), au = lds4(up.d[1] + t4), pu = lds4(up.d[2] + t4);
+    const double wl = wred(ce.d[0][t4 - 1], ce.d[1][t4 - 1], ce.d[2][t4 - 1]);
+    const double wr = wred(ce.d[0][t4 + 4], ce.d[1][t4 + 4], ce.d[2][t4 + 4]);
+    const int gy = y + g.yoff;
+    const size_t c = gidx(g, x, y);
+    D4 sv, pv;
+    if (c_next == c) { sv = s_next; pv = p_next; }
+    else { sv = ld4(s + c); pv = ld4(p + c); }
+    c_next = c + g.pitch;                                    // next row of the tile (or a guard
+    s_next = ld4(s + c_next);                                // row / the next tile's halo: unused)
+    p_next = ld4(p + c_next);
+    D4 rout, qout;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      rout.v[k] = rc.v[k];
+      qout.v[k] = 0.0;
+      if (!mbit(mc, k)) continue;
+      pv.v[k] = pv.v[k] + sv.v[k] * alpha;                   // fmadd(s, alpha, p), main.c:753
+      const double r1 = rn(rc.v[k], ac.v[k]);
+      rout.v[k] = r1;
+      double t = r1;
+      if ((x + k + gy) & 1) {                                // black: + red neighbours, l r d u
+        const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
+        const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
+        if (l_ok) t = t + (k == 0 ? wl : wred(rc.v[(k + 3) & 3], ac.v[(k + 3) & 3], pc.v[(k + 3) & 3]));
+        if (r_ok) t = t + (k == 3 ? wr : wred(rc.v[(k + 1) & 3], ac.v[(k + 1) & 3], pc.v[(k + 1) & 3]));
+        if (mbit(md, k)) t = t + wred(rd.v[k], ad.v[k], pd.v[k]);
+        if (mbit(mu, k)) t = t + wred(ru.v[k], au.v[k], pu.v[k]);
+      }
+      qout.v[k] = t * pc.v[k];
+      if (y >= a0 && y < a1) {
+        const double a = fabs(r1);
+        if (a > mx) mx = a;                                  // NaN-dropping max, main.c:659-662
+      }
+    }
+    st4(p + c, pv);
+    st4(r_new + c, rout);
+    st4(q + c, qout);
+  }
+};
+
+template <int NS>
+__global__ void __launch_bounds__(TT) k_fused_axpy_forward(
+    Grid g, TileList active, const double* __restrict__ r, const double* __restrict__ as,
+    const double* __restrict__ precon, const uint8_t* __restrict__ fluid,
+    const double* __restrict__ s, double* __restrict__ p, double* __restrict__ r_new,
+    double* __restrict__ q, double* partials, DevScalars* sc, double tol, int dist, int acc0,
+    int acc1) {
+  if (sc->done) return;
+  FusedAxpyForward op{g, s, p, r_new, q, sc->alpha, 0.0, acc0, acc1, {}, {}, ~(size_t)0};
+  pipe::Planes<3, 1> in;
+  in.d[0] = r; in.d[1] = as; in.d[2] = precon; in.b[0] = fluid;
+  pipe::run<3, 1, NS, TH>(g, active.list, (int)*active.count, in, op);
+  const double bmax = block_reduce<true>(op.mx);
+  grid_reduce_last_block<true>(bmax, partials, &sc->ctr[CTR_NORM], [&](double total) {
+    if (dist) { sc->part[1] = total; return; }
+    sc->resid = total;
+    sc->iters += 1;
+    if (total <= tol) sc->done = 1;                          // main.c:756-758
+  });
+}
+
+constexpr int NS_KA = 6, NS_KB = 5;
+
 // persistent grid: resident blocks per SM (occupancy of that kernel) x SM count, capped by
 // the number of tiles
 template <class K>
@@ -797,10 +971,10 @@ void launch_apply_a(Ctx& c, bool) {
   }
 }
 
-void launch_axpy(Ctx& c, double tol) {
+void launch_axpy(Ctx& c, double tol, bool as_in_q) {
   ProfScope ps(c, KC_AXPY);
   const PV v = pview(c);
-  k_axpy<<<pcg_blocks(c, k_axpy), TT, 0, c.stream>>>(v.g, TL, v.s, v.z, v.fluid, v.p, v.r, c.partials,
+  k_axpy<<<pcg_blocks(c, k_axpy), TT, 0, c.stream>>>(v.g, TL, v.s, as_in_q ? v.q : v.z, v.fluid, v.p, v.r, c.partials,
                                                      c.sc, tol, c.distributed ? 1 : 0, v.a0, v.a1);
   c.launches += 1;
 }
@@ -858,6 +1032,36 @@ void launch_rb_backward(Ctx& c, bool init) {
 void launch_rb_apply(Ctx& c, bool init) {
   launch_rb_forward(c);
   launch_rb_backward(c, init);
+}
+
+// fused iteration (see k_fused_*).  Invariant at the start of an iteration: c.z = M^-1 r.
+//   search_apply : reads c.z, s            writes s' (twin plane, swapped in), A s' -> c.q
+//   axpy_forward : reads A s' (c.q), r, pc writes p, r' (twin, swapped in), q -> c.z; then
+//                  c.z <-> c.q so that the ordinary k_rb_backward reads q from c.q and leaves
+//                  the new M^-1 r' in c.z
+void launch_fused_search_apply(Ctx& c, bool init) {
+  ProfScope ps(c, KC_FUSED_A);
+  const PV v = pview(c);
+  const size_t o = (size_t)(v.s - c.s);
+  constexpr int smem = pipe::smem_bytes<2, 2, NS_KA>();
+  k_fused_search_apply<NS_KA><<<pcg_blocks(c, k_fused_search_apply<NS_KA>, smem), TT, smem, c.stream>>>(
+      v.g, TL, v.z, v.s, v.fluid, v.adiag, c.s2 + o, v.q, c.partials, c.sc, init ? 1 : 0,
+      c.distributed ? 2 : 0, v.a0, v.a1);
+  c.launches += 1;
+  double* t = c.s; c.s = c.s2; c.s2 = t;
+}
+
+void launch_fused_axpy_forward(Ctx& c, double tol) {
+  ProfScope ps(c, KC_FUSED_B);
+  const PV v = pview(c);
+  const size_t o = (size_t)(v.r - c.r);
+  constexpr int smem = pipe::smem_bytes<3, 1, NS_KB>();
+  k_fused_axpy_forward<NS_KB><<<pcg_blocks(c, k_fused_axpy_forward<NS_KB>, smem), TT, smem, c.stream>>>(
+      v.g, TL, v.r, v.q, v.precon, v.fluid, v.s, v.p, c.r2 + o, v.z, c.partials, c.sc, tol,
+      c.distributed ? 1 : 0, v.a0, v.a1);
+  c.launches += 1;
+  double* t = c.r; c.r = c.r2; c.r2 = t;
+  t = c.z; c.z = c.q; c.q = t;
 }
 
 void launch_dot_zr_exact(Ctx& c, bool init) {

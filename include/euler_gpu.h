@@ -133,8 +133,10 @@ typedef struct euler_params {
   int   device;          /* CUDA device ordinal; default 0 */
   void *stream;          /* cudaStream_t to enqueue on; NULL = the library creates one */
   int   pcg_check_every; /* iterations enqueued between convergence polls; default 8 */
-  int   stencil_variant; /* PCG stencil kernels: 0 = TMA bulk-copy row pipeline (default),
-                            1 = register sliding window (kept for A/B measurements) */
+  int   stencil_variant; /* PCG kernels: 0 = TMA bulk-copy row pipeline, update_search fused
+                            into apply_a (default); 1 = register sliding window, nothing
+                            fused; 2 = as 0 plus axpy fused into the forward solve (kept for
+                            A/B measurements) */
   /* row-slab decomposition: this handle owns global rows
    * [slab_row0, slab_row0 + slab_rows) of the nx x ny grid passed to create(); slab_rows = 0
    * means "not decomposed".  create() is given the GLOBAL planes and markers on every rank
