@@ -40,7 +40,11 @@ sys.path.insert(0, ROOT)
 ALG_BYTES_PER_CELL = {
     "apply_a": 18.0,            # R s 8 + fluid,a_diag 2 + W z 8
     "axpy_norm": 48.0,          # R s,p,z,r 32 + W p,r 16
-    "precon_apply": 56.0,       # fwd R r,pc 16 W q 8; bwd R q,pc 16 W z 8; R r 8
+    "precon_apply": 56.0,       # IC(0) wavefront: fwd R r,pc 16 W q 8; bwd R q,pc 16 W z 8; R r 8
+    "rb_forward": 25.0,         # R r,pc 16 + fluid 1 + W q 8
+    "rb_backward": 33.0,        # R q,pc,r 24 + fluid 1 + W z 8 (fused with z.r)
+    "fused_search_apply_a": 34.0,  # R z,s 16 + fluid,a_diag 2 + W s',A s' 16
+    "fused_axpy_forward": 65.0,    # R s,As,p,r,pc 40 + fluid 1 + W p,r',q 24
     "update_search": 24.0,      # R z,s 16 + W s 8
     "build_rhs": 19.0,
     "pressure_update": 26.0,
@@ -49,7 +53,8 @@ ALG_BYTES_PER_CELL = {
     "maxsq": 8.0,
 }
 ALG_BYTES_PER_MARKER = {"advect_markers": 16.0}
-PCG_KERNELS = ("apply_a", "axpy_norm", "precon_apply", "update_search")
+PCG_KERNELS = ("apply_a", "axpy_norm", "precon_apply", "update_search", "rb_forward", "rb_backward",
+               "fused_search_apply_a", "fused_axpy_forward")
 
 
 def peaks():
@@ -171,6 +176,8 @@ def run_gpu(args):
     # ---- device-resident timing (value) --------------------------------------------
     sim = make()
     cells = n * n
+    # rows this rank stores (owned + halo rows): what the grid-stage kernels stream
+    cells_local = cells if world == 1 else n * (rows + 8)
     for _ in range(args.warmup):
         one_step(sim)
     sim.set_profiling(True)
@@ -236,7 +243,7 @@ def run_gpu(args):
                 # which touches only is_fluid cells): units = cells of those tiles
                 b = ALG_BYTES_PER_CELL[name] * active_cells
             elif name in ALG_BYTES_PER_CELL:
-                b = ALG_BYTES_PER_CELL[name] * cells
+                b = ALG_BYTES_PER_CELL[name] * cells_local
             elif name in ALG_BYTES_PER_MARKER:
                 b = ALG_BYTES_PER_MARKER[name] * n_markers
             else:
@@ -249,8 +256,8 @@ def run_gpu(args):
             k = kernels[dom[0]]
             roof = {"kernel": dom[0], "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": k["frac"], "traffic": None, "peak_source": peak_src,
-                    "alg_bytes_per_launch": ALG_BYTES_PER_CELL[dom[0]] * (active_cells if dom[0] in PCG_KERNELS else cells),
-                    "units_per_launch": active_cells if dom[0] in PCG_KERNELS else cells,
+                    "alg_bytes_per_launch": ALG_BYTES_PER_CELL[dom[0]] * (active_cells if dom[0] in PCG_KERNELS else cells_local),
+                    "units_per_launch": active_cells if dom[0] in PCG_KERNELS else cells_local,
                     "bytes_per_unit": ALG_BYTES_PER_CELL[dom[0]],
                     "ms_per_launch": k["ms_avg"], "share_of_step": k["share"]}
         value = cells * args.steps / (ms_max * 1e-3)

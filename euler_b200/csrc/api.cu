@@ -816,7 +816,8 @@ const char* euler_gpu_kernel_class_name(int i) {
   static const char* names[KC__COUNT] = {
       "maxsq", "advect_markers", "refresh_counts", "sources", "extrapolate_bounds",
       "advect_velocity", "build_rhs", "precon_build", "precon_apply", "apply_a", "axpy_norm",
-      "update_search", "pressure_update", "misc", "fused_search_apply_a", "fused_axpy_forward"};
+      "update_search", "pressure_update", "misc", "fused_search_apply_a", "fused_axpy_forward",
+      "rb_forward", "rb_backward"};
   return (i >= 0 && i < KC__COUNT) ? names[i] : nullptr;
 }
 

@@ -11,7 +11,8 @@ namespace euler {
 enum KernelClass {
   KC_MAXSQ = 0, KC_ADVECT_MARKERS, KC_REFRESH_COUNTS, KC_SOURCES, KC_EXTRAPOLATE,
   KC_ADVECT_VELOCITY, KC_BUILD_RHS, KC_PRECON_BUILD, KC_PRECON_APPLY, KC_APPLY_A, KC_AXPY,
-  KC_UPDATE_SEARCH, KC_PRESSURE_UPDATE, KC_MISC, KC_FUSED_A, KC_FUSED_B, KC__COUNT
+  KC_UPDATE_SEARCH, KC_PRESSURE_UPDATE, KC_MISC, KC_FUSED_A, KC_FUSED_B,
+  KC_PRECON_FWD, KC_PRECON_BWD, KC__COUNT
 };
 
 struct Prof {

@@ -1002,7 +1002,7 @@ void launch_rb_build(Ctx& c) {
 }
 
 void launch_rb_forward(Ctx& c) {
-  ProfScope ps(c, KC_PRECON_APPLY);
+  ProfScope ps(c, KC_PRECON_FWD);
   const PV v = pview(c);
   if (c.use_pipe) {
     constexpr int sf = pipe::smem_bytes<2, 1, NS_F>();
@@ -1015,7 +1015,7 @@ void launch_rb_forward(Ctx& c) {
 }
 
 void launch_rb_backward(Ctx& c, bool init) {
-  ProfScope ps(c, KC_PRECON_APPLY);
+  ProfScope ps(c, KC_PRECON_BWD);
   const PV v = pview(c);
   if (c.use_pipe) {
     constexpr int sb = pipe::smem_bytes<3, 1, NS_B>();

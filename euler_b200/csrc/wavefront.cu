@@ -11,8 +11,8 @@
 //   * the value of the left neighbour never leaves the lane's registers; the value of the
 //     lower neighbour is what lane l-1 produced one step earlier -> one __shfl_up per step;
 //   * lane 0 needs the top row of the strip below.  Strips are chained through a progress
-//     counter per strip (st.release / ld.acquire, published every WF_PUBLISH columns), so
-//     strip k runs ~32+WF_PUBLISH columns behind strip k-1: a software pipeline of warps
+//     counter per strip (st.release / ld.acquire, published every 8 columns), so
+//     strip k runs ~32+8 columns behind strip k-1: a software pipeline of warps
 //     across the SMs.  Strip ids are handed out by an atomic ticket so a strip can only wait
 //     on a strip that has already started (no reliance on block scheduling order).
 //   * the backward solve is the mirror image (rows and columns descending).
@@ -27,11 +27,12 @@
 // by the dependent fp64 chain (mul, add, add, mul per column), not by HBM — see DESIGN.md.
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace euler {
 
 namespace {
 
-constexpr int WF_PUBLISH = 8;
 constexpr int WF_PREFETCH = 32;   // columns ahead for prefetch.global.L1
 
 enum { WF_BUILD = 0, WF_FORWARD = 1, WF_BACKWARD = 2 };
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(32) k_ic0_sweep(
     Grid g, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
     double* precon, const double* __restrict__ in, double* out, const double* __restrict__ rvec,
     unsigned int* progress, unsigned int* ticket, double* partials, DevScalars* sc, int init,
-    int exact) {
+    int exact, int dbg) {
   if (MODE != WF_BUILD && sc->done) return;
   const int lane = threadIdx.x;
   const int n_strips = gridDim.x;
@@ -91,85 +92,142 @@ __global__ void __launch_bounds__(32) k_ic0_sweep(
   unsigned int avail = 0;                           // columns of the dependency row known done
   double acc = 0.0;
 
+  // Steps are processed in blocks of WB columns, software-pipelined one block deep: while block
+  // b is being computed out of registers, the loads of block b+1 are already in flight (own
+  // row: operand, precon, fluid; lane 0: the row of the strip below, if that strip has
+  // published it — otherwise lane 0 falls back to a blocking wait at the top of b+1).  One
+  // memory latency is hidden behind WB dependent steps; progress is published once per block.
+  constexpr int WB = 8;
   const int nsteps = ncols + 31;
-  for (int t = 0; t < nsteps; ++t) {
-    const int k = t - lane;                         // 0-based position along the sweep
-    const int x = fwd ? 1 + k : (g.nx - 2) - k;
-    const bool col_ok = k >= 0 && k < ncols;
-
-    double dep_val = __shfl_up_sync(EULER_FULL_MASK, last_val, 1);
-    double dep_pc = __shfl_up_sync(EULER_FULL_MASK, last_pc, 1);
-    bool dep_fl = __shfl_up_sync(EULER_FULL_MASK, (int)last_fl, 1) != 0;
-
-    if (lane == 0 && col_ok && row_ok) {
-      // dependency row belongs to the previous strip (or is the never-fluid border row)
-      if (strip > 0) {
-        const unsigned int need = (unsigned int)(k + 1);
-        if (avail < need) {
-          do { avail = ld_acquire(progress + (strip - 1)); } while (avail < need);
-        }
-        if (MODE != WF_BUILD) dep_val = __ldcg(out + row_dep + x);
-        dep_pc = __ldcg(precon + row_dep + x);
-      } else {
-        dep_val = 0.0;
-        dep_pc = precon[row_dep + x];
+  struct Buf {
+    double in_v[WB], pc_v[WB], r_v[WB], dval[WB], dpc[WB];
+    unsigned char fl_v[WB], dfl[WB];
+    signed char ad_v[WB];
+    bool dep_loaded;
+  };
+  auto load_own = [&](Buf& b, int t0) {
+#pragma unroll
+    for (int j = 0; j < WB; ++j) {
+      const int k = t0 + j - lane;
+      const int x = fwd ? 1 + k : (g.nx - 2) - k;
+      const bool ok = row_ok && k >= 0 && k < ncols;
+      b.in_v[j] = 0.0; b.pc_v[j] = 0.0; b.r_v[j] = 0.0; b.fl_v[j] = 0; b.ad_v[j] = 0;
+      if (ok) {
+        const size_t c = row + x;
+        b.fl_v[j] = fluid[c];
+        if (MODE == WF_BUILD) { b.ad_v[j] = adiag[c]; if (!b.fl_v[j]) b.pc_v[j] = precon[c]; }
+        else { b.pc_v[j] = precon[c]; b.in_v[j] = in[c]; }
+        if (MODE == WF_BACKWARD) b.r_v[j] = rvec[c];
       }
-      dep_fl = fluid[row_dep + x] != 0;
     }
-
-    if (col_ok && row_ok) {
-      const size_t c = row + x;
-      const bool fl = fluid[c] != 0;
-      if (((x & 3) == 0)) {
-        const int xp = fwd ? x + WF_PREFETCH : x - WF_PREFETCH;
-        if (xp >= 0 && xp < g.nx) {
-          if (MODE != WF_BUILD) { prefetch_l1(in + row + xp); }
-          prefetch_l1(precon + row + xp);
-          if (MODE == WF_BACKWARD) prefetch_l1(rvec + row + xp);
-        }
+  };
+  // lane 0: the dependency row for the block starting at t0; `blocking` = must succeed now
+  auto load_dep = [&](Buf& b, int t0, bool blocking) {
+    b.dep_loaded = false;
+    if (lane != 0 || !row_ok || t0 >= nsteps) return;
+    const int klast = min(t0 + WB - 1, ncols - 1);
+    if (!(dbg & 1) && strip > 0 && klast >= 0 && avail < (unsigned int)(klast + 1)) {
+      avail = ld_acquire(progress + (strip - 1));
+      if (avail < (unsigned int)(klast + 1)) {
+        if (!blocking) return;
+        do { avail = ld_acquire(progress + (strip - 1)); } while (avail < (unsigned int)(klast + 1));
       }
-      if (MODE == WF_BUILD) {
-        double pc;
-        if (fl) {
-          const double a = (double)adiag[c];
-          const double wl = -1.0 * prev_pc;                  // get_a_minus_i == -1
-          const double wd = -1.0 * dep_pc;
-          double e = a - wl * wl - wd * wd;                  // main.c:590-593
-          if (e < 0.25 * a) e = a != 0.0 ? a : 1.0;          // main.c:594-596
-          pc = 1.0 / sqrt(e);
-          precon[c] = pc;
+    }
+#pragma unroll
+    for (int j = 0; j < WB; ++j) {
+      const int k = t0 + j;
+      const int x = fwd ? 1 + k : (g.nx - 2) - k;
+      b.dval[j] = 0.0; b.dpc[j] = 0.0; b.dfl[j] = 0;
+      if (k < ncols && !(dbg & 4)) {
+        if (strip > 0) {
+          if (MODE != WF_BUILD) b.dval[j] = __ldcg(out + row_dep + x);
+          b.dpc[j] = __ldcg(precon + row_dep + x);
         } else {
-          pc = precon[c];                                    // stale value stays
+          b.dpc[j] = precon[row_dep + x];                    // border row: never fluid
         }
-        prev_pc = pc;
-        last_pc = pc;
-      } else if (MODE == WF_FORWARD) {
-        const double pc = precon[c];
-        double qv = 0.0;
-        if (fl) {
-          const double tt = in[c] - (-1.0 * prev_pc) * prev_val - (-1.0 * dep_pc) * dep_val;
-          qv = tt * pc;                                      // main.c:607-610
-        }
-        out[c] = qv;
-        prev_val = qv; prev_pc = pc;
-        last_val = qv; last_pc = pc;
-      } else {
-        double zv = 0.0;
-        if (fl) {
-          const double pc = precon[c];
-          const double ar = prev_fl ? -1.0 : 0.0;            // get_a_plus_i(y,x)
-          const double au = dep_fl ? -1.0 : 0.0;             // get_a_plus_j(y,x)
-          const double tt = in[c] - ar * pc * prev_val - au * pc * dep_val;
-          zv = tt * pc;                                      // main.c:620-623
-          acc += zv * rvec[c];
-        }
-        out[c] = zv;
-        prev_val = zv; prev_fl = fl;
-        last_val = zv; last_fl = fl;
+        b.dfl[j] = fluid[row_dep + x];
       }
-      if (publisher && (((k + 1) % WF_PUBLISH) == 0 || k == ncols - 1)) {
-        st_release(progress + strip, (unsigned int)(k + 1));
+    }
+    b.dep_loaded = true;
+  };
+
+  Buf nxt;
+  load_own(nxt, 0);
+  load_dep(nxt, 0, true);
+  for (int t0 = 0; t0 < nsteps; t0 += WB) {
+    Buf cur = nxt;
+    if (lane == 0 && row_ok && !cur.dep_loaded) load_dep(cur, t0, true);
+    if (t0 + WB < nsteps) {
+      load_own(nxt, t0 + WB);
+      load_dep(nxt, t0 + WB, false);
+    }
+    {   // pull the lines of the blocks after next into L1
+      const int k = t0 + 2 * WB - lane;
+      const int xp = fwd ? 1 + k + WF_PREFETCH : (g.nx - 2) - k - WF_PREFETCH;
+      if (row_ok && xp >= 0 && xp < g.nx) {
+        if (MODE != WF_BUILD) prefetch_l1(in + row + xp);
+        prefetch_l1(precon + row + xp);
+        if (MODE == WF_BACKWARD) prefetch_l1(rvec + row + xp);
       }
+    }
+#pragma unroll
+    for (int j = 0; j < WB; ++j) {
+      const int k = t0 + j - lane;                  // 0-based position along the sweep
+      const int x = fwd ? 1 + k : (g.nx - 2) - k;
+      const bool col_ok = k >= 0 && k < ncols;
+
+      double dep_val = __shfl_up_sync(EULER_FULL_MASK, last_val, 1);
+      double dep_pc = __shfl_up_sync(EULER_FULL_MASK, last_pc, 1);
+      bool dep_fl = __shfl_up_sync(EULER_FULL_MASK, (int)last_fl, 1) != 0;
+      if (lane == 0) { dep_val = cur.dval[j]; dep_pc = cur.dpc[j]; dep_fl = cur.dfl[j] != 0; }
+
+      if (col_ok && row_ok) {
+        const size_t c = row + x;
+        const bool fl = cur.fl_v[j] != 0;
+        if (MODE == WF_BUILD) {
+          double pc;
+          if (fl) {
+            const double a = (double)cur.ad_v[j];
+            const double wl = -1.0 * prev_pc;                  // get_a_minus_i == -1
+            const double wd = -1.0 * dep_pc;
+            double e = a - wl * wl - wd * wd;                  // main.c:590-593
+            if (e < 0.25 * a) e = a != 0.0 ? a : 1.0;          // main.c:594-596
+            pc = 1.0 / sqrt(e);
+            precon[c] = pc;
+          } else {
+            pc = cur.pc_v[j];                                      // stale value stays
+          }
+          prev_pc = pc;
+          last_pc = pc;
+        } else if (MODE == WF_FORWARD) {
+          const double pc = cur.pc_v[j];
+          double qv = 0.0;
+          if (fl) {
+            const double tt = cur.in_v[j] - (-1.0 * prev_pc) * prev_val - (-1.0 * dep_pc) * dep_val;
+            qv = tt * pc;                                      // main.c:607-610
+          }
+          out[c] = qv;
+          prev_val = qv; prev_pc = pc;
+          last_val = qv; last_pc = pc;
+        } else {
+          double zv = 0.0;
+          if (fl) {
+            const double pc = cur.pc_v[j];
+            const double ar = prev_fl ? -1.0 : 0.0;            // get_a_plus_i(y,x)
+            const double au = dep_fl ? -1.0 : 0.0;             // get_a_plus_j(y,x)
+            const double tt = cur.in_v[j] - ar * pc * prev_val - au * pc * dep_val;
+            zv = tt * pc;                                      // main.c:620-623
+            acc += zv * cur.r_v[j];
+          }
+          out[c] = zv;
+          prev_val = zv; prev_fl = fl;
+          last_val = zv; last_fl = fl;
+        }
+      }
+    }
+    if (publisher && row_ok) {
+      const int kdone = min(t0 + WB - 1 - lane, ncols - 1);  // last column this lane finished
+      if (kdone >= 0 && !(dbg & 2)) st_release(progress + strip, (unsigned int)(kdone + 1));
     }
   }
 
@@ -185,6 +243,8 @@ __global__ void __launch_bounds__(32) k_ic0_sweep(
 
 }  // namespace
 
+static int wf_dbg() { static int v = -1; if (v < 0) { const char* e = getenv("EULER_WF_DEBUG"); v = e ? atoi(e) : 0; } return v; }
+
 static void reset_wavefront(Ctx& c) {
   cudaMemsetAsync(c.wf_progress, 0, sizeof(unsigned int) * (size_t)c.n_strips, c.stream);
 }
@@ -194,7 +254,7 @@ void launch_ic0_build(Ctx& c) {
   reset_wavefront(c);
   k_ic0_sweep<WF_BUILD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, nullptr, nullptr, nullptr, c.wf_progress,
-      &c.sc->ticket[0], c.partials, c.sc, 0, 0);
+      &c.sc->ticket[0], c.partials, c.sc, 0, 0, wf_dbg());
   c.launches += 1;
 }
 
@@ -203,11 +263,11 @@ void launch_ic0_apply(Ctx& c, bool init) {
   reset_wavefront(c);
   k_ic0_sweep<WF_FORWARD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, c.r, c.q, nullptr, c.wf_progress, &c.sc->ticket[1],
-      c.partials, c.sc, 0, 0);
+      c.partials, c.sc, 0, 0, wf_dbg());
   reset_wavefront(c);
   k_ic0_sweep<WF_BACKWARD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, c.q, c.z, c.r, c.wf_progress, &c.sc->ticket[2],
-      c.partials, c.sc, init ? 1 : 0, c.dot_mode);
+      c.partials, c.sc, init ? 1 : 0, c.dot_mode, wf_dbg());
   c.launches += 2;
   launch_dot_zr_exact(c, init);
 }

@@ -49,7 +49,7 @@ class Stats(C.Structure):
                 ("device_bytes", C.c_uint64),
                 ("ms_markers", C.c_double), ("ms_grid", C.c_double), ("ms_project", C.c_double),
                 ("active_cells", C.c_uint64),
-                ("kernel_ms", C.c_double * 16), ("kernel_count", C.c_uint64 * 16)]
+                ("kernel_ms", C.c_double * 24), ("kernel_count", C.c_uint64 * 24)]
 
 
 class EulerGpuError(RuntimeError):
@@ -186,7 +186,7 @@ class EulerGpu:
         """{class name: (total ms, timed launch groups)} accumulated while profiling was on."""
         st = self.stats()
         out = {}
-        for i in range(16):
+        for i in range(24):
             name = _L.euler_gpu_kernel_class_name(i)
             if name and st.kernel_count[i]:
                 out[name.decode()] = (float(st.kernel_ms[i]), int(st.kernel_count[i]))

@@ -146,7 +146,7 @@ typedef struct euler_params {
   int   slab_rows;
 } euler_params;
 
-#define EULER_KERNEL_CLASSES 16
+#define EULER_KERNEL_CLASSES 24
 
 typedef struct euler_stats {
   uint64_t frames, substeps;        /* since create */

@@ -25,11 +25,14 @@ def main():
     st = sim.stats()
     cells = n * n
     print("grid %d precon %d: %.1f ms/substep, iters %d resid %.3e" % (n, precon, wall / steps * 1e3, st.last_iterations, st.last_residual))
-    bpc = {"apply_a": 18, "axpy_norm": 48, "precon_apply": 56, "update_search": 24, "build_rhs": 19,
-           "pressure_update": 26, "extrapolate_bounds": 19, "advect_velocity": 18, "maxsq": 8}
+    bpc = {"build_rhs": 19, "pressure_update": 26, "extrapolate_bounds": 19, "advect_velocity": 18, "maxsq": 8}
+    pcg = {"apply_a": 18, "axpy_norm": 48, "precon_apply": 56, "update_search": 24, "rb_forward": 25,
+           "rb_backward": 33, "fused_search_apply_a": 34, "fused_axpy_forward": 65}
+    active = st.active_cells
     for name, (ms, cnt) in sorted(sim.kernel_profile().items(), key=lambda kv: -kv[1][0]):
         avg = ms / cnt
-        gbs = bpc.get(name, 0) * cells / avg / 1e6 if name in bpc else (16 * st.n_markers / avg / 1e6 if name == "advect_markers" else 0)
+        gbs = (bpc[name] * cells / avg / 1e6 if name in bpc else pcg[name] * active / avg / 1e6 if name in pcg
+               else 16 * st.n_markers / avg / 1e6 if name == "advect_markers" else 0)
         print("  %-20s total %9.2f ms  n %5d  avg %8.4f ms  %7.0f GB/s alg" % (name, ms, cnt, avg, gbs))
 
 if __name__ == "__main__":
