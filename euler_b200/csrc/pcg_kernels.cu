@@ -31,6 +31,8 @@
 #include "kernels.h"
 #include "pcg_pipe.cuh"
 
+#include <stdlib.h>
+
 namespace euler {
 
 namespace {
@@ -703,7 +705,14 @@ __global__ void k_dist_beta(DevScalars* sc, const double* __restrict__ gathered,
   sc->sigma = zr;
 }
 
-constexpr int NS_A = 8, NS_F = 6, NS_B = 5;
+// ring depths: measured on B200 at 16384^2, shallower rings win (more resident blocks per SM
+// hide the consumers' shared-memory latency better than a deeper prefetch does)
+constexpr int NS_A = 4, NS_F = 4, NS_B = 4;
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 // =========================================================================================
 // Fused iteration for the red-black mode: TWO kernels per PCG iteration instead of five.
@@ -877,7 +886,7 @@ __global__ void __launch_bounds__(TT) k_fused_axpy_forward(
   });
 }
 
-constexpr int NS_KA = 6, NS_KB = 5;
+constexpr int NS_KA = 4, NS_KB = 5;
 
 // persistent grid: resident blocks per SM (occupancy of that kernel) x SM count, capped by
 // the number of tiles
@@ -1005,9 +1014,12 @@ void launch_rb_forward(Ctx& c) {
   ProfScope ps(c, KC_PRECON_FWD);
   const PV v = pview(c);
   if (c.use_pipe) {
-    constexpr int sf = pipe::smem_bytes<2, 1, NS_F>();
-    k_rb_forward_pipe<NS_F><<<pcg_blocks(c, k_rb_forward_pipe<NS_F>, sf), TT, sf, c.stream>>>(
-        v.g, TL, v.r, v.fluid, v.precon, v.q, c.sc);
+    static const int ns = env_int("EULER_NS_F", NS_F);
+#define FWD(N) { constexpr int sf = pipe::smem_bytes<2, 1, N>(); \
+    k_rb_forward_pipe<N><<<pcg_blocks(c, k_rb_forward_pipe<N>, sf), TT, sf, c.stream>>>( \
+        v.g, TL, v.r, v.fluid, v.precon, v.q, c.sc); }
+    if (ns == 6) FWD(6) else if (ns == 5) FWD(5) else if (ns == 8) FWD(8) else FWD(4)
+#undef FWD
   } else {
     k_rb_forward<<<pcg_blocks(c, k_rb_forward), TT, 0, c.stream>>>(v.g, TL, v.r, v.fluid, v.precon, v.q, c.sc);
   }
@@ -1018,9 +1030,12 @@ void launch_rb_backward(Ctx& c, bool init) {
   ProfScope ps(c, KC_PRECON_BWD);
   const PV v = pview(c);
   if (c.use_pipe) {
-    constexpr int sb = pipe::smem_bytes<3, 1, NS_B>();
-    k_rb_backward_pipe<NS_B><<<pcg_blocks(c, k_rb_backward_pipe<NS_B>, sb), TT, sb, c.stream>>>(
-        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c), v.a0, v.a1);
+    static const int ns = env_int("EULER_NS_B", NS_B);
+#define BWD(N) { constexpr int sb = pipe::smem_bytes<3, 1, N>(); \
+    k_rb_backward_pipe<N><<<pcg_blocks(c, k_rb_backward_pipe<N>, sb), TT, sb, c.stream>>>( \
+        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c), v.a0, v.a1); }
+    if (ns == 5) BWD(5) else if (ns == 6) BWD(6) else if (ns == 8) BWD(8) else BWD(4)
+#undef BWD
   } else {
     k_rb_backward<<<pcg_blocks(c, k_rb_backward), TT, 0, c.stream>>>(
         v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c), v.a0, v.a1);
@@ -1043,10 +1058,13 @@ void launch_fused_search_apply(Ctx& c, bool init) {
   ProfScope ps(c, KC_FUSED_A);
   const PV v = pview(c);
   const size_t o = (size_t)(v.s - c.s);
-  constexpr int smem = pipe::smem_bytes<2, 2, NS_KA>();
-  k_fused_search_apply<NS_KA><<<pcg_blocks(c, k_fused_search_apply<NS_KA>, smem), TT, smem, c.stream>>>(
-      v.g, TL, v.z, v.s, v.fluid, v.adiag, c.s2 + o, v.q, c.partials, c.sc, init ? 1 : 0,
-      c.distributed ? 2 : 0, v.a0, v.a1);
+  static const int ns = env_int("EULER_NS_KA", NS_KA);
+#define KA(N) { constexpr int smem = pipe::smem_bytes<2, 2, N>(); \
+  k_fused_search_apply<N><<<pcg_blocks(c, k_fused_search_apply<N>, smem), TT, smem, c.stream>>>( \
+      v.g, TL, v.z, v.s, v.fluid, v.adiag, c.s2 + o, v.q, c.partials, c.sc, init ? 1 : 0, \
+      c.distributed ? 2 : 0, v.a0, v.a1); }
+  if (ns == 6) KA(6) else if (ns == 5) KA(5) else if (ns == 8) KA(8) else KA(4)
+#undef KA
   c.launches += 1;
   double* t = c.s; c.s = c.s2; c.s2 = t;
 }
