@@ -252,10 +252,19 @@ def run_gpu(args):
             kernels[name] = {"ms_avg": round(avg, 4), "launches": cnt, "share": round(kms / total_ms, 4),
                              "gbs": round(b / avg / 1e6, 1) if b else None,
                              "frac": round(b / avg / 1e6 / peak, 4) if b else None}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tt = json.load(f)
+            if n == 16384 and world == 1 and args.scenario == "basic-fill" and dom:
+                traffic = tt.get(dom[0])
+        except (OSError, ValueError):
+            pass
         if dom and kernels[dom[0]]["gbs"]:
             k = kernels[dom[0]]
             roof = {"kernel": dom[0], "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": k["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": k["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "traffic_source": "ncu capture committed under profiles/ (same workload)" if traffic else None,
                     "alg_bytes_per_launch": ALG_BYTES_PER_CELL[dom[0]] * (active_cells if dom[0] in PCG_KERNELS else cells_local),
                     "units_per_launch": active_cells if dom[0] in PCG_KERNELS else cells_local,
                     "bytes_per_unit": ALG_BYTES_PER_CELL[dom[0]],
