@@ -518,6 +518,26 @@ __device__ __forceinline__ D4 lds4(const double* p) {                   // 16 B 
   return r;
 }
 
+template <int C> struct DV { double v[C]; };
+template <int C> __device__ __forceinline__ DV<C> ldsv(const double* p) {      // 16 B aligned
+  DV<C> r;
+#pragma unroll
+  for (int i = 0; i < C; i += 2) {
+    const double2 a = *reinterpret_cast<const double2*>(p + i);
+    r.v[i] = a.x; r.v[i + 1] = a.y;
+  }
+  return r;
+}
+template <int C> __device__ __forceinline__ void stv(double* __restrict__ p, const DV<C>& d) {
+#pragma unroll
+  for (int i = 0; i < C; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(d.v[i], d.v[i + 1]);
+}
+template <int C> __device__ __forceinline__ DV<C> ldg_v(const double* __restrict__ p) { return ldsv<C>(p); }
+template <int C> __device__ __forceinline__ unsigned ldsm(const uint8_t* p) {   // C-byte aligned
+  if (C == 4) return *reinterpret_cast<const unsigned*>(p);
+  return (unsigned)*reinterpret_cast<const unsigned short*>(p);
+}
+
 struct ApplyAPipe {
   // planes: d0 = s ; b0 = fluid, b1 = adiag
   const Grid g;
@@ -572,6 +592,7 @@ __global__ void __launch_bounds__(TT) k_apply_a_pipe(
   });
 }
 
+template <int C>
 struct RbForwardPipe {
   // planes: d0 = r, d1 = pc ; b0 = fluid
   const Grid g;
@@ -579,46 +600,47 @@ struct RbForwardPipe {
   __device__ __forceinline__ static double w(double r, double p) { return p * (r * p); }
   __device__ __forceinline__ void row(const pipe::RowView<2, 1>& dn, const pipe::RowView<2, 1>& ce,
                                       const pipe::RowView<2, 1>& up, int t4, int x, int y, bool live) {
-    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    const unsigned mc = live ? ldsm<C>(ce.b[0] + t4) : 0u;
     if (!mc) return;
-    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
-    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
-    const D4 rc = lds4(ce.d[0] + t4), pc = lds4(ce.d[1] + t4);
-    const D4 rd = lds4(dn.d[0] + t4), pd = lds4(dn.d[1] + t4);
-    const D4 ru = lds4(up.d[0] + t4), pu = lds4(up.d[1] + t4);
-    const double wl = w(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), wr = w(ce.d[0][t4 + 4], ce.d[1][t4 + 4]);
-    D4 out;
+    const unsigned md = ldsm<C>(dn.b[0] + t4), mu = ldsm<C>(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + C] != 0;
+    const DV<C> rc = ldsv<C>(ce.d[0] + t4), pc = ldsv<C>(ce.d[1] + t4);
+    const DV<C> rd = ldsv<C>(dn.d[0] + t4), pd = ldsv<C>(dn.d[1] + t4);
+    const DV<C> ru = ldsv<C>(up.d[0] + t4), pu = ldsv<C>(up.d[1] + t4);
+    const double wl = w(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), wr = w(ce.d[0][t4 + C], ce.d[1][t4 + C]);
+    DV<C> out;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C; ++k) {
       out.v[k] = 0.0;
       if (!mbit(mc, k)) continue;
       double t = rc.v[k];
       if ((x + k + y + g.yoff) & 1) {                        // black: + sum over red neighbours
         const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
-        const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
+        const bool r_ok = k == C - 1 ? fr : mbit(mc, k + 1);
         if (l_ok) t = t + (k == 0 ? wl : w(rc.v[k - 1], pc.v[k - 1]));
-        if (r_ok) t = t + (k == 3 ? wr : w(rc.v[k + 1], pc.v[k + 1]));
+        if (r_ok) t = t + (k == C - 1 ? wr : w(rc.v[k + 1], pc.v[k + 1]));
         if (mbit(md, k)) t = t + w(rd.v[k], pd.v[k]);
         if (mbit(mu, k)) t = t + w(ru.v[k], pu.v[k]);
       }
       out.v[k] = t * pc.v[k];
     }
-    st4(q + gidx(g, x, y), out);
+    stv<C>(q + gidx(g, x, y), out);
   }
 };
 
-template <int NS>
-__global__ void __launch_bounds__(TT) k_rb_forward_pipe(
+template <int NS, int C>
+__global__ void __launch_bounds__(TW / C) k_rb_forward_pipe(
     Grid g, TileList active, const double* __restrict__ r,
     const uint8_t* __restrict__ fluid, const double* __restrict__ precon, double* __restrict__ q,
     const DevScalars* sc) {
   if (sc->done) return;
-  RbForwardPipe op{g, q};
+  RbForwardPipe<C> op{g, q};
   pipe::Planes<2, 1> in;
   in.d[0] = r; in.d[1] = precon; in.b[0] = fluid;
-  pipe::run<2, 1, NS, TH>(g, active.list, (int)*active.count, in, op);
+  pipe::run<2, 1, NS, TH, RbForwardPipe<C>, C>(g, active.list, (int)*active.count, in, op);
 }
 
+template <int C>
 struct RbBackwardPipe {
   // planes: d0 = q, d1 = pc, d2 = r ; b0 = fluid
   const Grid g;
@@ -627,17 +649,17 @@ struct RbBackwardPipe {
   int a0, a1;
   __device__ __forceinline__ void row(const pipe::RowView<3, 1>& dn, const pipe::RowView<3, 1>& ce,
                                       const pipe::RowView<3, 1>& up, int t4, int x, int y, bool live) {
-    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    const unsigned mc = live ? ldsm<C>(ce.b[0] + t4) : 0u;
     if (!mc) return;
-    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
-    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
-    const D4 qc = lds4(ce.d[0] + t4), pc = lds4(ce.d[1] + t4), rc = lds4(ce.d[2] + t4);
-    const D4 qd = lds4(dn.d[0] + t4), pd = lds4(dn.d[1] + t4);
-    const D4 qu = lds4(up.d[0] + t4), pu = lds4(up.d[1] + t4);
-    const double zl = ce.d[0][t4 - 1] * ce.d[1][t4 - 1], zr = ce.d[0][t4 + 4] * ce.d[1][t4 + 4];
-    D4 out;
+    const unsigned md = ldsm<C>(dn.b[0] + t4), mu = ldsm<C>(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + C] != 0;
+    const DV<C> qc = ldsv<C>(ce.d[0] + t4), pc = ldsv<C>(ce.d[1] + t4), rc = ldsv<C>(ce.d[2] + t4);
+    const DV<C> qd = ldsv<C>(dn.d[0] + t4), pd = ldsv<C>(dn.d[1] + t4);
+    const DV<C> qu = ldsv<C>(up.d[0] + t4), pu = ldsv<C>(up.d[1] + t4);
+    const double zl = ce.d[0][t4 - 1] * ce.d[1][t4 - 1], zr = ce.d[0][t4 + C] * ce.d[1][t4 + C];
+    DV<C> out;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C; ++k) {
       out.v[k] = 0.0;
       if (!mbit(mc, k)) continue;
       double zc;
@@ -646,10 +668,10 @@ struct RbBackwardPipe {
         zc = qc.v[k] * p;                                    // black: q*pc
       } else {
         const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
-        const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
+        const bool r_ok = k == C - 1 ? fr : mbit(mc, k + 1);
         double t = qc.v[k];
         if (l_ok) t = t + p * (k == 0 ? zl : qc.v[k - 1] * pc.v[k - 1]);
-        if (r_ok) t = t + p * (k == 3 ? zr : qc.v[k + 1] * pc.v[k + 1]);
+        if (r_ok) t = t + p * (k == C - 1 ? zr : qc.v[k + 1] * pc.v[k + 1]);
         if (mbit(md, k)) t = t + p * (qd.v[k] * pd.v[k]);
         if (mbit(mu, k)) t = t + p * (qu.v[k] * pu.v[k]);
         zc = t * p;
@@ -657,21 +679,21 @@ struct RbBackwardPipe {
       out.v[k] = zc;
       if (y >= a0 && y < a1) acc += zc * rc.v[k];
     }
-    st4(z + gidx(g, x, y), out);
+    stv<C>(z + gidx(g, x, y), out);
   }
 };
 
-template <int NS>
-__global__ void __launch_bounds__(TT) k_rb_backward_pipe(
+template <int NS, int C>
+__global__ void __launch_bounds__(TW / C) k_rb_backward_pipe(
     Grid g, TileList active, const double* __restrict__ q,
     const double* __restrict__ r, const uint8_t* __restrict__ fluid,
     const double* __restrict__ precon, double* __restrict__ z, double* partials, DevScalars* sc,
     int init, int exact, int acc0, int acc1) {
   if (sc->done) return;
-  RbBackwardPipe op{g, z, 0.0, acc0, acc1};
+  RbBackwardPipe<C> op{g, z, 0.0, acc0, acc1};
   pipe::Planes<3, 1> in;
   in.d[0] = q; in.d[1] = precon; in.d[2] = r; in.b[0] = fluid;
-  pipe::run<3, 1, NS, TH>(g, active.list, (int)*active.count, in, op);
+  pipe::run<3, 1, NS, TH, RbBackwardPipe<C>, C>(g, active.list, (int)*active.count, in, op);
   const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZR], [&](double total) {
     if (exact == 2) { sc->part[0] = total; return; }
@@ -707,7 +729,7 @@ __global__ void k_dist_beta(DevScalars* sc, const double* __restrict__ gathered,
 
 // ring depths: measured on B200 at 16384^2, shallower rings win (more resident blocks per SM
 // hide the consumers' shared-memory latency better than a deeper prefetch does)
-constexpr int NS_A = 4, NS_F = 4, NS_B = 4;
+constexpr int NS_A = 4, NS_F = 4, NS_B = 5;
 
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -734,6 +756,7 @@ static int env_int(const char* name, int dflt) {
 // the new s / r cannot be written in place: s and r ping-pong between two planes each.
 // =========================================================================================
 
+template <int C>
 struct FusedSearchApply {
   // planes: d0 = z (M^-1 r), d1 = s ; b0 = fluid, b1 = adiag
   const Grid g;
@@ -746,48 +769,48 @@ struct FusedSearchApply {
   __device__ __forceinline__ double sn(double z, double s) const { return init ? z : z + beta * s; }
   __device__ __forceinline__ void row(const pipe::RowView<2, 2>& dn, const pipe::RowView<2, 2>& ce,
                                       const pipe::RowView<2, 2>& up, int t4, int x, int y, bool live) {
-    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    const unsigned mc = live ? ldsm<C>(ce.b[0] + t4) : 0u;
     if (!mc) return;
-    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
-    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
-    const unsigned am = lds_mask4(ce.b[1] + t4);
-    const D4 zc = lds4(ce.d[0] + t4), sc = lds4(ce.d[1] + t4);
-    const D4 zd = lds4(dn.d[0] + t4), sd = lds4(dn.d[1] + t4);
-    const D4 zu = lds4(up.d[0] + t4), su = lds4(up.d[1] + t4);
-    const double nl = sn(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), nr = sn(ce.d[0][t4 + 4], ce.d[1][t4 + 4]);
-    D4 nc, out;
+    const unsigned md = ldsm<C>(dn.b[0] + t4), mu = ldsm<C>(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + C] != 0;
+    const unsigned am = ldsm<C>(ce.b[1] + t4);
+    const DV<C> zc = ldsv<C>(ce.d[0] + t4), sc = ldsv<C>(ce.d[1] + t4);
+    const DV<C> zd = ldsv<C>(dn.d[0] + t4), sd = ldsv<C>(dn.d[1] + t4);
+    const DV<C> zu = ldsv<C>(up.d[0] + t4), su = ldsv<C>(up.d[1] + t4);
+    const double nl = sn(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), nr = sn(ce.d[0][t4 + C], ce.d[1][t4 + C]);
+    DV<C> nc, out;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) nc.v[k] = sn(zc.v[k], sc.v[k]);
+    for (int k = 0; k < C; ++k) nc.v[k] = sn(zc.v[k], sc.v[k]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C; ++k) {
       out.v[k] = 0.0;
       if (!mbit(mc, k)) { nc.v[k] = sc.v[k]; continue; }       // non-fluid: s untouched
       double o = (double)(int)(signed char)((am >> (8 * k)) & 0xffu) * nc.v[k];
-      const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
+      const bool r_ok = k == C - 1 ? fr : mbit(mc, k + 1);
       const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
-      o -= r_ok ? (k == 3 ? nr : sn(zc.v[(k + 1) & 3], sc.v[(k + 1) & 3])) : 0.0;
+      o -= r_ok ? (k == C - 1 ? nr : sn(zc.v[(k + 1) % C], sc.v[(k + 1) % C])) : 0.0;
       o -= mbit(mu, k) ? sn(zu.v[k], su.v[k]) : 0.0;
-      o -= l_ok ? (k == 0 ? nl : sn(zc.v[(k + 3) & 3], sc.v[(k + 3) & 3])) : 0.0;
+      o -= l_ok ? (k == 0 ? nl : sn(zc.v[(k + C - 1) % C], sc.v[(k + C - 1) % C])) : 0.0;
       o -= mbit(md, k) ? sn(zd.v[k], sd.v[k]) : 0.0;
       out.v[k] = o;
       if (y >= a0 && y < a1) acc += o * nc.v[k];
     }
     const size_t c = gidx(g, x, y);
-    st4(s_new + c, nc);
-    st4(as + c, out);
+    stv<C>(s_new + c, nc);
+    stv<C>(as + c, out);
   }
 };
 
-template <int NS>
-__global__ void __launch_bounds__(TT) k_fused_search_apply(
+template <int NS, int C>
+__global__ void __launch_bounds__(TW / C) k_fused_search_apply(
     Grid g, TileList active, const double* __restrict__ z, const double* __restrict__ s,
     const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ s_new,
     double* __restrict__ as, double* partials, DevScalars* sc, int init, int exact, int acc0, int acc1) {
   if (sc->done) return;
-  FusedSearchApply op{g, s_new, as, sc->beta, init != 0, 0.0, acc0, acc1};
+  FusedSearchApply<C> op{g, s_new, as, sc->beta, init != 0, 0.0, acc0, acc1};
   pipe::Planes<2, 2> in;
   in.d[0] = z; in.d[1] = s; in.b[0] = fluid; in.b[1] = reinterpret_cast<const uint8_t*>(adiag);
-  pipe::run<2, 2, NS, TH>(g, active.list, (int)*active.count, in, op);
+  pipe::run<2, 2, NS, TH, FusedSearchApply<C>, C>(g, active.list, (int)*active.count, in, op);
   const double bsum = block_reduce<false>(op.acc);
   grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZS], [&](double total) {
     if (exact == 2) { sc->part[0] = total; return; }
@@ -796,6 +819,7 @@ __global__ void __launch_bounds__(TT) k_fused_search_apply(
   });
 }
 
+template <int C>
 struct FusedAxpyForward {
   // planes: d0 = r, d1 = A s, d2 = pc ; b0 = fluid
   const Grid g;
@@ -808,7 +832,7 @@ struct FusedAxpyForward {
   int a0, a1;
   // s and p are plain element-wise operands (no halo): they bypass the TMA ring and are
   // fetched one row ahead into registers instead
-  D4 s_next, p_next;
+  DV<C> s_next, p_next;
   size_t c_next;
   using RV = pipe::RowView<3, 1>;
   __device__ __forceinline__ double rn(double r, double as) const {
@@ -818,26 +842,26 @@ struct FusedAxpyForward {
   __device__ __forceinline__ double wred(double r, double as, double pc) const { return pc * (rn(r, as) * pc); }
   __device__ __forceinline__ void row(const RV& dn, const RV& ce, const RV& up, int t4, int x, int y,
                                       bool live) {
-    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    const unsigned mc = live ? ldsm<C>(ce.b[0] + t4) : 0u;
     if (!mc) return;
-    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
-    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
-    const D4 rc = lds4(ce.d[0] + t4), ac = lds4(ce.d[1] + t4), pc = lds4(ce.d[2] + t4);
-    const D4 rd = lds4(dn.d[0] + t4), ad = lds4(dn.d[1] + t4), pd = lds4(dn.d[2] + t4);
-    const D4 ru = lds4(up.d[0] + t4), au = lds4(up.d[1] + t4), pu = lds4(up.d[2] + t4);
+    const unsigned md = ldsm<C>(dn.b[0] + t4), mu = ldsm<C>(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + C] != 0;
+    const DV<C> rc = ldsv<C>(ce.d[0] + t4), ac = ldsv<C>(ce.d[1] + t4), pc = ldsv<C>(ce.d[2] + t4);
+    const DV<C> rd = ldsv<C>(dn.d[0] + t4), ad = ldsv<C>(dn.d[1] + t4), pd = ldsv<C>(dn.d[2] + t4);
+    const DV<C> ru = ldsv<C>(up.d[0] + t4), au = ldsv<C>(up.d[1] + t4), pu = ldsv<C>(up.d[2] + t4);
     const double wl = wred(ce.d[0][t4 - 1], ce.d[1][t4 - 1], ce.d[2][t4 - 1]);
-    const double wr = wred(ce.d[0][t4 + 4], ce.d[1][t4 + 4], ce.d[2][t4 + 4]);
+    const double wr = wred(ce.d[0][t4 + C], ce.d[1][t4 + C], ce.d[2][t4 + C]);
     const int gy = y + g.yoff;
     const size_t c = gidx(g, x, y);
-    D4 sv, pv;
+    DV<C> sv, pv;
     if (c_next == c) { sv = s_next; pv = p_next; }
-    else { sv = ld4(s + c); pv = ld4(p + c); }
+    else { sv = ldg_v<C>(s + c); pv = ldg_v<C>(p + c); }
     c_next = c + g.pitch;                                    // next row of the tile (or a guard
-    s_next = ld4(s + c_next);                                // row / the next tile's halo: unused)
-    p_next = ld4(p + c_next);
-    D4 rout, qout;
+    s_next = ldg_v<C>(s + c_next);                                // row / the next tile's halo: unused)
+    p_next = ldg_v<C>(p + c_next);
+    DV<C> rout, qout;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C; ++k) {
       rout.v[k] = rc.v[k];
       qout.v[k] = 0.0;
       if (!mbit(mc, k)) continue;
@@ -847,9 +871,9 @@ struct FusedAxpyForward {
       double t = r1;
       if ((x + k + gy) & 1) {                                // black: + red neighbours, l r d u
         const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
-        const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
-        if (l_ok) t = t + (k == 0 ? wl : wred(rc.v[(k + 3) & 3], ac.v[(k + 3) & 3], pc.v[(k + 3) & 3]));
-        if (r_ok) t = t + (k == 3 ? wr : wred(rc.v[(k + 1) & 3], ac.v[(k + 1) & 3], pc.v[(k + 1) & 3]));
+        const bool r_ok = k == C - 1 ? fr : mbit(mc, k + 1);
+        if (l_ok) t = t + (k == 0 ? wl : wred(rc.v[(k + C - 1) % C], ac.v[(k + C - 1) % C], pc.v[(k + C - 1) % C]));
+        if (r_ok) t = t + (k == C - 1 ? wr : wred(rc.v[(k + 1) % C], ac.v[(k + 1) % C], pc.v[(k + 1) % C]));
         if (mbit(md, k)) t = t + wred(rd.v[k], ad.v[k], pd.v[k]);
         if (mbit(mu, k)) t = t + wred(ru.v[k], au.v[k], pu.v[k]);
       }
@@ -859,24 +883,24 @@ struct FusedAxpyForward {
         if (a > mx) mx = a;                                  // NaN-dropping max, main.c:659-662
       }
     }
-    st4(p + c, pv);
-    st4(r_new + c, rout);
-    st4(q + c, qout);
+    stv<C>(p + c, pv);
+    stv<C>(r_new + c, rout);
+    stv<C>(q + c, qout);
   }
 };
 
-template <int NS>
-__global__ void __launch_bounds__(TT) k_fused_axpy_forward(
+template <int NS, int C>
+__global__ void __launch_bounds__(TW / C) k_fused_axpy_forward(
     Grid g, TileList active, const double* __restrict__ r, const double* __restrict__ as,
     const double* __restrict__ precon, const uint8_t* __restrict__ fluid,
     const double* __restrict__ s, double* __restrict__ p, double* __restrict__ r_new,
     double* __restrict__ q, double* partials, DevScalars* sc, double tol, int dist, int acc0,
     int acc1) {
   if (sc->done) return;
-  FusedAxpyForward op{g, s, p, r_new, q, sc->alpha, 0.0, acc0, acc1, {}, {}, ~(size_t)0};
+  FusedAxpyForward<C> op{g, s, p, r_new, q, sc->alpha, 0.0, acc0, acc1, {}, {}, ~(size_t)0};
   pipe::Planes<3, 1> in;
   in.d[0] = r; in.d[1] = as; in.d[2] = precon; in.b[0] = fluid;
-  pipe::run<3, 1, NS, TH>(g, active.list, (int)*active.count, in, op);
+  pipe::run<3, 1, NS, TH, FusedAxpyForward<C>, C>(g, active.list, (int)*active.count, in, op);
   const double bmax = block_reduce<true>(op.mx);
   grid_reduce_last_block<true>(bmax, partials, &sc->ctr[CTR_NORM], [&](double total) {
     if (dist) { sc->part[1] = total; return; }
@@ -886,16 +910,17 @@ __global__ void __launch_bounds__(TT) k_fused_axpy_forward(
   });
 }
 
-constexpr int NS_KA = 4, NS_KB = 5;
+constexpr int NS_KA = 4, NS_KB = 4;
+constexpr int CPT_F = 2, CPT_B = 2, CPT_KA = 4;   // cells per thread of the pipe kernels
 
 // persistent grid: resident blocks per SM (occupancy of that kernel) x SM count, capped by
 // the number of tiles
 template <class K>
-int pcg_blocks(const Ctx& c, K kernel, int smem = 0) {
+int pcg_blocks(const Ctx& c, K kernel, int smem = 0, int threads = TT) {
   int per_sm = 0;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TT, smem) != cudaSuccess || per_sm < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
     per_sm = 1;
   const Tiles T = tiles_of(c.g);
   const long want = (long)c.sm_count * per_sm;
@@ -1015,10 +1040,12 @@ void launch_rb_forward(Ctx& c) {
   const PV v = pview(c);
   if (c.use_pipe) {
     static const int ns = env_int("EULER_NS_F", NS_F);
-#define FWD(N) { constexpr int sf = pipe::smem_bytes<2, 1, N>(); \
-    k_rb_forward_pipe<N><<<pcg_blocks(c, k_rb_forward_pipe<N>, sf), TT, sf, c.stream>>>( \
+    static const int cpt = env_int("EULER_CPT_F", CPT_F);
+#define FWD(N, C) { constexpr int sf = pipe::smem_bytes<2, 1, N>(); \
+    k_rb_forward_pipe<N, C><<<pcg_blocks(c, k_rb_forward_pipe<N, C>, sf, TW / C), TW / C, sf, c.stream>>>( \
         v.g, TL, v.r, v.fluid, v.precon, v.q, c.sc); }
-    if (ns == 6) FWD(6) else if (ns == 5) FWD(5) else if (ns == 8) FWD(8) else FWD(4)
+    if (cpt == 2) { if (ns == 6) FWD(6, 2) else if (ns == 5) FWD(5, 2) else FWD(4, 2) }
+    else { if (ns == 6) FWD(6, 4) else if (ns == 5) FWD(5, 4) else FWD(4, 4) }
 #undef FWD
   } else {
     k_rb_forward<<<pcg_blocks(c, k_rb_forward), TT, 0, c.stream>>>(v.g, TL, v.r, v.fluid, v.precon, v.q, c.sc);
@@ -1031,10 +1058,12 @@ void launch_rb_backward(Ctx& c, bool init) {
   const PV v = pview(c);
   if (c.use_pipe) {
     static const int ns = env_int("EULER_NS_B", NS_B);
-#define BWD(N) { constexpr int sb = pipe::smem_bytes<3, 1, N>(); \
-    k_rb_backward_pipe<N><<<pcg_blocks(c, k_rb_backward_pipe<N>, sb), TT, sb, c.stream>>>( \
+    static const int cpt = env_int("EULER_CPT_B", CPT_B);
+#define BWD(N, C) { constexpr int sb = pipe::smem_bytes<3, 1, N>(); \
+    k_rb_backward_pipe<N, C><<<pcg_blocks(c, k_rb_backward_pipe<N, C>, sb, TW / C), TW / C, sb, c.stream>>>( \
         v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c), v.a0, v.a1); }
-    if (ns == 5) BWD(5) else if (ns == 6) BWD(6) else if (ns == 8) BWD(8) else BWD(4)
+    if (cpt == 2) { if (ns == 4) BWD(4, 2) else if (ns == 6) BWD(6, 2) else BWD(5, 2) }
+    else { if (ns == 4) BWD(4, 4) else if (ns == 6) BWD(6, 4) else BWD(5, 4) }
 #undef BWD
   } else {
     k_rb_backward<<<pcg_blocks(c, k_rb_backward), TT, 0, c.stream>>>(
@@ -1059,11 +1088,13 @@ void launch_fused_search_apply(Ctx& c, bool init) {
   const PV v = pview(c);
   const size_t o = (size_t)(v.s - c.s);
   static const int ns = env_int("EULER_NS_KA", NS_KA);
-#define KA(N) { constexpr int smem = pipe::smem_bytes<2, 2, N>(); \
-  k_fused_search_apply<N><<<pcg_blocks(c, k_fused_search_apply<N>, smem), TT, smem, c.stream>>>( \
+  static const int cpt = env_int("EULER_CPT_KA", CPT_KA);
+#define KA(N, C) { constexpr int smem = pipe::smem_bytes<2, 2, N>(); \
+  k_fused_search_apply<N, C><<<pcg_blocks(c, k_fused_search_apply<N, C>, smem, TW / C), TW / C, smem, c.stream>>>( \
       v.g, TL, v.z, v.s, v.fluid, v.adiag, c.s2 + o, v.q, c.partials, c.sc, init ? 1 : 0, \
       c.distributed ? 2 : 0, v.a0, v.a1); }
-  if (ns == 6) KA(6) else if (ns == 5) KA(5) else if (ns == 8) KA(8) else KA(4)
+  if (cpt == 2) { if (ns == 6) KA(6, 2) else if (ns == 5) KA(5, 2) else KA(4, 2) }
+  else { if (ns == 6) KA(6, 4) else if (ns == 5) KA(5, 4) else KA(4, 4) }
 #undef KA
   c.launches += 1;
   double* t = c.s; c.s = c.s2; c.s2 = t;
@@ -1074,7 +1105,8 @@ void launch_fused_axpy_forward(Ctx& c, double tol) {
   const PV v = pview(c);
   const size_t o = (size_t)(v.r - c.r);
   constexpr int smem = pipe::smem_bytes<3, 1, NS_KB>();
-  k_fused_axpy_forward<NS_KB><<<pcg_blocks(c, k_fused_axpy_forward<NS_KB>, smem), TT, smem, c.stream>>>(
+  constexpr int C = 2;
+  k_fused_axpy_forward<NS_KB, C><<<pcg_blocks(c, k_fused_axpy_forward<NS_KB, C>, smem, TW / C), TW / C, smem, c.stream>>>(
       v.g, TL, v.r, v.q, v.precon, v.fluid, v.s, v.p, c.r2 + o, v.z, c.partials, c.sc, tol,
       c.distributed ? 1 : 0, v.a0, v.a1);
   c.launches += 1;

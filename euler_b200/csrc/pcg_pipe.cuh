@@ -135,18 +135,19 @@ struct Planes {
 // The pipeline driver.  `Op::row(dn, ce, up, t4, x, y, live)` is called by every thread for
 // each output row of each active tile of the block: t4 = 4*threadIdx.x is the tile column of
 // the thread's first cell, x its global column; `live` is false for threads past the row end.
-template <int ND, int NB, int NS, int TH, class Op>
+template <int ND, int NB, int NS, int TH, class Op, int C = 4>
 __device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list, int n_active,
                                     const Planes<ND, NB>& in, Op& op) {
   using L = Layout<ND, NB>;
   constexpr int PF = NS - 3;
+  constexpr int NTHREADS = TW / C;                 // C cells per thread
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* stages = smem_raw;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NS * L::stage_bytes);
   uint64_t* empty = full + NS;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, TT / 32); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NTHREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -181,7 +182,7 @@ __device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list,
       const RowView<ND, NB> up = L::view(stages + (j % NS) * L::stage_bytes);
       const RowView<ND, NB> ce = L::view(stages + ((j + NS - 1) % NS) * L::stage_bytes);
       const RowView<ND, NB> dn = L::view(stages + ((j + NS - 2) % NS) * L::stage_bytes);
-      const int t4 = threadIdx.x * 4;
+      const int t4 = threadIdx.x * C;
       op.row(dn, ce, up, t4, cons.x0 + t4, cons.yy - 1, t4 < cons.w);
       // the row two behind is done with; at the end of a tile so are the last two
       __syncwarp();

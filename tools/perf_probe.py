@@ -14,7 +14,8 @@ def main():
     scn = Scenario(synthetic("basic-fill", n, n), n, n)
     print("host setup %.1fs markers %d" % (time.time() - t0, len(scn.markers)))
     t0 = time.time()
-    sim = G.EulerGpu.from_scenario(scn, precon=precon, marker_mode=G.MARKERS_FAST, pcg_check_every=25)
+    sim = G.EulerGpu.from_scenario(scn, precon=precon, marker_mode=G.MARKERS_FAST, pcg_check_every=25,
+                                   stencil_variant=int(os.environ.get('EULER_VARIANT', '0')))
     print("create %.2fs device GB %.2f" % (time.time() - t0, sim.stats().device_bytes / 1e9))
     sim.substep(sim.calculate_timestep(0.1))
     sim.set_profiling(True); sim.reset_profile()
