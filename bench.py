@@ -137,7 +137,8 @@ def run_gpu(args):
 
     t_host0 = time.perf_counter()
     text = synthetic(args.scenario, n, n)
-    scn = Scenario(text, n, n)
+    # FAST marker mode: array order is free, store the seeded markers in row-major cell order
+    scn = Scenario(text, n, n, row_major_markers=True)
     del text
     t_host = time.perf_counter() - t_host0
 

@@ -114,16 +114,16 @@ __global__ void __launch_bounds__(BX* BY) k_advect_velocity(
     // main.c:388-395: back-trace one Euler step, sample u there
     const float dx = u[c];
     const float dy = interpolate<FACE_V>(v, fluid, g, lim, x + 0.5f, gy - 0.5f);
-    const float px = x - dx * dt / h;
-    const float py = gy - dy * dt / h;
+    const float px = x - div_h(dx * dt, h);
+    const float py = gy - div_h(dy * dt, h);
     ru = interpolate<FACE_U>(u, fluid, g, lim, px, py);
   }
   if (gy < g.gny - 1 && face_has<FACE_V>(fluid, g, x, y) && !face_has<FACE_V>(solid, g, x, y)) {
     // main.c:411-418, then gravity main.c:542
     const float dy = v[c];
     const float dx = interpolate<FACE_U>(u, fluid, g, lim, x - 0.5f, gy + 0.5f);
-    const float px = x - dx * dt / h;
-    const float py = gy - dy * dt / h;
+    const float px = x - div_h(dx * dt, h);
+    const float py = gy - div_h(dy * dt, h);
     rv = interpolate<FACE_V>(v, fluid, g, lim, px, py);
     rv += gravity * dt;
   }
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(BX* BY) k_build_rhs(
     double b = 0.0;
     if (fluid[c]) {
       // main.c:720-721: divergence left to right in fp32, widened, scaled by h^2 rho/dt
-      const float div = (u[c] - u[c - 1] + v[c] - v[c - g.pitch]) / h;
+      const float div = div_h(u[c] - u[c - 1] + v[c] - v[c - g.pitch], h);
       b = -(double)div * scale;
       // main.c:554-559: 4 minus the number of solid neighbours
       adiag[c] = (int8_t)(4 - solid[c - 1] - solid[c + 1] - solid[c - g.pitch] - solid[c + g.pitch]);

@@ -48,11 +48,11 @@ __device__ __forceinline__ float2 walk_marker(const Grid& g, const InterpLimits&
   if (RECORD) rec->n = 0;
   float px = pos.x, py = pos.y;
   // velocity_at, main.c:440-449
-  float vx = interpolate<FACE_U>(u, fluid, g, lim, px / h - 1.f, py / h - 0.5f);
-  float vy = interpolate<FACE_V>(v, fluid, g, lim, px / h - 0.5f, py / h - 1.f);
+  float vx = interpolate<FACE_U>(u, fluid, g, lim, div_h(px, h) - 1.f, div_h(py, h) - 0.5f);
+  float vy = interpolate<FACE_V>(v, fluid, g, lim, div_h(px, h) - 0.5f, div_h(py, h) - 1.f);
 
-  int cx = (int)floorf(px / h);
-  int cy = (int)floorf(py / h);
+  int cx = (int)floorf(div_h(px, h));
+  int cy = (int)floorf(div_h(py, h));
   const int step_x = vx > 0 ? 1 : -1;
   const int step_y = vy > 0 ? 1 : -1;
   int line_x = cx + (vx > 0 ? 1 : 0);
@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(MTHREADS) k_advect_fixup(
 // ------------------------------------------------------------------- binning ----
 
 __device__ __forceinline__ bool marker_cell(const Grid& g, float h, float2 p, size_t* cell) {
-  int cx = (int)floorf(p.x / h);                             // main.c:106-107
-  int cy = (int)floorf(p.y / h);
+  int cx = (int)floorf(div_h(p.x, h));                       // main.c:106-107
+  int cy = (int)floorf(div_h(p.y, h));
   // the reference asserts 0 < x < X, 0 < y < Y (main.c:108, compiled out); clamp so a stray
   // marker lands in the sink ring and is deleted instead of indexing out of bounds
   cx = min(max(cx, 0), g.nx - 1);
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(MTHREADS) k_partition_markers(
     float2 m = make_float2(0.f, 0.f);
     if (i < n) {
       m = src[i];
-      const int gy = (int)floorf(m.y / h);
+      const int gy = (int)floorf(div_h(m.y, h));
       cls = gy < own_lo ? 1 : (gy >= own_hi ? 2 : 0);
     }
 #pragma unroll

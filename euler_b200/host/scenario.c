@@ -69,6 +69,28 @@ int euler_scenario_from_text(euler_scenario *s, const char *text, long length, i
   return 0;
 }
 
+int euler_scenario_markers_row_major(euler_scenario *s) {
+  const int nx = s->nx, ny = s->ny;
+  if (!s->n_markers) return 0;
+  float *out = malloc(s->n_markers * 2 * sizeof(float));
+  size_t *rank = malloc((size_t)nx * ny * sizeof(size_t));
+  if (!out || !rank) { free(out); free(rank); return -1; }
+  size_t r = 0;
+  for (size_t c = 0; c < (size_t)nx * ny; ++c) { rank[c] = r; r += s->fluid[c] ? 1 : 0; }
+  size_t src = 0;                       /* markers were seeded x outermost, y inner, 4 per cell */
+  for (int x = 0; x < nx; ++x)
+    for (int y = 0; y < ny; ++y) {
+      const size_t c = (size_t)y * nx + x;
+      if (!s->fluid[c]) continue;
+      memcpy(out + 8 * rank[c], s->markers + 2 * src, 8 * sizeof(float));
+      src += 4;
+    }
+  free(s->markers);
+  free(rank);
+  s->markers = out;
+  return 0;
+}
+
 int euler_scenario_load(euler_scenario *s, const char *path, int nx, int ny) {
   FILE *f = fopen(path, "rb");
   if (!f) return -2;

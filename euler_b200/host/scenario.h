@@ -32,6 +32,12 @@ int  euler_scenario_from_text(euler_scenario *s, const char *text, long length, 
 /* load_file (misc/file.c:5-42) + the above.  -2 if the file cannot be read. */
 int  euler_scenario_load(euler_scenario *s, const char *path, int nx, int ny);
 void euler_scenario_free(euler_scenario *s);
+/* Re-store the seeded markers in ROW-MAJOR cell order (x fastest) instead of the reference's
+ * column-major seeding order (main.c:256-257).  Positions are untouched — every marker keeps
+ * the jitter it drew — only the array order changes, so consecutive markers read neighbouring
+ * cells of the same grid rows (coalesced gathers on the GPU).  Only meaningful for
+ * EULER_MARKERS_FAST: the reference order is observable.  0, or -1 (no memory). */
+int  euler_scenario_markers_row_major(euler_scenario *s);
 
 /* Nearest-neighbour resample of a scenario text to out_w x out_h characters (+ newlines),
  * still in the scenario format: output row j takes input row j*H/out_h, output

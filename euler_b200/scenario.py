@@ -26,6 +26,7 @@ def _lib():
         L = C.CDLL(path)
         L.euler_scenario_from_text.argtypes = [C.POINTER(_Scn), C.c_char_p, C.c_long, C.c_int, C.c_int]
         L.euler_scenario_free.argtypes = [C.POINTER(_Scn)]
+        L.euler_scenario_markers_row_major.argtypes = [C.POINTER(_Scn)]
         L.euler_scenario_resample.restype = C.c_void_p
         L.euler_scenario_resample.argtypes = [C.c_char_p, C.c_long, C.c_int, C.c_int, C.POINTER(C.c_long)]
         L.euler_scenario_synthetic.restype = C.c_void_p
@@ -77,13 +78,16 @@ def shipped_text(name):
 class Scenario:
     """Parsed scenario: static masks, seeded markers and the RNG state after seeding."""
 
-    def __init__(self, text, nx, ny):
+    def __init__(self, text, nx, ny, row_major_markers=False):
         if isinstance(text, str):
             text = text.encode()
         s = _Scn()
         rc = _lib().euler_scenario_from_text(C.byref(s), text, len(text), nx, ny)
         if rc:
             raise MemoryError("scenario_from_text failed (%d)" % rc)
+        if row_major_markers and _lib().euler_scenario_markers_row_major(C.byref(s)):
+            _lib().euler_scenario_free(C.byref(s))
+            raise MemoryError("markers_row_major failed")
         try:
             shape = (ny, nx)
             self.nx, self.ny = nx, ny

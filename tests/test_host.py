@@ -59,3 +59,13 @@ def test_synthetic_scenarios():
     assert 0.15 < s.fluid.mean() < 0.25
     with pytest.raises(ValueError):
         synthetic("nope", 8, 8)
+
+
+def test_row_major_marker_order_is_a_permutation():
+    text = shipped_text("weird-edges")
+    a, b = Scenario(text, 100, 40), Scenario(text, 100, 40, row_major_markers=True)
+    assert a.rng_state == b.rng_state and len(a.markers) == len(b.markers)
+    key = lambda m: m[np.lexsort((m[:, 0], m[:, 1]))]
+    assert same_bits(key(a.markers), key(b.markers))
+    cells = (np.floor(b.markers[:, 1]).astype(np.int64) * 100 + np.floor(b.markers[:, 0]).astype(np.int64))
+    assert (np.diff(cells) >= 0).all()          # row-major, 4 per cell

@@ -11,7 +11,7 @@ def main():
     precon = G.PRECON_REDBLACK if (len(sys.argv) < 3 or sys.argv[2] == "rb") else G.PRECON_IC0_WAVEFRONT
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     t0 = time.time()
-    scn = Scenario(synthetic("basic-fill", n, n), n, n)
+    scn = Scenario(synthetic("basic-fill", n, n), n, n, row_major_markers=os.environ.get("EULER_ROWMAJOR", "1") == "1")
     print("host setup %.1fs markers %d" % (time.time() - t0, len(scn.markers)))
     t0 = time.time()
     sim = G.EulerGpu.from_scenario(scn, precon=precon, marker_mode=G.MARKERS_FAST, pcg_check_every=25,
