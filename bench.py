@@ -162,6 +162,12 @@ def run_gpu(args):
                 uid = torch.tensor(list(G.comm_unique_id()), dtype=torch.uint8, device="cuda")
             dist.broadcast(uid, src=0)
             sim.comm_init(rank, world, bytes(uid.cpu().tolist()))
+            if not args.no_p2p:
+                # NVLink fast path: all-gather the CUDA-IPC blobs (plumbing), then map the peers
+                mine = torch.tensor(list(sim.comm_p2p_export()), dtype=torch.uint8, device="cuda")
+                allb = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allb, mine)
+                sim.comm_p2p_import([bytes(b.cpu().tolist()) for b in allb])
         return sim
 
     def barrier():
@@ -282,7 +288,7 @@ def run_gpu(args):
                                    % (args.scenario, n, n, "red-black IC(0)" if args.precon == "rb" else "IC(0) wavefront"),
                        "grid": [n, n], "markers": n_markers, "active_cells": active_cells,
                        "parallelism": "single GPU" if world == 1 else
-                                      "%d row slabs balanced by fluid cells (rank 0: %d rows), NCCL halo exchange + marker migration" % (world, rows),
+                                      "%d row slabs balanced by fluid cells (rank 0: %d rows), NCCL halo exchange + marker migration, %s" % (world, rows, "NCCL per-iteration exchanges" if args.no_p2p else "per-iteration exchanges by NVLink peer stores (CUDA IPC)"),
                        "l2_policy": "inputs >> L2: every plane is %.0f MB..%.0f MB vs 126 MB L2, no flush needed"
                                     % (cells / 1e6, cells * 8 / 1e6),
                        "device_bytes": dev_bytes, "host_setup_s": round(t_host, 2)},
@@ -384,6 +390,7 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=1024)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-p2p", action="store_true", help="N>1: NCCL for every exchange (no CUDA-IPC fast path)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -9,6 +9,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "comm.h"
@@ -49,6 +51,8 @@ struct euler_gpu {
   Comm cm;
   bool comm_ready;
   unsigned long long* n_keep;    // device scratch of the marker partition
+  P2P pp;                        // NVLink peer-to-peer fast path of the per-iteration exchanges
+  void* z_raw;                   // cudaMalloc base of the z plane (for the IPC handle)
   bool own_stream;
   std::vector<void*> allocs;     // raw cudaMalloc pointers
   DevScalars* host_sc;           // pinned mirror
@@ -248,7 +252,25 @@ int dist_precon_apply(euler_gpu* h, bool init) {
   // pview), q and z are recomputed there
   launch_rb_forward(c);
   launch_rb_backward(c, init);
-  CM(comm_gather_scalars(c, h->cm, c.sc->part));    // {z.r partial, ||r||inf partial}
+  // one fused NCCL launch: the {z.r, ||r||inf} all-gather and — fused path — the halo exchange
+  // of the new z that the next iteration's search/apply kernel starts from
+  static const int dbg = getenv("EULER_P2P_DEBUG") ? atoi(getenv("EULER_P2P_DEBUG")) : 0;
+  if (h->pp.ready && c.fused == 1) {
+    // NVLink peer stores: halo rows of z into the neighbours' planes, partials into every
+    // rank's mailbox; one small kernel then waits for everybody and finishes beta / stop test
+    if (dbg & 1) CM(comm_halo(c, h->cm, c.z, 8, SLAB_HALO)); else p2p_halo_z(c, h->cm, h->pp, SLAB_HALO);
+    if (dbg & 2) {
+      CM(comm_gather_scalars(c, h->cm, c.sc->part));
+      launch_dist_beta(c, h->cm.gather, h->cm.nranks, init, h->prm.tol);
+    } else {
+      p2p_scalars(c, h->cm, h->pp, 1, init, h->prm.tol, !(dbg & 1));
+    }
+    return 0;
+  }
+  CM(comm_group_begin());
+  CM(comm_gather_scalars(c, h->cm, c.sc->part));
+  if (c.fused) CM(comm_halo(c, h->cm, c.z, 8, SLAB_HALO));
+  CM(comm_group_end());
   launch_dist_beta(c, h->cm.gather, h->cm.nranks, init, h->prm.tol);
   return 0;
 }
@@ -258,14 +280,18 @@ int dist_iteration(euler_gpu* h, bool first) {
   if (c.fused) {
     // the one exchange per iteration: z = M^-1 r, 4 rows deep; s' = z + beta s is then formed
     // redundantly on the halo rows (s itself was formed the same way one iteration earlier)
-    CM(comm_halo(c, h->cm, c.z, 8, SLAB_HALO));
+    // (z was exchanged together with the scalars at the end of the previous preconditioner)
     launch_fused_search_apply(c, first);            // s', A s' -> c.q, z.s partial
   } else {
     CM(comm_halo(c, h->cm, c.s, 8, SLAB_HALO));
     launch_apply_a(c, true);
   }
-  CM(comm_gather_scalars(c, h->cm, c.sc->part));    // {z.s partial}
-  launch_dist_alpha(c, h->cm.gather, h->cm.nranks);
+  if (h->pp.ready && c.fused == 1) {
+    p2p_scalars(c, h->cm, h->pp, 0, false, h->prm.tol, false);   // {z.s} over NVLink -> alpha
+  } else {
+    CM(comm_gather_scalars(c, h->cm, c.sc->part));  // {z.s partial}
+    launch_dist_alpha(c, h->cm.gather, h->cm.nranks);
+  }
   launch_axpy(c, h->prm.tol, c.fused != 0);
   int rc = dist_precon_apply(h, false);
   if (rc) return rc;
@@ -300,6 +326,8 @@ int run_project_dist(euler_gpu* h, float dt) {
       remaining -= chunk;
       rc = pull_scalars(h);
       if (rc) return rc;
+      if (h->host_sc->comm_timeout)
+        return fail(EULER_E_COMM, "peer-to-peer exchange timed out (a rank stopped participating)");
       if (h->host_sc->done) break;
     }
     h->last_iterations = h->host_sc->iters;
@@ -422,6 +450,7 @@ int euler_gpu_destroy(euler_gpu* h) {
   if (!h) return 0;
   cudaSetDevice(h->prm.device);
   if (h->c.stream) cudaStreamSynchronize(h->c.stream);
+  p2p_close(h->pp, h->cm);
   if (h->comm_ready) comm_destroy(&h->cm);
   for (void* p : h->allocs) cudaFree(p);
   if (h->host_sc) cudaFreeHost(h->host_sc);
@@ -481,6 +510,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   h->prm = prm; h->nx = nx; h->ny = ny;
   h->slab = slab; h->row0 = row0; h->rows = rows; h->lo = slab ? lo : 0;
   memset(&h->cm, 0, sizeof h->cm); h->comm_ready = false; h->n_keep = nullptr;
+  memset(&h->pp, 0, sizeof h->pp); h->z_raw = nullptr;
   h->host_sc = nullptr; h->device_bytes = 0; h->max_valid = false;
   h->frames = h->substeps = h->solves = h->solves_skipped = h->pcg_iterations = 0;
   h->last_iterations = 0; h->last_residual = 0; h->last_dt = 0; h->profiling = false;
@@ -524,7 +554,8 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   TRY(alloc_plane(h, &c.uext)); TRY(alloc_plane(h, &c.vext));
   TRY(alloc_plane(h, &c.adiag));
   TRY(alloc_plane(h, &c.precon)); TRY(alloc_plane(h, &c.q)); TRY(alloc_plane(h, &c.p));
-  TRY(alloc_plane(h, &c.r)); TRY(alloc_plane(h, &c.z)); TRY(alloc_plane(h, &c.s));
+  TRY(alloc_plane(h, &c.r)); TRY(alloc_plane(h, &c.z)); h->z_raw = h->allocs.back();
+  TRY(alloc_plane(h, &c.s));
   // stencil_variant 0: fused update_search+apply_a (default); 2: additionally axpy+forward fused
   // (measured slower: profiles/r01 notes); 1: nothing fused, register-window stencils
   c.fused = (prm.precon == EULER_PRECON_REDBLACK && prm.dot_mode == EULER_DOT_TREE && prm.stencil_variant != 1)
@@ -855,6 +886,23 @@ int euler_gpu_comm_init(euler_gpu* h, int rank, int n_ranks, const void* unique_
   // halo rows of the initial classification (create() binned only the owned markers)
   CM(comm_halo(c, h->cm, c.count, 1, SLAB_HALO));
   CU(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int euler_gpu_comm_p2p_export(euler_gpu* h, void* blob_256) {
+  ENTER(h);
+  if (!h->slab || !h->comm_ready) return fail(EULER_E_INVALID, "comm_init first");
+  if (!blob_256) return fail(EULER_E_INVALID, "blob is NULL");
+  if (p2p_export(h->c, h->cm, h->pp, h->z_raw, blob_256)) return fail(EULER_E_COMM, "%s", comm_last_error());
+  return 0;
+}
+
+int euler_gpu_comm_p2p_import(euler_gpu* h, const void* blobs) {
+  ENTER(h);
+  if (!h->slab || !h->comm_ready || !h->pp.mine) return fail(EULER_E_INVALID, "comm_p2p_export first");
+  if (!blobs) return fail(EULER_E_INVALID, "blobs is NULL");
+  CU(cudaStreamSynchronize(h->c.stream));
+  if (p2p_import(h->c, h->cm, h->pp, blobs)) return fail(EULER_E_COMM, "%s", comm_last_error());
   return 0;
 }
 

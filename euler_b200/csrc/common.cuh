@@ -65,6 +65,7 @@ struct DevScalars {
   double part[4];
   unsigned long long n_send_dn, n_send_up;   // markers leaving towards the lower/upper slab
   unsigned long long src_base, n_markers_global;
+  int comm_timeout, pad3;                    // a peer never showed up in a P2P exchange
 };
 
 // a / h in fp32; the reference's h is 1 (k_side_length, main.c:58) and a / 1.f == a exactly, so

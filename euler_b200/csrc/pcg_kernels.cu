@@ -414,7 +414,7 @@ struct RbBackward {
     out.v[k] = zc;
     if (y >= a0 && y < a1) acc += zc * rr.v[k];
   }
-  __device__ __forceinline__ void end_row(size_t c, unsigned) { st4(z + c, out); }
+  __device__ __forceinline__ void end_row(size_t c, unsigned) { st4(z + c, out); }   // single-GPU A/B variant only
 };
 
 __global__ void __launch_bounds__(TT) k_rb_backward(
@@ -679,7 +679,9 @@ struct RbBackwardPipe {
       out.v[k] = zc;
       if (y >= a0 && y < a1) acc += zc * rc.v[k];
     }
-    stv<C>(z + gidx(g, x, y), out);
+    // only the owned rows are stored: the halo rows of z belong to the neighbouring slabs,
+    // which write them directly (NVLink peer stores) or through the halo exchange
+    if (y >= a0 && y < a1) stv<C>(z + gidx(g, x, y), out);
   }
 };
 

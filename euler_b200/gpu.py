@@ -84,6 +84,8 @@ _L.euler_gpu_stream.argtypes = [_H]
 _L.euler_gpu_pcg_iterations.argtypes = [_H, C.c_int]
 _L.euler_gpu_comm_unique_id.argtypes = [C.c_void_p]
 _L.euler_gpu_comm_init.argtypes = [_H, C.c_int, C.c_int, C.c_void_p]
+_L.euler_gpu_comm_p2p_export.argtypes = [_H, C.c_void_p]
+_L.euler_gpu_comm_p2p_import.argtypes = [_H, C.c_void_p]
 _L.euler_gpu_slab_partition.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
 _L.euler_gpu_slab_partition_weighted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
 
@@ -164,6 +166,16 @@ class EulerGpu:
     def comm_init(self, rank, n_ranks, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _ck(_L.euler_gpu_comm_init(self._h, rank, n_ranks, buf))
+
+    def comm_p2p_export(self):
+        buf = C.create_string_buffer(256)
+        _ck(_L.euler_gpu_comm_p2p_export(self._h, buf))
+        return buf.raw
+
+    def comm_p2p_import(self, blobs):
+        data = b"".join(blobs)
+        buf = C.create_string_buffer(data, len(data))
+        _ck(_L.euler_gpu_comm_p2p_import(self._h, buf))
 
     def step_frame(self):
         n = C.c_int(0)

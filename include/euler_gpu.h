@@ -226,6 +226,15 @@ int euler_gpu_pcg_iterations(euler_gpu *h, int iterations);
  * produced on rank 0 by euler_gpu_comm_unique_id and distributed by the caller (any side
  * channel: torch.distributed, MPI, a file).  Collective over all ranks. */
 int euler_gpu_comm_unique_id(void *unique_id_128);
+/* Optional NVLink fast path for the per-iteration exchanges of the slab solve (two scalar
+ * all-gathers and one halo exchange per PCG iteration): CUDA-IPC mapped peer memory and
+ * hand-written store/flag kernels instead of NCCL (~5 us instead of ~45 us per exchange).
+ * After comm_init every rank calls export, the caller all-gathers the 256-byte blobs in rank
+ * order (any side channel) and every rank calls import.  Collective.  Without it the NCCL
+ * path is used. */
+#define EULER_P2P_BLOB_BYTES 256
+int euler_gpu_comm_p2p_export(euler_gpu *h, void *blob_256);
+int euler_gpu_comm_p2p_import(euler_gpu *h, const void *blobs /* n_ranks * 256 bytes */);
 /* Balanced contiguous split of global_ny rows over n_ranks (pure host arithmetic). */
 int euler_gpu_slab_partition(int global_ny, int n_ranks, int rank, int *row0, int *rows);
 /* Same, but balancing the sum of row_weight[y] (e.g. fluid cells per row + a small constant:

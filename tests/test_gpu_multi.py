@@ -21,7 +21,26 @@ def _gpu_count():
         return 0
 
 
-def _worker(rank, nranks, uid, text, nx, ny, frames, out_dir):
+def _exchange_blobs(out_dir, rank, nranks, blob):
+    """all-gather of the IPC blobs through files (the side channel is the caller's business)"""
+    import time
+    with open(os.path.join(out_dir, "blob%d.tmp" % rank), "wb") as f:
+        f.write(blob)
+    os.rename(os.path.join(out_dir, "blob%d.tmp" % rank), os.path.join(out_dir, "blob%d.bin" % rank))
+    blobs = []
+    for r in range(nranks):
+        path = os.path.join(out_dir, "blob%d.bin" % r)
+        t0 = time.time()
+        while not os.path.exists(path):
+            if time.time() - t0 > 60:
+                raise RuntimeError("peer blob missing")
+            time.sleep(0.01)
+        with open(path, "rb") as f:
+            blobs.append(f.read())
+    return blobs
+
+
+def _worker(rank, nranks, uid, text, nx, ny, frames, out_dir, p2p=False):
     sys.path.insert(0, ROOT)
     from euler_b200 import gpu as G
     scn = Scenario(text, nx, ny)
@@ -29,6 +48,8 @@ def _worker(rank, nranks, uid, text, nx, ny, frames, out_dir):
     g = G.EulerGpu.from_scenario(scn, precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST,
                                  device=rank, slab_row0=row0, slab_rows=rows)
     g.comm_init(rank, nranks, uid)
+    if p2p:
+        g.comm_p2p_import(_exchange_blobs(out_dir, rank, nranks, g.comm_p2p_export()))
     subs = [g.step_frame() for _ in range(frames)]
     st = g.stats()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), row0=row0, rows=rows,
@@ -39,16 +60,17 @@ def _worker(rank, nranks, uid, text, nx, ny, frames, out_dir):
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("name,nx,ny,frames", [("block", 100, 40, 12), ("waterfall", 160, 96, 30),
                                                ("weird-edges", 256, 256, 5)])
-def test_two_slabs_match_single_gpu(name, nx, ny, frames, tmp_path):
+def test_two_slabs_match_single_gpu(name, nx, ny, frames, p2p, tmp_path):
     import torch.multiprocessing as mp
     from euler_b200 import gpu as G
     text = shipped_text(name)
     if (nx, ny) != (100, 40):
         text = resample(text, nx - 2, ny - 2)
     uid = G.comm_unique_id()
-    mp.spawn(_worker, args=(2, uid, text, nx, ny, frames, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, uid, text, nx, ny, frames, str(tmp_path), p2p), nprocs=2, join=True)
     parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(2)]
 
     ref = G.EulerGpu.from_scenario(Scenario(text, nx, ny), precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST)
