@@ -236,6 +236,13 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(it, op=dist.ReduceOp.SUM)
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ksum = torch.tensor([sum(v[0] for v in prof.values()) / args.steps], dtype=torch.float64, device="cuda")
+    ksums = [torch.zeros_like(ksum) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(ksums, ksum)
+    else:
+        ksums = [ksum]
+    per_rank_kernel_ms = [round(float(k[0]), 3) for k in ksums]
     iters_all, launches_all = iters, int(it[0])      # one global solve: every rank counts the same iterations
 
     if rank == 0:
@@ -300,6 +307,7 @@ def run_gpu(args):
                     "note": "euler_gpu_create from host arrays + K sub-steps + per-step D2H of the count plane"},
             "roofline": roof,
             "kernels": kernels,
+            "per_rank_kernel_ms_per_step": per_rank_kernel_ms,
             "clocks": clocks,
         }
         if not args.no_cpu and world >= 1:

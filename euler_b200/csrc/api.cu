@@ -519,7 +519,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   Ctx& c = h->c;
   c.g.nx = nx; c.g.ny = ny_loc;
   c.g.pitch = (nx + PITCH_ALIGN - 1) / PITCH_ALIGN * PITCH_ALIGN;
-  c.g.yoff = h->lo; c.g.gny = ny;
+  c.g.yoff = h->lo; c.g.gny = ny; c.g.th = 32;
   c.own0 = row0 - h->lo; c.own1 = c.own0 + rows;
   c.distributed = 0;
   c.max_markers_global = max_markers_global;
@@ -817,7 +817,7 @@ int euler_gpu_stats(euler_gpu* h, euler_stats* out) {
   out->kernel_launches = h->c.launches;
   out->device_bytes = h->device_bytes;
   out->ms_markers = h->ms_markers; out->ms_grid = h->ms_grid; out->ms_project = h->ms_project;
-  out->active_cells = (uint64_t)h->host_sc->active_tiles * (uint64_t)pcg_tile_cells();
+  out->active_cells = (uint64_t)h->host_sc->active_tiles * (uint64_t)pcg_tile_cells(h->c);
   for (int i = 0; i < KC__COUNT; ++i) { out->kernel_ms[i] = h->c.prof.ms[i]; out->kernel_count[i] = h->c.prof.count[i]; }
   return 0;
 }

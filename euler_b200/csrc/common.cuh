@@ -30,6 +30,7 @@ struct Grid {
   int pitch;       // elements per row
   int yoff;        // global row index of row 0 of this view
   int gny;         // global number of rows
+  int th;          // PCG tile height in rows (32, or less when a slab has too few tiles per SM)
 };
 
 __host__ __device__ __forceinline__ size_t gidx(const Grid& g, int x, int y) {

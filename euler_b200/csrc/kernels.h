@@ -133,6 +133,6 @@ void launch_pcg_reset(Ctx& c);                               // iters=0, done=0
 void launch_tile_flags(Ctx& c);                              // per-tile fluid flags from count
 int pcg_tile_count(const Grid& g);
 void launch_dot_zr_exact(Ctx& c, bool init);                 // no-op unless dot_mode
-int pcg_tile_cells();
+int pcg_tile_cells(const Ctx& c);
 
 }  // namespace euler

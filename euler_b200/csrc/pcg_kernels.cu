@@ -44,7 +44,7 @@ struct Tiles { int tx, ty, n; };
 __host__ __device__ inline Tiles tiles_of(const Grid& g) {
   Tiles t;
   t.tx = (g.pitch + TW - 1) / TW;
-  t.ty = (g.ny + TH - 1) / TH;
+  t.ty = (g.ny + g.th - 1) / g.th;
   t.n = t.tx * t.ty;
   return t;
 }
@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(TT) k_tile_flags(Grid g, const uint8_t* __rest
                                                    uint8_t* __restrict__ active, DevScalars* sc) {
   const Tiles T = tiles_of(g);
   for (int tile = blockIdx.x; tile < T.n; tile += gridDim.x) {
-    const int x0 = (tile % T.tx) * TW + threadIdx.x * 4, y0 = (tile / T.tx) * TH;
-    const int y1 = min(y0 + TH, g.ny);
+    const int x0 = (tile % T.tx) * TW + threadIdx.x * 4, y0 = (tile / T.tx) * g.th;
+    const int y1 = min(y0 + g.th, g.ny);
     unsigned any = 0;
     if (x0 < g.pitch)
       for (int y = y0; y < y1; ++y) any |= ldmask(fluid + gidx(g, x0, y));
@@ -163,11 +163,11 @@ __device__ __forceinline__ void for_each_tile(const Grid& g, const TileList& tl,
   const int n = (int)*tl.count;
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
     const int tile = tl.list[i];
-    const int x0 = (tile % T.tx) * TW + threadIdx.x * 4, y0 = (tile / T.tx) * TH;
+    const int x0 = (tile % T.tx) * TW + threadIdx.x * 4, y0 = (tile / T.tx) * g.th;
     // threads past the row end keep participating in the shuffles with a clamped, harmless
     // address (their mask is the zero padding / they are never asked for a valid neighbour)
     const int xs = min(x0, g.pitch - 4);
-    body(xs, y0, min(y0 + TH, g.ny), x0 < g.pitch);
+    body(xs, y0, min(y0 + g.th, g.ny), x0 < g.pitch);
   }
 }
 
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256) k_dot_seq(
   const long nseg = (long)g.ny * T.tx;
   auto next_active = [&](long k) {
     for (; k < nseg; ++k)
-      if (active[(int)((k / T.tx) / TH) * T.tx + (int)(k % T.tx)]) break;
+      if (active[(int)((k / T.tx) / g.th) * T.tx + (int)(k % T.tx)]) break;
     return k;
   };
   auto products = [&](long k, double& p0, double& p1) {
@@ -954,6 +954,10 @@ static PV pview(const Ctx& c) {
   PV v;
   v.g = c.g; v.g.ny = hi - lo; v.g.yoff = c.g.yoff + lo;
   v.a0 = c.own0 - lo; v.a1 = c.own1 - lo;
+  // tile height: 32 rows amortise the two halo rows best, but a thin slab must still give
+  // every resident block (~5 per SM) a few tiles to pipeline over
+  v.g.th = TH;
+  while (v.g.th > 8 && (long)tiles_of(v.g).n < 12L * c.sm_count) v.g.th >>= 1;
   v.fluid = c.count + o; v.adiag = c.adiag + o;
   v.s = c.s + o; v.z = c.z + o; v.r = c.r + o; v.p = c.p + o; v.q = c.q + o; v.precon = c.precon + o;
   return v;
@@ -1124,7 +1128,8 @@ void launch_dot_zr_exact(Ctx& c, bool init) {
   c.launches += 1;
 }
 
-int pcg_tile_count(const Grid& g) { return tiles_of(g).n; }
-int pcg_tile_cells() { return TW * TH; }
+// capacity for the smallest tile height
+int pcg_tile_count(const Grid& g) { Grid t = g; t.th = 4; return tiles_of(t).n; }
+int pcg_tile_cells(const Ctx& c) { return TW * pview(c).g.th; }
 
 }  // namespace euler

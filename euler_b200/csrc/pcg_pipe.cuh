@@ -153,9 +153,10 @@ __device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list,
   }
   __syncthreads();
 
-  const Tiles T = tiles_of(g, TH);
+  const int th = g.th;                             // run-time tile height (TH is the default)
+  const Tiles T = tiles_of(g, th);
   JobIter cons, prod;
-  cons.start(g, T, TH, list, n_active);
+  cons.start(g, T, th, list, n_active);
   prod = cons;
   int issued = 0;
 
@@ -171,7 +172,7 @@ __device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list,
 #pragma unroll
     for (int i = 0; i < NB; ++i) bulk_g2s(st + ND * ROW8 + i * ROW1, in.b[i] + row - HX1, b1, full + s);
     ++issued;
-    prod.next(g, T, TH, list, n_active);
+    prod.next(g, T, th, list, n_active);
   };
 
   for (int j = 0; cons.valid; ++j) {
@@ -194,7 +195,7 @@ __device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list,
         }
       }
     }
-    cons.next(g, T, TH, list, n_active);
+    cons.next(g, T, th, list, n_active);
   }
 }
 
@@ -219,10 +220,11 @@ __device__ __forceinline__ void run_radius(const Grid& g, const int* __restrict_
   }
   __syncthreads();
 
-  const Tiles T = tiles_of(g, TH);
+  const int th = g.th;                             // run-time tile height (TH is the default)
+  const Tiles T = tiles_of(g, th);
   JobIter cons, prod;
   cons.rad = R;
-  cons.start(g, T, TH, list, n_active);
+  cons.start(g, T, th, list, n_active);
   prod = cons;
   int issued = 0;
 
@@ -238,7 +240,7 @@ __device__ __forceinline__ void run_radius(const Grid& g, const int* __restrict_
 #pragma unroll
     for (int i = 0; i < NB; ++i) bulk_g2s(st + ND * ROW8 + i * ROW1, in.b[i] + row - HX1, b1, full + s);
     ++issued;
-    prod.next(g, T, TH, list, n_active);
+    prod.next(g, T, th, list, n_active);
   };
 
   for (int j = 0; cons.valid; ++j) {
@@ -258,7 +260,7 @@ __device__ __forceinline__ void run_radius(const Grid& g, const int* __restrict_
           for (int k = 1; k < W; ++k) mbar_arrive(empty + ((j + NS - (W - 1) + k) % NS));
       }
     }
-    cons.next(g, T, TH, list, n_active);
+    cons.next(g, T, th, list, n_active);
   }
 }
 
