@@ -41,6 +41,7 @@ int fail(int code, const char* fmt, ...) {
 }  // namespace
 
 constexpr int SLAB_HALO = 4;     // halo rows kept on each side of the owned rows
+static_assert(SLAB_HALO == P2P_HALO_DEPTH, "p2p.cuh halo depth");
 
 struct euler_gpu {
   Ctx c;
@@ -51,6 +52,7 @@ struct euler_gpu {
   Comm cm;
   bool comm_ready;
   unsigned long long* n_keep;    // device scratch of the marker partition
+  size_t source_cap;             // capacity of Ctx::source_cells
   P2P pp;                        // NVLink peer-to-peer fast path of the per-iteration exchanges
   void* z_raw;                   // cudaMalloc base of the z plane (for the IPC handle)
   bool own_stream;
@@ -144,6 +146,108 @@ int check_launch(const char* what) {
 
 void prof_mark(euler_gpu* h, int i) {
   if (h->profiling) cudaEventRecord(h->ev[i], h->c.stream);
+}
+
+
+template <class T>
+int zero_plane(euler_gpu* h, T* plane) {
+  if (!plane) return 0;
+  const Grid& g = h->c.g;
+  const size_t rows = (size_t)g.ny + 2 * GUARD_ROWS;
+  CU(cudaMemsetAsync(plane - (size_t)GUARD_ROWS * g.pitch, 0, rows * g.pitch * sizeof(T), h->c.stream));
+  return 0;
+}
+
+// The state hand-over at the end of sim_init (main.c:209-274) into an existing handle: the
+// three static masks, the seeded markers and the RNG state go to the device, every dynamic
+// plane starts from zero (the reference's globals are zero-initialised: main.c:64-100, 577),
+// and refresh_marker_counts runs once (main.c:268).  `fresh`: the planes were just allocated
+// (already zero).  Host buffers may be pageable or pinned; nothing is retained.
+int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const uint8_t* sink,
+               const float* markers_xy, size_t n_markers, uint64_t rng_state, bool fresh) {
+  Ctx& c = h->c;
+  const int nx = h->nx, ny = h->ny;
+  if (!fresh) {
+    int rc = 0;
+    rc |= zero_plane(h, c.u); rc |= zero_plane(h, c.v); rc |= zero_plane(h, c.utmp); rc |= zero_plane(h, c.vtmp);
+    rc |= zero_plane(h, c.uext); rc |= zero_plane(h, c.vext);
+    rc |= zero_plane(h, c.count); rc |= zero_plane(h, c.prev_count); rc |= zero_plane(h, c.count32);
+    rc |= zero_plane(h, c.adiag); rc |= zero_plane(h, c.precon); rc |= zero_plane(h, c.q);
+    rc |= zero_plane(h, c.p); rc |= zero_plane(h, c.r); rc |= zero_plane(h, c.z); rc |= zero_plane(h, c.s);
+    rc |= zero_plane(h, c.s2); rc |= zero_plane(h, c.r2);
+    if (rc) return rc;
+    h->max_valid = false;
+  }
+  int rc;
+  if ((rc = upload_plane(h, c.solid, solid, 1))) return rc;
+  if ((rc = upload_plane(h, c.source, source, 1))) return rc;
+  if ((rc = upload_plane(h, c.sink, sink, 1))) return rc;
+
+  memset(h->host_sc, 0, sizeof(DevScalars));
+  h->host_sc->n_markers = h->slab ? 0 : n_markers;
+  h->host_sc->rng_state = rng_state;
+  CU(cudaMemcpyAsync(c.sc, h->host_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, c.stream));
+  if (!h->slab) {
+    if (n_markers > c.max_markers) return fail(EULER_E_INVALID, "too many markers");
+    if (n_markers)
+      CU(cudaMemcpyAsync(c.markers, markers_xy, n_markers * sizeof(float2), cudaMemcpyHostToDevice, c.stream));
+  } else {
+    // keep the markers whose cell row this slab owns: the global array streams through the
+    // scratch marker array in chunks and a kernel appends the owned ones (order is free in
+    // FAST marker mode, the only one slabs support)
+    const size_t chunk = c.max_markers;
+    for (size_t off = 0; off < n_markers; off += chunk) {
+      const size_t n = n_markers - off < chunk ? n_markers - off : chunk;
+      CU(cudaMemcpyAsync(c.markers_alt, markers_xy + 2 * off, n * sizeof(float2), cudaMemcpyHostToDevice, c.stream));
+      launch_filter_markers(c, c.markers_alt, n, h->row0, h->row0 + h->rows);
+    }
+    unsigned long long kept = 0;
+    CU(cudaMemcpyAsync(&kept, &c.sc->n_markers, sizeof kept, cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    if (kept > c.max_markers) return fail(EULER_E_INVALID, "too many markers in slab");
+  }
+
+  // static row-major list of source cells (main.c:284-286 visits them in this order); rows
+  // are scanned a machine word at a time: almost all of them hold no source
+  std::vector<unsigned int> cells;
+  size_t n_src_global = 0;
+  for (int y = 0; y < ny; ++y) {
+    const uint8_t* row = source + (size_t)y * nx;
+    const bool mine = y >= h->row0 && y < h->row0 + h->rows;
+    for (int x = 0; x < nx;) {
+      if (x + 8 <= nx) {
+        uint64_t w;
+        memcpy(&w, row + x, 8);
+        if (!w) { x += 8; continue; }
+      }
+      const int xe = x + 8 <= nx ? x + 8 : nx;
+      for (; x < xe; ++x)
+        if (row[x]) {
+          n_src_global++;
+          if (mine) cells.push_back((unsigned int)((size_t)(y - h->lo) * c.g.pitch + x));
+        }
+    }
+  }
+  c.n_source_cells = cells.size();
+  c.n_source_cells_global = n_src_global;
+  if (cells.size() > h->source_cap || !c.source_cells) {
+    int arc = alloc_array(h, &c.source_cells, cells.size());
+    if (arc) return arc;
+    h->source_cap = cells.size();
+  }
+  if (!cells.empty())
+    CU(cudaMemcpyAsync(c.source_cells, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaStreamSynchronize(c.stream));      // `cells` and pageable host buffers go out of scope
+
+  launch_refresh_counts(c);                                  // sim_init, main.c:268
+  if (h->slab && h->comm_ready) {
+    // halo rows of the initial classification (only the owned markers were binned)
+    if (comm_halo(c, h->cm, c.count, 1, SLAB_HALO)) return fail(EULER_E_COMM, "%s", comm_last_error());
+  }
+  int lrc = check_launch("load_state");
+  if (lrc) return lrc;
+  CU(cudaStreamSynchronize(c.stream));
+  return 0;
 }
 
 // ---- project(), main.c:709-806 ------------------------------------------------------
@@ -252,21 +356,15 @@ int dist_precon_apply(euler_gpu* h, bool init) {
   // pview), q and z are recomputed there
   launch_rb_forward(c);
   launch_rb_backward(c, init);
-  // one fused NCCL launch: the {z.r, ||r||inf} all-gather and — fused path — the halo exchange
-  // of the new z that the next iteration's search/apply kernel starts from
-  static const int dbg = getenv("EULER_P2P_DEBUG") ? atoi(getenv("EULER_P2P_DEBUG")) : 0;
-  if (h->pp.ready && c.fused == 1) {
-    // NVLink peer stores: halo rows of z into the neighbours' planes, partials into every
-    // rank's mailbox; one small kernel then waits for everybody and finishes beta / stop test
-    if (dbg & 1) CM(comm_halo(c, h->cm, c.z, 8, SLAB_HALO)); else p2p_halo_z(c, h->cm, h->pp, SLAB_HALO);
-    if (dbg & 2) {
-      CM(comm_gather_scalars(c, h->cm, c.sc->part));
-      launch_dist_beta(c, h->cm.gather, h->cm.nranks, init, h->prm.tol);
-    } else {
-      p2p_scalars(c, h->cm, h->pp, 1, init, h->prm.tol, !(dbg & 1));
-    }
+  if (c.p2p_mode == 2) return 0;   // NVLink: halo stores + scalars happened inside k_rb_backward_pipe
+  if (c.p2p_mode == 1) {
+    // the same exchanges as two separate small kernels (A/B: EULER_P2P_SEPARATE=1)
+    p2p_halo_z(c, h->cm, h->pp, SLAB_HALO);
+    p2p_scalars(c, h->cm, h->pp, 1, init, h->prm.tol, true);
     return 0;
   }
+  // one fused NCCL launch: the {z.r, ||r||inf} all-gather and — fused path — the halo exchange
+  // of the new z that the next iteration's search/apply kernel starts from
   CM(comm_group_begin());
   CM(comm_gather_scalars(c, h->cm, c.sc->part));
   if (c.fused) CM(comm_halo(c, h->cm, c.z, 8, SLAB_HALO));
@@ -286,8 +384,10 @@ int dist_iteration(euler_gpu* h, bool first) {
     CM(comm_halo(c, h->cm, c.s, 8, SLAB_HALO));
     launch_apply_a(c, true);
   }
-  if (h->pp.ready && c.fused == 1) {
-    p2p_scalars(c, h->cm, h->pp, 0, false, h->prm.tol, false);   // {z.s} over NVLink -> alpha
+  if (c.p2p_mode == 2) {
+    // {z.s} went over NVLink in the kernel's last block -> alpha
+  } else if (c.p2p_mode == 1) {
+    p2p_scalars(c, h->cm, h->pp, 0, false, h->prm.tol, false);
   } else {
     CM(comm_gather_scalars(c, h->cm, c.sc->part));  // {z.s partial}
     launch_dist_alpha(c, h->cm.gather, h->cm.nranks);
@@ -510,7 +610,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   h->prm = prm; h->nx = nx; h->ny = ny;
   h->slab = slab; h->row0 = row0; h->rows = rows; h->lo = slab ? lo : 0;
   memset(&h->cm, 0, sizeof h->cm); h->comm_ready = false; h->n_keep = nullptr;
-  memset(&h->pp, 0, sizeof h->pp); h->z_raw = nullptr;
+  memset(&h->pp, 0, sizeof h->pp); h->z_raw = nullptr; h->source_cap = 0;
   h->host_sc = nullptr; h->device_bytes = 0; h->max_valid = false;
   h->frames = h->substeps = h->solves = h->solves_skipped = h->pcg_iterations = 0;
   h->last_iterations = 0; h->last_residual = 0; h->last_dt = 0; h->profiling = false;
@@ -529,6 +629,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.lim.v_y = nextafterf((float)(ny - 2), 0.f);
   c.h = prm.h; c.rho = prm.rho; c.gravity = prm.gravity;
   c.dot_mode = prm.dot_mode ? 1 : 0;
+  c.tol = prm.tol;
   c.use_pipe = prm.stencil_variant != 1 ? 1 : 0;
   c.max_markers = max_markers;
 
@@ -586,58 +687,35 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   TRY(alloc_array(h, &c.sc, 1));
   TRY(alloc_array(h, &c.rng_jump, 64 * 64));
 
-  TRY(upload_plane(h, c.solid, solid, 1));
-  TRY(upload_plane(h, c.source, source, 1));
-  TRY(upload_plane(h, c.sink, sink, 1));
-  std::vector<float> mine;
-  if (slab) {                    // keep the markers whose cell row this slab owns
-    for (size_t i = 0; i < n_markers; ++i) {
-      const int gy = (int)floorf(markers_xy[2 * i + 1] / prm.h);
-      if (gy >= row0 && gy < row0 + rows) { mine.push_back(markers_xy[2 * i]); mine.push_back(markers_xy[2 * i + 1]); }
-    }
-    markers_xy = mine.data();
-    n_markers = mine.size() / 2;
-    if (n_markers > max_markers) { euler_gpu_destroy(h); return fail(EULER_E_INVALID, "too many markers in slab"); }
+  {
+    std::vector<unsigned long long> jump(64 * 64);
+    init_rng_jump_table(jump.data());
+    TRYCU(cudaMemcpyAsync(c.rng_jump, jump.data(), jump.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    TRYCU(cudaStreamSynchronize(c.stream));
   }
-  if (n_markers)
-    TRYCU(cudaMemcpyAsync(c.markers, markers_xy, n_markers * sizeof(float2), cudaMemcpyHostToDevice, c.stream));
-
-  // static row-major list of source cells (main.c:284-286 visits them in this order)
-  std::vector<unsigned int> cells;
-  size_t n_src_global = 0;
-  for (int y = 0; y < ny; ++y)
-    for (int x = 0; x < nx; ++x)
-      if (source[(size_t)y * nx + x]) {
-        n_src_global++;
-        if (y >= row0 && y < row0 + rows) cells.push_back((unsigned int)((size_t)(y - h->lo) * c.g.pitch + x));
-      }
-  c.n_source_cells = cells.size();
-  c.n_source_cells_global = n_src_global;
-  TRY(alloc_array(h, &c.source_cells, cells.size()));
-  if (!cells.empty())
-    TRYCU(cudaMemcpyAsync(c.source_cells, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice, c.stream));
-  std::vector<unsigned long long> jump(64 * 64);
-  init_rng_jump_table(jump.data());
-  TRYCU(cudaMemcpyAsync(c.rng_jump, jump.data(), jump.size() * 8, cudaMemcpyHostToDevice, c.stream));
-
-  memset(h->host_sc, 0, sizeof(DevScalars));
-  h->host_sc->n_markers = n_markers;
-  h->host_sc->rng_state = prm.rng_state;
-  TRYCU(cudaMemcpyAsync(c.sc, h->host_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, c.stream));
-  TRYCU(cudaStreamSynchronize(c.stream));   // host vectors above go out of scope
-
-  launch_refresh_counts(c);                                  // sim_init, main.c:268
-  if (slab) {
-    // halo rows of the initial count plane: counted from the host's copy of the markers
-    // (before any communicator exists); afterwards they are refreshed by halo exchange
-    TRY(alloc_array(h, &h->n_keep, 1));
-  }
-  TRY(check_launch("create"));
-  TRYCU(cudaStreamSynchronize(c.stream));
+  if (slab) TRY(alloc_array(h, &h->n_keep, 1));
+  // (slab handles: the halo rows of the count plane are filled by comm_init's halo exchange)
+  TRY(load_state(h, solid, source, sink, markers_xy, n_markers, prm.rng_state, true));
 #undef TRY
 #undef TRYCU
   *out = h;
   return 0;
+}
+
+#define ENTER0(h)                                                  \
+  if (!(h)) return fail(EULER_E_INVALID, "handle is NULL");        \
+  CU(cudaSetDevice((h)->prm.device))
+
+int euler_gpu_reinit(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const uint8_t* sink,
+                     const float* markers_xy, size_t n_markers, uint64_t rng_state) {
+  ENTER0(h);
+  if (!solid || !source || !sink) return fail(EULER_E_INVALID, "mask planes must not be NULL");
+  if (n_markers && !markers_xy) return fail(EULER_E_INVALID, "markers is NULL");
+  if (n_markers > h->c.max_markers_global) return fail(EULER_E_INVALID, "too many markers");
+  if (h->slab && !h->comm_ready) return fail(EULER_E_COMM, "slab handle: call euler_gpu_comm_init first");
+  CU(cudaStreamSynchronize(h->c.stream));
+  h->prm.rng_state = rng_state;
+  return load_state(h, solid, source, sink, markers_xy, n_markers, rng_state, false);
 }
 
 #define ENTER(h)                                                   \
@@ -903,6 +981,10 @@ int euler_gpu_comm_p2p_import(euler_gpu* h, const void* blobs) {
   if (!blobs) return fail(EULER_E_INVALID, "blobs is NULL");
   CU(cudaStreamSynchronize(h->c.stream));
   if (p2p_import(h->c, h->cm, h->pp, blobs)) return fail(EULER_E_COMM, "%s", comm_last_error());
+  if (h->c.fused == 1) {
+    const char* e = getenv("EULER_P2P_SEPARATE");
+    h->c.p2p_mode = (e && atoi(e)) ? 1 : 2;
+  }
   return 0;
 }
 

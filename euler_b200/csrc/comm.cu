@@ -176,32 +176,16 @@ int alloc_base(const void* p, unsigned long long* off) {
 }
 static_assert(sizeof(Blob) <= P2P_BLOB_BYTES, "blob too large");
 
-constexpr unsigned long long P2P_POLL_LIMIT = 1ull << 24;    // seconds at most; then give up, no hang
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long want) {
-  for (unsigned long long i = 0; i < P2P_POLL_LIMIT; ++i)
-    if (ld_acquire_sys(p) >= want) return true;
-  return false;
-}
-
 struct PeerPtrs { Mailbox* p[P2P_MAX_RANKS]; };
 
 // One block.  Thread t < nranks: store my partials into rank t's mailbox, then wait for rank
 // t's partials in mine.  Thread 0 folds them in rank order (deterministic) and finishes the
-// scalar step exactly like k_dist_alpha / k_dist_beta.
+// scalar step exactly like k_dist_alpha / k_dist_beta.  (Separate-kernel form of p2p_finish.)
 __global__ void __launch_bounds__(32) k_p2p_scalars(PeerPtrs peers, Mailbox* mine, DevScalars* sc,
-                                                    int rank, int nranks, unsigned long long seq,
-                                                    int kind, int init, double tol, int wait_halo,
-                                                    unsigned long long halo_seq, int has_dn, int has_up) {
+                                                    int rank, int nranks, int kind, int init,
+                                                    double tol, int wait_halo, int has_dn, int has_up) {
   const int t = threadIdx.x;
+  const unsigned long long seq = mine->seq_ctr, halo_seq = mine->halo_ctr;
   const int par = (int)(seq & 1ull);
   __shared__ int ok_sh;
   if (t == 0) ok_sh = 1;
@@ -220,6 +204,7 @@ __global__ void __launch_bounds__(32) k_p2p_scalars(PeerPtrs peers, Mailbox* min
   }
   __syncthreads();
   if (t != 0) return;
+  mine->seq_ctr = seq + 1;
   if (!ok_sh) { sc->comm_timeout = 1; sc->done = 1; return; }
   if (sc->done) return;
   double sum = 0.0, mx = 0.0;
@@ -238,8 +223,7 @@ __global__ void __launch_bounds__(32) k_p2p_scalars(PeerPtrs peers, Mailbox* min
 __global__ void __launch_bounds__(256) k_p2p_halo(const double* __restrict__ z, int pitch, int own0,
                                                   int own1, int depth, double* z_dn, int dn_own1,
                                                   double* z_up, int up_own0, Mailbox* mine,
-                                                  Mailbox* mb_dn, Mailbox* mb_up,
-                                                  unsigned long long halo_seq) {
+                                                  Mailbox* mb_dn, Mailbox* mb_up) {
   const size_t n2 = (size_t)depth * pitch / 2;             // double2 elements per direction
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += stride) {
@@ -259,6 +243,8 @@ __global__ void __launch_bounds__(256) k_p2p_halo(const double* __restrict__ z, 
   __syncthreads();
   if (!last || threadIdx.x != 0) return;
   mine->halo_done = 0;
+  const unsigned long long halo_seq = mine->halo_ctr + 1;
+  mine->halo_ctr = halo_seq;
   __threadfence_system();
   if (mb_dn) st_release_sys(&mb_dn->halo_flag[1], halo_seq);   // I am its UPPER neighbour
   if (mb_up) st_release_sys(&mb_up->halo_flag[0], halo_seq);   // I am its LOWER neighbour
@@ -305,7 +291,16 @@ int p2p_import(Ctx& c, Comm& cm, P2P& pp, const void* blobs) {
       else { pp.z_up = row0; pp.up_own0 = b.own0; }
     }
   }
-  pp.seq = 0; pp.halo_seq = 0;
+  // what the kernels need (p2p.cuh); z_dn / z_up are biased per view by the launchers
+  DistArgs& d = c.dist;
+  memset(&d, 0, sizeof d);
+  d.mine = pp.mine;
+  for (int r = 0; r < cm.nranks; ++r) d.peer[r] = pp.peer[r];
+  d.mb_dn = cm.rank > 0 ? pp.peer[cm.rank - 1] : nullptr;
+  d.mb_up = cm.rank + 1 < cm.nranks ? pp.peer[cm.rank + 1] : nullptr;
+  d.z_dn = pp.z_dn; d.z_up = pp.z_up;
+  d.rank = cm.rank; d.nranks = cm.nranks;
+  c.p2p_dn_own1 = pp.dn_own1; c.p2p_up_own0 = pp.up_own0;
   pp.ready = true;
   return 0;
 }
@@ -319,21 +314,19 @@ void p2p_close(P2P& pp, Comm& cm) {
 }
 
 void p2p_halo_z(Ctx& c, Comm& cm, P2P& pp, int depth) {
-  pp.halo_seq += 1;
   Mailbox* mb_dn = cm.rank > 0 ? pp.peer[cm.rank - 1] : nullptr;
   Mailbox* mb_up = cm.rank + 1 < cm.nranks ? pp.peer[cm.rank + 1] : nullptr;
   k_p2p_halo<<<32, 256, 0, c.stream>>>(c.z, c.g.pitch, c.own0, c.own1, depth, pp.z_dn, pp.dn_own1,
-                                       pp.z_up, pp.up_own0, pp.mine, mb_dn, mb_up, pp.halo_seq);
+                                       pp.z_up, pp.up_own0, pp.mine, mb_dn, mb_up);
   c.launches += 1;
 }
 
 void p2p_scalars(Ctx& c, Comm& cm, P2P& pp, int kind, bool init, double tol, bool wait_halo) {
   PeerPtrs peers;
   for (int r = 0; r < P2P_MAX_RANKS; ++r) peers.p[r] = r < cm.nranks ? pp.peer[r] : nullptr;
-  k_p2p_scalars<<<1, 32, 0, c.stream>>>(peers, pp.mine, c.sc, cm.rank, cm.nranks, pp.seq, kind,
-                                        init ? 1 : 0, tol, wait_halo ? 1 : 0, pp.halo_seq,
+  k_p2p_scalars<<<1, 32, 0, c.stream>>>(peers, pp.mine, c.sc, cm.rank, cm.nranks, kind,
+                                        init ? 1 : 0, tol, wait_halo ? 1 : 0,
                                         cm.rank > 0 ? 1 : 0, cm.rank + 1 < cm.nranks ? 1 : 0);
-  pp.seq += 1;
   c.launches += 1;
 }
 

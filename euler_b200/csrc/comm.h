@@ -45,21 +45,12 @@ int comm_exchange(Ctx& c, Comm& cm, const void* to_dn, size_t n_to_dn, void* fro
 // ---- peer-to-peer (NVLink) fast path for the per-iteration exchanges ------------------------
 // NCCL costs ~40-50 us per small operation; a PCG iteration needs two global scalar exchanges
 // and one halo exchange.  With CUDA IPC every rank maps its neighbours' z plane and all ranks'
-// mailboxes, and two small kernels do the same job in a few microseconds: partial sums are
-// STORED into every peer's mailbox (double-buffered by sequence parity), halo rows are stored
-// straight into the neighbour's halo rows, then a system-scope fence and a flag; consumers
-// spin on flags in their OWN memory (with a bounded poll count: a lost peer sets
-// DevScalars::comm_timeout instead of hanging the GPU).
+// mailboxes; partial sums are STORED into every peer's mailbox (double-buffered by sequence
+// parity), halo rows are stored straight into the neighbour's halo rows, then a system-scope
+// fence and a flag; consumers spin on flags in their OWN memory (with a bounded poll count: a
+// lost peer sets DevScalars::comm_timeout instead of hanging the GPU).  Device side: p2p.cuh.
 namespace euler {
-constexpr int P2P_MAX_RANKS = 16;
-constexpr int P2P_BLOB_BYTES = 256;
-
-struct Mailbox {                       // lives in each rank's device memory, zero-initialised
-  double pay[2][P2P_MAX_RANKS][4];
-  unsigned long long flag[2][P2P_MAX_RANKS];
-  unsigned long long halo_flag[2];     // [0] written by the lower neighbour, [1] by the upper
-  unsigned int halo_done;              // block counter of k_p2p_halo
-};
+constexpr int P2P_BLOB_BYTES = 256;      // Mailbox, DistArgs: p2p.cuh
 
 struct P2P {
   bool ready;
@@ -68,13 +59,12 @@ struct P2P {
   double* z_dn;                        // lower / upper neighbour's z plane (row 0 of its storage)
   double* z_up;
   int dn_own1, up_own0;                // their owned-row bounds in their local rows
-  unsigned long long seq;              // scalar exchanges done so far
-  unsigned long long halo_seq;
 };
 
 int p2p_export(Ctx& c, Comm& cm, P2P& pp, void* z_raw_base, void* blob /*P2P_BLOB_BYTES*/);
 int p2p_import(Ctx& c, Comm& cm, P2P& pp, const void* blobs /*nranks * P2P_BLOB_BYTES*/);
 void p2p_close(P2P& pp, Comm& cm);
+// The exchanges as separate small kernels (Ctx::p2p_mode 1; A/B against the fused epilogues):
 // stores the top/bottom `depth` owned rows of z into the neighbours' halo rows
 void p2p_halo_z(Ctx& c, Comm& cm, P2P& pp, int depth);
 // all ranks' DevScalars::part[] -> alpha (kind 0) or beta / sigma / stop test (kind 1);

@@ -143,4 +143,41 @@ __device__ __forceinline__ void grid_reduce_last_block(double block_value, doubl
   }
 }
 
+// Same reduction, but control returns to EVERY thread of the block that arrived last (return
+// value true, `total` valid in all of its threads), so that the caller can finish the scalar
+// step with the whole block — the slab solve exchanges the totals with the other ranks there
+// (p2p.cuh).  All other blocks get false.
+template <bool IS_MAX>
+__device__ __forceinline__ bool grid_reduce_last_block_all(double block_value, double* partials,
+                                                           unsigned int* counter, double& total) {
+  __shared__ bool is_last_all;
+  __shared__ double total_sh;
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+  const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (tid == 0) {
+    partials[bid] = block_value;
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last_all = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (!is_last_all) return false;
+  __threadfence();
+  double acc = 0.0;
+  for (unsigned int i = tid; i < nblocks; i += nthreads) {
+    double p = __ldcg(partials + i);
+    acc = IS_MAX ? fmax(acc, p) : acc + p;
+  }
+  acc = block_reduce<IS_MAX>(acc);
+  if (tid == 0) {
+    *counter = 0;
+    total_sh = acc;
+  }
+  __syncthreads();
+  total = total_sh;
+  return true;
+}
+
 }  // namespace euler

@@ -7,9 +7,15 @@
 //   k_build_rhs               b, a_diag, p=0 (first part of project) main.c:713-733, 739
 //   k_pressure_update         clamp p, subtract grad p            main.c:769-805
 //
-// All of them are HBM-bound streaming stencils (DESIGN.md §4 has the byte counts).  One
-// thread owns one P cell and the U face on its right and the V face above it; a warp covers
-// 32 consecutive x, so every plane access is a fully coalesced 32/128/256 B row segment.
+// All of them are HBM-bound streaming stencils (DESIGN.md §4 has the byte counts).  A thread
+// owns FOUR consecutive P cells of a row, with the U faces on their right and the V faces
+// above them: masks come in as one 32-bit word per plane and row, fp32 planes as float4, fp64
+// planes as 2 x double2, so a warp moves 128 B / 512 B / 1 KiB per instruction, and a quad
+// whose neighbourhood holds no fluid (most of a free-surface scene) costs two mask loads and
+// two 16 B stores.  The one-cell-per-thread forms (`*_scalar`, EULER_GRID_VARIANT=1) are kept
+// for A/B runs: they were issue-bound on byte loads at 33-42 % of the HBM peak (profiles/r01c).
+#include <stdlib.h>
+
 #include "interp.cuh"
 #include "kernels.h"
 
@@ -88,7 +94,7 @@ __device__ __forceinline__ float extrapolated_face(const Grid& g, const float* _
 
 // Out of place: a face that stops being wet is zeroed here while a neighbour may still need
 // its old value for the 3x3 mean (in the reference the two passes are sequential).
-__global__ void __launch_bounds__(BX* BY) k_extrapolate_bounds(
+__global__ void __launch_bounds__(BX* BY) k_extrapolate_bounds_scalar(
     Grid g, const float* __restrict__ u, const float* __restrict__ v,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ prev,
     const uint8_t* __restrict__ solid, float* __restrict__ uo, float* __restrict__ vo) {
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(BX* BY) k_extrapolate_bounds(
 
 // ------------------------------------------------------------ velocity advect ----
 
-__global__ void __launch_bounds__(BX* BY) k_advect_velocity(
+__global__ void __launch_bounds__(BX* BY) k_advect_velocity_scalar(
     Grid g, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
     float* __restrict__ uo, float* __restrict__ vo, float dt, float h, float gravity) {
@@ -133,7 +139,7 @@ __global__ void __launch_bounds__(BX* BY) k_advect_velocity(
 
 // ------------------------------------------------------------------ rhs build ----
 
-__global__ void __launch_bounds__(BX* BY) k_build_rhs(
+__global__ void __launch_bounds__(BX* BY) k_build_rhs_scalar(
     Grid g, const float* __restrict__ u, const float* __restrict__ v,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
     double* __restrict__ r, double* __restrict__ p, int8_t* __restrict__ adiag, float h,
@@ -165,7 +171,7 @@ __device__ __forceinline__ double clamped_p(const double* __restrict__ p,
   return (fluid[c] && v < 0.0) ? 0.0 : v;                    // main.c:773-779
 }
 
-__global__ void __launch_bounds__(BX* BY) k_pressure_update(
+__global__ void __launch_bounds__(BX* BY) k_pressure_update_scalar(
     Grid g, double* __restrict__ p, const float* __restrict__ ut, const float* __restrict__ vt,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
     float* __restrict__ uo, float* __restrict__ vo, float dt, float k, DevScalars* sc,
@@ -207,6 +213,281 @@ __global__ void __launch_bounds__(BX* BY) k_pressure_update(
   }
 }
 
+
+// ============================================================== 4 cells per thread ====
+
+constexpr int QX = 32, QY = 8;           // threads per block: 32 quads (128 cells) x 8 rows
+inline dim3 grid4(const Grid& g) { return dim3((g.pitch / 4 + QX - 1) / QX, (g.ny + QY - 1) / QY); }
+
+__device__ __forceinline__ unsigned ld_u8x4(const uint8_t* __restrict__ p) {
+  return *reinterpret_cast<const unsigned*>(p);
+}
+__device__ __forceinline__ bool byte_set(unsigned m, int k) { return ((m >> (8 * k)) & 0xffu) != 0; }
+__device__ __forceinline__ int byte_of(unsigned m, int k) { return (int)((m >> (8 * k)) & 0xffu); }
+
+// Masks of one quad's neighbourhood in one u8 plane: the quad itself, the cell right of it and
+// the row above — everything the U faces (x, x+1) and V faces (y, y+1) of four cells need.
+struct QuadMask {
+  unsigned c, up;     // 4 bytes each
+  unsigned r;         // low byte: cell x0+4 of the quad's row
+  __device__ __forceinline__ bool cell(int k) const { return byte_set(c, k); }
+  __device__ __forceinline__ bool right(int k) const { return k == 3 ? (r & 0xffu) != 0 : byte_set(c, k + 1); }
+  __device__ __forceinline__ bool above(int k) const { return byte_set(up, k); }
+  __device__ __forceinline__ bool face_u(int k) const { return cell(k) | right(k); }   // main.c:128-132
+  __device__ __forceinline__ bool face_v(int k) const { return cell(k) | above(k); }   // main.c:134-138
+  __device__ __forceinline__ bool any() const { return (c | up | (r & 0xffu)) != 0; }
+};
+// The fluid plane, read by every quad: ALL 32 lanes of the warp must call this (the byte right
+// of the quad is the next lane's first byte; lane 31 loads it).
+__device__ __forceinline__ QuadMask load_quad_mask_warp(const uint8_t* __restrict__ m, const Grid& g, size_t c) {
+  QuadMask q;
+  q.c = ld_u8x4(m + c);
+  q.up = ld_u8x4(m + c + g.pitch);
+  q.r = __shfl_down_sync(EULER_FULL_MASK, q.c, 1);
+  if ((threadIdx.x & 31) == 31) q.r = m[c + 4];
+  return q;
+}
+// Any other plane, read only by the quads that touch fluid (divergent code: no shuffle).
+__device__ __forceinline__ QuadMask load_quad_mask(const uint8_t* __restrict__ m, const Grid& g, size_t c) {
+  QuadMask q;
+  q.c = ld_u8x4(m + c);
+  q.up = ld_u8x4(m + c + g.pitch);
+  q.r = m[c + 4];
+  return q;
+}
+
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld_f4(const float* __restrict__ p) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  F4 r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  return r;
+}
+__device__ __forceinline__ void st_f4(float* __restrict__ p, const F4& a) {
+  *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+struct D4g { double v[4]; };
+__device__ __forceinline__ D4g ld_d4(const double* __restrict__ p) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  D4g r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  return r;
+}
+__device__ __forceinline__ void st_d4(double* __restrict__ p, const D4g& a) {
+  *reinterpret_cast<double2*>(p) = make_double2(a.v[0], a.v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(a.v[2], a.v[3]);
+}
+
+// Quad addressing shared by the four kernels.  A warp is one row of 32 quads; lanes past the
+// row end keep a clamped, harmless address so that they can take part in the shuffle.
+struct QuadPos { int x0, y; size_t c; bool row_ok, inside; };
+__device__ __forceinline__ QuadPos quad_pos(const Grid& g) {
+  QuadPos q;
+  q.x0 = (blockIdx.x * QX + threadIdx.x) * 4;
+  q.y = blockIdx.y * QY + threadIdx.y;
+  q.row_ok = q.y < g.ny;                         // uniform per warp
+  q.inside = q.row_ok && q.x0 < g.pitch;
+  q.c = gidx(g, q.x0 < g.pitch ? q.x0 : g.pitch - 4, q.row_ok ? q.y : 0);
+  return q;
+}
+
+// ---- extrapolate + zero_bounds ------------------------------------------------------
+// mean of the clamped 3x3 block's faces that were wet last sub-step (main.c:158-171, 179-181),
+// row-major accumulation order; 0/0 -> NaN when there is none (the assert is off).  The rare
+// path of extrapolate: a face that has just become wet.
+template <int TYPE>
+__device__ __noinline__ float newly_wet_mean(const Grid& g, const float* __restrict__ q,
+                                             const uint8_t* __restrict__ prev, int x, int y) {
+  const int sx = g.nx - (TYPE == FACE_U), sy = g.gny - (TYPE == FACE_V) - g.yoff;
+  const int x0 = max(x - 1, 0), x1 = min(x + 1, sx - 1);
+  const int y0 = max(y - 1, -g.yoff), y1 = min(y + 1, sy - 1);
+  float total = 0.f;
+  int n = 0;
+  for (int yy = y0; yy <= y1; ++yy)
+    for (int xx = x0; xx <= x1; ++xx)
+      if (face_has<TYPE>(prev, g, xx, yy)) { total += q[gidx(g, xx, yy)]; ++n; }
+  return total / (float)n;
+}
+
+// Out of place: a face that stops being wet is zeroed here while a neighbour may still need
+// its old value for the 3x3 mean (in the reference the two passes are sequential).
+__global__ void __launch_bounds__(QX* QY) k_extrapolate_bounds(
+    Grid g, const float* __restrict__ u, const float* __restrict__ v,
+    const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ prev,
+    const uint8_t* __restrict__ solid, float* __restrict__ uo, float* __restrict__ vo) {
+  const QuadPos q = quad_pos(g);
+  if (!q.row_ok) return;
+  const QuadMask f = load_quad_mask_warp(fluid, g, q.c);
+  if (!q.inside) return;
+  F4 ru, rv;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ru.v[k] = rv.v[k] = 0.f;
+  if (f.any()) {
+    const QuadMask s = load_quad_mask(solid, g, q.c), pv = load_quad_mask(prev, g, q.c);
+    const F4 uc = ld_f4(u + q.c), vc = ld_f4(v + q.c);
+    const bool v_row = q.y + g.yoff < g.gny - 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = q.x0 + k;
+      // zero_bounds (main.c:827): not touching fluid, or touching a solid -> 0
+      if (x < g.nx - 1 && f.face_u(k) && !s.face_u(k))
+        ru.v[k] = pv.face_u(k) ? uc.v[k] : newly_wet_mean<FACE_U>(g, u, prev, x, q.y);
+      if (x < g.nx && v_row && f.face_v(k) && !s.face_v(k))
+        rv.v[k] = pv.face_v(k) ? vc.v[k] : newly_wet_mean<FACE_V>(g, v, prev, x, q.y);
+    }
+  }
+  st_f4(uo + q.c, ru);
+  st_f4(vo + q.c, rv);
+}
+
+// ---- advect_u, advect_v + gravity + zero_bounds ---------------------------------------
+__global__ void __launch_bounds__(QX* QY) k_advect_velocity(
+    Grid g, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
+    const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
+    float* __restrict__ uo, float* __restrict__ vo, float dt, float h, float gravity) {
+  const QuadPos q = quad_pos(g);
+  if (!q.row_ok) return;
+  const QuadMask f = load_quad_mask_warp(fluid, g, q.c);
+  if (!q.inside) return;
+  F4 ru, rv;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ru.v[k] = rv.v[k] = 0.f;
+  if (f.any()) {
+    const QuadMask s = load_quad_mask(solid, g, q.c);
+    const F4 uc = ld_f4(u + q.c), vc = ld_f4(v + q.c);
+    const int gy = q.y + g.yoff;               // sample positions are in global index space
+    const bool v_row = gy < g.gny - 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = q.x0 + k;
+      if (x < g.nx - 1 && f.face_u(k) && !s.face_u(k)) {
+        // main.c:388-395: back-trace one Euler step, sample u there
+        const float dx = uc.v[k];
+        const float dy = interpolate<FACE_V>(v, fluid, g, lim, x + 0.5f, gy - 0.5f);
+        const float px = x - div_h(dx * dt, h);
+        const float py = gy - div_h(dy * dt, h);
+        ru.v[k] = interpolate<FACE_U>(u, fluid, g, lim, px, py);
+      }
+      if (x < g.nx && v_row && f.face_v(k) && !s.face_v(k)) {
+        // main.c:411-418, then gravity main.c:542
+        const float dy = vc.v[k];
+        const float dx = interpolate<FACE_U>(u, fluid, g, lim, x - 0.5f, gy + 0.5f);
+        const float px = x - div_h(dx * dt, h);
+        const float py = gy - div_h(dy * dt, h);
+        float r = interpolate<FACE_V>(v, fluid, g, lim, px, py);
+        r += gravity * dt;
+        rv.v[k] = r;
+      }
+    }
+  }
+  st_f4(uo + q.c, ru);
+  st_f4(vo + q.c, rv);
+}
+
+// ---- rhs build --------------------------------------------------------------------------
+__global__ void __launch_bounds__(QX* QY) k_build_rhs(
+    Grid g, const float* __restrict__ u, const float* __restrict__ v,
+    const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
+    double* __restrict__ r, double* __restrict__ p, int8_t* __restrict__ adiag, float h,
+    double scale, DevScalars* sc, int own0, int own1) {
+  const QuadPos q = quad_pos(g);
+  bool nz = false;
+  if (q.inside) {
+    const unsigned mf = ld_u8x4(fluid + q.c);
+    D4g b, zero;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b.v[k] = zero.v[k] = 0.0;
+    if (mf) {
+      const F4 uc = ld_f4(u + q.c), vc = ld_f4(v + q.c), vd = ld_f4(v + q.c - g.pitch);
+      const float ul = u[q.c - 1];
+      const uint8_t* sp = solid + q.c;
+      const unsigned s_c = ld_u8x4(sp), s_dn = ld_u8x4(sp - g.pitch), s_up = ld_u8x4(sp + g.pitch);
+      const int s_l = sp[-1], s_r = sp[4];
+      unsigned am = ld_u8x4(reinterpret_cast<const uint8_t*>(adiag) + q.c);
+      const bool owned = q.y >= own0 && q.y < own1;      // halo rows are the neighbour slab's business
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!byte_set(mf, k)) continue;
+        // main.c:720-721: divergence left to right in fp32, widened, scaled by h^2 rho/dt
+        const float div = div_h(uc.v[k] - (k == 0 ? ul : uc.v[k - 1]) + vc.v[k] - vd.v[k], h);
+        b.v[k] = -(double)div * scale;
+        // main.c:554-559: 4 minus the number of solid neighbours (left, right, down, up)
+        const int a = 4 - (k == 0 ? s_l : byte_of(s_c, k - 1)) - (k == 3 ? s_r : byte_of(s_c, k + 1)) -
+                      byte_of(s_dn, k) - byte_of(s_up, k);
+        am = (am & ~(0xffu << (8 * k))) | (((unsigned)a & 0xffu) << (8 * k));
+        nz |= (b.v[k] != 0.0) && owned;
+      }
+      *reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(adiag) + q.c) = am;
+    }
+    st_d4(r + q.c, b);
+    st_d4(p + q.c, zero);                                 // p = 0, main.c:739
+  }
+  if (__any_sync(EULER_FULL_MASK, nz) && (threadIdx.x & 31) == 0) atomicOr(&sc->nonzero_rhs, 1);
+}
+
+// ---- pressure update ----------------------------------------------------------------------
+__global__ void __launch_bounds__(QX* QY) k_pressure_update(
+    Grid g, double* __restrict__ p, const float* __restrict__ ut, const float* __restrict__ vt,
+    const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
+    float* __restrict__ uo, float* __restrict__ vo, float dt, float kk, DevScalars* sc,
+    int own0, int own1) {
+  const QuadPos q = quad_pos(g);
+  float mu = 0.f, mv = 0.f;
+  if (q.row_ok) {
+    const QuadMask f = load_quad_mask_warp(fluid, g, q.c);
+    if (q.inside) {
+      F4 ru, rv;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ru.v[k] = rv.v[k] = 0.f;
+      if (f.any()) {
+        const QuadMask s = load_quad_mask(solid, g, q.c);
+        D4g pc = ld_d4(p + q.c), pu = ld_d4(p + q.c + g.pitch);
+        double pr = p[q.c + 4];
+        const F4 uc = ld_f4(ut + q.c), vc = ld_f4(vt + q.c);
+        // p = max(p, 0) on fluid cells (main.c:773-779), applied to every operand as it is read
+        bool clamped = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (f.cell(k) && pc.v[k] < 0.0) { pc.v[k] = 0.0; clamped = true; }
+          if (f.above(k) && pu.v[k] < 0.0) pu.v[k] = 0.0;
+        }
+        if ((f.r & 0xffu) && pr < 0.0) pr = 0.0;
+        const bool v_row = q.y + g.yoff < g.gny - 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int x = q.x0 + k;
+          if (x < g.nx - 1 && !s.face_u(k) && f.face_u(k)) {
+            const float dp = (float)((k == 3 ? pr : pc.v[k + 1]) - pc.v[k]);   // main.c:787, 705-707
+            ru.v[k] = uc.v[k] + (-kk * dp) * dt;
+          }
+          if (x < g.nx && v_row && !s.face_v(k) && f.face_v(k)) {
+            const float dp = (float)(pu.v[k] - pc.v[k]);                       // main.c:800
+            rv.v[k] = vc.v[k] + (-kk * dp) * dt;
+          }
+        }
+        // the clamp is idempotent, so writing it while neighbours may still read the old value
+        // is race-free in value (they clamp what they read themselves)
+        if (clamped) st_d4(p + q.c, pc);
+      }
+      st_f4(uo + q.c, ru);
+      st_f4(vo + q.c, rv);
+      // fused max u^2 / max v^2 for the next calculate_timestep (main.c:808-820)
+      if (q.y >= own0 && q.y < own1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = ru.v[k] * ru.v[k], b = rv.v[k] * rv.v[k];
+          if (a > mu) mu = a;                    // drops NaN like the reference's `value > max`
+          if (b > mv) mv = b;
+        }
+      }
+    }
+  }
+  mu = warp_maxf(mu);
+  mv = warp_maxf(mv);
+  if ((threadIdx.x & 31) == 0) {
+    if (mu > 0.f) atomicMax(&sc->max_u2_bits, __float_as_uint(mu));
+    if (mv > 0.f) atomicMax(&sc->max_v2_bits, __float_as_uint(mv));
+  }
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------- launchers ----
@@ -225,17 +506,31 @@ void launch_timestep(Ctx& c, float frame_time, float cfl) {
   c.launches += 1;
 }
 
+// EULER_GRID_VARIANT=1 selects the one-cell-per-thread kernels (A/B runs)
+static bool scalar_variant() {
+  static const int v = getenv("EULER_GRID_VARIANT") ? atoi(getenv("EULER_GRID_VARIANT")) : 0;
+  return v == 1;
+}
+
 void launch_extrapolate(Ctx& c) {
   ProfScope ps(c, KC_EXTRAPOLATE);
-  k_extrapolate_bounds<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
-      c.g, c.u, c.v, c.count, c.prev_count, c.solid, c.uext, c.vext);
+  if (scalar_variant())
+    k_extrapolate_bounds_scalar<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
+        c.g, c.u, c.v, c.count, c.prev_count, c.solid, c.uext, c.vext);
+  else
+    k_extrapolate_bounds<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
+        c.g, c.u, c.v, c.count, c.prev_count, c.solid, c.uext, c.vext);
   c.launches += 1;
 }
 
 void launch_advect_velocity(Ctx& c, float dt) {
   ProfScope ps(c, KC_ADVECT_VELOCITY);
-  k_advect_velocity<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
-      c.g, c.lim, c.u, c.v, c.count, c.solid, c.utmp, c.vtmp, dt, c.h, c.gravity);
+  if (scalar_variant())
+    k_advect_velocity_scalar<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
+        c.g, c.lim, c.u, c.v, c.count, c.solid, c.utmp, c.vtmp, dt, c.h, c.gravity);
+  else
+    k_advect_velocity<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
+        c.g, c.lim, c.u, c.v, c.count, c.solid, c.utmp, c.vtmp, dt, c.h, c.gravity);
   c.launches += 1;
 }
 
@@ -243,8 +538,12 @@ void launch_build_rhs(Ctx& c, float dt) {
   ProfScope ps(c, KC_BUILD_RHS);
   cudaMemsetAsync(&c.sc->nonzero_rhs, 0, sizeof(int), c.stream);
   const double scale = (double)((c.h * c.h) * c.rho / dt);     // fp32 expression, main.c:713
-  k_build_rhs<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
-      c.g, c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc, c.own0, c.own1);
+  if (scalar_variant())
+    k_build_rhs_scalar<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
+        c.g, c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc, c.own0, c.own1);
+  else
+    k_build_rhs<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
+        c.g, c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc, c.own0, c.own1);
   c.launches += 1;
 }
 
@@ -252,8 +551,12 @@ void launch_pressure_update(Ctx& c, float dt) {
   ProfScope ps(c, KC_PRESSURE_UPDATE);
   cudaMemsetAsync(&c.sc->max_u2_bits, 0, 2 * sizeof(unsigned int), c.stream);
   const float k = 1.f / (c.rho * c.h);                          // invf(rho*h), main.c:706
-  k_pressure_update<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
-      c.g, c.p, c.utmp, c.vtmp, c.count, c.solid, c.u, c.v, dt, k, c.sc, c.own0, c.own1);
+  if (scalar_variant())
+    k_pressure_update_scalar<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
+        c.g, c.p, c.utmp, c.vtmp, c.count, c.solid, c.u, c.v, dt, k, c.sc, c.own0, c.own1);
+  else
+    k_pressure_update<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
+        c.g, c.p, c.utmp, c.vtmp, c.count, c.solid, c.u, c.v, dt, k, c.sc, c.own0, c.own1);
   c.launches += 1;
 }
 

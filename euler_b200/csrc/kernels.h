@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "interp.cuh"
+#include "p2p.cuh"
 
 namespace euler {
 
@@ -72,6 +73,12 @@ struct Ctx {
   unsigned int* wf_progress;      // wavefront strip progress flags
   int n_strips;
   DevScalars* sc;                 // device scalars
+  // row slabs, NVLink path (p2p.cuh): 0 = exchanges by NCCL, 1 = separate exchange kernels,
+  // 2 = exchanges fused into the producing kernels' epilogues (default when peers are mapped)
+  int p2p_mode;
+  DistArgs dist;                  // z_dn / z_up here are row 0 of the neighbours' planes
+  int p2p_dn_own1, p2p_up_own0;   // the neighbours' owned-row bounds in their local rows
+  double tol;                     // PCG stop tolerance (main.c:736)
 };
 
 // RAII: when profiling is on, brackets the launches of one kernel class with CUDA events on
@@ -111,6 +118,8 @@ void launch_sources_count(Ctx& c);
 void launch_sources_prep(Ctx& c, const double* gathered, int rank, int nranks);
 void launch_partition_markers(Ctx& c, int own_lo_global, int own_hi_global, float2* send_dn,
                               float2* send_up, size_t send_cap, unsigned long long* n_keep);
+// slab create/reinit: append the staged markers of rows [lo, hi) to c.markers at sc->n_markers
+void launch_filter_markers(Ctx& c, const float2* staged, size_t n, int own_lo_global, int own_hi_global);
 void init_rng_jump_table(unsigned long long* host_table /* 64*64 */);
 size_t marker_candidate_bytes();
 

@@ -526,6 +526,36 @@ __global__ void __launch_bounds__(MTHREADS) k_partition_markers(
   }
 }
 
+// create()/reinit() of a slab handle: of `n` staged markers, append those whose cell row is
+// in [own_lo, own_hi) to `dst` at sc->n_markers (warp-aggregated append; order is free in
+// FAST marker mode).  Markers beyond `cap` are counted but not stored: the caller checks.
+__global__ void __launch_bounds__(MTHREADS) k_filter_markers(
+    float h, int own_lo, int own_hi, const float2* __restrict__ src, size_t n,
+    float2* __restrict__ dst, size_t cap, DevScalars* sc) {
+  const size_t per = (size_t)gridDim.x * blockDim.x;
+  const size_t rounds = (n + per - 1) / per;
+  const int lane = threadIdx.x & 31;
+  for (size_t rd = 0; rd < rounds; ++rd) {
+    const size_t i = rd * per + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool mine = false;
+    float2 m = make_float2(0.f, 0.f);
+    if (i < n) {
+      m = src[i];
+      const int gy = (int)floorf(div_h(m.y, h));
+      mine = gy >= own_lo && gy < own_hi;
+    }
+    const unsigned bal = __ballot_sync(EULER_FULL_MASK, mine);
+    if (!bal) continue;
+    unsigned long long base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(&sc->n_markers, (unsigned long long)__popc(bal));
+    base = __shfl_sync(EULER_FULL_MASK, base, __ffs(bal) - 1);
+    if (mine) {
+      const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+      if (pos < cap) dst[pos] = m;
+    }
+  }
+}
+
 // source cells of this slab that need a marker (main.c:287), for the cross-rank prefix
 __global__ void __launch_bounds__(1024) k_sources_count(const unsigned int* __restrict__ cells,
                                                         size_t ncells, const uint8_t* __restrict__ count,
@@ -745,6 +775,13 @@ void launch_partition_markers(Ctx& c, int own_lo_global, int own_hi_global, floa
       c.h, own_lo_global, own_hi_global, c.markers, c.markers_alt, send_dn, send_up, send_cap, c.sc, n_keep);
   c.launches += 1;
   float2* t = c.markers; c.markers = c.markers_alt; c.markers_alt = t;
+}
+
+void launch_filter_markers(Ctx& c, const float2* staged, size_t n, int own_lo_global, int own_hi_global) {
+  if (!n) return;
+  k_filter_markers<<<c.sm_count * 8, MTHREADS, 0, c.stream>>>(c.h, own_lo_global, own_hi_global, staged, n,
+                                                              c.markers, c.max_markers, c.sc);
+  c.launches += 1;
 }
 
 }  // namespace euler

@@ -1,0 +1,112 @@
+// euler_b200/csrc/p2p.cuh — device side of the NVLink peer-to-peer exchanges of the slab solve
+// ("PCG s halo, every iteration" and "PCG scalars, every iteration").
+//
+// With CUDA IPC every rank maps its neighbours' z plane and all ranks' mailboxes (comm.cu).
+// The exchanges are then plain stores over NVLink followed by a system-scope release of a flag
+// in the RECEIVER's memory; consumers spin on flags in their own memory with a bounded poll
+// count (a lost peer sets DevScalars::comm_timeout instead of hanging the GPU).
+//
+// The exchanges are fused into the kernels that produce the data (pcg_kernels.cu):
+//   * k_rb_backward_pipe stores the edge rows of z = M^-1 r into the neighbours' halo rows as
+//     it computes them, and the block that finishes last raises the neighbours' halo flags,
+//     pushes {z.r, ||r||inf} into every rank's mailbox, waits for everybody's and finishes
+//     beta / sigma / the stop test (reference main.c:756-765);
+//   * k_fused_search_apply's last block does the same for {z.s} -> alpha (main.c:752).
+// A PCG iteration on a slab is therefore the same four launches as on a single GPU.
+#pragma once
+#include "common.cuh"
+
+namespace euler {
+
+constexpr int P2P_MAX_RANKS = 16;
+constexpr int P2P_HALO_DEPTH = 4;      // rows of z exchanged per iteration (== SLAB_HALO, api.cu)
+
+struct Mailbox {                       // lives in each rank's device memory, zero-initialised
+  double pay[2][P2P_MAX_RANKS][4];     // [sequence parity][sender][slot]
+  unsigned long long flag[2][P2P_MAX_RANKS];
+  unsigned long long halo_flag[2];     // [0] written by the lower neighbour, [1] by the upper
+  unsigned long long seq_ctr;          // scalar exchanges this rank has completed (owner-private)
+  unsigned long long halo_ctr;         // halo exchanges this rank has posted (owner-private)
+  unsigned int halo_done;              // block counter of k_p2p_halo
+};
+
+// What a kernel needs to finish a reduction across ranks / to store halo rows into the
+// neighbours.  All zero (mine == nullptr) on a single GPU and on the NCCL path.
+struct DistArgs {
+  Mailbox* mine;
+  Mailbox* peer[P2P_MAX_RANKS];        // peer[r] = rank r's mailbox as mapped here
+  Mailbox *mb_dn, *mb_up;              // the neighbours' mailboxes (null at the ends)
+  double *z_dn, *z_up;                 // neighbours' z plane, biased so that index gidx(view, x, y)
+                                       // of an owned edge row lands in the matching halo row
+  int rank, nranks;
+  int depth;                           // halo rows exchanged
+  int pad;
+};
+
+constexpr unsigned long long P2P_POLL_LIMIT = 1ull << 24;    // seconds at most; then give up, no hang
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long want) {
+  for (unsigned long long i = 0; i < P2P_POLL_LIMIT; ++i)
+    if (ld_acquire_sys(p) >= want) return true;
+  return false;
+}
+
+// The scalar step that follows a grid-wide reduction, finished across ranks.  Called by ALL
+// threads of ONE block (>= 64 threads) after the local reduction is complete and — with
+// `halo` — after every block of the grid has fenced its peer stores at system scope.
+//   kind 0: part0 = z.s partial            -> alpha                      (main.c:752)
+//   kind 1: part0 = z.r partial, part[1] = ||r||inf partial left by k_axpy
+//           init: sigma = z.r (main.c:748); else stop test + beta, sigma (main.c:756-765)
+// Partials are folded in rank order on every rank: identical, deterministic results.
+__device__ __forceinline__ void p2p_finish(const DistArgs& d, DevScalars* sc, int kind, int init,
+                                           double tol, double part0, bool halo) {
+  const int t = threadIdx.x;
+  __shared__ int ok_sh;
+  Mailbox* mine = d.mine;
+  const unsigned long long seq = mine->seq_ctr;
+  const unsigned long long hseq = mine->halo_ctr + 1;
+  const int par = (int)(seq & 1ull);
+  if (t == 0) ok_sh = 1;
+  __syncthreads();
+  if (halo) {
+    // I am the lower neighbour's UPPER neighbour and vice versa
+    if (t == 32 && d.mb_dn) { __threadfence_system(); st_release_sys(&d.mb_dn->halo_flag[1], hseq); }
+    if (t == 33 && d.mb_up) { __threadfence_system(); st_release_sys(&d.mb_up->halo_flag[0], hseq); }
+  }
+  if (t < d.nranks) {
+    Mailbox* dst = d.peer[t];
+    dst->pay[par][d.rank][0] = part0;
+    dst->pay[par][d.rank][1] = sc->part[1];
+    __threadfence_system();
+    st_release_sys(&dst->flag[par][d.rank], seq + 1);
+    if (!wait_flag(&mine->flag[par][t], seq + 1)) ok_sh = 0;
+  }
+  if (halo) {
+    if (t == 34 && d.mb_dn && !wait_flag(&mine->halo_flag[0], hseq)) ok_sh = 0;
+    if (t == 35 && d.mb_up && !wait_flag(&mine->halo_flag[1], hseq)) ok_sh = 0;
+  }
+  __syncthreads();
+  if (t != 0) return;
+  mine->seq_ctr = seq + 1;
+  if (halo) mine->halo_ctr = hseq;
+  if (!ok_sh) { sc->comm_timeout = 1; sc->done = 1; return; }
+  double sum = 0.0, mx = 0.0;
+  for (int r = 0; r < d.nranks; ++r) { sum += mine->pay[par][r][0]; mx = fmax(mx, mine->pay[par][r][1]); }
+  if (kind == 0) { sc->zs = sum; sc->alpha = sc->sigma / sum; return; }      // main.c:752
+  if (init) { sc->sigma = sum; return; }                                      // main.c:748
+  sc->resid = mx;
+  sc->iters += 1;
+  if (mx <= tol) { sc->done = 1; return; }                                    // main.c:756-758
+  sc->beta = sum / sc->sigma;                                                 // main.c:762-765
+  sc->sigma = sum;
+}
+
+}  // namespace euler

@@ -29,9 +29,14 @@
 // every element-wise result bit-identical to the CPU's; only the order of the dot-product
 // sums differs.
 #include "kernels.h"
+#include "p2p.cuh"
 #include "pcg_pipe.cuh"
 
 #include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <utility>
 
 namespace euler {
 
@@ -159,15 +164,17 @@ __device__ __forceinline__ void stencil_tile(const Grid& g, const uint8_t* __res
 
 template <class Body>
 __device__ __forceinline__ void for_each_tile(const Grid& g, const TileList& tl, Body body) {
-  const Tiles T = tiles_of(g);
-  const int n = (int)*tl.count;
-  for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    const int tile = tl.list[i];
-    const int x0 = (tile % T.tx) * TW + threadIdx.x * 4, y0 = (tile / T.tx) * g.th;
+  // balanced split of the active tiles' rows over the persistent grid (pcg_pipe.cuh ChunkIter)
+  const pipe::Tiles T = pipe::tiles_of(g, g.th);
+  pipe::ChunkIter ch;
+  ch.start((int)*tl.count, g.th);
+  pipe::Piece p;
+  while (ch.next(g, T, g.th, tl.list, p)) {
+    const int x0 = p.x0 + threadIdx.x * 4;
     // threads past the row end keep participating in the shuffles with a clamped, harmless
     // address (their mask is the zero padding / they are never asked for a valid neighbour)
     const int xs = min(x0, g.pitch - 4);
-    body(xs, y0, min(y0 + g.th, g.ny), x0 < g.pitch);
+    body(xs, p.y0, p.y1, x0 < g.pitch);
   }
 }
 
@@ -304,24 +311,32 @@ __device__ __forceinline__ double rb_e_red(const int8_t* __restrict__ adiag, siz
   return a != 0.0 ? a : 1.0;
 }
 
+// A thread looks at four consecutive cells through one 32-bit mask load and leaves at once
+// when none of them is fluid (most of a free-surface scene).
 __global__ void __launch_bounds__(256) k_rb_build(
     Grid g, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
     double* __restrict__ precon) {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if (x < 1 || y + g.yoff < 1 || x >= g.nx - 1 || y + g.yoff >= g.gny - 1 || y >= g.ny) return;
-  const size_t c = gidx(g, x, y);
-  if (!fluid[c]) return;
-  if (((x + y + g.yoff) & 1) == 0) { precon[c] = 1.0 / sqrt(rb_e_red(adiag, c)); return; }
-  const double a = (double)adiag[c];
-  double e = a;
-  const long off[4] = {-1, 1, -(long)g.pitch, (long)g.pitch};
+  const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
+  if (x0 >= g.pitch || y >= g.ny || y + g.yoff < 1 || y + g.yoff >= g.gny - 1) return;
+  const unsigned mf = ldmask(fluid + gidx(g, x0, y));
+  if (!mf) return;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const size_t nb = c + off[k];
-    if (fluid[nb]) e = e - 1.0 / rb_e_red(adiag, nb);
+    const int x = x0 + k;
+    if (!mbit(mf, k) || x < 1 || x >= g.nx - 1) continue;
+    const size_t c = gidx(g, x, y);
+    if (((x + y + g.yoff) & 1) == 0) { precon[c] = 1.0 / sqrt(rb_e_red(adiag, c)); continue; }
+    const double a = (double)adiag[c];
+    double e = a;
+    const long off[4] = {-1, 1, -(long)g.pitch, (long)g.pitch};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t nb = c + off[j];
+      if (fluid[nb]) e = e - 1.0 / rb_e_red(adiag, nb);
+    }
+    if (e < 0.25 * a) e = a != 0.0 ? a : 1.0;
+    precon[c] = 1.0 / sqrt(e);
   }
-  if (e < 0.25 * a) e = a != 0.0 ? a : 1.0;
-  precon[c] = 1.0 / sqrt(e);
 }
 
 // q = L^-1 r.  Red: q = r*pc.  Black: q = (r + sum_nb pc_nb*(r_nb*pc_nb)) * pc.  The window
@@ -629,7 +644,7 @@ struct RbForwardPipe {
 };
 
 template <int NS, int C>
-__global__ void __launch_bounds__(TW / C) k_rb_forward_pipe(
+__global__ void __launch_bounds__(TW / C, C == 2 ? 4 : 5) k_rb_forward_pipe(
     Grid g, TileList active, const double* __restrict__ r,
     const uint8_t* __restrict__ fluid, const double* __restrict__ precon, double* __restrict__ q,
     const DevScalars* sc) {
@@ -647,6 +662,10 @@ struct RbBackwardPipe {
   double* __restrict__ z;
   double acc;
   int a0, a1;
+  // slab mode, NVLink path: the neighbours' z planes (biased, see DistArgs) and the halo depth
+  double* __restrict__ z_dn;
+  double* __restrict__ z_up;
+  int depth;
   __device__ __forceinline__ void row(const pipe::RowView<3, 1>& dn, const pipe::RowView<3, 1>& ce,
                                       const pipe::RowView<3, 1>& up, int t4, int x, int y, bool live) {
     const unsigned mc = live ? ldsm<C>(ce.b[0] + t4) : 0u;
@@ -681,7 +700,13 @@ struct RbBackwardPipe {
     }
     // only the owned rows are stored: the halo rows of z belong to the neighbouring slabs,
     // which write them directly (NVLink peer stores) or through the halo exchange
-    if (y >= a0 && y < a1) stv<C>(z + gidx(g, x, y), out);
+    if (y >= a0 && y < a1) {
+      const size_t c = gidx(g, x, y);
+      stv<C>(z + c, out);
+      // my edge rows are the neighbours' halo rows: stored there as they are produced
+      if (z_dn && y < a0 + depth) stv<C>(z_dn + c, out);
+      if (z_up && y >= a1 - depth) stv<C>(z_up + c, out);
+    }
   }
 };
 
@@ -690,19 +715,26 @@ __global__ void __launch_bounds__(TW / C) k_rb_backward_pipe(
     Grid g, TileList active, const double* __restrict__ q,
     const double* __restrict__ r, const uint8_t* __restrict__ fluid,
     const double* __restrict__ precon, double* __restrict__ z, double* partials, DevScalars* sc,
-    int init, int exact, int acc0, int acc1) {
+    int init, int exact, int acc0, int acc1, double tol, const __grid_constant__ DistArgs dist) {
   if (sc->done) return;
-  RbBackwardPipe<C> op{g, z, 0.0, acc0, acc1};
+  RbBackwardPipe<C> op{g, z, 0.0, acc0, acc1, dist.z_dn, dist.z_up, dist.depth};
   pipe::Planes<3, 1> in;
   in.d[0] = q; in.d[1] = precon; in.d[2] = r; in.b[0] = fluid;
   pipe::run<3, 1, NS, TH, RbBackwardPipe<C>, C>(g, active.list, (int)*active.count, in, op);
+  // peer stores of this thread are performed system-wide before the block reports in
+  if (dist.mine) __threadfence_system();
   const double bsum = block_reduce<false>(op.acc);
-  grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZR], [&](double total) {
-    if (exact == 2) { sc->part[0] = total; return; }
-    if (exact) return;
-    if (init) { sc->sigma = total; }                         // main.c:748
-    else { sc->beta = total / sc->sigma; sc->sigma = total; }  // main.c:762-765
-  });
+  double total;
+  if (!grid_reduce_last_block_all<false>(bsum, partials, &sc->ctr[CTR_ZR], total)) return;
+  if (dist.mine) {                                           // halo flags + {z.r, ||r||inf} over NVLink
+    p2p_finish(dist, sc, 1, init, tol, total, true);
+    return;
+  }
+  if (threadIdx.x != 0) return;
+  if (exact == 2) { sc->part[0] = total; return; }
+  if (exact) return;
+  if (init) { sc->sigma = total; }                           // main.c:748
+  else { sc->beta = total / sc->sigma; sc->sigma = total; }  // main.c:762-765
 }
 
 // ---- slab mode: fold the all-gathered partials (rank order => deterministic) --------------
@@ -807,18 +839,24 @@ template <int NS, int C>
 __global__ void __launch_bounds__(TW / C) k_fused_search_apply(
     Grid g, TileList active, const double* __restrict__ z, const double* __restrict__ s,
     const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ s_new,
-    double* __restrict__ as, double* partials, DevScalars* sc, int init, int exact, int acc0, int acc1) {
+    double* __restrict__ as, double* partials, DevScalars* sc, int init, int exact, int acc0, int acc1,
+    const __grid_constant__ DistArgs dist) {
   if (sc->done) return;
   FusedSearchApply<C> op{g, s_new, as, sc->beta, init != 0, 0.0, acc0, acc1};
   pipe::Planes<2, 2> in;
   in.d[0] = z; in.d[1] = s; in.b[0] = fluid; in.b[1] = reinterpret_cast<const uint8_t*>(adiag);
   pipe::run<2, 2, NS, TH, FusedSearchApply<C>, C>(g, active.list, (int)*active.count, in, op);
   const double bsum = block_reduce<false>(op.acc);
-  grid_reduce_last_block<false>(bsum, partials, &sc->ctr[CTR_ZS], [&](double total) {
-    if (exact == 2) { sc->part[0] = total; return; }
-    sc->zs = total;
-    sc->alpha = sc->sigma / total;                           // main.c:752
-  });
+  double total;
+  if (!grid_reduce_last_block_all<false>(bsum, partials, &sc->ctr[CTR_ZS], total)) return;
+  if (dist.mine) {                                           // {z.s} over NVLink -> alpha
+    p2p_finish(dist, sc, 0, 0, 0.0, total, false);
+    return;
+  }
+  if (threadIdx.x != 0) return;
+  if (exact == 2) { sc->part[0] = total; return; }
+  sc->zs = total;
+  sc->alpha = sc->sigma / total;                             // main.c:752
 }
 
 template <int C>
@@ -919,14 +957,30 @@ constexpr int CPT_F = 2, CPT_B = 2, CPT_KA = 4;   // cells per thread of the pip
 // the number of tiles
 template <class K>
 int pcg_blocks(const Ctx& c, K kernel, int smem = 0, int threads = TT) {
+  // occupancy is a property of (kernel, threads, smem) on this architecture: asked once per
+  // kernel and host thread, not on every launch (two driver calls per launch were a visible
+  // share of the host time per PCG iteration on thin slabs)
+  // (the shared-memory opt-in is per device, hence the device in the key)
+  thread_local std::map<std::pair<const void*, int>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), dev);
   int per_sm = 0;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
-    per_sm = 1;
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    per_sm = it->second;
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    cache[key] = per_sm;
+  }
+  // at most one block per 8 rows of a tile column, so that tiny grids do not pay two halo
+  // rows per output row
   const Tiles T = tiles_of(c.g);
-  const long want = (long)c.sm_count * per_sm;
-  return (int)(T.n < want ? T.n : want);
+  const long want = (long)c.sm_count * per_sm, cap = (long)T.n * c.g.th / 8;
+  return (int)(cap < 1 ? 1 : (cap < want ? cap : want));
 }
 
 }  // namespace
@@ -954,10 +1008,9 @@ static PV pview(const Ctx& c) {
   PV v;
   v.g = c.g; v.g.ny = hi - lo; v.g.yoff = c.g.yoff + lo;
   v.a0 = c.own0 - lo; v.a1 = c.own1 - lo;
-  // tile height: 32 rows amortise the two halo rows best, but a thin slab must still give
-  // every resident block (~5 per SM) a few tiles to pipeline over
+  // tiles are only the unit of the "contains fluid" flags; the persistent kernels split the
+  // active tiles' ROWS evenly over their blocks, so a thin slab needs no smaller tile
   v.g.th = TH;
-  while (v.g.th > 8 && (long)tiles_of(v.g).n < 12L * c.sm_count) v.g.th >>= 1;
   v.fluid = c.count + o; v.adiag = c.adiag + o;
   v.s = c.s + o; v.z = c.z + o; v.r = c.r + o; v.p = c.p + o; v.q = c.q + o; v.precon = c.precon + o;
   return v;
@@ -1036,7 +1089,7 @@ void launch_copy_search(Ctx& c) {
 void launch_rb_build(Ctx& c) {
   // over ALL locally stored rows: halo rows get their own (identical) factor, no exchange
   ProfScope ps(c, KC_PRECON_BUILD);
-  k_rb_build<<<dim3((c.g.nx + 31) / 32, (c.g.ny + 7) / 8), dim3(32, 8), 0, c.stream>>>(
+  k_rb_build<<<dim3((c.g.pitch / 4 + 31) / 32, (c.g.ny + 7) / 8), dim3(32, 8), 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon);
   c.launches += 1;
 }
@@ -1065,9 +1118,24 @@ void launch_rb_backward(Ctx& c, bool init) {
   if (c.use_pipe) {
     static const int ns = env_int("EULER_NS_B", NS_B);
     static const int cpt = env_int("EULER_CPT_B", CPT_B);
+    // NVLink path: this kernel also stores its edge rows into the neighbours' halo rows and its
+    // last block finishes {z.r, ||r||inf} across ranks (p2p.cuh).  The neighbours' planes are
+    // biased so that gidx(view, x, y) of an owned edge row addresses the matching halo row:
+    // view row y = local row y + lo; my first owned row <-> their first row above their owned
+    // rows, my last owned row <-> their last row below their owned rows.
+    DistArgs d;
+    memset(&d, 0, sizeof d);
+    if (c.p2p_mode == 2) {
+      d = c.dist;
+      d.depth = P2P_HALO_DEPTH;
+      const long lo = (long)((v.z - c.z) / c.g.pitch);
+      if (d.z_dn) d.z_dn += (lo + c.p2p_dn_own1 - c.own0) * (long)c.g.pitch;
+      if (d.z_up) d.z_up += (lo + c.p2p_up_own0 - c.own1) * (long)c.g.pitch;
+    }
 #define BWD(N, C) { constexpr int sb = pipe::smem_bytes<3, 1, N>(); \
     k_rb_backward_pipe<N, C><<<pcg_blocks(c, k_rb_backward_pipe<N, C>, sb, TW / C), TW / C, sb, c.stream>>>( \
-        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c), v.a0, v.a1); }
+        v.g, TL, v.q, v.r, v.fluid, v.precon, v.z, c.partials, c.sc, init ? 1 : 0, dotflag(c), v.a0, v.a1, \
+        c.tol, d); }
     if (cpt == 2) { if (ns == 4) BWD(4, 2) else if (ns == 6) BWD(6, 2) else BWD(5, 2) }
     else { if (ns == 4) BWD(4, 4) else if (ns == 6) BWD(6, 4) else BWD(5, 4) }
 #undef BWD
@@ -1095,10 +1163,13 @@ void launch_fused_search_apply(Ctx& c, bool init) {
   const size_t o = (size_t)(v.s - c.s);
   static const int ns = env_int("EULER_NS_KA", NS_KA);
   static const int cpt = env_int("EULER_CPT_KA", CPT_KA);
+  DistArgs d;                     // NVLink path: the last block finishes {z.s} across ranks
+  memset(&d, 0, sizeof d);
+  if (c.p2p_mode == 2) d = c.dist;
 #define KA(N, C) { constexpr int smem = pipe::smem_bytes<2, 2, N>(); \
   k_fused_search_apply<N, C><<<pcg_blocks(c, k_fused_search_apply<N, C>, smem, TW / C), TW / C, smem, c.stream>>>( \
       v.g, TL, v.z, v.s, v.fluid, v.adiag, c.s2 + o, v.q, c.partials, c.sc, init ? 1 : 0, \
-      c.distributed ? 2 : 0, v.a0, v.a1); }
+      c.distributed ? 2 : 0, v.a0, v.a1, d); }
   if (cpt == 2) { if (ns == 6) KA(6, 2) else if (ns == 5) KA(5, 2) else KA(4, 2) }
   else { if (ns == 6) KA(6, 4) else if (ns == 5) KA(5, 4) else KA(4, 4) }
 #undef KA

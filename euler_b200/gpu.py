@@ -64,6 +64,7 @@ _L.euler_gpu_default_params.argtypes = [C.POINTER(Params)]
 _L.euler_gpu_create.argtypes = [C.POINTER(_H), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_size_t, C.POINTER(Params)]
 _L.euler_gpu_destroy.argtypes = [_H]
+_L.euler_gpu_reinit.argtypes = [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]
 _L.euler_gpu_step_frame.argtypes = [_H, C.POINTER(C.c_int)]
 _L.euler_gpu_calculate_timestep.argtypes = [_H, C.c_float, C.POINTER(C.c_float)]
 _L.euler_gpu_substep.argtypes = [_H, C.c_float]
@@ -148,6 +149,18 @@ class EulerGpu:
     def from_scenario(cls, scn, **overrides):
         overrides.setdefault("rng_state", scn.rng_state)
         return cls(scn.nx, scn.ny, scn.solid, scn.source, scn.sink, scn.markers, **overrides)
+
+    def reinit(self, solid, source, sink, markers, rng_state):
+        """sim_init() again on this handle (euler_gpu_reinit): host arrays in, no allocation."""
+        solid = np.ascontiguousarray(solid, dtype=np.uint8)
+        source = np.ascontiguousarray(source, dtype=np.uint8)
+        sink = np.ascontiguousarray(sink, dtype=np.uint8)
+        markers = np.ascontiguousarray(markers, dtype=np.float32).reshape(-1, 2)
+        for a in (solid, source, sink):
+            if a.shape != (self.ny, self.nx):
+                raise ValueError("shape %r != %r" % (a.shape, (self.ny, self.nx)))
+        _ck(_L.euler_gpu_reinit(self._h, solid.ctypes.data, source.ctypes.data, sink.ctypes.data,
+                                markers.ctypes.data, len(markers), int(rng_state)))
 
     def close(self):
         if getattr(self, "_h", None):

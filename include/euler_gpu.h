@@ -185,6 +185,14 @@ int euler_gpu_create(euler_gpu **out, int nx, int ny,
                      const float *markers_xy, size_t n_markers,
                      const euler_params *params);
 int euler_gpu_destroy(euler_gpu *h);
+/* sim_init() again on an existing handle (same grid, same params): the hand-over of create()
+ * without the allocation — new masks, markers and RNG state go to the device, every dynamic
+ * plane (u, v, counts, the persistent g_precon, the PCG vectors) restarts from zero like the
+ * reference's zero-initialised globals (main.c:64-100, 577), refresh_marker_counts runs once
+ * (main.c:268).  Statistics keep counting.  On slab handles: collective (halo exchange of the
+ * count plane), after euler_gpu_comm_init. */
+int euler_gpu_reinit(euler_gpu *h, const uint8_t *solid, const uint8_t *source, const uint8_t *sink,
+                     const float *markers_xy, size_t n_markers, uint64_t rng_state);
 
 /* sim_step() (main.c:843-900): up to max_substeps adaptive sub-steps covering frame_time.
  * Returns after the frame's work is complete on the device.  *substeps may be NULL. */

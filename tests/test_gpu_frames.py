@@ -189,3 +189,26 @@ def test_known_answers_through_gpu(known_answers):
         assert int(st.n_markers) == want["markers"] and "%016x" % st.rng_state == want["rng_state"]
         assert abs(float(np.abs(g.get(G.F_U).astype(np.float64)).sum()) - want["sum_abs_u"]) < 1e-9
         g.close()
+
+
+@pytest.mark.parametrize("precon,marker_mode", [(0, 0), (1, 1)])
+def test_reinit_equals_fresh_handle(precon, marker_mode):
+    """euler_gpu_reinit == sim_init (main.c:209-274) into an existing handle: after dirtying every
+    plane (incl. the persistent g_precon) the run that follows is bit-identical to a
+    fresh handle's."""
+    from euler_b200 import gpu as G
+    nx, ny = 160, 90
+    text = resample(shipped_text("waterfall"), nx - 2, ny - 2)
+    scn = Scenario(text, nx, ny)
+    other = Scenario(resample(shipped_text("block"), nx - 2, ny - 2), nx, ny)
+    a = G.EulerGpu.from_scenario(other, precon=precon, marker_mode=marker_mode)
+    for _ in range(8):
+        a.step_frame()
+    a.reinit(scn.solid, scn.source, scn.sink, scn.markers, scn.rng_state)
+    b = G.EulerGpu.from_scenario(scn, precon=precon, marker_mode=marker_mode)
+    for _ in range(20):
+        assert a.step_frame() == b.step_frame()
+    for f in (G.F_COUNT, G.F_PREV_COUNT, G.F_U, G.F_V, G.F_MARKERS, G.F_PRECON, G.F_P):
+        assert same_bits(a.get(f), b.get(f)), f
+    assert int(a.stats().rng_state) == int(b.stats().rng_state)
+    a.close(); b.close()
