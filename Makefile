@@ -33,9 +33,11 @@ host: $(LIBDIR)/libeuler_host.so bin/euler-gpu
 $(LIBDIR)/libeuler_host.so: $(HOST)/scenario.c $(HOST)/scenario.h
 	@mkdir -p $(LIBDIR)
 	$(CC) -std=gnu99 -O2 -ffp-contract=off -Wall -Wextra -fPIC -shared $< -lm -o $@
-bin/euler-gpu: $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c $(HOST)/scenario.h $(HOST)/render.h include/euler_gpu.h
+bin/euler-gpu: $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c $(HOST)/checkpoint.c $(HOST)/scenario.h $(HOST)/render.h \
+               $(HOST)/checkpoint.h include/euler_gpu.h
 	@mkdir -p bin
 	$(CC) -std=gnu99 -O2 -ffp-contract=off -Wall -Wextra -Iinclude $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c \
+	  $(HOST)/checkpoint.c \
 	  -ldl -lm -o $@
 
 oracle:

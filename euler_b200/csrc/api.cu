@@ -125,6 +125,9 @@ FieldInfo field_info(euler_gpu* h, int f) {
     case EULER_F_R: return {c.r, 8};
     case EULER_F_Z: return {c.z, 8};
     case EULER_F_S: return {c.s, 8};
+    case EULER_F_CR: return {c.cr, 4};
+    case EULER_F_CG: return {c.cg, 4};
+    case EULER_F_CB: return {c.cb, 4};
     default: return {nullptr, 0};
   }
 }
@@ -175,6 +178,8 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
     rc |= zero_plane(h, c.adiag); rc |= zero_plane(h, c.precon); rc |= zero_plane(h, c.q);
     rc |= zero_plane(h, c.p); rc |= zero_plane(h, c.r); rc |= zero_plane(h, c.z); rc |= zero_plane(h, c.s);
     rc |= zero_plane(h, c.s2); rc |= zero_plane(h, c.r2);
+    rc |= zero_plane(h, c.cr); rc |= zero_plane(h, c.cg); rc |= zero_plane(h, c.cb);
+    rc |= zero_plane(h, c.crtmp); rc |= zero_plane(h, c.cgtmp); rc |= zero_plane(h, c.cbtmp);
     if (rc) return rc;
     h->max_valid = false;
   }
@@ -240,6 +245,7 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
   CU(cudaStreamSynchronize(c.stream));      // `cells` and pageable host buffers go out of scope
 
   launch_refresh_counts(c);                                  // sim_init, main.c:268
+  launch_colorize(c);                                        // --rainbow, main.c:271-273
   if (h->slab && h->comm_ready) {
     // halo rows of the initial classification (only the owned markers were binned)
     if (comm_halo(c, h->cm, c.count, 1, SLAB_HALO)) return fail(EULER_E_COMM, "%s", comm_last_error());
@@ -324,11 +330,14 @@ int run_substep(euler_gpu* h, float dt) {
   prof_mark(h, 0);
   launch_advect_markers(c, dt, h->prm.marker_mode);          // main.c:855
   launch_refresh_counts(c);                                  // main.c:856
+  launch_extrapolate_color(c);                               // main.c:859-863 (--rainbow)
   launch_sources(c);                                         // main.c:864
+  launch_source_colors(c, (unsigned int)h->frames);          // main.c:283, 292-294 (--rainbow)
   prof_mark(h, 1);
   launch_extrapolate(c);                                     // main.c:865-868
   { float* t = c.u; c.u = c.uext; c.uext = t; t = c.v; c.v = c.vext; c.vext = t; }
   launch_advect_velocity(c, dt);                             // main.c:871-889
+  launch_advect_color(c, dt);                                // main.c:873-882 (--rainbow)
   prof_mark(h, 2);
   int rc = run_project(h, dt);                               // main.c:893
   if (rc) return rc;
@@ -586,6 +595,8 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
       return fail(EULER_E_UNSUPPORTED, "row slabs need precon=REDBLACK, marker_mode=FAST, dot_mode=TREE "
                   "(the IC(0) wavefront and the reference orders are sequential across the whole grid)");
   }
+  if (slab && prm.rainbow)
+    return fail(EULER_E_UNSUPPORTED, "--rainbow colour transport is not decomposed into slabs yet");
   const int row0 = slab ? prm.slab_row0 : 0, rows = slab ? prm.slab_rows : ny;
   const int lo = row0 - SLAB_HALO > 0 ? row0 - SLAB_HALO : 0;
   const int hi = row0 + rows + SLAB_HALO < ny ? row0 + rows + SLAB_HALO : ny;
@@ -627,6 +638,8 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.lim.u_y = nextafterf((float)(ny - 1), 0.f);
   c.lim.v_x = nextafterf((float)(nx - 1), 0.f);              // V is X x (Y-1)
   c.lim.v_y = nextafterf((float)(ny - 2), 0.f);
+  c.lim.p_x = nextafterf((float)(nx - 1), 0.f);              // P is X x Y
+  c.lim.p_y = nextafterf((float)(ny - 1), 0.f);
   c.h = prm.h; c.rho = prm.rho; c.gravity = prm.gravity;
   c.dot_mode = prm.dot_mode ? 1 : 0;
   c.tol = prm.tol;
@@ -662,6 +675,10 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.fused = (prm.precon == EULER_PRECON_REDBLACK && prm.dot_mode == EULER_DOT_TREE && prm.stencil_variant != 1)
                 ? (prm.stencil_variant == 2 ? 2 : 1) : 0;
   if (c.fused) { TRY(alloc_plane(h, &c.s2)); TRY(alloc_plane(h, &c.r2)); }
+  if (prm.rainbow) {
+    TRY(alloc_plane(h, &c.cr)); TRY(alloc_plane(h, &c.cg)); TRY(alloc_plane(h, &c.cb));
+    TRY(alloc_plane(h, &c.crtmp)); TRY(alloc_plane(h, &c.cgtmp)); TRY(alloc_plane(h, &c.cbtmp));
+  }
   TRY(alloc_array(h, &c.markers, max_markers));
   TRY(alloc_array(h, &c.markers_alt, max_markers));
   c.n_segments = (max_markers + 1023) / 1024;
@@ -784,6 +801,11 @@ int euler_gpu_run_stage(euler_gpu* h, int stage, float dt) {
       break;
     case EULER_S_APPLY_A: launch_pcg_reset(c); launch_tile_flags(c); launch_apply_a(c, false); break;
     case EULER_S_PRESSURE_UPDATE: launch_pressure_update(c, dt); h->max_valid = true; break;
+    case EULER_S_EXTRAPOLATE_COLOR:
+    case EULER_S_ADVECT_COLOR:
+      if (!c.cr) return fail(EULER_E_INVALID, "handle was created without params.rainbow");
+      if (stage == EULER_S_EXTRAPOLATE_COLOR) launch_extrapolate_color(c); else launch_advect_color(c, dt);
+      break;
     default: return fail(EULER_E_INVALID, "unknown stage %d", stage);
   }
   int rc = check_launch("run_stage");
@@ -834,6 +856,27 @@ int euler_gpu_get(euler_gpu* h, int field, void* dst, size_t bytes) {
   return 0;
 }
 
+int euler_gpu_read_window(euler_gpu* h, int field, int x0, int y0, int w, int hh, void* dst_global) {
+  ENTER(h);
+  if (!dst_global) return fail(EULER_E_INVALID, "dst is NULL");
+  FieldInfo fi = field_info(h, field);
+  if (!fi.ptr) return fail(EULER_E_INVALID, "field %d is not a plane", field);
+  if (x0 < 0 || y0 < 0 || w < 0 || hh < 0 || x0 + w > h->nx || y0 + hh > h->ny)
+    return fail(EULER_E_INVALID, "window [%d,%d)x[%d,%d) outside the %dx%d grid", x0, x0 + w, y0, y0 + hh, h->nx, h->ny);
+  const Grid& g = h->c.g;
+  // slab mode: the part of the window inside the rows this handle owns
+  const int ya = y0 > h->row0 ? y0 : h->row0;
+  const int yb = y0 + hh < h->row0 + h->rows ? y0 + hh : h->row0 + h->rows;
+  if (w > 0 && yb > ya) {
+    char* to = reinterpret_cast<char*>(dst_global) + ((size_t)ya * g.nx + x0) * fi.elem;
+    const char* from = reinterpret_cast<const char*>(fi.ptr) + ((size_t)(ya - h->lo) * g.pitch + x0) * fi.elem;
+    CU(cudaMemcpy2DAsync(to, (size_t)g.nx * fi.elem, from, g.pitch * fi.elem, (size_t)w * fi.elem,
+                         (size_t)(yb - ya), cudaMemcpyDeviceToHost, h->c.stream));
+  }
+  CU(cudaStreamSynchronize(h->c.stream));
+  return 0;
+}
+
 int euler_gpu_set(euler_gpu* h, int field, const void* src, size_t bytes) {
   ENTER(h);
   if (!src && bytes) return fail(EULER_E_INVALID, "src is NULL");
@@ -861,11 +904,25 @@ int euler_gpu_set(euler_gpu* h, int field, const void* src, size_t bytes) {
   return 0;
 }
 
+int euler_gpu_colorize(euler_gpu* h) {
+  ENTER(h);
+  if (!h->c.cr) return fail(EULER_E_INVALID, "handle was created without params.rainbow");
+  launch_colorize(h->c);
+  CU(cudaStreamSynchronize(h->c.stream));
+  return check_launch("colorize");
+}
+
 int euler_gpu_set_rng_state(euler_gpu* h, uint64_t state) {
   ENTER(h);
   unsigned long long s = state;
   CU(cudaMemcpyAsync(&h->c.sc->rng_state, &s, sizeof s, cudaMemcpyHostToDevice, h->c.stream));
   CU(cudaStreamSynchronize(h->c.stream));
+  return 0;
+}
+
+int euler_gpu_set_frame_count(euler_gpu* h, uint64_t frames) {
+  ENTER(h);
+  h->frames = frames;            // g_frame_count (main.c:89): only the source colours read it
   return 0;
 }
 
@@ -926,7 +983,7 @@ const char* euler_gpu_kernel_class_name(int i) {
       "maxsq", "advect_markers", "refresh_counts", "sources", "extrapolate_bounds",
       "advect_velocity", "build_rhs", "precon_build", "precon_apply", "apply_a", "axpy_norm",
       "update_search", "pressure_update", "misc", "fused_search_apply_a", "fused_axpy_forward",
-      "rb_forward", "rb_backward"};
+      "rb_forward", "rb_backward", "color_transport"};
   return (i >= 0 && i < KC__COUNT) ? names[i] : nullptr;
 }
 

@@ -488,6 +488,94 @@ __global__ void __launch_bounds__(QX* QY) k_pressure_update(
   }
 }
 
+
+// ===================================================== --rainbow colour transport ====
+// A passive RGB scalar on the P cells (reference main.c:76-84): colorize :187-201,
+// extrapolate(P) :859-863, source colours :292-294, advect_p :424-438 + the whole-plane copies
+// :873-882.  Off unless euler_params.rainbow; single-GPU handles only.
+
+// misc/color.h hsv_basis: periodic in t with period 6, values in [0,1]
+__device__ __forceinline__ float hsv_basis(float t) {
+  t -= 6.f * floorf(1.f / 6 * t);
+  if (t < 0.f) t += 6.f;
+  if (t < 1.f) return t;
+  if (t < 3.f) return 1.f;
+  if (t < 4.f) return 4.f - t;
+  return 0.f;
+}
+
+// colorize(), main.c:187-201: hue ramps along x+y with a period of 60 cells (k_initial_color_
+// period); source cells start at t = 0.  Fluid cells only.
+__global__ void __launch_bounds__(BX* BY) k_colorize(
+    Grid g, const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ source,
+    float* __restrict__ cr, float* __restrict__ cg, float* __restrict__ cb) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
+  if (x >= g.nx || y >= g.ny) return;
+  const size_t c = gidx(g, x, y);
+  if (!fluid[c]) return;
+  float t = 0.f;
+  if (!source[c]) t = (x + y + g.yoff) * 6.f / 60.f;
+  cr[c] = hsv_basis(t + 2.f);
+  cg[c] = hsv_basis(t);
+  cb[c] = hsv_basis(t - 2.f);
+}
+
+// extrapolate(g_r|g_g|g_b, P), main.c:859-863 with :158-185: a cell that is fluid now but was
+// not last sub-step takes the mean of the cells of its clamped 3x3 block that were.  In place:
+// the cells written are exactly those no other cell reads (they fail the `prev` test).
+__global__ void __launch_bounds__(BX* BY) k_extrapolate_color(
+    Grid g, const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ prev,
+    float* __restrict__ cr, float* __restrict__ cg, float* __restrict__ cb) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
+  if (x >= g.nx || y >= g.ny) return;
+  const size_t c = gidx(g, x, y);
+  if (prev[c] || !fluid[c]) return;
+  const int x0 = max(x - 1, 0), x1 = min(x + 1, g.nx - 1);
+  const int y0 = max(y - 1, -g.yoff), y1 = min(y + 1, g.gny - 1 - g.yoff);
+  float tr = 0.f, tg = 0.f, tb = 0.f;
+  int n = 0;
+  for (int yy = y0; yy <= y1; ++yy)
+    for (int xx = x0; xx <= x1; ++xx) {
+      const size_t k = gidx(g, xx, yy);
+      if (prev[k]) { tr += cr[k]; tg += cg[k]; tb += cb[k]; ++n; }
+    }
+  cr[c] = tr / (float)n;            // n == 0 -> NaN, as in the reference (assert off)
+  cg[c] = tg / (float)n;
+  cb[c] = tb / (float)n;
+}
+
+// the colour writes of update_fluid_sources, main.c:283, 292-294
+__global__ void k_source_colors(const unsigned int* __restrict__ cells, size_t n, float t,
+                                float* __restrict__ cr, float* __restrict__ cg, float* __restrict__ cb) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned int c = cells[i];
+  cr[c] = hsv_basis(t + 2.f);
+  cg[c] = hsv_basis(t);
+  cb[c] = hsv_basis(t - 2.f);
+}
+
+// advect_p x 3, main.c:424-438: back-trace from the cell centre with the mean of the two faces
+// either side, masked-bilinear sample of each colour plane there.  Only fluid cells are
+// written (the tmp planes keep their own older values elsewhere, like the reference's).
+__global__ void __launch_bounds__(BX* BY) k_advect_color(
+    Grid g, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
+    const uint8_t* __restrict__ fluid, const float* __restrict__ cr, const float* __restrict__ cg,
+    const float* __restrict__ cb, float* __restrict__ ro, float* __restrict__ go,
+    float* __restrict__ bo, float dt, float h) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
+  if (x >= g.nx || y >= g.ny) return;
+  const size_t c = gidx(g, x, y);
+  if (!fluid[c]) return;
+  const float dy = (v[c] + v[c - g.pitch]) / 2;
+  const float dx = (u[c] + u[c - 1]) / 2;
+  const float px = x - div_h(dx * dt, h);
+  const float py = (y + g.yoff) - div_h(dy * dt, h);
+  ro[c] = interpolate<CELL_P>(cr, fluid, g, lim, px, py);
+  go[c] = interpolate<CELL_P>(cg, fluid, g, lim, px, py);
+  bo[c] = interpolate<CELL_P>(cb, fluid, g, lim, px, py);
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------- launchers ----
@@ -558,6 +646,43 @@ void launch_pressure_update(Ctx& c, float dt) {
     k_pressure_update<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
         c.g, c.p, c.utmp, c.vtmp, c.count, c.solid, c.u, c.v, dt, k, c.sc, c.own0, c.own1);
   c.launches += 1;
+}
+
+// ---- --rainbow (no-ops unless the colour planes exist) -----------------------------------
+void launch_colorize(Ctx& c) {
+  if (!c.cr) return;
+  ProfScope ps(c, KC_COLOR);
+  k_colorize<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(c.g, c.count, c.source, c.cr, c.cg, c.cb);
+  c.launches += 1;
+}
+
+void launch_extrapolate_color(Ctx& c) {
+  if (!c.cr) return;
+  ProfScope ps(c, KC_COLOR);
+  k_extrapolate_color<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(c.g, c.count, c.prev_count, c.cr, c.cg, c.cb);
+  c.launches += 1;
+}
+
+void launch_source_colors(Ctx& c, unsigned int frame_count) {
+  if (!c.cr || !c.n_source_cells) return;
+  ProfScope ps(c, KC_COLOR);
+  const float t = 0.6f / 10.f * (float)(unsigned short)frame_count;    // main.c:83, 283 (uint16 count)
+  k_source_colors<<<(unsigned)((c.n_source_cells + 255) / 256), 256, 0, c.stream>>>(
+      c.source_cells, c.n_source_cells, t, c.cr, c.cg, c.cb);
+  c.launches += 1;
+}
+
+void launch_advect_color(Ctx& c, float dt) {
+  if (!c.cr) return;
+  ProfScope ps(c, KC_COLOR);
+  k_advect_color<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
+      c.g, c.lim, c.u, c.v, c.count, c.cr, c.cg, c.cb, c.crtmp, c.cgtmp, c.cbtmp, dt, c.h);
+  c.launches += 1;
+  // memcpy(g_r, g_rtmp, sizeof(g_r)) etc., main.c:875-881: whole planes
+  const size_t bytes = (size_t)c.g.ny * c.g.pitch * sizeof(float);
+  cudaMemcpyAsync(c.cr, c.crtmp, bytes, cudaMemcpyDeviceToDevice, c.stream);
+  cudaMemcpyAsync(c.cg, c.cgtmp, bytes, cudaMemcpyDeviceToDevice, c.stream);
+  cudaMemcpyAsync(c.cb, c.cbtmp, bytes, cudaMemcpyDeviceToDevice, c.stream);
 }
 
 }  // namespace euler

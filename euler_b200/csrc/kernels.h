@@ -13,7 +13,7 @@ enum KernelClass {
   KC_MAXSQ = 0, KC_ADVECT_MARKERS, KC_REFRESH_COUNTS, KC_SOURCES, KC_EXTRAPOLATE,
   KC_ADVECT_VELOCITY, KC_BUILD_RHS, KC_PRECON_BUILD, KC_PRECON_APPLY, KC_APPLY_A, KC_AXPY,
   KC_UPDATE_SEARCH, KC_PRESSURE_UPDATE, KC_MISC, KC_FUSED_A, KC_FUSED_B,
-  KC_PRECON_FWD, KC_PRECON_BWD, KC__COUNT
+  KC_PRECON_FWD, KC_PRECON_BWD, KC_COLOR, KC__COUNT
 };
 
 struct Prof {
@@ -45,6 +45,8 @@ struct Ctx {
   unsigned int* count32;          // atomic binning target, folded to uint8 afterwards
   // velocities (main.c:64-67) + one scratch pair for the out-of-place extrapolation
   float *u, *v, *utmp, *vtmp, *uext, *vext;
+  // --rainbow colour planes (main.c:77-82); null unless euler_params.rainbow
+  float *cr, *cg, *cb, *crtmp, *cgtmp, *cbtmp;
   // markers (main.c:92-95): ping-pong AoS float2 arrays
   float2 *markers, *markers_alt;
   size_t max_markers;             // capacity of the local arrays
@@ -109,6 +111,11 @@ void launch_extrapolate(Ctx& c);                             // (u,v) -> (uext,v
 void launch_advect_velocity(Ctx& c, float dt);               // (u,v) -> (utmp,vtmp)
 void launch_build_rhs(Ctx& c, float dt);                     // -> r, p=0, adiag, sc.nonzero_rhs
 void launch_pressure_update(Ctx& c, float dt);               // p,utmp,vtmp -> u,v (+max u2,v2)
+// --rainbow colour transport; all four return at once when the colour planes do not exist
+void launch_colorize(Ctx& c);                                // colorize(), main.c:187-201
+void launch_extrapolate_color(Ctx& c);                       // extrapolate(r|g|b, P), main.c:859-863
+void launch_source_colors(Ctx& c, unsigned int frame_count); // colour writes of main.c:292-294
+void launch_advect_color(Ctx& c, float dt);                  // advect_p x3 + copies, main.c:873-882
 
 // ---- markers (marker_kernels.cu)
 void launch_advect_markers(Ctx& c, float dt, int mode);      // in: markers, out: markers (swapped inside)

@@ -19,14 +19,16 @@ PRECON_IC0_WAVEFRONT, PRECON_REDBLACK = 0, 1
 MARKERS_REFERENCE, MARKERS_FAST = 0, 1
 DOT_TREE, DOT_REFERENCE_ORDER = 0, 1
 (F_U, F_V, F_UTMP, F_VTMP, F_SOLID, F_SOURCE, F_SINK, F_COUNT, F_PREV_COUNT, F_MARKERS,
- F_PRECON, F_Q, F_ADIAG, F_P, F_R, F_Z, F_S) = range(17)
+ F_PRECON, F_Q, F_ADIAG, F_P, F_R, F_Z, F_S, F_CR, F_CG, F_CB) = range(20)
 (S_ADVECT_MARKERS, S_REFRESH_COUNTS, S_SOURCES, S_EXTRAPOLATE, S_ADVECT_VELOCITY, S_PROJECT,
- S_BUILD_RHS, S_PRECONDITION, S_APPLY_A, S_PRESSURE_UPDATE) = range(10)
+ S_BUILD_RHS, S_PRECONDITION, S_APPLY_A, S_PRESSURE_UPDATE, S_EXTRAPOLATE_COLOR,
+ S_ADVECT_COLOR) = range(12)
 
 _DTYPES = {F_U: np.float32, F_V: np.float32, F_UTMP: np.float32, F_VTMP: np.float32,
            F_SOLID: np.uint8, F_SOURCE: np.uint8, F_SINK: np.uint8, F_COUNT: np.uint8,
            F_PREV_COUNT: np.uint8, F_PRECON: np.float64, F_Q: np.float64, F_ADIAG: np.int8,
-           F_P: np.float64, F_R: np.float64, F_Z: np.float64, F_S: np.float64}
+           F_P: np.float64, F_R: np.float64, F_Z: np.float64, F_S: np.float64,
+           F_CR: np.float32, F_CG: np.float32, F_CB: np.float32}
 
 
 class Params(C.Structure):
@@ -36,7 +38,7 @@ class Params(C.Structure):
                 ("precon", C.c_int), ("marker_mode", C.c_int), ("dot_mode", C.c_int),
                 ("rng_state", C.c_uint64),
                 ("device", C.c_int), ("stream", C.c_void_p), ("pcg_check_every", C.c_int), ("stencil_variant", C.c_int),
-                ("slab_row0", C.c_int), ("slab_rows", C.c_int)]
+                ("slab_row0", C.c_int), ("slab_rows", C.c_int), ("rainbow", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -71,9 +73,12 @@ _L.euler_gpu_substep.argtypes = [_H, C.c_float]
 _L.euler_gpu_run_stage.argtypes = [_H, C.c_int, C.c_float]
 _L.euler_gpu_read_marker_count.argtypes = [_H, C.c_void_p]
 _L.euler_gpu_get.argtypes = [_H, C.c_int, C.c_void_p, C.c_size_t]
+_L.euler_gpu_read_window.argtypes = [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
 _L.euler_gpu_set.argtypes = [_H, C.c_int, C.c_void_p, C.c_size_t]
 _L.euler_gpu_set_rng_state.argtypes = [_H, C.c_uint64]
+_L.euler_gpu_colorize.argtypes = [_H]
 _L.euler_gpu_set_source_exhausted.argtypes = [_H, C.c_int]
+_L.euler_gpu_set_frame_count.argtypes = [_H, C.c_uint64]
 _L.euler_gpu_stats.argtypes = [_H, C.POINTER(Stats)]
 _L.euler_gpu_set_profiling.argtypes = [_H, C.c_int]
 _L.euler_gpu_synchronize.argtypes = [_H]
@@ -217,7 +222,9 @@ class EulerGpu:
                 out[name.decode()] = (float(st.kernel_ms[i]), int(st.kernel_count[i]))
         return out
 
+    def colorize(self): _ck(_L.euler_gpu_colorize(self._h))
     def set_rng_state(self, s): _ck(_L.euler_gpu_set_rng_state(self._h, s))
+    def set_frame_count(self, n): _ck(_L.euler_gpu_set_frame_count(self._h, int(n)))
     def set_source_exhausted(self, e): _ck(_L.euler_gpu_set_source_exhausted(self._h, 1 if e else 0))
 
     @property
@@ -232,6 +239,13 @@ class EulerGpu:
         if out is None:
             out = np.empty((self.ny, self.nx), dtype=np.uint8)
         _ck(_L.euler_gpu_read_marker_count(self._h, out.ctypes.data))
+        return out
+
+    def read_window(self, field, x0, y0, w, h, out):
+        """Rectangle [x0,x0+w) x [y0,y0+h) of a plane into the same place of a global-shaped array."""
+        if out.shape != (self.ny, self.nx) or out.dtype != _DTYPES[field] or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous (ny, nx) array of the field's dtype")
+        _ck(_L.euler_gpu_read_window(self._h, field, x0, y0, w, h, out.ctypes.data))
         return out
 
     def get(self, field):

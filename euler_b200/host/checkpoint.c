@@ -1,0 +1,87 @@
+/* euler_b200/host/checkpoint.c — see checkpoint.h. */
+#include "checkpoint.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static const char MAGIC[8] = {'E', 'U', 'L', 'E', 'R', 'C', 'K', '1'};
+
+typedef struct header {
+  char magic[8];
+  int32_t nx, ny;
+  uint32_t flags;
+  uint32_t pad0;
+  uint64_t n_markers, rng_state, frames;
+  int32_t source_exhausted, pad1;
+} header;
+
+typedef struct plane_desc { int field; size_t elem; } plane_desc;
+static const plane_desc BASE[] = {{EULER_F_U, 4}, {EULER_F_V, 4}, {EULER_F_COUNT, 1}, {EULER_F_PREV_COUNT, 1},
+                                  {EULER_F_PRECON, 8}};
+static const plane_desc COLOR[] = {{EULER_F_CR, 4}, {EULER_F_CG, 4}, {EULER_F_CB, 4}};
+
+int euler_checkpoint_save(const euler_ckpt_api *a, euler_gpu *sim, int nx, int ny, int rainbow, const char *path) {
+  euler_stats st;
+  int rc = a->stats(sim, &st);
+  if (rc) return -rc;
+  header h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, MAGIC, 8);
+  h.nx = nx; h.ny = ny; h.flags = rainbow ? 1u : 0u;
+  h.n_markers = st.n_markers; h.rng_state = st.rng_state; h.frames = st.frames;
+  h.source_exhausted = st.source_exhausted;
+  const size_t cells = (size_t)nx * ny;
+  size_t big = cells * 8 > h.n_markers * 8 ? cells * 8 : (size_t)h.n_markers * 8;
+  void *buf = malloc(big ? big : 1);
+  FILE *f = fopen(path, "wb");
+  if (!buf || !f) { free(buf); if (f) fclose(f); return -1; }
+  int err = fwrite(&h, sizeof h, 1, f) != 1;
+  for (size_t i = 0; !err && i < sizeof BASE / sizeof BASE[0]; ++i) {
+    if ((rc = a->get(sim, BASE[i].field, buf, cells * BASE[i].elem))) break;
+    err = fwrite(buf, BASE[i].elem, cells, f) != cells;
+  }
+  for (size_t i = 0; !err && !rc && rainbow && i < 3; ++i) {
+    if ((rc = a->get(sim, COLOR[i].field, buf, cells * 4))) break;
+    err = fwrite(buf, 4, cells, f) != cells;
+  }
+  if (!err && !rc && h.n_markers) {
+    if (!(rc = a->get(sim, EULER_F_MARKERS, buf, (size_t)h.n_markers * 8)))
+      err = fwrite(buf, 8, (size_t)h.n_markers, f) != (size_t)h.n_markers;
+  }
+  if (fclose(f)) err = 1;
+  free(buf);
+  return rc ? -rc : (err ? -1 : 0);
+}
+
+int euler_checkpoint_load(const euler_ckpt_api *a, euler_gpu *sim, int nx, int ny, int rainbow, const char *path) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return -1;
+  header h;
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, MAGIC, 8)) { fclose(f); return -1; }
+  if (h.nx != nx || h.ny != ny || ((h.flags & 1u) != 0) != (rainbow != 0) ||
+      h.n_markers > 4ull * (uint64_t)nx * (uint64_t)ny) { fclose(f); return -2; }
+  const size_t cells = (size_t)nx * ny;
+  size_t big = cells * 8 > h.n_markers * 8 ? cells * 8 : (size_t)h.n_markers * 8;
+  void *buf = malloc(big ? big : 1);
+  if (!buf) { fclose(f); return -1; }
+  int rc = 0, err = 0;
+  for (size_t i = 0; !err && !rc && i < sizeof BASE / sizeof BASE[0]; ++i) {
+    err = fread(buf, BASE[i].elem, cells, f) != cells;
+    if (!err) rc = a->set(sim, BASE[i].field, buf, cells * BASE[i].elem);
+  }
+  for (size_t i = 0; !err && !rc && rainbow && i < 3; ++i) {
+    err = fread(buf, 4, cells, f) != cells;
+    if (!err) rc = a->set(sim, COLOR[i].field, buf, cells * 4);
+  }
+  if (!err && !rc) {
+    if (h.n_markers) err = fread(buf, 8, (size_t)h.n_markers, f) != (size_t)h.n_markers;
+    if (!err) rc = a->set(sim, EULER_F_MARKERS, buf, (size_t)h.n_markers * 8);
+  }
+  if (!err && !rc) rc = a->set_rng_state(sim, h.rng_state);
+  if (!err && !rc) rc = a->set_source_exhausted(sim, h.source_exhausted);
+  if (!err && !rc) rc = a->set_frame_count(sim, h.frames);
+  fclose(f);
+  free(buf);
+  return rc ? -rc : (err ? -1 : 0);
+}

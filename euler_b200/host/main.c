@@ -29,6 +29,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "checkpoint.h"
 #include "euler_gpu.h"
 #include "render.h"
 #include "scenario.h"
@@ -41,9 +42,34 @@ typedef struct api {
   int (*destroy)(euler_gpu *);
   int (*step_frame)(euler_gpu *, int *);
   int (*read_marker_count)(euler_gpu *, uint8_t *);
+  int (*read_window)(euler_gpu *, int, int, int, int, int, void *);
+  int (*colorize)(euler_gpu *);
+  euler_ckpt_api ck;
   int (*stats)(euler_gpu *, euler_stats *);
   const char *(*last_error)(void);
 } api;
+
+/* What draw_rows() looks at (main.c:917-920): the top `rows` text rows and the left `cols`
+ * columns of the interior.  Only that rectangle of the count plane comes back from the GPU. */
+static int read_visible(const api *a, euler_gpu *sim, int nx, int ny, const euler_screen *scr, uint8_t *count,
+                        float *rgb[3]) {
+  int y_low = ny - 1 - scr->rows;
+  if (y_low < 1) y_low = 1;
+  int w = nx - 2 < scr->cols ? nx - 2 : scr->cols;
+  if (w < 0) w = 0;
+  int rc = a->read_window(sim, EULER_F_COUNT, 1, y_low, w, ny - 1 - y_low, count);
+  if (!rc && rgb[0]) {                                        /* --rainbow: g_r, g_g, g_b (main.c:938) */
+    static const int f[3] = {EULER_F_CR, EULER_F_CG, EULER_F_CB};
+    for (int k = 0; k < 3 && !rc; ++k) rc = a->read_window(sim, f[k], 1, y_low, w, ny - 1 - y_low, rgb[k]);
+  }
+  return rc;
+}
+
+static void draw_visible(euler_screen *scr, int nx, int ny, const euler_scenario *scn, const uint8_t *count,
+                         float *rgb[3]) {
+  if (rgb[0]) euler_draw_rainbow(scr, nx, ny, scn->solid, scn->sink, count, rgb[0], rgb[1], rgb[2]);
+  else euler_draw(scr, nx, ny, scn->solid, scn->sink, count);
+}
 
 static int bind_api(api *a, const char *argv0) {
   const char *env = getenv("EULER_GPU_LIB");
@@ -67,6 +93,14 @@ static int bind_api(api *a, const char *argv0) {
   BIND(destroy, "euler_gpu_destroy");
   BIND(step_frame, "euler_gpu_step_frame");
   BIND(read_marker_count, "euler_gpu_read_marker_count");
+  BIND(read_window, "euler_gpu_read_window");
+  BIND(colorize, "euler_gpu_colorize");
+  BIND(ck.get, "euler_gpu_get");
+  BIND(ck.set, "euler_gpu_set");
+  BIND(ck.stats, "euler_gpu_stats");
+  BIND(ck.set_rng_state, "euler_gpu_set_rng_state");
+  BIND(ck.set_source_exhausted, "euler_gpu_set_source_exhausted");
+  BIND(ck.set_frame_count, "euler_gpu_set_frame_count");
   BIND(stats, "euler_gpu_stats");
   BIND(last_error, "euler_gpu_last_error");
 #undef BIND
@@ -82,12 +116,13 @@ static uint64_t fnv1a(const uint8_t *p, size_t n) {
 static void usage(const char *argv0) {
   fprintf(stderr,
           "usage: %s [--rainbow] [--headless] [--frames N] [--grid WxH] [--synthetic NAME]\n"
-          "       [--precon ic0|rb] [--markers ref|fast] [--exact-dot] [--device D] [--print] <scenario>\n",
+          "       [--precon ic0|rb] [--markers ref|fast] [--exact-dot] [--device D] [--print]\n"
+          "       [--load CHECKPOINT] [--save CHECKPOINT] <scenario>\n",
           argv0);
 }
 
 int main(int argc, char **argv) {
-  const char *file = NULL, *synthetic = NULL;
+  const char *file = NULL, *synthetic = NULL, *load_path = NULL, *save_path = NULL;
   int headless = 0, frames = -1, nx = 100, ny = 40, do_print = 0;
   api a; memset(&a, 0, sizeof a);
   if (bind_api(&a, argv[0])) return 1;
@@ -96,13 +131,15 @@ int main(int argc, char **argv) {
 
   for (int i = 1; i < argc; ++i) {
     const char *s = argv[i];
-    if (!strcmp(s, "--rainbow")) fprintf(stderr, "note: --rainbow is not on the GPU path yet; drawing in blue\n");
+    if (!strcmp(s, "--rainbow")) prm.rainbow = 1;                /* main.c:991-992 */
     else if (!strcmp(s, "--headless")) headless = 1;
     else if (!strcmp(s, "--print")) do_print = 1;
     else if (!strcmp(s, "--exact-dot")) prm.dot_mode = EULER_DOT_REFERENCE_ORDER;
     else if (!strcmp(s, "--frames") && i + 1 < argc) frames = atoi(argv[++i]);
     else if (!strcmp(s, "--device") && i + 1 < argc) prm.device = atoi(argv[++i]);
     else if (!strcmp(s, "--synthetic") && i + 1 < argc) synthetic = argv[++i];
+    else if (!strcmp(s, "--load") && i + 1 < argc) load_path = argv[++i];
+    else if (!strcmp(s, "--save") && i + 1 < argc) save_path = argv[++i];
     else if (!strcmp(s, "--grid") && i + 1 < argc) {
       if (sscanf(argv[++i], "%dx%d", &nx, &ny) != 2 || nx < 4 || ny < 4) { usage(argv[0]); return 1; }
     } else if (!strcmp(s, "--precon") && i + 1 < argc) {
@@ -159,6 +196,10 @@ int main(int argc, char **argv) {
   }
   uint8_t *count = malloc((size_t)nx * ny);
   if (!count) return 1;
+  if (load_path) {            /* state of an earlier run; the scenario still supplies the static masks */
+    int lrc = euler_checkpoint_load(&a.ck, sim, nx, ny, prm.rainbow, load_path);
+    if (lrc) { fprintf(stderr, "cannot load checkpoint %s (%d): %s\n", load_path, lrc, lrc > 0 ? a.last_error() : "bad file"); return 1; }
+  }
 
   long long substeps_total = 0;
   euler_time t0 = euler_now();
@@ -177,14 +218,20 @@ int main(int argc, char **argv) {
     }
     euler_tty_raw_mode();
     euler_tty_clear();
-    a.read_marker_count(sim, count);
-    euler_draw(&scr, nx, ny, scn.solid, scn.sink, count);
+    memset(count, 0, (size_t)nx * ny);
+    float *rgb[3] = {NULL, NULL, NULL};
+    if (prm.rainbow)
+      for (int k = 0; k < 3; ++k)
+        if (!(rgb[k] = calloc((size_t)nx * ny, sizeof(float)))) return 1;   /* only the window is ever touched */
+    read_visible(&a, sim, nx, ny, &scr, count, rgb);
+    draw_visible(&scr, nx, ny, &scn, count, rgb);
     int pause = 0, pending = 0, done = 0, f = 0;
     euler_time start = euler_now();
     while (!done && (frames < 0 || f < frames)) {
       const char key = euler_tty_read_key();                 /* main.c:961-980 */
       if (key == 'p') pause = !pause;
       else if (key == 'f') pending++;
+      else if (key == 'r') { if (prm.rainbow) a.colorize(sim); }   /* main.c:971-974 */
       else if (key == 'q') { done = 1; break; }
       if (!pause || pending) {                               /* main.c:844-846, 896-898 */
         int sub = 0;
@@ -194,9 +241,10 @@ int main(int argc, char **argv) {
       }
       start = euler_wait_until(start, 100000000ll);          /* 10 fps, main.c:1036 */
       euler_tty_window_size(&scr.rows, &scr.cols);
-      a.read_marker_count(sim, count);
-      euler_draw(&scr, nx, ny, scn.solid, scn.sink, count);
+      read_visible(&a, sim, nx, ny, &scr, count, rgb);
+      draw_visible(&scr, nx, ny, &scn, count, rgb);
     }
+    for (int k = 0; k < 3; ++k) free(rgb[k]);
     euler_tty_clear();
     euler_tty_restore();
     euler_screen_free(&scr);
@@ -211,14 +259,35 @@ int main(int argc, char **argv) {
     char *pic = malloc(cap);
     if (pic) { euler_draw_plain(pic, cap, nx, ny, 200, 60, scn.solid, scn.sink, count); fputs(pic, stdout); free(pic); }
   }
+  char rainbow_json[160] = "";
+  if (headless && prm.rainbow) {
+    /* FNV-1a of g_r, g_g, g_b masked to the fluid cells (the ones draw_rows reads, main.c:938):
+     * the quantity tests/golden/rainbow_answers.json holds from the reference */
+    static const int fld[3] = {EULER_F_CR, EULER_F_CG, EULER_F_CB};
+    uint64_t hsh[3] = {0, 0, 0};
+    float *plane = malloc((size_t)nx * ny * sizeof(float));
+    if (!plane) return 1;
+    for (int k = 0; k < 3; ++k) {
+      if (a.read_window(sim, fld[k], 0, 0, nx, ny, plane)) { fprintf(stderr, "read: %s\n", a.last_error()); return 1; }
+      for (size_t i = 0; i < (size_t)nx * ny; ++i) if (!count[i]) plane[i] = 0.f;
+      hsh[k] = fnv1a((const uint8_t *)plane, (size_t)nx * ny * sizeof(float));
+    }
+    free(plane);
+    snprintf(rainbow_json, sizeof rainbow_json, ", \"fnv_r\": \"%016" PRIx64 "\", \"fnv_g\": \"%016" PRIx64
+             "\", \"fnv_b\": \"%016" PRIx64 "\"", hsh[0], hsh[1], hsh[2]);
+  }
   if (headless) {
     printf("{\"grid\": [%d, %d], \"frames\": %d, \"substeps\": %lld, \"seconds\": %.6f, "
            "\"cell_updates_per_s\": %.6e, \"pcg_iterations\": %" PRIu64 ", \"pcg_iters_per_s\": %.6e, "
            "\"solves\": %" PRIu64 ", \"solves_skipped\": %" PRIu64 ", \"markers\": %" PRIu64 ", "
-           "\"fnv_count\": \"%016" PRIx64 "\", \"rng_state\": \"%016" PRIx64 "\", \"kernel_launches\": %" PRIu64 "}\n",
+           "\"fnv_count\": \"%016" PRIx64 "\", \"rng_state\": \"%016" PRIx64 "\", \"kernel_launches\": %" PRIu64 "%s}\n",
            nx, ny, frames, substeps_total, secs, (double)nx * ny * (double)substeps_total / secs,
            st.pcg_iterations, (double)st.pcg_iterations / secs, st.solves, st.solves_skipped,
-           st.n_markers, fnv1a(count, (size_t)nx * ny), st.rng_state, st.kernel_launches);
+           st.n_markers, fnv1a(count, (size_t)nx * ny), st.rng_state, st.kernel_launches, rainbow_json);
+  }
+  if (save_path) {
+    int src = euler_checkpoint_save(&a.ck, sim, nx, ny, prm.rainbow, save_path);
+    if (src) { fprintf(stderr, "cannot save checkpoint %s (%d): %s\n", save_path, src, src > 0 ? a.last_error() : "I/O"); return 1; }
   }
   free(count);
   a.destroy(sim);

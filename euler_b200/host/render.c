@@ -3,6 +3,7 @@
 #include "render.h"
 
 #include <errno.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -91,6 +92,52 @@ void euler_draw(euler_screen *s, int nx, int ny, const uint8_t *solid, const uin
   }
   PUTS(s, "\x1b[?25l");
   if (write(STDOUT_FILENO, s->buf, s->len) < 0) {}
+}
+
+int euler_color_byte(float linear) {
+  /* misc/color.h: float_to_byte_color(linear_to_sRGB(x)) */
+  const float end = nextafterf(256.f, 0.f);
+  float v = end * powf(linear, 1 / 2.2f);
+  if (!(v > 0.f)) v = 0.f;
+  if (v > end) v = end;
+  return (int)v;
+}
+
+static void draw_frame(euler_screen *s, int nx, int ny, const uint8_t *solid, const uint8_t *sink,
+                       const uint8_t *count, const float *r, const float *g, const float *b) {
+  static const char glyph[4] = {' ', 'o', 'O', '0'};
+  s->len = 0;
+  PUTS(s, "\x1b[H");
+  int y_low = ny - 1 - s->rows;
+  if (y_low < 1) y_low = 1;
+  for (int y = ny - 2; y >= y_low; --y) {
+    int wet = 0;
+    for (int x = 1; x < nx - 1 && x < s->cols + 1; ++x) {
+      const size_t c = (size_t)y * nx + x;
+      if (solid[c]) { if (wet) PUTS(s, "\x1b[0m"); PUTS(s, "X"); wet = 0; }
+      else if (sink[c]) { if (wet) PUTS(s, "\x1b[0m"); PUTS(s, "="); wet = 0; }
+      else {
+        const int level = count[c] < 3 ? count[c] : 3;
+        if (level) {
+          char esc[24];
+          int n = snprintf(esc, sizeof esc, "\x1b[38;2;%d;%d;%dm", euler_color_byte(r[c]),
+                           euler_color_byte(g[c]), euler_color_byte(b[c]));
+          if (n > 0 && n < (int)sizeof esc) put(s, esc, (size_t)n);
+        } else if (wet) PUTS(s, "\x1b[0m");
+        put(s, &glyph[level], 1);
+        wet = level != 0;
+      }
+    }
+    PUTS(s, "\x1b[0m\x1b[K");
+    if (y > y_low) PUTS(s, "\r\n");
+  }
+  PUTS(s, "\x1b[?25l");
+  if (write(STDOUT_FILENO, s->buf, s->len) < 0) {}
+}
+
+void euler_draw_rainbow(euler_screen *s, int nx, int ny, const uint8_t *solid, const uint8_t *sink,
+                        const uint8_t *count, const float *r, const float *g, const float *b) {
+  draw_frame(s, nx, ny, solid, sink, count, r, g, b);
 }
 
 size_t euler_draw_plain(char *dst, size_t cap, int nx, int ny, int max_cols, int max_rows,

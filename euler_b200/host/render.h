@@ -23,6 +23,12 @@ char euler_tty_read_key(void);
 /* Compose one frame into scr->buf (cursor home, rows, hide cursor) and write it to stdout. */
 void euler_draw(euler_screen *scr, int nx, int ny, const uint8_t *solid, const uint8_t *sink,
                 const uint8_t *marker_count);
+/* Same with --rainbow: every wet cell in its own 24-bit colour, linear RGB -> sRGB bytes like
+ * buffer_append_color (main.c:902-912, misc/color.h).  r, g, b are [ny][nx] planes. */
+void euler_draw_rainbow(euler_screen *scr, int nx, int ny, const uint8_t *solid, const uint8_t *sink,
+                        const uint8_t *marker_count, const float *r, const float *g, const float *b);
+/* misc/color.h: linear [0,1] -> sRGB byte (x^(1/2.2) approximation, clamped) */
+int euler_color_byte(float linear);
 /* Same picture without escape codes into a caller buffer (for --headless --print). Returns
  * the number of bytes written (excluding the terminating NUL). */
 size_t euler_draw_plain(char *dst, size_t cap, int nx, int ny, int max_cols, int max_rows,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define EULER_GPU_ABI_VERSION 1
+#define EULER_GPU_ABI_VERSION 2
 
 enum euler_error {
   EULER_OK            =  0,
@@ -91,6 +91,9 @@ enum euler_field {
   EULER_F_R,              /* double           r / b          main.c:716,740 */
   EULER_F_Z,              /* double           z              main.c:743 */
   EULER_F_S,              /* double           s              main.c:745 */
+  EULER_F_CR,             /* float            g_r            main.c:77  (only with params.rainbow) */
+  EULER_F_CG,             /* float            g_g            main.c:78 */
+  EULER_F_CB,             /* float            g_b            main.c:79 */
   EULER_F__COUNT
 };
 
@@ -108,6 +111,8 @@ enum euler_stage {
   EULER_S_PRECONDITION,       /* z = M^-1 r                    main.c:580-627 */
   EULER_S_APPLY_A,            /* z = A s                       main.c:679-691 */
   EULER_S_PRESSURE_UPDATE,    /* clamp p, subtract gradient    main.c:769-805 */
+  EULER_S_EXTRAPOLATE_COLOR,  /* --rainbow: extrapolate(g_r|g_g|g_b, P)   main.c:859-863 */
+  EULER_S_ADVECT_COLOR,       /* --rainbow: advect_p x3 + plane copies    main.c:873-882 */
   EULER_S__COUNT
 };
 
@@ -144,6 +149,11 @@ typedef struct euler_params {
    * a global-shaped buffer.  Needs precon=REDBLACK, marker_mode=FAST.  See euler_gpu_comm_init. */
   int   slab_row0;
   int   slab_rows;
+  /* --rainbow (main.c:76, 984-993): transport a passive RGB colour with the fluid — colorize()
+   * at create/reinit (main.c:271-273), extrapolate(P) (:859-863), source colours (:292-294) and
+   * advect_p (:873-882) every sub-step.  Six more fp32 planes; single-GPU handles only.
+   * Default 0, like the reference. */
+  int   rainbow;
 } euler_params;
 
 #define EULER_KERNEL_CLASSES 24
@@ -207,12 +217,26 @@ int euler_gpu_run_stage(euler_gpu *h, int stage, float dt);
 /* What draw_rows() reads every frame (main.c:933): the uint8 marker-count plane. */
 int euler_gpu_read_marker_count(euler_gpu *h, uint8_t *dst /* ny*nx */);
 
+/* The renderer's feed for large grids: draw_rows() only looks at the part of the grid that fits
+ * the terminal window — rows [max(ny-1-g_wy, 1), ny-1), columns [1, min(nx-1, g_wx+1))
+ * (main.c:917-920).  Copies the rectangle [x0, x0+w) x [y0, y0+hh) of a plane (any EULER_F_*
+ * plane field) into the same position of a GLOBAL-shaped [ny][nx] host buffer and leaves the
+ * rest of the buffer untouched: a 16384^2 run ships kilobytes per drawn frame instead of the
+ * 268 MB plane.  Slab handles write the part of the window they own. */
+int euler_gpu_read_window(euler_gpu *h, int field, int x0, int y0, int w, int hh, void *dst_global);
+
 /* State access (checkpoint / parity).  `bytes` must equal the field's size: ny*nx*sizeof(T),
  * or n_markers*8 for EULER_F_MARKERS (set: any n <= 4*nx*ny; sets the length too). */
 int euler_gpu_get(euler_gpu *h, int field, void *dst, size_t bytes);
 int euler_gpu_set(euler_gpu *h, int field, const void *src, size_t bytes);
+/* colorize() (main.c:187-201): what the `r` key does with --rainbow (main.c:971-974).  Error on
+ * a handle without params.rainbow. */
+int euler_gpu_colorize(euler_gpu *h);
 int euler_gpu_set_rng_state(euler_gpu *h, uint64_t state);
 int euler_gpu_set_source_exhausted(euler_gpu *h, int exhausted);
+/* g_frame_count (main.c:89, incremented per euler_gpu_step_frame; read only by the source
+ * colours of --rainbow, main.c:283): restored by a checkpoint load. */
+int euler_gpu_set_frame_count(euler_gpu *h, uint64_t frames);
 
 int euler_gpu_stats(euler_gpu *h, euler_stats *out);
 /* Toggle per-stage-group CUDA-event timing (adds synchronisation; off by default). */

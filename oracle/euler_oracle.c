@@ -45,6 +45,8 @@ orc_sim *orc_create(int nx, int ny) {
   o->precon = zalloc(n, 8); o->q = zalloc(n, 8);
   o->b = zalloc(n, 8); o->p = zalloc(n, 8); o->r = zalloc(n, 8);
   o->z = zalloc(n, 8); o->s = zalloc(n, 8);
+  o->cr = zalloc(n, 4); o->cg = zalloc(n, 4); o->cb = zalloc(n, 4);
+  o->crtmp = zalloc(n, 4); o->cgtmp = zalloc(n, 4); o->cbtmp = zalloc(n, 4);
   return o;
 }
 
@@ -54,6 +56,7 @@ void orc_destroy(orc_sim *o) {
   free(o->solid); free(o->source); free(o->sink); free(o->count); free(o->prev_count);
   free(o->markers); free(o->adiag); free(o->precon); free(o->q);
   free(o->b); free(o->p); free(o->r); free(o->z); free(o->s);
+  free(o->cr); free(o->cg); free(o->cb); free(o->crtmp); free(o->cgtmp); free(o->cbtmp);
   free(o);
 }
 
@@ -160,15 +163,59 @@ void orc_init_from_text(orc_sim *o, const char *text, int length) {
   o->n_markers = m;
   free(fluid);
   orc_refresh_marker_counts(o);
+  if (o->rainbow) orc_colorize(o);                           /* ref :271-273 */
 }
 
-/* ref :276-298 (colour writes omitted).  Argument evaluation order of
+/* ------------------------------------------------------------------ rainbow ---- */
+
+/* misc/color.h hsv_basis: periodic in t with period 6, values in [0,1] */
+float orc_hsv_basis(float t) {
+  t -= 6.f * floorf(1.f / 6 * t);
+  if (t < 0.f) t += 6.f;
+  if (t < 1.f) return t;
+  if (t < 3.f) return 1.f;
+  if (t < 4.f) return 4.f - t;
+  return 0.f;
+}
+
+/* ref :187-201: hue ramps along x+y with a period of 60 cells; source cells start at t = 0 */
+void orc_colorize(orc_sim *o) {
+  for (int y = 0; y < o->ny; ++y) {
+    for (int x = 0; x < o->nx; ++x) {
+      size_t c = IDX(o, x, y);
+      if (!o->count[c]) continue;
+      float t = 0.f;
+      if (!o->source[c]) t = (x + y) * 6.f / 60.f;           /* k_initial_color_period, ref :84 */
+      o->cr[c] = orc_hsv_basis(t + 2.f);
+      o->cg[c] = orc_hsv_basis(t);
+      o->cb[c] = orc_hsv_basis(t - 2.f);
+    }
+  }
+}
+
+/* ref :424-438: back-trace from the cell centre with the mean of the two faces either side */
+void orc_advect_p(const orc_sim *o, const float *q, const float *u, const float *v, float dt, float *out) {
+  for (int y = 0; y < o->ny; ++y) {
+    for (int x = 0; x < o->nx; ++x) {
+      size_t c = IDX(o, x, y);
+      if (!o->count[c]) continue;
+      float dy = (v[c] + v[IDX(o, x, y - 1)]) / 2;
+      float dx = (u[c] + u[IDX(o, x - 1, y)]) / 2;
+      float px = x - dx * dt / o->h;
+      float py = y - dy * dt / o->h;
+      out[c] = orc_interpolate(o, q, px, py, CELL_P);
+    }
+  }
+}
+
+/* ref :276-298.  Argument evaluation order of
  * v2f(x+randf(), y+randf()) is unspecified in C; gcc 13 on x86-64 (the build that the
  * parity oracle oracle/_ref is made with) evaluates the SECOND argument first, i.e. the
  * y jitter takes the earlier draw.  tests/test_oracle_vs_ref.py pins this. */
 void orc_update_fluid_sources(orc_sim *o) {
   const size_t cap = o->max_markers - 1;
   o->source_exhausted |= (o->n_markers == cap);
+  const float t = 0.6f / 10.f * o->frame_count;              /* k_source_color_period, ref :83, :283 */
   for (int y = 0; y < o->ny; ++y) {
     for (int x = 0; x < o->nx; ++x) {
       size_t c = IDX(o, x, y);
@@ -182,6 +229,10 @@ void orc_update_fluid_sources(orc_sim *o) {
         o->count[c]++;
         o->source_exhausted |= (o->n_markers == cap);
       }
+      /* ref :292-294: written whether or not --rainbow is on (only read when it is) */
+      o->cr[c] = orc_hsv_basis(t + 2.f);
+      o->cg[c] = orc_hsv_basis(t);
+      o->cb[c] = orc_hsv_basis(t - 2.f);
     }
   }
 }
@@ -620,11 +671,17 @@ void orc_project(orc_sim *o, float dt, const float *u, const float *v, float *uo
 
 /* ------------------------------------------------------------- step driver ---- */
 
-/* body of the sub-step loop, ref :855-893 (no --rainbow) */
+/* body of the sub-step loop, ref :855-893 */
 void orc_substep(orc_sim *o, float dt) {
+  const size_t plane = (size_t)o->nx * o->ny * sizeof(float);
   o->last_dt = dt;
   orc_advect_markers(o, dt);
   orc_refresh_marker_counts(o);
+  if (o->rainbow) {                                          /* ref :859-863 */
+    orc_extrapolate(o, o->cr, CELL_P);
+    orc_extrapolate(o, o->cg, CELL_P);
+    orc_extrapolate(o, o->cb, CELL_P);
+  }
   orc_update_fluid_sources(o);
   orc_extrapolate(o, o->u, FACE_U);
   orc_extrapolate(o, o->v, FACE_V);
@@ -632,6 +689,11 @@ void orc_substep(orc_sim *o, float dt) {
   orc_zero_bounds(o, o->v, FACE_V);
   orc_advect_u(o, o->u, o->v, dt, o->utmp);
   orc_advect_v(o, o->u, o->v, dt, o->vtmp);
+  if (o->rainbow) {                                          /* ref :873-882: whole-plane copies */
+    orc_advect_p(o, o->cr, o->u, o->v, dt, o->crtmp); memcpy(o->cr, o->crtmp, plane);
+    orc_advect_p(o, o->cg, o->u, o->v, dt, o->cgtmp); memcpy(o->cg, o->cgtmp, plane);
+    orc_advect_p(o, o->cb, o->u, o->v, dt, o->cbtmp); memcpy(o->cb, o->cbtmp, plane);
+  }
   orc_apply_body_forces(o, o->vtmp, dt);
   orc_zero_bounds(o, o->utmp, FACE_U);
   orc_zero_bounds(o, o->vtmp, FACE_V);
@@ -648,6 +710,7 @@ int orc_step_frame(orc_sim *o) {
     frame_time -= dt;
     orc_substep(o, dt);
   }
+  o->frame_count++;                                          /* ref :899 */
   return steps;
 }
 

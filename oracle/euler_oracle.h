@@ -48,6 +48,10 @@ typedef struct orc_sim {
   int8_t *adiag;
   double *precon, *q;
   double *b, *p, *r, *z, *s;
+  /* --rainbow colour transport (main.c:76-84, 89): a passive RGB scalar on the P cells */
+  int    rainbow;              /* g_rainbow_enabled */
+  float *cr, *cg, *cb, *crtmp, *cgtmp, *cbtmp;   /* g_r g_g g_b g_rtmp g_gtmp g_btmp */
+  uint16_t frame_count;        /* g_frame_count (uint16, wraps), main.c:89 */
   /* bookkeeping for tests / benchmarks */
   int    last_iterations;      /* PCG iterations of the last project() (0 if skipped) */
   int    last_solve_skipped;   /* all_zero(r) fired, main.c:742 */
@@ -58,8 +62,12 @@ typedef struct orc_sim {
 
 orc_sim *orc_create(int nx, int ny);
 void     orc_destroy(orc_sim *o);
-/* sim_init, main.c:209-274 (without --rainbow) */
+/* sim_init, main.c:209-274 (colorize() at the end when o->rainbow is set before the call) */
 void     orc_init_from_text(orc_sim *o, const char *text, int length);
+/* --rainbow pieces */
+float    orc_hsv_basis(float t);                                          /* misc/color.h */
+void     orc_colorize(orc_sim *o);                                        /* main.c:187-201 */
+void     orc_advect_p(const orc_sim *o, const float *q, const float *u, const float *v, float dt, float *out); /* :424-438 */
 
 /* stages, in sim_step order (main.c:851-893) */
 float  orc_calculate_timestep(const orc_sim *o, float frame_time);       /* :834-841 */

@@ -42,6 +42,10 @@ class _Sim(C.Structure):
         ("b", C.POINTER(C.c_double)), ("p", C.POINTER(C.c_double)),
         ("r", C.POINTER(C.c_double)), ("z", C.POINTER(C.c_double)),
         ("s", C.POINTER(C.c_double)),
+        ("rainbow", C.c_int),
+        ("cr", C.POINTER(C.c_float)), ("cg", C.POINTER(C.c_float)), ("cb", C.POINTER(C.c_float)),
+        ("crtmp", C.POINTER(C.c_float)), ("cgtmp", C.POINTER(C.c_float)), ("cbtmp", C.POINTER(C.c_float)),
+        ("frame_count", C.c_uint16),
         ("last_iterations", C.c_int), ("last_solve_skipped", C.c_int),
         ("last_residual", C.c_double),
         ("total_iterations", C.c_long), ("total_substeps", C.c_long),
@@ -87,13 +91,16 @@ def lib():
         L.orc_interpolate.restype = C.c_float
         L.orc_interpolate.argtypes = [SP, FP, C.c_float, C.c_float, C.c_int]
         L.orc_randf.restype = C.c_float; L.orc_randf.argtypes = [SP]
+        L.orc_hsv_basis.restype = C.c_float; L.orc_hsv_basis.argtypes = [C.c_float]
+        L.orc_colorize.argtypes = [SP]
+        L.orc_advect_p.argtypes = [SP, FP, FP, FP, C.c_float, FP]
         L.orc_fnv1a.restype = C.c_uint64
         L.orc_fnv1a.argtypes = [C.POINTER(C.c_uint8), C.c_size_t]
         _lib = L
     return _lib
 
 
-_F32 = ("u", "v", "utmp", "vtmp")
+_F32 = ("u", "v", "utmp", "vtmp", "cr", "cg", "cb", "crtmp", "cgtmp", "cbtmp")
 _U8 = ("solid", "source", "sink", "count", "prev_count")
 _F64 = ("precon", "q", "b", "p", "r", "z", "s")
 
@@ -101,10 +108,11 @@ _F64 = ("precon", "q", "b", "p", "r", "z", "s")
 class Oracle:
     """The restatement.  Planes are exposed as numpy views [ny, nx] on the C arrays."""
 
-    def __init__(self, nx, ny, text=None):
+    def __init__(self, nx, ny, text=None, rainbow=False):
         self.L = lib()
         self.ptr = self.L.orc_create(nx, ny)
         self.c = self.ptr.contents
+        self.c.rainbow = 1 if rainbow else 0
         self.nx, self.ny = nx, ny
         shape = (ny, nx)
         for name in _F32 + _U8 + _F64 + ("adiag",):
@@ -178,6 +186,11 @@ class Oracle:
     def pressure_update(self, dt):
         self.L.orc_pressure_update(self.ptr, np.float32(dt), self.fptr(self.utmp), self.fptr(self.vtmp),
                                    self.fptr(self.u), self.fptr(self.v))
+
+    def colorize(self): self.L.orc_colorize(self.ptr)
+
+    def advect_p(self, q, dt, out):
+        self.L.orc_advect_p(self.ptr, self.fptr(q), self.fptr(self.u), self.fptr(self.v), np.float32(dt), self.fptr(out))
 
     def substep(self, dt): self.L.orc_substep(self.ptr, np.float32(dt))
     def step_frame(self): return int(self.L.orc_step_frame(self.ptr))
@@ -261,6 +274,9 @@ class Reference:
         self.count, self.prev_count = plane("g_marker_count", C.c_uint8), plane("g_prev_marker_count", C.c_uint8)
         self.precon, self.q = plane("g_precon", C.c_double), plane("g_q", C.c_double)
         self.adiag = plane("g_a", C.c_int8)
+        self.cr, self.cg, self.cb = (plane(s, C.c_float) for s in ("g_r", "g_g", "g_b"))
+        self._rainbow = C.c_bool.in_dll(self.L, "g_rainbow_enabled")
+        self._frame_count = C.c_uint16.in_dll(self.L, "g_frame_count")
         self._markers = np.ctypeslib.as_array((C.c_float * (8 * n)).in_dll(self.L, "g_markers")).reshape(-1, 2)
         self._len = C.c_size_t.in_dll(self.L, "g_markers_length")
         self._exhausted = C.c_bool.in_dll(self.L, "g_source_exhausted")
@@ -305,15 +321,16 @@ class Reference:
     @property
     def source_exhausted(self): return bool(self._exhausted.value)
 
-    def init_from_text(self, text):
+    def init_from_text(self, text, rainbow=False):
         import tempfile
         if isinstance(text, str):
             text = text.encode()
+        self._rainbow.value = bool(rainbow)          # main() sets the global before sim_init (main.c:1020)
         with tempfile.NamedTemporaryFile(suffix=".txt", delete=False) as f:
             f.write(text)
             name = f.name
         try:
-            a = _Args(name.encode(), False)
+            a = _Args(name.encode(), bool(rainbow))
             call_with_big_stack(self.L.sim_init, a, stack_mb=self.stack_mb)
         finally:
             os.unlink(name)

@@ -12,6 +12,10 @@ Run in the build container (needs /root/reference and oracle/_ref built by
                        marker-count plane, sum|u|, sum|v|, the RNG state and the number of
                        markers; plus a 64x48 resampled block scenario.  BASELINE.md §3 lists
                        the same quantities from the survey's probe.
+  rainbow_answers.json known answers of the --rainbow colour transport (main.c:187-201, 424-438,
+                       859-863, 873-882, 292-294) from the same reference build with
+                       g_rainbow_enabled set: FNV-1a of the g_r, g_g, g_b planes masked to the
+                       fluid cells (the only ones the renderer reads) at frames 0/1/10/30
   state_<name>_f<N>.npz   full reference state (u, v, counts, markers, precon) after N frames,
                        used as the common starting state of the per-stage parity tests.
 """
@@ -41,6 +45,15 @@ def snapshot(r):
         "sum_abs_v": float(np.abs(r.v.astype(np.float64)).sum()),
         "rng_state": "%016x" % r.rng_state,
     }
+
+
+def rainbow_snapshot(r):
+    fl = r.count != 0
+    out = {"fluid_cells": int(fl.sum()), "fnv_count": "%016x" % fnv1a(r.count)}
+    for k, plane in (("r", r.cr), ("g", r.cg), ("b", r.cb)):
+        masked = np.where(fl, plane, np.float32(0)).astype(np.float32)
+        out["fnv_" + k] = "%016x" % fnv1a(masked.view(np.uint8))
+    return out
 
 
 def main():
@@ -78,6 +91,19 @@ def main():
         answers["block@64x48/f%d" % target] = snapshot(r)
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(answers, f, indent=1, sort_keys=True)
+
+    rainbow = {}
+    for n in NAMES:
+        r = Reference(100, 40)
+        r.init_from_text(scenarios[n], rainbow=True)
+        frame = 0
+        for target in (0, 1, 10, 30):
+            while frame < target:
+                r.step_frame()
+                frame += 1
+            rainbow["%s@100x40/f%d" % (n, target)] = rainbow_snapshot(r)
+    with open(os.path.join(HERE, "rainbow_answers.json"), "w") as f:
+        json.dump(rainbow, f, indent=1, sort_keys=True)
     print("wrote %d known answers" % len(answers))
 
 

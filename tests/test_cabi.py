@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_default_params():
     from euler_b200 import gpu as G
-    assert G.abi_version() == 1
+    assert G.abi_version() == 2
     p = G.default_params()
     # the reference's constants (main.c:58-60, 735-736, 838, 849-851)
     assert (p.h, p.rho, p.gravity) == (1.0, 1.0, -10.0)

@@ -212,3 +212,146 @@ def test_reinit_equals_fresh_handle(precon, marker_mode):
         assert same_bits(a.get(f), b.get(f)), f
     assert int(a.stats().rng_state) == int(b.stats().rng_state)
     a.close(); b.close()
+
+
+# ---- --rainbow colour transport and the renderer's window feed (8f.2) -----------
+
+@pytest.mark.parametrize("name", ["block", "waterfall", "weird-edges", "filter"])
+def test_rainbow_frames_bit_exact(name):
+    """With reference-order dots the whole run is bit-identical to the oracle (itself pinned to
+    the reference's --rainbow run), so the colour planes must be too — whole planes, incl. the
+    stale values the reference's plane copies leave at non-fluid cells (main.c:875)."""
+    text = shipped_text(name)
+    from euler_b200 import gpu as G
+    from oracle.oracle import Oracle
+    o = Oracle(100, 40, rainbow=True); o.init_from_text(text)
+    g = G.EulerGpu.from_scenario(Scenario(text, 100, 40), precon=0, dot_mode=1,
+                                 marker_mode=G.MARKERS_REFERENCE, rainbow=1)
+    for f in range(25):
+        assert g.step_frame() == o.step_frame()
+        for fld, plane in ((G.F_CR, o.cr), (G.F_CG, o.cg), (G.F_CB, o.cb), (G.F_COUNT, o.count)):
+            assert same_bits(g.get(fld), plane), (name, f, fld)
+    o.colorize(); g.colorize()                   # the `r` key, main.c:971-974
+    for fld, plane in ((G.F_CR, o.cr), (G.F_CG, o.cg), (G.F_CB, o.cb)):
+        assert same_bits(g.get(fld), plane)
+    g.close()
+
+
+def test_rainbow_stages_from_identical_state():
+    """extrapolate(P) and advect_p one at a time from the oracle's state, on a resampled grid
+    whose pitch is not the row length."""
+    from euler_b200 import gpu as G
+    from oracle.oracle import Oracle, P
+    nx, ny = 333, 129
+    text = resample(shipped_text("waterfall"), nx - 2, ny - 2)
+    o = Oracle(nx, ny, rainbow=True); o.init_from_text(text)
+    o.c.precon_mode = 1; o.c.quirk_marker_dt_leak = 0
+    for _ in range(12):
+        o.step_frame()
+    g = G.EulerGpu.from_scenario(Scenario(text, nx, ny), precon=1, marker_mode=G.MARKERS_FAST, rainbow=1)
+    def push():
+        g.set(G.F_U, o.u); g.set(G.F_V, o.v); g.set(G.F_COUNT, o.count); g.set(G.F_PREV_COUNT, o.prev_count)
+        g.set(G.F_CR, o.cr); g.set(G.F_CG, o.cg); g.set(G.F_CB, o.cb)
+    dt = o.calculate_timestep(0.1)
+    o.advect_markers(dt); o.refresh_marker_counts()
+    push()
+    for q in (o.cr, o.cg, o.cb):
+        o.extrapolate(q, P)
+    g.run_stage(G.S_EXTRAPOLATE_COLOR)
+    for fld, plane in ((G.F_CR, o.cr), (G.F_CG, o.cg), (G.F_CB, o.cb)):
+        assert same_bits(g.get(fld), plane), fld
+    o.update_fluid_sources()
+    o.extrapolate(o.u, 1); o.extrapolate(o.v, 2); o.zero_bounds(o.u, 1); o.zero_bounds(o.v, 2)
+    push()
+    fl = o.count != 0
+    for q, t in ((o.cr, o.crtmp), (o.cg, o.cgtmp), (o.cb, o.cbtmp)):
+        o.advect_p(q, dt, t)
+    g.run_stage(G.S_ADVECT_COLOR, dt)
+    for fld, plane in ((G.F_CR, o.crtmp), (G.F_CG, o.cgtmp), (G.F_CB, o.cbtmp)):
+        assert same_bits(g.get(fld)[fl], plane[fl]), fld
+    g.close()
+
+
+def test_rainbow_off_and_errors():
+    from euler_b200 import gpu as G
+    g = G.EulerGpu.from_scenario(Scenario(shipped_text("block"), 100, 40))
+    with pytest.raises(G.EulerGpuError):
+        g.colorize()
+    with pytest.raises(G.EulerGpuError):
+        g.get(G.F_CR)
+    with pytest.raises(G.EulerGpuError):
+        g.run_stage(G.S_ADVECT_COLOR, 0.01)
+    g.close()
+    with pytest.raises(G.EulerGpuError):      # slabs do not carry the colour planes yet
+        G.EulerGpu.from_scenario(Scenario(shipped_text("block"), 100, 40), precon=1, marker_mode=1,
+                                 rainbow=1, slab_row0=0, slab_rows=20)
+
+
+def test_host_program_rainbow_matches_golden(tmp_path):
+    """bin/euler-gpu --rainbow --headless: colour-plane hashes equal the reference's known answers."""
+    import json, os, subprocess
+    from conftest import ROOT, GOLDEN
+    with open(os.path.join(GOLDEN, "rainbow_answers.json")) as f:
+        want = json.load(f)
+    exe = os.path.join(ROOT, "bin", "euler-gpu")
+    assert os.path.exists(exe), "run `make host`"
+    for name, frames in (("block", 10), ("waterfall", 30), ("weird-edges", 30)):
+        path = tmp_path / (name + ".txt")
+        path.write_bytes(shipped_text(name))
+        out = subprocess.run([exe, "--rainbow", "--headless", "--frames", str(frames), "--exact-dot", str(path)],
+                             check=True, capture_output=True, text=True, cwd=ROOT).stdout
+        res = json.loads(out.strip().splitlines()[-1])
+        w = want["%s@100x40/f%d" % (name, frames)]
+        assert res["fnv_count"] == w["fnv_count"], (name, frames)
+        assert (res["fnv_r"], res["fnv_g"], res["fnv_b"]) == (w["fnv_r"], w["fnv_g"], w["fnv_b"]), (name, frames)
+
+
+def test_window_feed_equals_full_plane():
+    """euler_gpu_read_window (what draw_rows needs, main.c:917-920) against the full plane."""
+    from euler_b200 import gpu as G
+    nx, ny = 333, 129
+    text = resample(shipped_text("block"), nx - 2, ny - 2)
+    g = G.EulerGpu.from_scenario(Scenario(text, nx, ny), precon=1, marker_mode=1)
+    for _ in range(6):
+        g.step_frame()
+    full = g.get(G.F_COUNT)
+    fu = g.get(G.F_U)
+    for (x0, y0, w, h) in ((1, 69, 80, 59), (0, 0, nx, ny), (17, 5, 1, 1), (300, 100, 33, 29), (5, 5, 0, 0)):
+        out = np.full((ny, nx), 255, np.uint8)
+        g.read_window(G.F_COUNT, x0, y0, w, h, out)
+        assert np.array_equal(out[y0:y0 + h, x0:x0 + w], full[y0:y0 + h, x0:x0 + w])
+        mask = np.ones((ny, nx), bool); mask[y0:y0 + h, x0:x0 + w] = False
+        assert (out[mask] == 255).all(), "outside the window must stay untouched"
+        outf = np.zeros((ny, nx), np.float32)
+        g.read_window(G.F_U, x0, y0, w, h, outf)
+        assert same_bits(outf[y0:y0 + h, x0:x0 + w], fu[y0:y0 + h, x0:x0 + w])
+    with pytest.raises(G.EulerGpuError):
+        g.read_window(G.F_COUNT, 300, 0, 40, 10, np.zeros((ny, nx), np.uint8))
+    g.close()
+
+
+@pytest.mark.parametrize("rainbow", [False, True])
+def test_host_program_checkpoint_round_trip(rainbow, tmp_path):
+    """bin/euler-gpu --save / --load (host/checkpoint.c over euler_gpu_get/set): 12 frames, save,
+    load into a fresh process, 13 more frames == 25 frames in one go, bit for bit (count-plane
+    hash, RNG state, marker count, colour planes)."""
+    import json, os, subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "bin", "euler-gpu")
+    path = tmp_path / "waterfall.txt"
+    path.write_bytes(shipped_text("waterfall"))
+    ck = str(tmp_path / "state.ck")
+    base = [exe, "--headless", "--exact-dot"] + (["--rainbow"] if rainbow else [])
+
+    def run(extra):
+        out = subprocess.run(base + extra + [str(path)], check=True, capture_output=True, text=True, cwd=ROOT).stdout
+        return json.loads(out.strip().splitlines()[-1])
+    whole = run(["--frames", "25"])
+    run(["--frames", "12", "--save", ck])
+    rest = run(["--frames", "13", "--load", ck])
+    keys = ["fnv_count", "rng_state", "markers"] + (["fnv_r", "fnv_g", "fnv_b"] if rainbow else [])
+    assert [rest[k] for k in keys] == [whole[k] for k in keys]
+    # a checkpoint of another grid size / colour mode is refused
+    bad = subprocess.run([exe, "--headless", "--frames", "1", "--grid", "64x48", "--load", ck, str(path)],
+                         capture_output=True, text=True, cwd=ROOT)
+    assert bad.returncode != 0 and "checkpoint" in bad.stderr

@@ -166,3 +166,51 @@ def test_source_exhaustion_latch():
     o.count[:] = 0
     o.update_fluid_sources()
     assert o.n_markers == cap
+
+
+# ---- --rainbow colour transport ------------------------------------------------
+
+def _rainbow_snapshot(o):
+    fl = o.count != 0
+    out = {"fluid_cells": int(fl.sum()), "fnv_count": "%016x" % fnv1a(o.count)}
+    for k, plane in (("r", o.cr), ("g", o.cg), ("b", o.cb)):
+        masked = np.where(fl, plane, np.float32(0)).astype(np.float32)
+        out["fnv_" + k] = "%016x" % fnv1a(masked.view(np.uint8))
+    return out
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_rainbow_known_answers(name):
+    """The restated colour transport against known answers produced by the UNMODIFIED reference
+    with g_rainbow_enabled (tests/golden/make_golden.py)."""
+    import json, os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "rainbow_answers.json")) as f:
+        want = json.load(f)
+    o = Oracle(100, 40, rainbow=True)
+    o.init_from_text(shipped_text(name))
+    frame = 0
+    for target in (0, 1, 10, 30):
+        while frame < target:
+            o.step_frame()
+            frame += 1
+        assert _rainbow_snapshot(o) == want["%s@100x40/f%d" % (name, target)], (name, target)
+
+
+@pytest.mark.skipif(not ref_available(100, 40), reason="oracle/_ref not built (no /root/reference)")
+@pytest.mark.parametrize("name", ["block", "waterfall", "weird-edges"])
+def test_rainbow_planes_bit_identical_to_reference(name):
+    """Whole g_r/g_g/g_b planes (stale values at non-fluid cells included: the reference copies
+    the whole tmp plane back, main.c:875) after every frame, and the planes of an `r` key press
+    (colorize on the evolved fluid, main.c:971-974)."""
+    text = shipped_text(name)
+    o = Oracle(100, 40, rainbow=True); o.init_from_text(text)
+    r = Reference(100, 40); r.init_from_text(text, rainbow=True)
+    for f in range(25):
+        assert o.step_frame() is not None
+        r.step_frame()
+        for a, b, what in ((o.cr, r.cr, "r"), (o.cg, r.cg, "g"), (o.cb, r.cb, "b"), (o.count, r.count, "count")):
+            assert same_bits(a, b), (name, f, what)
+    o.colorize(); r.L.colorize()
+    for a, b in ((o.cr, r.cr), (o.cg, r.cg), (o.cb, r.cb)):
+        assert same_bits(a, b)
