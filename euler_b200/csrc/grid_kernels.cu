@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(QX* QY) k_extrapolate_bounds(
 }
 
 // ---- advect_u, advect_v + gravity + zero_bounds ---------------------------------------
-__global__ void __launch_bounds__(QX* QY) k_advect_velocity(
+template <int MINB>
+__global__ void __launch_bounds__(QX* QY, MINB) k_advect_velocity(
     Grid g, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
     float* __restrict__ uo, float* __restrict__ vo, float dt, float h, float gravity) {
@@ -595,10 +596,11 @@ void launch_timestep(Ctx& c, float frame_time, float cfl) {
 }
 
 // EULER_GRID_VARIANT=1 selects the one-cell-per-thread kernels (A/B runs)
-static bool scalar_variant() {
+static int grid_variant() {
   static const int v = getenv("EULER_GRID_VARIANT") ? atoi(getenv("EULER_GRID_VARIANT")) : 0;
-  return v == 1;
+  return v;
 }
+static bool scalar_variant() { return grid_variant() == 1; }
 
 void launch_extrapolate(Ctx& c) {
   ProfScope ps(c, KC_EXTRAPOLATE);
@@ -616,9 +618,19 @@ void launch_advect_velocity(Ctx& c, float dt) {
   if (scalar_variant())
     k_advect_velocity_scalar<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
         c.g, c.lim, c.u, c.v, c.count, c.solid, c.utmp, c.vtmp, dt, c.h, c.gravity);
-  else
-    k_advect_velocity<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
-        c.g, c.lim, c.u, c.v, c.count, c.solid, c.utmp, c.vtmp, dt, c.h, c.gravity);
+  else {
+    // Resident blocks per SM the compiler must allow: the kernel waits on dependent gathers
+    // (ncu: 35 % long-scoreboard stalls, sm throughput 69 %), so more warps beat more registers.
+    // Measured at 16384^2: 1.21 ms at 4-5 blocks (48-56 registers), 1.17 ms at 6 (40), 1.12 ms
+    // at 8 (32 registers, 48 B of spills).  Taking the two fixed-offset samples from registers
+    // (quad-wide mask/value loads instead of 10 loads per sample) was tried as well: same time at
+    // equal occupancy, so the simpler kernel stays.
+    static const int minb = getenv("EULER_ADV_MINB") ? atoi(getenv("EULER_ADV_MINB")) : 8;
+#define ADV(M) k_advect_velocity<M><<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>( \
+        c.g, c.lim, c.u, c.v, c.count, c.solid, c.utmp, c.vtmp, dt, c.h, c.gravity)
+    if (minb == 4) ADV(4); else if (minb == 6) ADV(6); else ADV(8);
+#undef ADV
+  }
   c.launches += 1;
 }
 

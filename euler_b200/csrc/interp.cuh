@@ -35,6 +35,21 @@ __device__ __forceinline__ float snap_fraction(float f, bool lo_ok, bool hi_ok) 
   return !lo_ok ? 1.f : (!hi_ok ? 0.f : f);                  // main.c:301-309
 }
 
+// bilinear() of main.c:318-331 on four corner values with their usability flags: unusable
+// corners read as 0 (main.c:333-335) and are excluded by snapping the fraction; vertical lerps
+// first, then the horizontal one.
+__device__ __forceinline__ float bilinear_masked(float v00, float v10, float v01, float v11,
+                                                 bool ok00, bool ok10, bool ok01, bool ok11,
+                                                 float fx, float fy) {
+  const float q00 = ok00 ? v00 : 0.f;
+  const float q10 = ok10 ? v10 : 0.f;
+  const float q01 = ok01 ? v01 : 0.f;
+  const float q11 = ok11 ? v11 : 0.f;
+  const float left = lerp_ref(q00, q01, snap_fraction(fy, ok00, ok01));
+  const float right = lerp_ref(q10, q11, snap_fraction(fy, ok10, ok11));
+  return lerp_ref(left, right, snap_fraction(fx, ok00 | ok01, ok10 | ok11));
+}
+
 // One 64-bit index per sample; every other address is that pointer plus an immediate or plus
 // the pitch.  The four values are loaded unconditionally (every address is inside the
 // allocation: guard rows, clamped indices) and unusable corners are replaced by 0 afterwards, so
@@ -76,14 +91,7 @@ __device__ __forceinline__ float interpolate(const float* __restrict__ q,
     const bool c0 = m2[0] != 0, c1 = m2[1] != 0;
     ok00 = a0 | b0; ok10 = a1 | b1; ok01 = b0 | c0; ok11 = b1 | c1;
   }
-  const float q00 = ok00 ? v00 : 0.f;
-  const float q10 = ok10 ? v10 : 0.f;
-  const float q01 = ok01 ? v01 : 0.f;
-  const float q11 = ok11 ? v11 : 0.f;
-
-  const float left = lerp_ref(q00, q01, snap_fraction(fy, ok00, ok01));
-  const float right = lerp_ref(q10, q11, snap_fraction(fy, ok10, ok11));
-  return lerp_ref(left, right, snap_fraction(fx, ok00 | ok01, ok10 | ok11));
+  return bilinear_masked(v00, v10, v01, v11, ok00, ok10, ok01, ok11, fx, fy);
 }
 
 }  // namespace euler

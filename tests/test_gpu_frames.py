@@ -355,3 +355,66 @@ def test_host_program_checkpoint_round_trip(rainbow, tmp_path):
     bad = subprocess.run([exe, "--headless", "--frames", "1", "--grid", "64x48", "--load", ck, str(path)],
                          capture_output=True, text=True, cwd=ROOT)
     assert bad.returncode != 0 and "checkpoint" in bad.stderr
+
+
+def test_4096_operator_is_linear_and_symmetric():
+    """Size-independent properties of the stencil kernels at 4096^2 (BASELINE config[2] geometry,
+    no oracle run at this size): A is linear and symmetric on the fluid cells, and the red-black
+    preconditioner is symmetric too (M^-1 = (L L^T)^-1) — any masking or halo slip in the TMA
+    pipeline or the work split would break one of them."""
+    from euler_b200 import gpu as G
+    n = 4096
+    text = resample(shipped_text("waterfall"), n - 2, n - 2)
+    g = G.EulerGpu.from_scenario(Scenario(text, n, n), precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST)
+    g.step_frame()
+    g.run_stage(G.S_BUILD_RHS, 0.01)
+    fl = g.get(G.F_COUNT) != 0
+    rng = np.random.default_rng(7)
+    a = np.where(fl, rng.standard_normal((n, n)), 0.0)
+    b = np.where(fl, rng.standard_normal((n, n)), 0.0)
+
+    def apply_a(x):
+        g.set(G.F_S, x); g.run_stage(G.S_APPLY_A)
+        return np.where(fl, g.get(G.F_Z), 0.0)
+
+    def apply_m(x):
+        g.set(G.F_R, x); g.run_stage(G.S_PRECONDITION)
+        return np.where(fl, g.get(G.F_Z), 0.0)
+    Aa, Ab, Aab = apply_a(a), apply_a(b), apply_a(a + 2.0 * b)
+    scale = float(np.abs(Aab).max())
+    assert float(np.abs(Aab - (Aa + 2.0 * Ab)).max()) <= 1e-12 * scale
+    sab, sba = float((a * Ab).sum()), float((b * Aa).sum())
+    assert abs(sab - sba) <= 1e-10 * max(abs(sab), 1.0)
+    assert float((a * Aa).sum()) > 0.0                      # positive definite on the fluid cells
+    Ma, Mb = apply_m(a), apply_m(b)
+    mab, mba = float((a * Mb).sum()), float((b * Ma).sum())
+    assert abs(mab - mba) <= 1e-10 * max(abs(mab), 1.0)
+    assert float((a * Ma).sum()) > 0.0
+    g.close()
+
+
+def test_16384_properties():
+    """BASELINE config[4] size on one GPU (the bench workload): two sub-steps of basic-fill at
+    16384^2.  The count plane sums to the marker count, the fluid block is still the 40 % x 50 %
+    rectangle it started as (nothing leaks through the walls), the capped solve reduces the
+    residual, pressure is non-negative and finite, the device footprint is what DESIGN.md says."""
+    from euler_b200 import gpu as G
+    n = 16384
+    scn = Scenario(synthetic("basic-fill", n, n), n, n, row_major_markers=True)
+    g = G.EulerGpu.from_scenario(scn, precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST, pcg_check_every=25)
+    n0 = int(g.stats().n_markers)
+    res = []
+    for _ in range(2):
+        g.substep(g.calculate_timestep(0.1))
+        res.append(float(g.stats().last_residual))
+    st = g.stats()
+    assert st.last_iterations == 100 and np.isfinite(res).all()
+    cnt = g.read_marker_count()
+    assert int(cnt.astype(np.int64).sum()) == int(st.n_markers) == n0
+    assert not cnt[scn.solid != 0].any()
+    win = np.zeros((n, n), np.float64)
+    g.read_window(G.F_P, 0, 0, n, 64, win)                   # the bottom rows: deepest water
+    wet = cnt[:64] != 0
+    assert wet.any() and float(win[:64][wet].min()) >= 0.0 and np.isfinite(win[:64]).all()
+    assert 35e9 < int(st.device_bytes) < 50e9
+    g.close()
