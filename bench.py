@@ -39,7 +39,9 @@ sys.path.insert(0, ROOT)
 # reference's dtypes (fields fp32, PCG vectors fp64, masks u8): SURVEY §8d / DESIGN.md §4
 ALG_BYTES_PER_CELL = {
     "apply_a": 18.0,            # R s 8 + fluid,a_diag 2 + W z 8
-    "axpy_norm": 48.0,          # R s,p,z,r 32 + W p,r 16
+    "axpy_norm": 40.0,          # fused iteration: odd launches R As,r 16 + W r 8 = 24, even launches
+                                # R As,r,p,s',s 40 + W r,p 16 = 56 (p takes two updates at once): mean 40;
+                                # the reference's per-iteration form is 48 (R s,p,z,r 32 + W p,r 16)
     "precon_apply": 56.0,       # IC(0) wavefront: fwd R r,pc 16 W q 8; bwd R q,pc 16 W z 8; R r 8
     "rb_forward": 25.0,         # R r,pc 16 + fluid 1 + W q 8
     "rb_backward": 33.0,        # R q,pc,r 24 + fluid 1 + W z 8 (fused with z.r)

@@ -292,16 +292,19 @@ int run_project(euler_gpu* h, float dt) {
     if (!c.fused) launch_copy_search(c);                    // s = z                    (:746)
     int remaining = h->prm.max_iterations;
     const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
+    const double* s_odd = c.s2;                             // where iteration 1 leaves its s
+    int it = 0;
     while (remaining > 0) {
       const int chunk = remaining < every ? remaining : every;
       for (int i = 0; i < chunk; ++i) {
+        ++it;
         if (c.fused) {
           // c.z holds M^-1 r here; the fused kernels read it, leave A s in c.q ... and swap
           launch_fused_search_apply(c, first);              // s = z (+ beta s), A s -> c.q, alpha
           if (c.fused >= 2) {
             launch_fused_axpy_forward(c, h->prm.tol);       // p, r, ||r||inf, q = L^-1 r
           } else {
-            launch_axpy(c, h->prm.tol, true);               // p, r, ||r||inf (A s read from c.q)
+            launch_axpy(c, h->prm.tol, true, (it & 1) ? 0 : 1);  // r, ||r||inf; p every 2nd iteration
             launch_rb_forward(c);                           // q = L^-1 r -> c.q
           }
           launch_rb_backward(c, false);                     // z = L^-T q -> c.z, z.r, beta
@@ -315,6 +318,7 @@ int run_project(euler_gpu* h, float dt) {
       if (rc) return rc;
       if (h->host_sc->done) break;
     }
+    if (c.fused == 1) launch_p_fixup(c, s_odd);             // pending p update of an odd last iteration
     h->last_iterations = h->host_sc->iters;
     h->last_residual = h->host_sc->resid;
     h->pcg_iterations += (uint64_t)h->host_sc->iters;
@@ -382,7 +386,7 @@ int dist_precon_apply(euler_gpu* h, bool init) {
   return 0;
 }
 
-int dist_iteration(euler_gpu* h, bool first) {
+int dist_iteration(euler_gpu* h, bool first, int it) {
   Ctx& c = h->c;
   if (c.fused) {
     // the one exchange per iteration: z = M^-1 r, 4 rows deep; s' = z + beta s is then formed
@@ -401,7 +405,7 @@ int dist_iteration(euler_gpu* h, bool first) {
     CM(comm_gather_scalars(c, h->cm, c.sc->part));  // {z.s partial}
     launch_dist_alpha(c, h->cm.gather, h->cm.nranks);
   }
-  launch_axpy(c, h->prm.tol, c.fused != 0);
+  launch_axpy(c, h->prm.tol, c.fused != 0, c.fused == 1 ? ((it & 1) ? 0 : 1) : 2);
   int rc = dist_precon_apply(h, false);
   if (rc) return rc;
   if (!c.fused) launch_update_search(c);
@@ -429,9 +433,11 @@ int run_project_dist(euler_gpu* h, float dt) {
     bool first = true;
     int remaining = h->prm.max_iterations;
     const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
+    const double* s_odd = c.s2;                      // where iteration 1 leaves its s
+    int it = 0;
     while (remaining > 0) {
       const int chunk = remaining < every ? remaining : every;
-      for (int i = 0; i < chunk; ++i) { rc = dist_iteration(h, first); if (rc) return rc; first = false; }
+      for (int i = 0; i < chunk; ++i) { rc = dist_iteration(h, first, ++it); if (rc) return rc; first = false; }
       remaining -= chunk;
       rc = pull_scalars(h);
       if (rc) return rc;
@@ -439,6 +445,7 @@ int run_project_dist(euler_gpu* h, float dt) {
         return fail(EULER_E_COMM, "peer-to-peer exchange timed out (a rank stopped participating)");
       if (h->host_sc->done) break;
     }
+    if (c.fused == 1) launch_p_fixup(c, s_odd);      // pending p update of an odd last iteration
     h->last_iterations = h->host_sc->iters;
     h->last_residual = h->host_sc->resid;
     h->pcg_iterations += (uint64_t)h->host_sc->iters;

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(32) k_p2p_scalars(PeerPtrs peers, Mailbox* min
   if (sc->done) return;
   double sum = 0.0, mx = 0.0;
   for (int r = 0; r < nranks; ++r) { sum += mine->pay[par][r][0]; mx = fmax(mx, mine->pay[par][r][1]); }
-  if (kind == 0) { sc->zs = sum; sc->alpha = sc->sigma / sum; return; }      // main.c:752
+  if (kind == 0) { sc->zs = sum; sc->alpha_prev = sc->alpha; sc->alpha = sc->sigma / sum; return; }  // main.c:752
   if (init) { sc->sigma = sum; return; }                                      // main.c:748
   sc->resid = mx;
   sc->iters += 1;

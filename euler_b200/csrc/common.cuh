@@ -51,6 +51,7 @@ struct DevScalars {
   unsigned long long rng_state;
   // PCG (main.c:735-767)
   double sigma, zs, alpha, beta, resid;
+  double alpha_prev;              // alpha of the iteration before (deferred p update, k_axpy)
   int iters, done, nonzero_rhs, pad1;
   // grid-wide "last block done" counters, one per reducing kernel family
   unsigned int ctr[8];

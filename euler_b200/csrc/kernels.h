@@ -143,7 +143,13 @@ void launch_dist_alpha(Ctx& c, const double* gathered, int nranks);
 void launch_dist_beta(Ctx& c, const double* gathered, int nranks, bool init, double tol);
 void launch_copy_search(Ctx& c);                             // s = z
 void launch_apply_a(Ctx& c, bool with_alpha);                // z = A s (+ z.s, alpha)
-void launch_axpy(Ctx& c, double tol, bool as_in_q = false);  // p += a s, r -= a (A s), ||r||inf
+// mode 2: p += a s, r -= a (A s), ||r||inf every iteration (the reference's order of updates);
+// fused iteration: mode 0 on odd iterations (r only), mode 1 on even ones (r and both pending
+// p updates) — see k_axpy
+void launch_axpy(Ctx& c, double tol, bool as_in_q = false, int mode = 2);
+// completes p after a fused solve that stopped on an odd iteration; s_odd_plane = the plane
+// the first iteration wrote its search direction to (Ctx::s2 at the start of the solve)
+void launch_p_fixup(Ctx& c, const double* s_odd_plane);
 void launch_update_search(Ctx& c);                           // s = z + beta s
 void launch_pcg_reset(Ctx& c);                               // iters=0, done=0
 void launch_tile_flags(Ctx& c);                              // per-tile fluid flags from count

@@ -100,7 +100,7 @@ __device__ __forceinline__ void p2p_finish(const DistArgs& d, DevScalars* sc, in
   if (!ok_sh) { sc->comm_timeout = 1; sc->done = 1; return; }
   double sum = 0.0, mx = 0.0;
   for (int r = 0; r < d.nranks; ++r) { sum += mine->pay[par][r][0]; mx = fmax(mx, mine->pay[par][r][1]); }
-  if (kind == 0) { sc->zs = sum; sc->alpha = sc->sigma / sum; return; }      // main.c:752
+  if (kind == 0) { sc->zs = sum; sc->alpha_prev = sc->alpha; sc->alpha = sc->sigma / sum; return; }  // main.c:752
   if (init) { sc->sigma = sum; return; }                                      // main.c:748
   sc->resid = mx;
   sc->iters += 1;

@@ -259,19 +259,28 @@ __global__ void __launch_bounds__(TT) k_apply_a(
     if (exact == 2) { sc->part[0] = total; return; }         // slab mode: summed over ranks later
     if (exact) return;                                       // k_dot_seq supplies z.s instead
     sc->zs = total;
-    sc->alpha = sc->sigma / total;                           // main.c:752
+    sc->alpha_prev = sc->alpha; sc->alpha = sc->sigma / total;                           // main.c:752
   });
 }
 
 // ---- p += alpha s ; r -= alpha z ; ||r||inf ---------------------------------------------
+// `mode` (fused red-black iteration only; 2 = both updates every iteration, as the reference):
+// the two search directions of consecutive iterations live in two planes (s ping-pongs, see
+// k_fused_search_apply), so p can take TWO updates in one pass every second iteration,
+//   mode 0 (odd iterations)   r -= alpha (A s)                                  24 B/cell
+//   mode 1 (even iterations)  p = (p + alpha' s') + alpha s ; r -= alpha (A s)  56 B/cell
+// instead of 48 B/cell every iteration: p is read and written half as often and s is not read
+// again on odd iterations.  Same operations in the same order on every cell, so p is bit-
+// identical to the per-iteration update (main.c:753); a solve that ends on an odd iteration is
+// completed by k_p_fixup.
 __global__ void __launch_bounds__(TT) k_axpy(
-    Grid g, TileList active, const double* __restrict__ s,
+    Grid g, TileList active, const double* __restrict__ s, const double* __restrict__ s_prev,
     const double* __restrict__ z, const uint8_t* __restrict__ fluid, double* __restrict__ p,
     double* __restrict__ r, double* partials, DevScalars* sc, double tol, int defer, int acc0,
-    int acc1) {
+    int acc1, int mode) {
   pdl_prologue();
   if (sc->done) return;
-  const double alpha = sc->alpha;
+  const double alpha = sc->alpha, alpha_prev = sc->alpha_prev;
   double m = 0.0;
   for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
     if (!live) return;
@@ -279,17 +288,21 @@ __global__ void __launch_bounds__(TT) k_axpy(
     for (int y = y0; y < y1; ++y, c += g.pitch) {
       const unsigned mc = ldmask(fluid + c);
       if (!mc) continue;
-      const D4 sv = ld4(s + c), zv = ld4(z + c);
-      D4 pv = ld4(p + c), rv = ld4(r + c);
+      const D4 zv = ld4(z + c);
+      D4 rv = ld4(r + c);
+      D4 sv, spv, pv;
+      if (mode) { sv = ld4(s + c); pv = ld4(p + c); }
+      if (mode == 1) spv = ld4(s_prev + c);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (!mbit(mc, k)) continue;
-        pv.v[k] = pv.v[k] + sv.v[k] * alpha;                 // fmadd(s, alpha, p)  main.c:753
+        if (mode == 1) pv.v[k] = pv.v[k] + spv.v[k] * alpha_prev;   // the previous iteration's main.c:753
+        if (mode) pv.v[k] = pv.v[k] + sv.v[k] * alpha;       // fmadd(s, alpha, p)  main.c:753
         rv.v[k] = rv.v[k] + zv.v[k] * -alpha;                // fmadd(z, -alpha, r) main.c:754
         const double a = fabs(rv.v[k]);
         if (a > m && y >= acc0 && y < acc1) m = a;           // NaN-dropping, main.c:659-662
       }
-      st4(p + c, pv);
+      if (mode) st4(p + c, pv);
       st4(r + c, rv);
     }
   });
@@ -299,6 +312,29 @@ __global__ void __launch_bounds__(TT) k_axpy(
     sc->resid = total;
     sc->iters += 1;
     if (total <= tol) sc->done = 1;                          // main.c:756-758
+  });
+}
+
+// The deferred p update of a solve that stopped after an ODD number of iterations: the last
+// iteration's p += alpha s is still pending (s of iteration i lives in plane i & 1).
+__global__ void __launch_bounds__(TT) k_p_fixup(Grid g, TileList active, const double* __restrict__ s_odd,
+                                                const uint8_t* __restrict__ fluid, double* __restrict__ p,
+                                                const DevScalars* sc) {
+  if (!(sc->iters & 1)) return;
+  const double alpha = sc->alpha;
+  for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
+    if (!live) return;
+    size_t c = gidx(g, x0, y0);
+    for (int y = y0; y < y1; ++y, c += g.pitch) {
+      const unsigned mc = ldmask(fluid + c);
+      if (!mc) continue;
+      const D4 sv = ld4(s_odd + c);
+      D4 pv = ld4(p + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (mbit(mc, k)) pv.v[k] = pv.v[k] + sv.v[k] * alpha;
+      st4(p + c, pv);
+    }
   });
 }
 
@@ -549,7 +585,7 @@ __global__ void __launch_bounds__(256) k_dot_seq(
     k = kn;
   }
   if (threadIdx.x == 0) {
-    if (what == DOT_ZS) { sc->zs = total; sc->alpha = sc->sigma / total; }
+    if (what == DOT_ZS) { sc->zs = total; sc->alpha_prev = sc->alpha; sc->alpha = sc->sigma / total; }
     else if (what == DOT_ZR_INIT) { sc->sigma = total; }
     else { sc->beta = total / sc->sigma; sc->sigma = total; }
   }
@@ -641,7 +677,7 @@ __global__ void __launch_bounds__(TT) k_apply_a_pipe(
     if (exact == 2) { sc->part[0] = total; return; }
     if (exact) return;
     sc->zs = total;
-    sc->alpha = sc->sigma / total;                           // main.c:752
+    sc->alpha_prev = sc->alpha; sc->alpha = sc->sigma / total;                           // main.c:752
   });
 }
 
@@ -784,6 +820,7 @@ __global__ void k_dist_alpha(DevScalars* sc, const double* __restrict__ gathered
   double zs = 0.0;
   for (int r = 0; r < nranks; ++r) zs += gathered[r * 4 + 0];
   sc->zs = zs;
+  sc->alpha_prev = sc->alpha;
   sc->alpha = sc->sigma / zs;                                // main.c:752
 }
 // after the preconditioner: z.r (sum) and, except for the initial application, ||r||inf (max)
@@ -898,7 +935,7 @@ __global__ void __launch_bounds__(TW / C) k_fused_search_apply(
   if (threadIdx.x != 0) return;
   if (exact == 2) { sc->part[0] = total; return; }
   sc->zs = total;
-  sc->alpha = sc->sigma / total;                             // main.c:752
+  sc->alpha_prev = sc->alpha; sc->alpha = sc->sigma / total;                             // main.c:752
 }
 
 template <int C>
@@ -1106,11 +1143,21 @@ void launch_apply_a(Ctx& c, bool) {
   }
 }
 
-void launch_axpy(Ctx& c, double tol, bool as_in_q) {
+void launch_axpy(Ctx& c, double tol, bool as_in_q, int mode) {
   ProfScope ps(c, KC_AXPY);
   const PV v = pview(c);
-  launch_pdl(k_axpy, pcg_blocks(c, k_axpy), TT, 0, c.stream, v.g, TL, v.s, as_in_q ? v.q : v.z, v.fluid, v.p,
-             v.r, c.partials, c.sc, tol, c.distributed ? 1 : 0, v.a0, v.a1);
+  const size_t o = (size_t)(v.s - c.s);
+  launch_pdl(k_axpy, pcg_blocks(c, k_axpy), TT, 0, c.stream, v.g, TL, v.s, c.s2 ? c.s2 + o : v.s,
+             as_in_q ? v.q : v.z, v.fluid, v.p, v.r, c.partials, c.sc, tol, c.distributed ? 1 : 0, v.a0, v.a1,
+             mode);
+  c.launches += 1;
+}
+
+void launch_p_fixup(Ctx& c, const double* s_odd_plane) {
+  ProfScope ps(c, KC_AXPY);
+  const PV v = pview(c);
+  const size_t o = (size_t)(v.s - c.s);
+  k_p_fixup<<<pcg_blocks(c, k_p_fixup), TT, 0, c.stream>>>(v.g, TL, s_odd_plane + o, v.fluid, v.p, c.sc);
   c.launches += 1;
 }
 

@@ -27,7 +27,7 @@ def main():
     cells = n * n
     print("grid %d precon %d: %.1f ms/substep, iters %d resid %.3e" % (n, precon, wall / steps * 1e3, st.last_iterations, st.last_residual))
     bpc = {"build_rhs": 19, "pressure_update": 26, "extrapolate_bounds": 19, "advect_velocity": 18, "maxsq": 8}
-    pcg = {"apply_a": 18, "axpy_norm": 48, "precon_apply": 56, "update_search": 24, "rb_forward": 25,
+    pcg = {"apply_a": 18, "axpy_norm": 40, "precon_apply": 56, "update_search": 24, "rb_forward": 25,
            "rb_backward": 33, "fused_search_apply_a": 34, "fused_axpy_forward": 65}
     active = st.active_cells
     for name, (ms, cnt) in sorted(sim.kernel_profile().items(), key=lambda kv: -kv[1][0]):
