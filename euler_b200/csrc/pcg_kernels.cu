@@ -1154,7 +1154,7 @@ void launch_axpy(Ctx& c, double tol, bool as_in_q, int mode) {
 }
 
 void launch_p_fixup(Ctx& c, const double* s_odd_plane) {
-  ProfScope ps(c, KC_AXPY);
+  ProfScope ps(c, KC_MISC);
   const PV v = pview(c);
   const size_t o = (size_t)(v.s - c.s);
   k_p_fixup<<<pcg_blocks(c, k_p_fixup), TT, 0, c.stream>>>(v.g, TL, s_odd_plane + o, v.fluid, v.p, c.sc);
