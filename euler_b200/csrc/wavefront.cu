@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(32) k_ic0_sweep(
     Grid g, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
     double* precon, const double* __restrict__ in, double* out, const double* __restrict__ rvec,
     unsigned int* progress, unsigned int* ticket, double* partials, DevScalars* sc, int init,
-    int exact, int dbg) {
+    int exact, int dbg, int start_lag) {
   if (MODE != WF_BUILD && sc->done) return;
   const int lane = threadIdx.x;
   const int n_strips = gridDim.x;
@@ -91,6 +91,19 @@ __global__ void __launch_bounds__(32) k_ic0_sweep(
 
   unsigned int avail = 0;                           // columns of the dependency row known done
   double acc = 0.0;
+
+  // Start `start_lag` columns behind the strip below.  All strips advance at the same pace (the
+  // dependent fp64 chain), so the distance persists, and with it the one-block-ahead loads of
+  // the dependency row (load_dep, non-blocking) always find their columns published: the
+  // release -> acquire -> ld.cg hand-off latency (~1-2 us through L2) is paid once per strip
+  // instead of once per 8 columns.  Without the head start every strip ran at the minimum
+  // distance and blocked on the hand-off in every block — that, not the fp64 chain, bounded the
+  // sweep.  Costs n_strips x start_lag extra column steps of pipeline fill.
+  if (lane == 0 && row_ok && strip > 0 && start_lag > 0 && !(dbg & 1)) {
+    const unsigned int want = (unsigned int)min(ncols, start_lag);
+    do { avail = ld_acquire(progress + (strip - 1)); } while (avail < want);
+  }
+  __syncwarp();
 
   // Steps are processed in blocks of WB columns, software-pipelined one block deep: while block
   // b is being computed out of registers, the loads of block b+1 are already in flight (own
@@ -245,6 +258,9 @@ __global__ void __launch_bounds__(32) k_ic0_sweep(
 
 static int wf_dbg() { static int v = -1; if (v < 0) { const char* e = getenv("EULER_WF_DEBUG"); v = e ? atoi(e) : 0; } return v; }
 
+// head start of a strip over the next one, in columns (see k_ic0_sweep); EULER_WF_LAG overrides
+static int wf_lag() { static int v = -1; if (v < 0) { const char* e = getenv("EULER_WF_LAG"); v = e ? atoi(e) : 64; } return v; }
+
 static void reset_wavefront(Ctx& c) {
   cudaMemsetAsync(c.wf_progress, 0, sizeof(unsigned int) * (size_t)c.n_strips, c.stream);
 }
@@ -254,7 +270,7 @@ void launch_ic0_build(Ctx& c) {
   reset_wavefront(c);
   k_ic0_sweep<WF_BUILD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, nullptr, nullptr, nullptr, c.wf_progress,
-      &c.sc->ticket[0], c.partials, c.sc, 0, 0, wf_dbg());
+      &c.sc->ticket[0], c.partials, c.sc, 0, 0, wf_dbg(), wf_lag());
   c.launches += 1;
 }
 
@@ -263,11 +279,11 @@ void launch_ic0_apply(Ctx& c, bool init) {
   reset_wavefront(c);
   k_ic0_sweep<WF_FORWARD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, c.r, c.q, nullptr, c.wf_progress, &c.sc->ticket[1],
-      c.partials, c.sc, 0, 0, wf_dbg());
+      c.partials, c.sc, 0, 0, wf_dbg(), wf_lag());
   reset_wavefront(c);
   k_ic0_sweep<WF_BACKWARD><<<c.n_strips, 32, 0, c.stream>>>(
       c.g, c.count, c.adiag, c.precon, c.q, c.z, c.r, c.wf_progress, &c.sc->ticket[2],
-      c.partials, c.sc, init ? 1 : 0, c.dot_mode, wf_dbg());
+      c.partials, c.sc, init ? 1 : 0, c.dot_mode, wf_dbg(), wf_lag());
   c.launches += 2;
   launch_dot_zr_exact(c, init);
 }
