@@ -62,7 +62,16 @@ DRY_BYTES_PER_CELL = {"build_rhs": 17.0, "pressure_update": 9.0, "extrapolate_bo
                       "advect_velocity": 9.0}
 ALG_BYTES_PER_MARKER = {"advect_markers": 16.0}
 PCG_KERNELS = ("apply_a", "axpy_norm", "precon_apply", "update_search", "rb_forward", "rb_backward",
-               "fused_search_apply_a", "fused_axpy_forward")
+               "fused_search_apply_a", "fused_axpy_forward", "true_residual")
+# --pcg-dtype fp32 (euler_params.pcg_dtype = FP32, not the headline configuration): r, z, s, q,
+# A s and the preconditioner diagonal are fp32 planes, p stays fp64 — DESIGN.md §9 row 4
+ALG_BYTES_PER_CELL_FP32 = {
+    "fused_search_apply_a": 18.0,  # R z,s 8 + fluid,a_diag 2 + W s',A s' 8
+    "axpy_norm": 25.0,             # odd: R As,r 8 + fluid 1 + W r 4 = 13; even: + R s',s 8, p 8, W p 8 = 37
+    "rb_forward": 13.0,            # R r,pc 8 + fluid 1 + W q 4
+    "rb_backward": 17.0,           # R q,pc,r 12 + fluid 1 + W z 4
+    "true_residual": 22.0,         # R p 8, b 8, fluid,a_diag 2 + W r 4; once every 10 iterations
+}
 
 
 def peaks():
@@ -142,6 +151,10 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     n = args.grid
     precon = G.PRECON_REDBLACK if args.precon == "rb" else G.PRECON_IC0_WAVEFRONT
+    mixed = args.pcg_dtype == "fp32"
+    if mixed and (world > 1 or args.precon != "rb"):
+        raise SystemExit("--pcg-dtype fp32 is a single-GPU mode of the red-black solve")
+    alg_bytes = dict(ALG_BYTES_PER_CELL, **ALG_BYTES_PER_CELL_FP32) if mixed else ALG_BYTES_PER_CELL
 
     t_host0 = time.perf_counter()
     text = synthetic(args.scenario, n, n)
@@ -162,7 +175,8 @@ def run_gpu(args):
         sim = G.EulerGpu.from_scenario(scn, precon=precon, marker_mode=G.MARKERS_FAST,
                                        device=local, stream=stream.cuda_stream,
                                        pcg_check_every=args.check_every,
-                                       slab_row0=row0, slab_rows=rows)
+                                       slab_row0=row0, slab_rows=rows,
+                                       pcg_dtype=G.PCG_FP32 if mixed else G.PCG_FP64)
         if world > 1:
             # communicator id made on rank 0, broadcast over torch.distributed (plumbing only)
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -289,9 +303,9 @@ def run_gpu(args):
             if name in PCG_KERNELS:
                 # PCG kernels stream only the tiles that contain fluid (like the reference,
                 # which touches only is_fluid cells): units = cells of those tiles
-                b = ALG_BYTES_PER_CELL[name] * active_cells
-            elif name in ALG_BYTES_PER_CELL:
-                b = ALG_BYTES_PER_CELL[name] * cells_local
+                b = alg_bytes[name] * active_cells
+            elif name in alg_bytes:
+                b = alg_bytes[name] * cells_local
             elif name in ALG_BYTES_PER_MARKER:
                 b = ALG_BYTES_PER_MARKER[name] * n_markers
             else:
@@ -302,13 +316,13 @@ def run_gpu(args):
                              "frac": round(b / avg / 1e6 / peak, 4) if b else None}
             if name in DRY_BYTES_PER_CELL:
                 wet = min(active_cells, cells_local)
-                bt = ALG_BYTES_PER_CELL[name] * wet + DRY_BYTES_PER_CELL[name] * (cells_local - wet)
+                bt = alg_bytes[name] * wet + DRY_BYTES_PER_CELL[name] * (cells_local - wet)
                 kernels[name]["gbs_touched"] = round(bt / avg / 1e6, 1)
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tt = json.load(f)
-            if n == 16384 and world == 1 and args.scenario == "basic-fill" and dom:
+            if n == 16384 and world == 1 and args.scenario == "basic-fill" and dom and not mixed:
                 traffic = tt.get(dom[0])
         except (OSError, ValueError):
             pass
@@ -317,9 +331,9 @@ def run_gpu(args):
             roof = {"kernel": dom[0], "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": k["frac"], "traffic": traffic, "peak_source": peak_src,
                     "traffic_source": "ncu capture committed under profiles/ (same workload)" if traffic else None,
-                    "alg_bytes_per_launch": ALG_BYTES_PER_CELL[dom[0]] * (active_cells if dom[0] in PCG_KERNELS else cells_local),
+                    "alg_bytes_per_launch": alg_bytes[dom[0]] * (active_cells if dom[0] in PCG_KERNELS else cells_local),
                     "units_per_launch": active_cells if dom[0] in PCG_KERNELS else cells_local,
-                    "bytes_per_unit": ALG_BYTES_PER_CELL[dom[0]],
+                    "bytes_per_unit": alg_bytes[dom[0]],
                     "ms_per_launch": k["ms_avg"], "share_of_step": k["share"]}
         value = cells * args.steps / (ms_max * 1e-3)
         line = {
@@ -329,10 +343,13 @@ def run_gpu(args):
             "ms_per_step_with_kernel_timers": (ms_timers / args.steps) if ms_timers else None,
             "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 storage, f64 pressure and dot products" if mixed else "f64",
+            "data": "synthetic",
             "config": {"workload": "%s %dx%d (whole grid), one sub-step of sim_step per step, PCG cap 100 "
-                                   "(reference main.c:735), %s preconditioner, fp64 PCG vectors"
-                                   % (args.scenario, n, n, "red-black IC(0)" if args.precon == "rb" else "IC(0) wavefront"),
+                                   "(reference main.c:735), %s preconditioner, %s"
+                                   % (args.scenario, n, n, "red-black IC(0)" if args.precon == "rb" else "IC(0) wavefront",
+                                      "fp32 PCG vectors + fp64 p, residual replacement every 10 iterations "
+                                      "(NOT the reference's precision: opt-in mode)" if mixed else "fp64 PCG vectors"),
                        "grid": [n, n], "markers": n_markers, "active_cells": active_cells,
                        "parallelism": "single GPU" if world == 1 else
                                       "%d row slabs balanced by fluid cells (rank 0: %d rows), NCCL halo exchange + marker migration, %s" % (world, rows, "NCCL per-iteration exchanges" if args.no_p2p else "per-iteration exchanges by NVLink peer stores (CUDA IPC)"),
@@ -436,6 +453,8 @@ def main():
     ap.add_argument("--scenario", default="basic-fill")
     ap.add_argument("--precon", default="rb", choices=["rb", "ic0"])
     ap.add_argument("--check-every", type=int, default=25)
+    ap.add_argument("--pcg-dtype", default="fp64", choices=["fp64", "fp32"],
+                    help="fp32: opt-in mixed-precision PCG (not the headline configuration)")
     ap.add_argument("--cpu-grid", type=int, default=1024)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -128,6 +128,11 @@ FieldInfo field_info(euler_gpu* h, int f) {
     case EULER_F_CR: return {c.cr, 4};
     case EULER_F_CG: return {c.cg, 4};
     case EULER_F_CB: return {c.cb, 4};
+    case EULER_F_R32: return {c.r32, 4};
+    case EULER_F_Z32: return {c.z32, 4};
+    case EULER_F_S32: return {c.s32, 4};
+    case EULER_F_Q32: return {c.q32, 4};
+    case EULER_F_PRECON32: return {c.pc32, 4};
     default: return {nullptr, 0};
   }
 }
@@ -178,6 +183,8 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
     rc |= zero_plane(h, c.adiag); rc |= zero_plane(h, c.precon); rc |= zero_plane(h, c.q);
     rc |= zero_plane(h, c.p); rc |= zero_plane(h, c.r); rc |= zero_plane(h, c.z); rc |= zero_plane(h, c.s);
     rc |= zero_plane(h, c.s2); rc |= zero_plane(h, c.r2);
+    rc |= zero_plane(h, c.r32); rc |= zero_plane(h, c.z32); rc |= zero_plane(h, c.s32);
+    rc |= zero_plane(h, c.s32b); rc |= zero_plane(h, c.q32); rc |= zero_plane(h, c.pc32);
     rc |= zero_plane(h, c.cr); rc |= zero_plane(h, c.cg); rc |= zero_plane(h, c.cb);
     rc |= zero_plane(h, c.crtmp); rc |= zero_plane(h, c.cgtmp); rc |= zero_plane(h, c.cbtmp);
     if (rc) return rc;
@@ -292,7 +299,9 @@ int run_project(euler_gpu* h, float dt) {
     if (!c.fused) launch_copy_search(c);                    // s = z                    (:746)
     int remaining = h->prm.max_iterations;
     const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
-    const double* s_odd = c.s2;                             // where iteration 1 leaves its s
+    // where iteration 1 leaves its s
+    const void* s_odd = c.mixed ? static_cast<const void*>(c.s32b) : static_cast<const void*>(c.s2);
+    const int refresh = c.mixed ? h->prm.pcg_refresh_every : 0;
     int it = 0;
     while (remaining > 0) {
       const int chunk = remaining < every ? remaining : every;
@@ -305,6 +314,8 @@ int run_project(euler_gpu* h, float dt) {
             launch_fused_axpy_forward(c, h->prm.tol);       // p, r, ||r||inf, q = L^-1 r
           } else {
             launch_axpy(c, h->prm.tol, true, (it & 1) ? 0 : 1);  // r, ||r||inf; p every 2nd iteration
+            // mixed precision: r <- b - A p in fp64 (p is complete after an even iteration)
+            if (refresh > 0 && it % refresh == 0) launch_true_residual(c);
             launch_rb_forward(c);                           // q = L^-1 r -> c.q
           }
           launch_rb_backward(c, false);                     // z = L^-T q -> c.z, z.r, beta
@@ -559,6 +570,7 @@ int euler_gpu_default_params(euler_params* p) {
   p->rng_state = 0x9bd185c449534b91ull;                      // main.c:204
   p->device = 0; p->stream = nullptr; p->pcg_check_every = 8;
   p->slab_row0 = 0; p->slab_rows = 0;
+  p->pcg_dtype = EULER_PCG_FP64; p->pcg_refresh_every = 10;
   return 0;
 }
 
@@ -604,6 +616,17 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   }
   if (slab && prm.rainbow)
     return fail(EULER_E_UNSUPPORTED, "--rainbow colour transport is not decomposed into slabs yet");
+  if (prm.pcg_dtype != EULER_PCG_FP64 && prm.pcg_dtype != EULER_PCG_FP32)
+    return fail(EULER_E_INVALID, "unknown pcg_dtype %d", prm.pcg_dtype);
+  const bool mixed = prm.pcg_dtype == EULER_PCG_FP32;
+  if (mixed) {
+    if (prm.precon != EULER_PRECON_REDBLACK || prm.dot_mode != EULER_DOT_TREE || prm.stencil_variant != 0 || slab)
+      return fail(EULER_E_UNSUPPORTED, "pcg_dtype=FP32 needs precon=REDBLACK, dot_mode=TREE, stencil_variant=0 "
+                  "on a single-GPU handle (it is a mode of the fused red-black iteration)");
+    if (prm.pcg_refresh_every < 0 || (prm.pcg_refresh_every & 1))
+      return fail(EULER_E_INVALID, "pcg_refresh_every must be even (p is complete after even iterations) or 0, got %d",
+                  prm.pcg_refresh_every);
+  }
   const int row0 = slab ? prm.slab_row0 : 0, rows = slab ? prm.slab_rows : ny;
   const int lo = row0 - SLAB_HALO > 0 ? row0 - SLAB_HALO : 0;
   const int hi = row0 + rows + SLAB_HALO < ny ? row0 + rows + SLAB_HALO : ny;
@@ -674,14 +697,22 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   TRY(alloc_plane(h, &c.utmp)); TRY(alloc_plane(h, &c.vtmp));
   TRY(alloc_plane(h, &c.uext)); TRY(alloc_plane(h, &c.vext));
   TRY(alloc_plane(h, &c.adiag));
-  TRY(alloc_plane(h, &c.precon)); TRY(alloc_plane(h, &c.q)); TRY(alloc_plane(h, &c.p));
-  TRY(alloc_plane(h, &c.r)); TRY(alloc_plane(h, &c.z)); h->z_raw = h->allocs.back();
-  TRY(alloc_plane(h, &c.s));
   // stencil_variant 0: fused update_search+apply_a (default); 2: additionally axpy+forward fused
   // (measured slower: profiles/r01 notes); 1: nothing fused, register-window stencils
   c.fused = (prm.precon == EULER_PRECON_REDBLACK && prm.dot_mode == EULER_DOT_TREE && prm.stencil_variant != 1)
                 ? (prm.stencil_variant == 2 ? 2 : 1) : 0;
-  if (c.fused) { TRY(alloc_plane(h, &c.s2)); TRY(alloc_plane(h, &c.r2)); }
+  c.mixed = mixed ? 1 : 0;
+  if (mixed) {
+    // fp64: p and b (in the r plane) only; everything the iteration streams is fp32
+    TRY(alloc_plane(h, &c.p)); TRY(alloc_plane(h, &c.r));
+    TRY(alloc_plane(h, &c.r32)); TRY(alloc_plane(h, &c.z32)); TRY(alloc_plane(h, &c.s32));
+    TRY(alloc_plane(h, &c.s32b)); TRY(alloc_plane(h, &c.q32)); TRY(alloc_plane(h, &c.pc32));
+  } else {
+    TRY(alloc_plane(h, &c.precon)); TRY(alloc_plane(h, &c.q)); TRY(alloc_plane(h, &c.p));
+    TRY(alloc_plane(h, &c.r)); TRY(alloc_plane(h, &c.z)); h->z_raw = h->allocs.back();
+    TRY(alloc_plane(h, &c.s));
+    if (c.fused) { TRY(alloc_plane(h, &c.s2)); TRY(alloc_plane(h, &c.r2)); }
+  }
   if (prm.rainbow) {
     TRY(alloc_plane(h, &c.cr)); TRY(alloc_plane(h, &c.cg)); TRY(alloc_plane(h, &c.cb));
     TRY(alloc_plane(h, &c.crtmp)); TRY(alloc_plane(h, &c.cgtmp)); TRY(alloc_plane(h, &c.cbtmp));
@@ -806,7 +837,9 @@ int euler_gpu_run_stage(euler_gpu* h, int stage, float dt) {
       if (h->prm.precon == EULER_PRECON_REDBLACK) launch_rb_build(c); else launch_ic0_build(c);
       enqueue_precon_apply(h, true);
       break;
-    case EULER_S_APPLY_A: launch_pcg_reset(c); launch_tile_flags(c); launch_apply_a(c, false); break;
+    case EULER_S_APPLY_A:
+      if (c.mixed) return fail(EULER_E_UNSUPPORTED, "pcg_dtype=FP32 has no stand-alone apply_a (fused into the search update)");
+      launch_pcg_reset(c); launch_tile_flags(c); launch_apply_a(c, false); break;
     case EULER_S_PRESSURE_UPDATE: launch_pressure_update(c, dt); h->max_valid = true; break;
     case EULER_S_EXTRAPOLATE_COLOR:
     case EULER_S_ADVECT_COLOR:
@@ -823,6 +856,7 @@ int euler_gpu_run_stage(euler_gpu* h, int stage, float dt) {
 
 int euler_gpu_pcg_iterations(euler_gpu* h, int iterations) {
   ENTER(h);
+  if (h->c.mixed) return fail(EULER_E_UNSUPPORTED, "pcg_iterations drives the unfused fp64 iteration");
   for (int i = 0; i < iterations; ++i) {
     enqueue_iteration(h);
     if (h->c.prof.on && h->c.prof.n + 16 > h->c.prof.cap) {
@@ -851,7 +885,7 @@ int euler_gpu_get(euler_gpu* h, int field, void* dst, size_t bytes) {
     return 0;
   }
   FieldInfo fi = field_info(h, field);
-  if (!fi.ptr) return fail(EULER_E_INVALID, "unknown field %d", field);
+  if (!fi.ptr) return fail(EULER_E_INVALID, "field %d unknown or not allocated on this handle (params.rainbow / pcg_dtype)", field);
   const size_t want = (size_t)g.nx * h->ny * fi.elem;
   if (bytes != want) return fail(EULER_E_INVALID, "field %d: %zu bytes given, %zu needed", field, bytes, want);
   // slab mode: only the rows this handle OWNS are written (at their global position)
@@ -901,7 +935,7 @@ int euler_gpu_set(euler_gpu* h, int field, const void* src, size_t bytes) {
   }
   if (field == EULER_F_SOURCE) return fail(EULER_E_UNSUPPORTED, "source plane is fixed at create()");
   FieldInfo fi = field_info(h, field);
-  if (!fi.ptr) return fail(EULER_E_INVALID, "unknown field %d", field);
+  if (!fi.ptr) return fail(EULER_E_INVALID, "field %d unknown or not allocated on this handle (params.rainbow / pcg_dtype)", field);
   const size_t want = (size_t)g.nx * h->ny * fi.elem;
   if (bytes != want) return fail(EULER_E_INVALID, "field %d: %zu bytes given, %zu needed", field, bytes, want);
   int rc = upload_plane(h, fi.ptr, src, fi.elem);
@@ -990,7 +1024,7 @@ const char* euler_gpu_kernel_class_name(int i) {
       "maxsq", "advect_markers", "refresh_counts", "sources", "extrapolate_bounds",
       "advect_velocity", "build_rhs", "precon_build", "precon_apply", "apply_a", "axpy_norm",
       "update_search", "pressure_update", "misc", "fused_search_apply_a", "fused_axpy_forward",
-      "rb_forward", "rb_backward", "color_transport"};
+      "rb_forward", "rb_backward", "color_transport", "true_residual"};
   return (i >= 0 && i < KC__COUNT) ? names[i] : nullptr;
 }
 

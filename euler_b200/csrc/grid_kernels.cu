@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(BX* BY) k_build_rhs_scalar(
     Grid g, const float* __restrict__ u, const float* __restrict__ v,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
     double* __restrict__ r, double* __restrict__ p, int8_t* __restrict__ adiag, float h,
-    double scale, DevScalars* sc, int own0, int own1) {
+    double scale, DevScalars* sc, int own0, int own1, float* __restrict__ r32) {
   const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
   bool nz = false;
   if (x < g.nx && y < g.ny) {
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(BX* BY) k_build_rhs_scalar(
     }
     r[c] = b;
     p[c] = 0.0;
+    if (r32) r32[c] = (float)b;                              // mixed-precision PCG: r starts as fp32(b)
   }
   if (__any_sync(EULER_FULL_MASK, nz) && (threadIdx.x & 31) == 0) atomicOr(&sc->nonzero_rhs, 1);
 }
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(QX* QY) k_build_rhs(
     Grid g, const float* __restrict__ u, const float* __restrict__ v,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
     double* __restrict__ r, double* __restrict__ p, int8_t* __restrict__ adiag, float h,
-    double scale, DevScalars* sc, int own0, int own1) {
+    double scale, DevScalars* sc, int own0, int own1, float* __restrict__ r32) {
   const QuadPos q = quad_pos(g);
   bool nz = false;
   if (q.inside) {
@@ -420,6 +421,8 @@ __global__ void __launch_bounds__(QX* QY) k_build_rhs(
     }
     st_d4(r + q.c, b);
     st_d4(p + q.c, zero);                                 // p = 0, main.c:739
+    if (r32)                                              // mixed-precision PCG: r starts as fp32(b)
+      *reinterpret_cast<float4*>(r32 + q.c) = make_float4((float)b.v[0], (float)b.v[1], (float)b.v[2], (float)b.v[3]);
   }
   if (__any_sync(EULER_FULL_MASK, nz) && (threadIdx.x & 31) == 0) atomicOr(&sc->nonzero_rhs, 1);
 }
@@ -640,10 +643,12 @@ void launch_build_rhs(Ctx& c, float dt) {
   const double scale = (double)((c.h * c.h) * c.rho / dt);     // fp32 expression, main.c:713
   if (scalar_variant())
     k_build_rhs_scalar<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
-        c.g, c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc, c.own0, c.own1);
+        c.g, c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc, c.own0, c.own1,
+        c.mixed ? c.r32 : nullptr);
   else
     k_build_rhs<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
-        c.g, c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc, c.own0, c.own1);
+        c.g, c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc, c.own0, c.own1,
+        c.mixed ? c.r32 : nullptr);
   c.launches += 1;
 }
 

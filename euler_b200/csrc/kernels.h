@@ -13,7 +13,7 @@ enum KernelClass {
   KC_MAXSQ = 0, KC_ADVECT_MARKERS, KC_REFRESH_COUNTS, KC_SOURCES, KC_EXTRAPOLATE,
   KC_ADVECT_VELOCITY, KC_BUILD_RHS, KC_PRECON_BUILD, KC_PRECON_APPLY, KC_APPLY_A, KC_AXPY,
   KC_UPDATE_SEARCH, KC_PRESSURE_UPDATE, KC_MISC, KC_FUSED_A, KC_FUSED_B,
-  KC_PRECON_FWD, KC_PRECON_BWD, KC_COLOR, KC__COUNT
+  KC_PRECON_FWD, KC_PRECON_BWD, KC_COLOR, KC_RESIDUAL, KC__COUNT
 };
 
 struct Prof {
@@ -67,6 +67,10 @@ struct Ctx {
   int8_t* adiag;
   double *precon, *q, *p, *r, *z, *s;
   double *s2, *r2;                // twins of s and r for the fused red-black iteration
+  // mixed-precision mode (euler_params.pcg_dtype = FP32): fp32 twins of r, z, s (two planes,
+  // ping-pong), q and the preconditioner diagonal; p stays fp64 and the fp64 r plane keeps b
+  int mixed;
+  float *r32, *z32, *s32, *s32b, *q32, *pc32;
   int fused;                      // red-black: two fused kernels per iteration
   uint8_t* tile_active;           // per PCG tile: contains fluid (pcg_kernels.cu)
   int* tile_list;                 // ordered compact list of those tiles
@@ -149,7 +153,9 @@ void launch_apply_a(Ctx& c, bool with_alpha);                // z = A s (+ z.s, 
 void launch_axpy(Ctx& c, double tol, bool as_in_q = false, int mode = 2);
 // completes p after a fused solve that stopped on an odd iteration; s_odd_plane = the plane
 // the first iteration wrote its search direction to (Ctx::s2 at the start of the solve)
-void launch_p_fixup(Ctx& c, const double* s_odd_plane);
+void launch_p_fixup(Ctx& c, const void* s_odd_plane);
+// mixed-precision mode: r32 <- b - A p evaluated in fp64 (residual replacement)
+void launch_true_residual(Ctx& c);
 void launch_update_search(Ctx& c);                           // s = z + beta s
 void launch_pcg_reset(Ctx& c);                               // iters=0, done=0
 void launch_tile_flags(Ctx& c);                              // per-tile fluid flags from count

@@ -28,6 +28,15 @@
 // All vectors are fp64 like the reference's.  -fmad=false + source-order arithmetic make
 // every element-wise result bit-identical to the CPU's; only the order of the dot-product
 // sums differs.
+//
+// Mixed-precision mode (euler_params.pcg_dtype = EULER_PCG_FP32; not in the
+// reference): the kernels of the fused red-black iteration are templates on the STORAGE type T
+// of r, z, s, q, A s and the preconditioner diagonal.  With T = float every element-wise
+// operation is one fp32 operation in the same order (CPU mirror: oracle/euler_oracle.c
+// pcg_mixed), p stays fp64, the dot products multiply and accumulate in fp64, and every
+// `pcg_refresh_every` iterations k_true_residual replaces r by b - A p evaluated in fp64.
+// 73 B/cell per iteration instead of 132.  T = double instantiates exactly the code that was
+// here before the template (checked: identical SASS).
 #include "kernels.h"
 #include "p2p.cuh"
 #include "pcg_pipe.cuh"
@@ -105,6 +114,21 @@ __device__ __forceinline__ void st4(double* __restrict__ p, const D4& d) {
   *reinterpret_cast<double2*>(p) = make_double2(d.v[0], d.v[1]);
   *reinterpret_cast<double2*>(p + 2) = make_double2(d.v[2], d.v[3]);
 }
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float* __restrict__ p) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  F4 r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  return r;
+}
+__device__ __forceinline__ void st4(float* __restrict__ p, const F4& d) {
+  *reinterpret_cast<float4*>(p) = make_float4(d.v[0], d.v[1], d.v[2], d.v[3]);
+}
+template <class T> struct Vec4;
+template <> struct Vec4<double> { using type = D4; };
+template <> struct Vec4<float> { using type = F4; };
+__device__ __forceinline__ double abs_of(double a) { return fabs(a); }
+__device__ __forceinline__ float abs_of(float a) { return fabsf(a); }
+
 __device__ __forceinline__ unsigned ldmask(const uint8_t* __restrict__ p) {
   return *reinterpret_cast<const unsigned*>(p);            // 4 cells, one byte each
 }
@@ -273,40 +297,46 @@ __global__ void __launch_bounds__(TT) k_apply_a(
 // again on odd iterations.  Same operations in the same order on every cell, so p is bit-
 // identical to the per-iteration update (main.c:753); a solve that ends on an odd iteration is
 // completed by k_p_fixup.
+// T = storage type of s, A s and r (p is fp64 in both modes; with T = float alpha is narrowed
+// once for the r update and s is widened for the p update).
+template <class T>
 __global__ void __launch_bounds__(TT) k_axpy(
-    Grid g, TileList active, const double* __restrict__ s, const double* __restrict__ s_prev,
-    const double* __restrict__ z, const uint8_t* __restrict__ fluid, double* __restrict__ p,
-    double* __restrict__ r, double* partials, DevScalars* sc, double tol, int defer, int acc0,
+    Grid g, TileList active, const T* __restrict__ s, const T* __restrict__ s_prev,
+    const T* __restrict__ z, const uint8_t* __restrict__ fluid, double* __restrict__ p,
+    T* __restrict__ r, double* partials, DevScalars* sc, double tol, int defer, int acc0,
     int acc1, int mode) {
+  using V4 = typename Vec4<T>::type;
   pdl_prologue();
   if (sc->done) return;
   const double alpha = sc->alpha, alpha_prev = sc->alpha_prev;
-  double m = 0.0;
+  const T neg_alpha = (T)-alpha;
+  T m = (T)0;
   for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
     if (!live) return;
     size_t c = gidx(g, x0, y0);
     for (int y = y0; y < y1; ++y, c += g.pitch) {
       const unsigned mc = ldmask(fluid + c);
       if (!mc) continue;
-      const D4 zv = ld4(z + c);
-      D4 rv = ld4(r + c);
-      D4 sv, spv, pv;
+      const V4 zv = ld4(z + c);
+      V4 rv = ld4(r + c);
+      V4 sv, spv;
+      D4 pv;
       if (mode) { sv = ld4(s + c); pv = ld4(p + c); }
       if (mode == 1) spv = ld4(s_prev + c);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (!mbit(mc, k)) continue;
-        if (mode == 1) pv.v[k] = pv.v[k] + spv.v[k] * alpha_prev;   // the previous iteration's main.c:753
-        if (mode) pv.v[k] = pv.v[k] + sv.v[k] * alpha;       // fmadd(s, alpha, p)  main.c:753
-        rv.v[k] = rv.v[k] + zv.v[k] * -alpha;                // fmadd(z, -alpha, r) main.c:754
-        const double a = fabs(rv.v[k]);
+        if (mode == 1) pv.v[k] = pv.v[k] + (double)spv.v[k] * alpha_prev;   // the previous iteration's main.c:753
+        if (mode) pv.v[k] = pv.v[k] + (double)sv.v[k] * alpha;       // fmadd(s, alpha, p)  main.c:753
+        rv.v[k] = rv.v[k] + zv.v[k] * neg_alpha;             // fmadd(z, -alpha, r) main.c:754
+        const T a = abs_of(rv.v[k]);
         if (a > m && y >= acc0 && y < acc1) m = a;           // NaN-dropping, main.c:659-662
       }
       if (mode) st4(p + c, pv);
       st4(r + c, rv);
     }
   });
-  const double bmax = block_reduce<true>(m);
+  const double bmax = block_reduce<true>((double)m);
   grid_reduce_last_block<true>(bmax, partials, &sc->ctr[CTR_NORM], [&](double total) {
     if (defer) { sc->part[1] = total; return; }              // slab mode: max over ranks later
     sc->resid = total;
@@ -317,9 +347,11 @@ __global__ void __launch_bounds__(TT) k_axpy(
 
 // The deferred p update of a solve that stopped after an ODD number of iterations: the last
 // iteration's p += alpha s is still pending (s of iteration i lives in plane i & 1).
-__global__ void __launch_bounds__(TT) k_p_fixup(Grid g, TileList active, const double* __restrict__ s_odd,
+template <class T>
+__global__ void __launch_bounds__(TT) k_p_fixup(Grid g, TileList active, const T* __restrict__ s_odd,
                                                 const uint8_t* __restrict__ fluid, double* __restrict__ p,
                                                 const DevScalars* sc) {
+  using V4 = typename Vec4<T>::type;
   if (!(sc->iters & 1)) return;
   const double alpha = sc->alpha;
   for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
@@ -328,11 +360,11 @@ __global__ void __launch_bounds__(TT) k_p_fixup(Grid g, TileList active, const d
     for (int y = y0; y < y1; ++y, c += g.pitch) {
       const unsigned mc = ldmask(fluid + c);
       if (!mc) continue;
-      const D4 sv = ld4(s_odd + c);
+      const V4 sv = ld4(s_odd + c);
       D4 pv = ld4(p + c);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (mbit(mc, k)) pv.v[k] = pv.v[k] + sv.v[k] * alpha;
+        if (mbit(mc, k)) pv.v[k] = pv.v[k] + (double)sv.v[k] * alpha;
       st4(p + c, pv);
     }
   });
@@ -387,9 +419,10 @@ __device__ __forceinline__ double rb_e_red(const int8_t* __restrict__ adiag, siz
 
 // A thread looks at four consecutive cells through one 32-bit mask load and leaves at once
 // when none of them is fluid (most of a free-surface scene).
+template <class T>
 __global__ void __launch_bounds__(256) k_rb_build(
     Grid g, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
-    double* __restrict__ precon) {
+    T* __restrict__ precon) {
   const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
   if (x0 >= g.pitch || y >= g.ny || y + g.yoff < 1 || y + g.yoff >= g.gny - 1) return;
   const unsigned mf = ldmask(fluid + gidx(g, x0, y));
@@ -399,7 +432,7 @@ __global__ void __launch_bounds__(256) k_rb_build(
     const int x = x0 + k;
     if (!mbit(mf, k) || x < 1 || x >= g.nx - 1) continue;
     const size_t c = gidx(g, x, y);
-    if (((x + y + g.yoff) & 1) == 0) { precon[c] = 1.0 / sqrt(rb_e_red(adiag, c)); continue; }
+    if (((x + y + g.yoff) & 1) == 0) { precon[c] = (T)(1.0 / sqrt(rb_e_red(adiag, c))); continue; }
     const double a = (double)adiag[c];
     double e = a;
     const long off[4] = {-1, 1, -(long)g.pitch, (long)g.pitch};
@@ -409,7 +442,7 @@ __global__ void __launch_bounds__(256) k_rb_build(
       if (fluid[nb]) e = e - 1.0 / rb_e_red(adiag, nb);
     }
     if (e < 0.25 * a) e = a != 0.0 ? a : 1.0;
-    precon[c] = 1.0 / sqrt(e);
+    precon[c] = (T)(1.0 / sqrt(e));                          // fp64 factor, narrowed once for T = float
   }
 }
 
@@ -607,7 +640,7 @@ __device__ __forceinline__ D4 lds4(const double* p) {                   // 16 B 
   return r;
 }
 
-template <int C> struct DV { double v[C]; };
+template <int C, class T = double> struct DV { T v[C]; };
 template <int C> __device__ __forceinline__ DV<C> ldsv(const double* p) {      // 16 B aligned
   DV<C> r;
 #pragma unroll
@@ -617,9 +650,24 @@ template <int C> __device__ __forceinline__ DV<C> ldsv(const double* p) {      /
   }
   return r;
 }
+template <int C> __device__ __forceinline__ DV<C, float> ldsv(const float* p) {   // C*4 B aligned
+  DV<C, float> r;
+  if (C == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[C - 2] = a.z; r.v[C - 1] = a.w;
+  } else {
+    const float2 a = *reinterpret_cast<const float2*>(p);
+    r.v[0] = a.x; r.v[1] = a.y;
+  }
+  return r;
+}
 template <int C> __device__ __forceinline__ void stv(double* __restrict__ p, const DV<C>& d) {
 #pragma unroll
   for (int i = 0; i < C; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(d.v[i], d.v[i + 1]);
+}
+template <int C> __device__ __forceinline__ void stv(float* __restrict__ p, const DV<C, float>& d) {
+  if (C == 4) *reinterpret_cast<float4*>(p) = make_float4(d.v[0], d.v[1], d.v[C - 2], d.v[C - 1]);
+  else *reinterpret_cast<float2*>(p) = make_float2(d.v[0], d.v[1]);
 }
 template <int C> __device__ __forceinline__ DV<C> ldg_v(const double* __restrict__ p) { return ldsv<C>(p); }
 template <int C> __device__ __forceinline__ unsigned ldsm(const uint8_t* p) {   // C-byte aligned
@@ -681,28 +729,28 @@ __global__ void __launch_bounds__(TT) k_apply_a_pipe(
   });
 }
 
-template <int C>
+template <int C, class T = double>
 struct RbForwardPipe {
   // planes: d0 = r, d1 = pc ; b0 = fluid
+  using RV = pipe::RowView<2, 1, T>;
   const Grid g;
-  double* __restrict__ q;
-  __device__ __forceinline__ static double w(double r, double p) { return p * (r * p); }
-  __device__ __forceinline__ void row(const pipe::RowView<2, 1>& dn, const pipe::RowView<2, 1>& ce,
-                                      const pipe::RowView<2, 1>& up, int t4, int x, int y, bool live) {
+  T* __restrict__ q;
+  __device__ __forceinline__ static T w(T r, T p) { return p * (r * p); }
+  __device__ __forceinline__ void row(const RV& dn, const RV& ce, const RV& up, int t4, int x, int y, bool live) {
     const unsigned mc = live ? ldsm<C>(ce.b[0] + t4) : 0u;
     if (!mc) return;
     const unsigned md = ldsm<C>(dn.b[0] + t4), mu = ldsm<C>(up.b[0] + t4);
     const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + C] != 0;
-    const DV<C> rc = ldsv<C>(ce.d[0] + t4), pc = ldsv<C>(ce.d[1] + t4);
-    const DV<C> rd = ldsv<C>(dn.d[0] + t4), pd = ldsv<C>(dn.d[1] + t4);
-    const DV<C> ru = ldsv<C>(up.d[0] + t4), pu = ldsv<C>(up.d[1] + t4);
-    const double wl = w(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), wr = w(ce.d[0][t4 + C], ce.d[1][t4 + C]);
-    DV<C> out;
+    const DV<C, T> rc = ldsv<C>(ce.d[0] + t4), pc = ldsv<C>(ce.d[1] + t4);
+    const DV<C, T> rd = ldsv<C>(dn.d[0] + t4), pd = ldsv<C>(dn.d[1] + t4);
+    const DV<C, T> ru = ldsv<C>(up.d[0] + t4), pu = ldsv<C>(up.d[1] + t4);
+    const T wl = w(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), wr = w(ce.d[0][t4 + C], ce.d[1][t4 + C]);
+    DV<C, T> out;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-      out.v[k] = 0.0;
+      out.v[k] = (T)0;
       if (!mbit(mc, k)) continue;
-      double t = rc.v[k];
+      T t = rc.v[k];
       if ((x + k + y + g.yoff) & 1) {                        // black: + sum over red neighbours
         const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
         const bool r_ok = k == C - 1 ? fr : mbit(mc, k + 1);
@@ -717,54 +765,54 @@ struct RbForwardPipe {
   }
 };
 
-template <int NS, int C>
+template <int NS, int C, class T = double>
 __global__ void __launch_bounds__(TW / C, C == 2 ? 4 : 5) k_rb_forward_pipe(
-    Grid g, TileList active, const double* __restrict__ r,
-    const uint8_t* __restrict__ fluid, const double* __restrict__ precon, double* __restrict__ q,
+    Grid g, TileList active, const T* __restrict__ r,
+    const uint8_t* __restrict__ fluid, const T* __restrict__ precon, T* __restrict__ q,
     const DevScalars* sc) {
   pdl_prologue();
   if (sc->done) return;
-  RbForwardPipe<C> op{g, q};
-  pipe::Planes<2, 1> in;
+  RbForwardPipe<C, T> op{g, q};
+  pipe::Planes<2, 1, T> in;
   in.d[0] = r; in.d[1] = precon; in.b[0] = fluid;
-  pipe::run<2, 1, NS, TH, RbForwardPipe<C>, C>(g, active.list, (int)*active.count, in, op);
+  pipe::run<2, 1, NS, TH, RbForwardPipe<C, T>, C, T>(g, active.list, (int)*active.count, in, op);
 }
 
-template <int C>
+template <int C, class T = double>
 struct RbBackwardPipe {
   // planes: d0 = q, d1 = pc, d2 = r ; b0 = fluid
+  using RV = pipe::RowView<3, 1, T>;
   const Grid g;
-  double* __restrict__ z;
+  T* __restrict__ z;
   double acc;
   int a0, a1;
   // slab mode, NVLink path: the neighbours' z planes (biased, see DistArgs) and the halo depth
-  double* __restrict__ z_dn;
-  double* __restrict__ z_up;
+  T* __restrict__ z_dn;
+  T* __restrict__ z_up;
   int depth;
   bool peer_stored;
-  __device__ __forceinline__ void row(const pipe::RowView<3, 1>& dn, const pipe::RowView<3, 1>& ce,
-                                      const pipe::RowView<3, 1>& up, int t4, int x, int y, bool live) {
+  __device__ __forceinline__ void row(const RV& dn, const RV& ce, const RV& up, int t4, int x, int y, bool live) {
     const unsigned mc = live ? ldsm<C>(ce.b[0] + t4) : 0u;
     if (!mc) return;
     const unsigned md = ldsm<C>(dn.b[0] + t4), mu = ldsm<C>(up.b[0] + t4);
     const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + C] != 0;
-    const DV<C> qc = ldsv<C>(ce.d[0] + t4), pc = ldsv<C>(ce.d[1] + t4), rc = ldsv<C>(ce.d[2] + t4);
-    const DV<C> qd = ldsv<C>(dn.d[0] + t4), pd = ldsv<C>(dn.d[1] + t4);
-    const DV<C> qu = ldsv<C>(up.d[0] + t4), pu = ldsv<C>(up.d[1] + t4);
-    const double zl = ce.d[0][t4 - 1] * ce.d[1][t4 - 1], zr = ce.d[0][t4 + C] * ce.d[1][t4 + C];
-    DV<C> out;
+    const DV<C, T> qc = ldsv<C>(ce.d[0] + t4), pc = ldsv<C>(ce.d[1] + t4), rc = ldsv<C>(ce.d[2] + t4);
+    const DV<C, T> qd = ldsv<C>(dn.d[0] + t4), pd = ldsv<C>(dn.d[1] + t4);
+    const DV<C, T> qu = ldsv<C>(up.d[0] + t4), pu = ldsv<C>(up.d[1] + t4);
+    const T zl = ce.d[0][t4 - 1] * ce.d[1][t4 - 1], zr = ce.d[0][t4 + C] * ce.d[1][t4 + C];
+    DV<C, T> out;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-      out.v[k] = 0.0;
+      out.v[k] = (T)0;
       if (!mbit(mc, k)) continue;
-      double zc;
-      const double p = pc.v[k];
+      T zc;
+      const T p = pc.v[k];
       if ((x + k + y + g.yoff) & 1) {
         zc = qc.v[k] * p;                                    // black: q*pc
       } else {
         const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
         const bool r_ok = k == C - 1 ? fr : mbit(mc, k + 1);
-        double t = qc.v[k];
+        T t = qc.v[k];
         if (l_ok) t = t + p * (k == 0 ? zl : qc.v[k - 1] * pc.v[k - 1]);
         if (r_ok) t = t + p * (k == C - 1 ? zr : qc.v[k + 1] * pc.v[k + 1]);
         if (mbit(md, k)) t = t + p * (qd.v[k] * pd.v[k]);
@@ -772,7 +820,7 @@ struct RbBackwardPipe {
         zc = t * p;
       }
       out.v[k] = zc;
-      if (y >= a0 && y < a1) acc += zc * rc.v[k];
+      if (y >= a0 && y < a1) acc += (double)zc * (double)rc.v[k];
     }
     // only the owned rows are stored: the halo rows of z belong to the neighbouring slabs,
     // which write them directly (NVLink peer stores) or through the halo exchange
@@ -786,18 +834,20 @@ struct RbBackwardPipe {
   }
 };
 
-template <int NS, int C>
+template <int NS, int C, class T = double>
 __global__ void __launch_bounds__(TW / C) k_rb_backward_pipe(
-    Grid g, TileList active, const double* __restrict__ q,
-    const double* __restrict__ r, const uint8_t* __restrict__ fluid,
-    const double* __restrict__ precon, double* __restrict__ z, double* partials, DevScalars* sc,
+    Grid g, TileList active, const T* __restrict__ q,
+    const T* __restrict__ r, const uint8_t* __restrict__ fluid,
+    const T* __restrict__ precon, T* __restrict__ z, double* partials, DevScalars* sc,
     int init, int exact, int acc0, int acc1, double tol, const __grid_constant__ DistArgs dist) {
   pdl_prologue();
   if (sc->done) return;
-  RbBackwardPipe<C> op{g, z, 0.0, acc0, acc1, dist.z_dn, dist.z_up, dist.depth, false};
-  pipe::Planes<3, 1> in;
+  // (the peer planes are fp64: slabs run the fp64 solve; with T = float dist is all zeros)
+  RbBackwardPipe<C, T> op{g, z, 0.0, acc0, acc1, reinterpret_cast<T*>(dist.z_dn), reinterpret_cast<T*>(dist.z_up),
+                          dist.depth, false};
+  pipe::Planes<3, 1, T> in;
   in.d[0] = q; in.d[1] = precon; in.d[2] = r; in.b[0] = fluid;
-  pipe::run<3, 1, NS, TH, RbBackwardPipe<C>, C>(g, active.list, (int)*active.count, in, op);
+  pipe::run<3, 1, NS, TH, RbBackwardPipe<C, T>, C, T>(g, active.list, (int)*active.count, in, op);
   // peer stores of this thread are performed system-wide before the block reports in
   if (op.peer_stored) __threadfence_system();
   const double bsum = block_reduce<false>(op.acc);
@@ -868,44 +918,44 @@ static int env_int(const char* name, int dflt) {
 // the new s / r cannot be written in place: s and r ping-pong between two planes each.
 // =========================================================================================
 
-template <int C>
+template <int C, class T = double>
 struct FusedSearchApply {
   // planes: d0 = z (M^-1 r), d1 = s ; b0 = fluid, b1 = adiag
+  using RV = pipe::RowView<2, 2, T>;
   const Grid g;
-  double* __restrict__ s_new;
-  double* __restrict__ as;
-  double beta;
+  T* __restrict__ s_new;
+  T* __restrict__ as;
+  T beta;
   bool init;                      // first iteration: s' = z (memcpy(s, z), main.c:746)
   double acc;
   int a0, a1;
-  __device__ __forceinline__ double sn(double z, double s) const { return init ? z : z + beta * s; }
-  __device__ __forceinline__ void row(const pipe::RowView<2, 2>& dn, const pipe::RowView<2, 2>& ce,
-                                      const pipe::RowView<2, 2>& up, int t4, int x, int y, bool live) {
+  __device__ __forceinline__ T sn(T z, T s) const { return init ? z : z + beta * s; }
+  __device__ __forceinline__ void row(const RV& dn, const RV& ce, const RV& up, int t4, int x, int y, bool live) {
     const unsigned mc = live ? ldsm<C>(ce.b[0] + t4) : 0u;
     if (!mc) return;
     const unsigned md = ldsm<C>(dn.b[0] + t4), mu = ldsm<C>(up.b[0] + t4);
     const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + C] != 0;
     const unsigned am = ldsm<C>(ce.b[1] + t4);
-    const DV<C> zc = ldsv<C>(ce.d[0] + t4), sc = ldsv<C>(ce.d[1] + t4);
-    const DV<C> zd = ldsv<C>(dn.d[0] + t4), sd = ldsv<C>(dn.d[1] + t4);
-    const DV<C> zu = ldsv<C>(up.d[0] + t4), su = ldsv<C>(up.d[1] + t4);
-    const double nl = sn(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), nr = sn(ce.d[0][t4 + C], ce.d[1][t4 + C]);
-    DV<C> nc, out;
+    const DV<C, T> zc = ldsv<C>(ce.d[0] + t4), sc = ldsv<C>(ce.d[1] + t4);
+    const DV<C, T> zd = ldsv<C>(dn.d[0] + t4), sd = ldsv<C>(dn.d[1] + t4);
+    const DV<C, T> zu = ldsv<C>(up.d[0] + t4), su = ldsv<C>(up.d[1] + t4);
+    const T nl = sn(ce.d[0][t4 - 1], ce.d[1][t4 - 1]), nr = sn(ce.d[0][t4 + C], ce.d[1][t4 + C]);
+    DV<C, T> nc, out;
 #pragma unroll
     for (int k = 0; k < C; ++k) nc.v[k] = sn(zc.v[k], sc.v[k]);
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-      out.v[k] = 0.0;
+      out.v[k] = (T)0;
       if (!mbit(mc, k)) { nc.v[k] = sc.v[k]; continue; }       // non-fluid: s untouched
-      double o = (double)(int)(signed char)((am >> (8 * k)) & 0xffu) * nc.v[k];
+      T o = (T)(int)(signed char)((am >> (8 * k)) & 0xffu) * nc.v[k];
       const bool r_ok = k == C - 1 ? fr : mbit(mc, k + 1);
       const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
-      o -= r_ok ? (k == C - 1 ? nr : sn(zc.v[(k + 1) % C], sc.v[(k + 1) % C])) : 0.0;
-      o -= mbit(mu, k) ? sn(zu.v[k], su.v[k]) : 0.0;
-      o -= l_ok ? (k == 0 ? nl : sn(zc.v[(k + C - 1) % C], sc.v[(k + C - 1) % C])) : 0.0;
-      o -= mbit(md, k) ? sn(zd.v[k], sd.v[k]) : 0.0;
+      o -= r_ok ? (k == C - 1 ? nr : sn(zc.v[(k + 1) % C], sc.v[(k + 1) % C])) : (T)0;
+      o -= mbit(mu, k) ? sn(zu.v[k], su.v[k]) : (T)0;
+      o -= l_ok ? (k == 0 ? nl : sn(zc.v[(k + C - 1) % C], sc.v[(k + C - 1) % C])) : (T)0;
+      o -= mbit(md, k) ? sn(zd.v[k], sd.v[k]) : (T)0;
       out.v[k] = o;
-      if (y >= a0 && y < a1) acc += o * nc.v[k];
+      if (y >= a0 && y < a1) acc += (double)o * (double)nc.v[k];
     }
     const size_t c = gidx(g, x, y);
     stv<C>(s_new + c, nc);
@@ -913,18 +963,18 @@ struct FusedSearchApply {
   }
 };
 
-template <int NS, int C>
+template <int NS, int C, class T = double>
 __global__ void __launch_bounds__(TW / C) k_fused_search_apply(
-    Grid g, TileList active, const double* __restrict__ z, const double* __restrict__ s,
-    const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, double* __restrict__ s_new,
-    double* __restrict__ as, double* partials, DevScalars* sc, int init, int exact, int acc0, int acc1,
+    Grid g, TileList active, const T* __restrict__ z, const T* __restrict__ s,
+    const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, T* __restrict__ s_new,
+    T* __restrict__ as, double* partials, DevScalars* sc, int init, int exact, int acc0, int acc1,
     const __grid_constant__ DistArgs dist) {
   pdl_prologue();
   if (sc->done) return;
-  FusedSearchApply<C> op{g, s_new, as, sc->beta, init != 0, 0.0, acc0, acc1};
-  pipe::Planes<2, 2> in;
+  FusedSearchApply<C, T> op{g, s_new, as, (T)sc->beta, init != 0, 0.0, acc0, acc1};
+  pipe::Planes<2, 2, T> in;
   in.d[0] = z; in.d[1] = s; in.b[0] = fluid; in.b[1] = reinterpret_cast<const uint8_t*>(adiag);
-  pipe::run<2, 2, NS, TH, FusedSearchApply<C>, C>(g, active.list, (int)*active.count, in, op);
+  pipe::run<2, 2, NS, TH, FusedSearchApply<C, T>, C, T>(g, active.list, (int)*active.count, in, op);
   const double bsum = block_reduce<false>(op.acc);
   double total;
   if (!grid_reduce_last_block_all<false>(bsum, partials, &sc->ctr[CTR_ZS], total)) return;
@@ -936,6 +986,58 @@ __global__ void __launch_bounds__(TW / C) k_fused_search_apply(
   if (exact == 2) { sc->part[0] = total; return; }
   sc->zs = total;
   sc->alpha_prev = sc->alpha; sc->alpha = sc->sigma / total;                             // main.c:752
+}
+
+// ---- mixed-precision mode: residual replacement ---------------------------------------------
+// r <- b - A p with A p and the subtraction in fp64 (main.c:683-687 applied to p), narrowed to
+// fp32 on store.  The fp32 recurrence r -= alpha A s drifts away from the true residual by
+// ~2^-24 |A||p| per update; replacing it every `pcg_refresh_every` iterations keeps the
+// converged pressure within fp32 rounding of the fp64 solve's (oracle: true_residual32).
+// p must be complete (even iteration, see k_axpy).  22 B/cell, once every R iterations.
+struct TrueResidual {
+  // planes: d0 = p ; b0 = fluid, b1 = adiag
+  using RV = pipe::RowView<1, 2>;
+  const Grid g;
+  const double* __restrict__ b;
+  float* __restrict__ r;
+  __device__ __forceinline__ void row(const RV& dn, const RV& ce, const RV& up, int t4, int x, int y, bool live) {
+    const unsigned mc = live ? lds_mask4(ce.b[0] + t4) : 0u;
+    if (!mc) return;
+    const unsigned md = lds_mask4(dn.b[0] + t4), mu = lds_mask4(up.b[0] + t4);
+    const bool fl = ce.b[0][t4 - 1] != 0, fr = ce.b[0][t4 + 4] != 0;
+    const unsigned am = lds_mask4(ce.b[1] + t4);
+    const D4 pc = lds4(ce.d[0] + t4), pd = lds4(dn.d[0] + t4), pu = lds4(up.d[0] + t4);
+    const double pl = ce.d[0][t4 - 1], pr = ce.d[0][t4 + 4];
+    const size_t c = gidx(g, x, y);
+    const D4 bv = ld4(b + c);
+    F4 out;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      out.v[k] = 0.f;
+      if (!mbit(mc, k)) continue;
+      double o = (double)(int)(signed char)((am >> (8 * k)) & 0xffu) * pc.v[k];
+      const bool r_ok = k == 3 ? fr : mbit(mc, k + 1);
+      const bool l_ok = k == 0 ? fl : mbit(mc, k - 1);
+      o -= r_ok ? (k == 3 ? pr : pc.v[k + 1]) : 0.0;
+      o -= mbit(mu, k) ? pu.v[k] : 0.0;
+      o -= l_ok ? (k == 0 ? pl : pc.v[k - 1]) : 0.0;
+      o -= mbit(md, k) ? pd.v[k] : 0.0;
+      out.v[k] = (float)(bv.v[k] - o);
+    }
+    st4(r + c, out);
+  }
+};
+
+template <int NS>
+__global__ void __launch_bounds__(TT) k_true_residual(
+    Grid g, TileList active, const double* __restrict__ p, const double* __restrict__ b,
+    const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, float* __restrict__ r,
+    const DevScalars* sc) {
+  if (sc->done) return;
+  TrueResidual op{g, b, r};
+  pipe::Planes<1, 2> in;
+  in.d[0] = p; in.b[0] = fluid; in.b[1] = reinterpret_cast<const uint8_t*>(adiag);
+  pipe::run<1, 2, NS, TH>(g, active.list, (int)*active.count, in, op);
 }
 
 template <int C>
@@ -1031,6 +1133,8 @@ __global__ void __launch_bounds__(TW / C) k_fused_axpy_forward(
 
 constexpr int NS_KA = 4, NS_KB = 4;
 constexpr int CPT_F = 2, CPT_B = 2, CPT_KA = 4;   // cells per thread of the pipe kernels
+// mixed-precision (fp32 storage) instantiations: 4 cells = one 16 B vector per thread and plane
+constexpr int NS_MIXED = 4, CPT_MIXED = 4;
 
 // persistent grid: resident blocks per SM (occupancy of that kernel) x SM count, capped by
 // the number of tiles
@@ -1073,6 +1177,7 @@ struct PV {
   const uint8_t* fluid;
   const int8_t* adiag;
   double *s, *z, *r, *p, *q, *precon;
+  float *s32, *z32, *r32, *q32, *pc32;     // mixed-precision mode only (null otherwise)
 };
 // Slab mode: the view is the owned rows +-PCG_EXT halo rows.  Every vector update is done
 // redundantly on those halo rows with the owner's exact arithmetic, so one exchange of s
@@ -1092,6 +1197,8 @@ static PV pview(const Ctx& c) {
   v.g.th = TH;
   v.fluid = c.count + o; v.adiag = c.adiag + o;
   v.s = c.s + o; v.z = c.z + o; v.r = c.r + o; v.p = c.p + o; v.q = c.q + o; v.precon = c.precon + o;
+  v.s32 = v.z32 = v.r32 = v.q32 = v.pc32 = nullptr;
+  if (c.mixed) { v.s32 = c.s32 + o; v.z32 = c.z32 + o; v.r32 = c.r32 + o; v.q32 = c.q32 + o; v.pc32 = c.pc32 + o; }
   return v;
 }
 static inline int dotflag(const Ctx& c) { return c.distributed ? 2 : c.dot_mode; }
@@ -1147,17 +1254,37 @@ void launch_axpy(Ctx& c, double tol, bool as_in_q, int mode) {
   ProfScope ps(c, KC_AXPY);
   const PV v = pview(c);
   const size_t o = (size_t)(v.s - c.s);
-  launch_pdl(k_axpy, pcg_blocks(c, k_axpy), TT, 0, c.stream, v.g, TL, v.s, c.s2 ? c.s2 + o : v.s,
-             as_in_q ? v.q : v.z, v.fluid, v.p, v.r, c.partials, c.sc, tol, c.distributed ? 1 : 0, v.a0, v.a1,
-             mode);
+  if (c.mixed)                    // fused red-black iteration only: A s is in q32
+    launch_pdl(k_axpy<float>, pcg_blocks(c, k_axpy<float>), TT, 0, c.stream, v.g, TL, v.s32, c.s32b + o,
+               v.q32, v.fluid, v.p, v.r32, c.partials, c.sc, tol, 0, v.a0, v.a1, mode);
+  else
+    launch_pdl(k_axpy<double>, pcg_blocks(c, k_axpy<double>), TT, 0, c.stream, v.g, TL, v.s, c.s2 ? c.s2 + o : v.s,
+               as_in_q ? v.q : v.z, v.fluid, v.p, v.r, c.partials, c.sc, tol, c.distributed ? 1 : 0, v.a0, v.a1,
+               mode);
   c.launches += 1;
 }
 
-void launch_p_fixup(Ctx& c, const double* s_odd_plane) {
+void launch_p_fixup(Ctx& c, const void* s_odd_plane) {
   ProfScope ps(c, KC_MISC);
   const PV v = pview(c);
   const size_t o = (size_t)(v.s - c.s);
-  k_p_fixup<<<pcg_blocks(c, k_p_fixup), TT, 0, c.stream>>>(v.g, TL, s_odd_plane + o, v.fluid, v.p, c.sc);
+  if (c.mixed)
+    k_p_fixup<float><<<pcg_blocks(c, k_p_fixup<float>), TT, 0, c.stream>>>(
+        v.g, TL, static_cast<const float*>(s_odd_plane) + o, v.fluid, v.p, c.sc);
+  else
+    k_p_fixup<double><<<pcg_blocks(c, k_p_fixup<double>), TT, 0, c.stream>>>(
+        v.g, TL, static_cast<const double*>(s_odd_plane) + o, v.fluid, v.p, c.sc);
+  c.launches += 1;
+}
+
+// mixed-precision mode: r32 <- b - A p in fp64 (b is what k_build_rhs left in the fp64 r plane,
+// which this mode never updates)
+void launch_true_residual(Ctx& c) {
+  ProfScope ps(c, KC_RESIDUAL);
+  const PV v = pview(c);
+  constexpr int smem = pipe::smem_bytes<1, 2, NS_A>();
+  k_true_residual<NS_A><<<pcg_blocks(c, k_true_residual<NS_A>, smem), TT, smem, c.stream>>>(
+      v.g, TL, v.p, v.r, v.fluid, v.adiag, v.r32, c.sc);
   c.launches += 1;
 }
 
@@ -1178,15 +1305,21 @@ void launch_copy_search(Ctx& c) {
 void launch_rb_build(Ctx& c) {
   // over ALL locally stored rows: halo rows get their own (identical) factor, no exchange
   ProfScope ps(c, KC_PRECON_BUILD);
-  k_rb_build<<<dim3((c.g.pitch / 4 + 31) / 32, (c.g.ny + 7) / 8), dim3(32, 8), 0, c.stream>>>(
-      c.g, c.count, c.adiag, c.precon);
+  const dim3 grid((c.g.pitch / 4 + 31) / 32, (c.g.ny + 7) / 8), block(32, 8);
+  if (c.mixed) k_rb_build<float><<<grid, block, 0, c.stream>>>(c.g, c.count, c.adiag, c.pc32);
+  else k_rb_build<double><<<grid, block, 0, c.stream>>>(c.g, c.count, c.adiag, c.precon);
   c.launches += 1;
 }
 
 void launch_rb_forward(Ctx& c) {
   ProfScope ps(c, KC_PRECON_FWD);
   const PV v = pview(c);
-  if (c.use_pipe) {
+  if (c.mixed) {
+    constexpr int C = CPT_MIXED;
+    constexpr int sf = pipe::smem_bytes<2, 1, NS_MIXED, float>();
+    launch_pdl(k_rb_forward_pipe<NS_MIXED, C, float>, pcg_blocks(c, k_rb_forward_pipe<NS_MIXED, C, float>, sf, TW / C),
+               TW / C, sf, c.stream, v.g, TL, v.r32, v.fluid, v.pc32, v.q32, c.sc);
+  } else if (c.use_pipe) {
     static const int ns = env_int("EULER_NS_F", NS_F);
     static const int cpt = env_int("EULER_CPT_F", CPT_F);
 #define FWD(N, C) { constexpr int sf = pipe::smem_bytes<2, 1, N>(); \
@@ -1204,7 +1337,15 @@ void launch_rb_forward(Ctx& c) {
 void launch_rb_backward(Ctx& c, bool init) {
   ProfScope ps(c, KC_PRECON_BWD);
   const PV v = pview(c);
-  if (c.use_pipe) {
+  if (c.mixed) {
+    constexpr int C = CPT_MIXED;
+    constexpr int sb = pipe::smem_bytes<3, 1, NS_MIXED, float>();
+    DistArgs d;
+    memset(&d, 0, sizeof d);
+    launch_pdl(k_rb_backward_pipe<NS_MIXED, C, float>, pcg_blocks(c, k_rb_backward_pipe<NS_MIXED, C, float>, sb, TW / C),
+               TW / C, sb, c.stream, v.g, TL, v.q32, v.r32, v.fluid, v.pc32, v.z32, c.partials, c.sc, init ? 1 : 0, 0,
+               v.a0, v.a1, c.tol, d);
+  } else if (c.use_pipe) {
     static const int ns = env_int("EULER_NS_B", NS_B);
     static const int cpt = env_int("EULER_CPT_B", CPT_B);
     // NVLink path: this kernel also stores its edge rows into the neighbours' halo rows and its
@@ -1254,6 +1395,17 @@ void launch_fused_search_apply(Ctx& c, bool init) {
   static const int cpt = env_int("EULER_CPT_KA", CPT_KA);
   DistArgs d;                     // NVLink path: the last block finishes {z.s} across ranks
   memset(&d, 0, sizeof d);
+  if (c.mixed) {
+    constexpr int C = CPT_MIXED;
+    constexpr int smem = pipe::smem_bytes<2, 2, NS_MIXED, float>();
+    launch_pdl(k_fused_search_apply<NS_MIXED, C, float>,
+               pcg_blocks(c, k_fused_search_apply<NS_MIXED, C, float>, smem, TW / C), TW / C, smem, c.stream,
+               v.g, TL, v.z32, v.s32, v.fluid, v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0,
+               v.a0, v.a1, d);
+    c.launches += 1;
+    float* t32 = c.s32; c.s32 = c.s32b; c.s32b = t32;
+    return;
+  }
   if (c.p2p_mode == 2) d = c.dist;
 #define KA(N, C) { constexpr int smem = pipe::smem_bytes<2, 2, N>(); \
   launch_pdl(k_fused_search_apply<N, C>, pcg_blocks(c, k_fused_search_apply<N, C>, smem, TW / C), TW / C, smem, c.stream, \

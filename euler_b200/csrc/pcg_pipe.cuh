@@ -24,10 +24,15 @@ namespace euler {
 namespace pipe {
 
 constexpr int TW = 512, TT = 128;            // tile width in cells, threads per block
-constexpr int HX8 = 2;                       // halo columns of an fp64 plane (16 B)
 constexpr int HX1 = 16;                      // halo columns of a u8 plane (16 B)
-constexpr int ROW8 = (TW + 2 * HX8) * 8;     // bytes of one fp64 row segment in smem
 constexpr int ROW1 = (TW + 2 * HX1);         // bytes of one u8 row segment in smem
+// The value planes are fp64 (the reference's precision) or fp32 (mixed-precision mode,
+// pcg_dtype = FP32): T is the element type, a row segment carries 16 B of halo columns on
+// each side whatever T is (bulk copies need 16 B-aligned addresses and sizes).
+template <class T> struct Elem {
+  static constexpr int HX = 16 / (int)sizeof(T);          // halo columns: 2 (fp64) / 4 (fp32)
+  static constexpr int ROW = (TW + 2 * HX) * (int)sizeof(T);   // bytes of one row segment in smem
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -156,39 +161,41 @@ struct JobIter {
 };
 
 // One stage of the ring, as seen by the consumers: pointers are biased so that index i is tile
-// column i (fp64 planes valid for i in [-2, TW+2), u8 planes for i in [-16, TW+16)).
-template <int ND, int NB>
+// column i (value planes valid for i in [-HX, TW+HX), u8 planes for i in [-16, TW+16)).
+template <int ND, int NB, class T = double>
 struct RowView {
-  const double* d[ND];
+  const T* d[ND];
   const uint8_t* b[NB];
 };
 
-template <int ND, int NB>
+template <int ND, int NB, class T = double>
 struct Layout {
-  static constexpr int stage_bytes = ND * ROW8 + NB * ROW1;
-  __device__ static __forceinline__ RowView<ND, NB> view(unsigned char* stage) {
-    RowView<ND, NB> v;
+  static constexpr int ROWT = Elem<T>::ROW, HXT = Elem<T>::HX;
+  static constexpr int stage_bytes = ND * ROWT + NB * ROW1;
+  __device__ static __forceinline__ RowView<ND, NB, T> view(unsigned char* stage) {
+    RowView<ND, NB, T> v;
 #pragma unroll
-    for (int i = 0; i < ND; ++i) v.d[i] = reinterpret_cast<const double*>(stage + i * ROW8) + HX8;
+    for (int i = 0; i < ND; ++i) v.d[i] = reinterpret_cast<const T*>(stage + i * ROWT) + HXT;
 #pragma unroll
-    for (int i = 0; i < NB; ++i) v.b[i] = stage + ND * ROW8 + i * ROW1 + HX1;
+    for (int i = 0; i < NB; ++i) v.b[i] = stage + ND * ROWT + i * ROW1 + HX1;
     return v;
   }
 };
 
-template <int ND, int NB>
+template <int ND, int NB, class T = double>
 struct Planes {
-  const double* d[ND];
+  const T* d[ND];
   const uint8_t* b[NB];
 };
 
 // The pipeline driver.  `Op::row(dn, ce, up, t4, x, y, live)` is called by every thread for
 // each output row of each active tile of the block: t4 = 4*threadIdx.x is the tile column of
 // the thread's first cell, x its global column; `live` is false for threads past the row end.
-template <int ND, int NB, int NS, int TH, class Op, int C = 4>
+template <int ND, int NB, int NS, int TH, class Op, int C = 4, class E = double>
 __device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list, int n_active,
-                                    const Planes<ND, NB>& in, Op& op) {
-  using L = Layout<ND, NB>;
+                                    const Planes<ND, NB, E>& in, Op& op) {
+  using L = Layout<ND, NB, E>;
+  constexpr int ROWT = L::ROWT, HXT = L::HXT;
   constexpr int PF = NS - 3;
   constexpr int NTHREADS = TW / C;                 // C cells per thread
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -214,13 +221,13 @@ __device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list,
     const int s = issued % NS, use = issued / NS;
     mbar_wait(empty + s, (use & 1) ^ 1);
     unsigned char* st = stages + s * L::stage_bytes;
-    const uint32_t b8 = (uint32_t)(prod.p.w + 2 * HX8) * 8u, b1 = (uint32_t)(prod.p.w + 2 * HX1);
+    const uint32_t b8 = (uint32_t)(prod.p.w + 2 * HXT) * (uint32_t)sizeof(E), b1 = (uint32_t)(prod.p.w + 2 * HX1);
     mbar_expect_tx(full + s, ND * b8 + NB * b1);
     const long row = (long)prod.yy * g.pitch + prod.p.x0;
 #pragma unroll
-    for (int i = 0; i < ND; ++i) bulk_g2s(st + i * ROW8, in.d[i] + row - HX8, b8, full + s);
+    for (int i = 0; i < ND; ++i) bulk_g2s(st + i * ROWT, in.d[i] + row - HXT, b8, full + s);
 #pragma unroll
-    for (int i = 0; i < NB; ++i) bulk_g2s(st + ND * ROW8 + i * ROW1, in.b[i] + row - HX1, b1, full + s);
+    for (int i = 0; i < NB; ++i) bulk_g2s(st + ND * ROWT + i * ROW1, in.b[i] + row - HX1, b1, full + s);
     ++issued;
     prod.next(g, T, th, list);
   };
@@ -230,9 +237,9 @@ __device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list,
       while (prod.valid && issued <= j + PF) issue();
     mbar_wait(full + (j % NS), (j / NS) & 1);
     if (cons.yy >= cons.p.y0 + 1) {
-      const RowView<ND, NB> up = L::view(stages + (j % NS) * L::stage_bytes);
-      const RowView<ND, NB> ce = L::view(stages + ((j + NS - 1) % NS) * L::stage_bytes);
-      const RowView<ND, NB> dn = L::view(stages + ((j + NS - 2) % NS) * L::stage_bytes);
+      const RowView<ND, NB, E> up = L::view(stages + (j % NS) * L::stage_bytes);
+      const RowView<ND, NB, E> ce = L::view(stages + ((j + NS - 1) % NS) * L::stage_bytes);
+      const RowView<ND, NB, E> dn = L::view(stages + ((j + NS - 2) % NS) * L::stage_bytes);
       const int t4 = threadIdx.x * C;
       op.row(dn, ce, up, t4, cons.p.x0 + t4, cons.yy - 1, t4 < cons.p.w);
       // the row two behind is done with; at the end of a tile so are the last two
@@ -255,6 +262,7 @@ template <int ND, int NB, int NS, int TH, int R, class Op>
 __device__ __forceinline__ void run_radius(const Grid& g, const int* __restrict__ list, int n_active,
                                            const Planes<ND, NB>& in, Op& op) {
   using L = Layout<ND, NB>;
+  constexpr int ROW8 = L::ROWT, HX8 = L::HXT;
   constexpr int W = 2 * R + 1;
   constexpr int PF = NS - W;
   static_assert(PF >= 1, "ring too short for the window");
@@ -314,8 +322,8 @@ __device__ __forceinline__ void run_radius(const Grid& g, const int* __restrict_
   }
 }
 
-template <int ND, int NB, int NS>
-constexpr int smem_bytes() { return NS * Layout<ND, NB>::stage_bytes + 2 * NS * 8; }
+template <int ND, int NB, int NS, class T = double>
+constexpr int smem_bytes() { return NS * Layout<ND, NB, T>::stage_bytes + 2 * NS * 8; }
 
 }  // namespace pipe
 }  // namespace euler

@@ -18,8 +18,10 @@ _L = C.CDLL(LIB_PATH)
 PRECON_IC0_WAVEFRONT, PRECON_REDBLACK = 0, 1
 MARKERS_REFERENCE, MARKERS_FAST = 0, 1
 DOT_TREE, DOT_REFERENCE_ORDER = 0, 1
+PCG_FP64, PCG_FP32 = 0, 1
 (F_U, F_V, F_UTMP, F_VTMP, F_SOLID, F_SOURCE, F_SINK, F_COUNT, F_PREV_COUNT, F_MARKERS,
- F_PRECON, F_Q, F_ADIAG, F_P, F_R, F_Z, F_S, F_CR, F_CG, F_CB) = range(20)
+ F_PRECON, F_Q, F_ADIAG, F_P, F_R, F_Z, F_S, F_CR, F_CG, F_CB,
+ F_R32, F_Z32, F_S32, F_Q32, F_PRECON32) = range(25)
 (S_ADVECT_MARKERS, S_REFRESH_COUNTS, S_SOURCES, S_EXTRAPOLATE, S_ADVECT_VELOCITY, S_PROJECT,
  S_BUILD_RHS, S_PRECONDITION, S_APPLY_A, S_PRESSURE_UPDATE, S_EXTRAPOLATE_COLOR,
  S_ADVECT_COLOR) = range(12)
@@ -28,7 +30,9 @@ _DTYPES = {F_U: np.float32, F_V: np.float32, F_UTMP: np.float32, F_VTMP: np.floa
            F_SOLID: np.uint8, F_SOURCE: np.uint8, F_SINK: np.uint8, F_COUNT: np.uint8,
            F_PREV_COUNT: np.uint8, F_PRECON: np.float64, F_Q: np.float64, F_ADIAG: np.int8,
            F_P: np.float64, F_R: np.float64, F_Z: np.float64, F_S: np.float64,
-           F_CR: np.float32, F_CG: np.float32, F_CB: np.float32}
+           F_CR: np.float32, F_CG: np.float32, F_CB: np.float32,
+           F_R32: np.float32, F_Z32: np.float32, F_S32: np.float32, F_Q32: np.float32,
+           F_PRECON32: np.float32}
 
 
 class Params(C.Structure):
@@ -38,7 +42,8 @@ class Params(C.Structure):
                 ("precon", C.c_int), ("marker_mode", C.c_int), ("dot_mode", C.c_int),
                 ("rng_state", C.c_uint64),
                 ("device", C.c_int), ("stream", C.c_void_p), ("pcg_check_every", C.c_int), ("stencil_variant", C.c_int),
-                ("slab_row0", C.c_int), ("slab_rows", C.c_int), ("rainbow", C.c_int)]
+                ("slab_row0", C.c_int), ("slab_rows", C.c_int), ("rainbow", C.c_int),
+                ("pcg_dtype", C.c_int), ("pcg_refresh_every", C.c_int)]
 
 
 class Stats(C.Structure):

@@ -17,10 +17,12 @@
  *   --precon ic0|rb     reference-faithful IC(0) wavefront (default) | red-black IC(0)
  *   --markers ref|fast  reference marker order & dt carry-over (default) | per-marker dt
  *   --exact-dot         reference-order dot products (bit-identical solve)
+ *   --pcg-dtype fp64|fp32  storage precision of the PCG vectors: the reference's doubles
+ *                       (default) | fp32 planes with fp64 pressure, dot products and residual
+ *                       replacement (needs --precon rb; include/euler_gpu.h euler_pcg_dtype)
  *   --device D          CUDA device
  *   --print             in --headless: print the final picture (plain ASCII)
- *   --rainbow           accepted for CLI compatibility; colour transport is not on the GPU
- *                       path yet, the picture is drawn in blue
+ *   --load / --save F   restore / write a checkpoint of the dynamic state (checkpoint.c)
  */
 #define _POSIX_C_SOURCE 200809L
 #include <dlfcn.h>
@@ -116,7 +118,8 @@ static uint64_t fnv1a(const uint8_t *p, size_t n) {
 static void usage(const char *argv0) {
   fprintf(stderr,
           "usage: %s [--rainbow] [--headless] [--frames N] [--grid WxH] [--synthetic NAME]\n"
-          "       [--precon ic0|rb] [--markers ref|fast] [--exact-dot] [--device D] [--print]\n"
+          "       [--precon ic0|rb] [--markers ref|fast] [--exact-dot] [--pcg-dtype fp64|fp32]\n"
+          "       [--device D] [--print]\n"
           "       [--load CHECKPOINT] [--save CHECKPOINT] <scenario>\n",
           argv0);
 }
@@ -146,6 +149,11 @@ int main(int argc, char **argv) {
       const char *v = argv[++i];
       if (!strcmp(v, "ic0")) prm.precon = EULER_PRECON_IC0_WAVEFRONT;
       else if (!strcmp(v, "rb")) prm.precon = EULER_PRECON_REDBLACK;
+      else { usage(argv[0]); return 1; }
+    } else if (!strcmp(s, "--pcg-dtype") && i + 1 < argc) {
+      const char *v = argv[++i];
+      if (!strcmp(v, "fp64")) prm.pcg_dtype = EULER_PCG_FP64;
+      else if (!strcmp(v, "fp32")) prm.pcg_dtype = EULER_PCG_FP32;   /* needs --precon rb */
       else { usage(argv[0]); return 1; }
     } else if (!strcmp(s, "--markers") && i + 1 < argc) {
       const char *v = argv[++i];

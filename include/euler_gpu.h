@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define EULER_GPU_ABI_VERSION 2
+#define EULER_GPU_ABI_VERSION 3
 
 enum euler_error {
   EULER_OK            =  0,
@@ -61,6 +61,21 @@ enum euler_dot_mode {
                                     the reference stops unconverged at its iteration cap and
                                     1-ulp differences would otherwise be amplified.  Latency-
                                     bound (one dependent add per cell). */
+};
+
+/* Storage precision of the PCG vectors (SURVEY §8b `pcg_dtype`, §8f row 4). */
+enum euler_pcg_dtype {
+  EULER_PCG_FP64 = 0, /* the reference's: every vector of project() is double (main.c:716-745). */
+  EULER_PCG_FP32 = 1  /* NOT in the reference.  r, z, s, q, A s and the preconditioner diagonal
+                         are stored and combined in fp32; the pressure p, the dot products and
+                         alpha / beta / sigma stay fp64, and every `pcg_refresh_every` iterations
+                         r is replaced by the true residual b - A p evaluated in fp64.  73 instead
+                         of 132 B/cell per iteration.  Converged solves agree with the fp64 solve
+                         to fp32 rounding of u, v (measured <= 1e-7 relative on the shipped
+                         scenarios); a solve cut off at max_iterations is a different, equally
+                         unconverged iterate.  Needs precon = REDBLACK, dot_mode = TREE,
+                         stencil_variant = 0; single-GPU handles only.  CPU mirror:
+                         oracle/euler_oracle.c pcg_mixed. */
 };
 
 /* How the marker array is kept. */
@@ -94,6 +109,12 @@ enum euler_field {
   EULER_F_CR,             /* float            g_r            main.c:77  (only with params.rainbow) */
   EULER_F_CG,             /* float            g_g            main.c:78 */
   EULER_F_CB,             /* float            g_b            main.c:79 */
+  /* fp32 twins of the PCG vectors (only with params.pcg_dtype = EULER_PCG_FP32) */
+  EULER_F_R32,            /* float            r */
+  EULER_F_Z32,            /* float            z = M^-1 r */
+  EULER_F_S32,            /* float            s */
+  EULER_F_Q32,            /* float            q (forward solve) / A s inside an iteration */
+  EULER_F_PRECON32,       /* float            red-black preconditioner diagonal */
   EULER_F__COUNT
 };
 
@@ -154,6 +175,10 @@ typedef struct euler_params {
    * advect_p (:873-882) every sub-step.  Six more fp32 planes; single-GPU handles only.
    * Default 0, like the reference. */
   int   rainbow;
+  /* mixed-precision PCG (enum euler_pcg_dtype); default EULER_PCG_FP64, like the reference */
+  int   pcg_dtype;
+  int   pcg_refresh_every; /* FP32 mode: iterations between residual replacements; even, or 0 =
+                              never; default 10 */
 } euler_params;
 
 #define EULER_KERNEL_CLASSES 24

@@ -47,6 +47,8 @@ orc_sim *orc_create(int nx, int ny) {
   o->z = zalloc(n, 8); o->s = zalloc(n, 8);
   o->cr = zalloc(n, 4); o->cg = zalloc(n, 4); o->cb = zalloc(n, 4);
   o->crtmp = zalloc(n, 4); o->cgtmp = zalloc(n, 4); o->cbtmp = zalloc(n, 4);
+  o->r32 = zalloc(n, 4); o->z32 = zalloc(n, 4); o->s32 = zalloc(n, 4);
+  o->q32 = zalloc(n, 4); o->as32 = zalloc(n, 4); o->pc32 = zalloc(n, 4);
   return o;
 }
 
@@ -57,6 +59,7 @@ void orc_destroy(orc_sim *o) {
   free(o->markers); free(o->adiag); free(o->precon); free(o->q);
   free(o->b); free(o->p); free(o->r); free(o->z); free(o->s);
   free(o->cr); free(o->cg); free(o->cb); free(o->crtmp); free(o->cgtmp); free(o->cbtmp);
+  free(o->r32); free(o->z32); free(o->s32); free(o->q32); free(o->as32); free(o->pc32);
   free(o);
 }
 
@@ -637,6 +640,132 @@ void orc_pressure_update(orc_sim *o, float dt, const float *u, const float *v, f
     }
 }
 
+/* ------------------------------------------- mixed-precision PCG (NOT in the reference) ----
+ * CPU mirror of the GPU's pcg_dtype = FP32 mode (red-black preconditioner
+ * only).  Same algorithm and the same order of operations as project()'s loop (ref :735-767)
+ * and precon_redblack above, but r, z, s, q, A s and the preconditioner diagonal are fp32
+ * planes and every element-wise operation is ONE fp32 IEEE operation in source order (the
+ * CUDA kernels reproduce them bit for bit).  What stays fp64: the pressure p (it accumulates
+ * ~100 updates), the products and sums of the dot products, and sigma / alpha / beta (each
+ * narrowed to fp32 once, where it multiplies a plane). */
+
+/* the fp64 factor of precon_redblack, narrowed once */
+void orc_rb_build32(orc_sim *o) {
+  const int nx = o->nx, ny = o->ny;
+  const long off[4] = { -1, 1, -(long)nx, (long)nx };
+  for (int y = 1; y < ny - 1; ++y)
+    for (int x = 1; x < nx - 1; ++x) {
+      size_t c = IDX(o, x, y);
+      if (!o->count[c]) continue;
+      if (((x + y) & 1) == 0) { o->pc32[c] = (float)(1 / sqrt(rb_e_red(o, c))); continue; }
+      double a = o->adiag[c];
+      double e = a;
+      for (int k = 0; k < 4; ++k) {
+        size_t nb = c + off[k];
+        if (o->count[nb]) e = e - 1 / rb_e_red(o, nb);
+      }
+      if (e < 0.25 * a) e = a != 0 ? a : 1;
+      o->pc32[c] = (float)(1 / sqrt(e));
+    }
+}
+
+void orc_rb_apply32(orc_sim *o, const float *r, float *z) {
+  const int nx = o->nx, ny = o->ny;
+  size_t n = (size_t)nx * ny;
+  const long off[4] = { -1, 1, -(long)nx, (long)nx };
+  const float *pc = o->pc32;
+  float *q = o->q32;
+  memset(q, 0, n * sizeof(float));
+  memset(z, 0, n * sizeof(float));
+  for (int colour = 0; colour < 2; ++colour)
+    for (int y = 1; y < ny - 1; ++y)
+      for (int x = 1; x < nx - 1; ++x) {
+        size_t c = IDX(o, x, y);
+        if (!o->count[c] || ((x + y) & 1) != colour) continue;
+        float t = r[c];
+        if (colour == 1)
+          for (int k = 0; k < 4; ++k) {
+            size_t nb = c + off[k];
+            if (o->count[nb]) t = t + pc[nb] * q[nb];
+          }
+        q[c] = t * pc[c];
+      }
+  for (int colour = 1; colour >= 0; --colour)
+    for (int y = 1; y < ny - 1; ++y)
+      for (int x = 1; x < nx - 1; ++x) {
+        size_t c = IDX(o, x, y);
+        if (!o->count[c] || ((x + y) & 1) != colour) continue;
+        float t = q[c];
+        if (colour == 0)
+          for (int k = 0; k < 4; ++k) {
+            size_t nb = c + off[k];
+            if (o->count[nb]) t = t + pc[c] * z[nb];
+          }
+        z[c] = t * pc[c];
+      }
+}
+
+void orc_apply_a32(const orc_sim *o, const float *s, float *out) {
+  for (int y = 0; y < o->ny; ++y)
+    for (int x = 0; x < o->nx; ++x) {
+      if (!FLUID(o, x, y)) continue;
+      size_t c = IDX(o, x, y);
+      float t = (float)o->adiag[c] * s[c];
+      t = t - (FLUID(o, x + 1, y) ? s[c + 1] : 0.f);
+      t = t - (FLUID(o, x, y + 1) ? s[c + o->nx] : 0.f);
+      t = t - (FLUID(o, x - 1, y) ? s[c - 1] : 0.f);
+      t = t - (FLUID(o, x, y - 1) ? s[c + 0 - o->nx] : 0.f);
+      out[c] = t;
+    }
+}
+
+static double dot32(const orc_sim *o, const float *a, const float *b) {
+  double total = 0.0;
+  size_t n = (size_t)o->nx * o->ny;
+  for (size_t c = 0; c < n; ++c)
+    if (o->count[c]) total += (double)a[c] * (double)b[c];
+  return total;
+}
+
+/* r32 <- b - A p evaluated in fp64 on the current p (residual replacement) */
+static void true_residual32(orc_sim *o) {
+  orc_apply_a(o, o->p, o->z);                /* z (fp64 plane) is free in this mode */
+  size_t n = (size_t)o->nx * o->ny;
+  for (size_t c = 0; c < n; ++c)
+    if (o->count[c]) o->r32[c] = (float)(o->b[c] - o->z[c]);
+}
+
+static void pcg_mixed(orc_sim *o) {
+  size_t n = (size_t)o->nx * o->ny;
+  for (size_t c = 0; c < n; ++c) o->r32[c] = (float)o->b[c];
+  orc_rb_build32(o);
+  orc_rb_apply32(o, o->r32, o->z32);
+  memcpy(o->s32, o->z32, n * sizeof(float));
+  double sigma = dot32(o, o->z32, o->r32);
+  for (int it = 0; it < o->max_iterations; ++it) {
+    orc_apply_a32(o, o->s32, o->as32);
+    double alpha = sigma / dot32(o, o->as32, o->s32);
+    const float na = (float)-alpha;
+    float best = 0.f;
+    for (size_t c = 0; c < n; ++c) {
+      if (!o->count[c]) continue;
+      o->p[c] = o->p[c] + (double)o->s32[c] * alpha;
+      o->r32[c] = o->r32[c] + o->as32[c] * na;
+      float a = fabsf(o->r32[c]);
+      if (a > best) best = a;
+    }
+    o->last_iterations = it + 1;
+    o->last_residual = best;
+    if (o->last_residual <= o->tol) break;
+    if (o->refresh_every > 0 && (it + 1) % o->refresh_every == 0) true_residual32(o);
+    orc_rb_apply32(o, o->r32, o->z32);
+    double sigma_new = dot32(o, o->z32, o->r32);
+    const float beta = (float)(sigma_new / sigma);
+    for (size_t c = 0; c < n; ++c) if (o->count[c]) o->s32[c] = o->z32[c] + beta * o->s32[c];
+    sigma = sigma_new;
+  }
+}
+
 /* ref :709-806 */
 void orc_project(orc_sim *o, float dt, const float *u, const float *v, float *uout, float *vout) {
   size_t n = (size_t)o->nx * o->ny;
@@ -647,6 +776,12 @@ void orc_project(orc_sim *o, float dt, const float *u, const float *v, float *uo
   o->last_solve_skipped = orc_all_zero(o, o->r);
   if (!o->last_solve_skipped) {
     o->total_solves++;
+    if (o->pcg_dtype == ORC_PCG_FP32) {
+      pcg_mixed(o);
+      o->total_iterations += o->last_iterations;
+      orc_pressure_update(o, dt, u, v, uout, vout);
+      return;
+    }
     orc_apply_preconditioner(o, o->r, o->z);
     memcpy(o->s, o->z, n * sizeof(double));
     double sigma = orc_dot(o, o->z, o->r);

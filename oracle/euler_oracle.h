@@ -25,6 +25,8 @@ enum { ORC_PRECON_IC0 = 0,      /* reference-faithful natural-order IC(0), main.
        ORC_PRECON_REDBLACK = 1  /* NOT in the reference: red-black ordered IC(0); CPU
                                    mirror of the GPU-parallel mode, same arithmetic order */ };
 
+enum { ORC_PCG_FP64 = 0, ORC_PCG_FP32 = 1 };
+
 typedef struct orc_sim {
   int nx, ny;
   /* constants, main.c:58-60, 735-736, 838, 849-851 */
@@ -58,6 +60,14 @@ typedef struct orc_sim {
   double last_residual;        /* ||r||inf at exit */
   long   total_iterations, total_substeps, total_solves;
   float  last_dt;
+  /* NOT in the reference: mixed-precision PCG, CPU mirror of the GPU's
+   * euler_params.pcg_dtype = EULER_PCG_FP32 — red-black mode only.  The vectors r, z, s, q,
+   * A s and the preconditioner diagonal are STORED and combined in fp32; the pressure p, the
+   * dot products and the scalars alpha, beta, sigma stay fp64.  Every `refresh_every`
+   * iterations (0 = never) r is replaced by the true residual b - A p evaluated in fp64. */
+  int    pcg_dtype;            /* ORC_PCG_FP64 (default) / ORC_PCG_FP32 */
+  int    refresh_every;
+  float *r32, *z32, *s32, *q32, *as32, *pc32;
 } orc_sim;
 
 orc_sim *orc_create(int nx, int ny);
@@ -93,6 +103,11 @@ int    orc_all_zero(const orc_sim *o, const double *r);                        /
 void   orc_pressure_update(orc_sim *o, float dt, const float *u, const float *v, float *uout, float *vout); /* :769-805 */
 float  orc_interpolate(const orc_sim *o, const float *q, float ix, float iy, int type);  /* :337-364 */
 float  orc_randf(orc_sim *o);                                                  /* :203-207 */
+
+/* mixed-precision mirror pieces (fp32 planes), exposed for per-kernel parity */
+void   orc_rb_build32(orc_sim *o);                                              /* -> pc32 */
+void   orc_rb_apply32(orc_sim *o, const float *r, float *z);                    /* z = M^-1 r, scratch q32 */
+void   orc_apply_a32(const orc_sim *o, const float *s, float *out);
 
 /* 64-bit FNV-1a over a byte plane (BASELINE.md §3 known-answer hashes) */
 uint64_t orc_fnv1a(const uint8_t *data, size_t n);

@@ -16,6 +16,7 @@ REF_DIR = os.path.join(HERE, "_ref")
 
 P, U, V = 0, 1, 2
 PRECON_IC0, PRECON_REDBLACK = 0, 1
+PCG_FP64, PCG_FP32 = 0, 1
 
 
 class _Vec2(C.Structure):
@@ -50,6 +51,10 @@ class _Sim(C.Structure):
         ("last_residual", C.c_double),
         ("total_iterations", C.c_long), ("total_substeps", C.c_long),
         ("total_solves", C.c_long), ("last_dt", C.c_float),
+        ("pcg_dtype", C.c_int), ("refresh_every", C.c_int),
+        ("r32", C.POINTER(C.c_float)), ("z32", C.POINTER(C.c_float)),
+        ("s32", C.POINTER(C.c_float)), ("q32", C.POINTER(C.c_float)),
+        ("as32", C.POINTER(C.c_float)), ("pc32", C.POINTER(C.c_float)),
     ]
 
 
@@ -94,13 +99,17 @@ def lib():
         L.orc_hsv_basis.restype = C.c_float; L.orc_hsv_basis.argtypes = [C.c_float]
         L.orc_colorize.argtypes = [SP]
         L.orc_advect_p.argtypes = [SP, FP, FP, FP, C.c_float, FP]
+        L.orc_rb_build32.argtypes = [SP]
+        L.orc_rb_apply32.argtypes = [SP, FP, FP]
+        L.orc_apply_a32.argtypes = [SP, FP, FP]
         L.orc_fnv1a.restype = C.c_uint64
         L.orc_fnv1a.argtypes = [C.POINTER(C.c_uint8), C.c_size_t]
         _lib = L
     return _lib
 
 
-_F32 = ("u", "v", "utmp", "vtmp", "cr", "cg", "cb", "crtmp", "cgtmp", "cbtmp")
+_F32 = ("u", "v", "utmp", "vtmp", "cr", "cg", "cb", "crtmp", "cgtmp", "cbtmp",
+        "r32", "z32", "s32", "q32", "as32", "pc32")
 _U8 = ("solid", "source", "sink", "count", "prev_count")
 _F64 = ("precon", "q", "b", "p", "r", "z", "s")
 
@@ -182,6 +191,11 @@ class Oracle:
     def apply_a(self, s, out): self.L.orc_apply_a(self.ptr, self.dptr(s), self.dptr(out))
     def dot(self, a, b): return float(self.L.orc_dot(self.ptr, self.dptr(a), self.dptr(b)))
     def inf_norm(self, r): return float(self.L.orc_inf_norm(self.ptr, self.dptr(r)))
+
+    # mixed-precision mirror (fp32 planes r32, z32, s32, q32, as32, pc32; see euler_oracle.h)
+    def rb_build32(self): self.L.orc_rb_build32(self.ptr)
+    def rb_apply32(self, r, z): self.L.orc_rb_apply32(self.ptr, self.fptr(r), self.fptr(z))
+    def apply_a32(self, s, out): self.L.orc_apply_a32(self.ptr, self.fptr(s), self.fptr(out))
 
     def pressure_update(self, dt):
         self.L.orc_pressure_update(self.ptr, np.float32(dt), self.fptr(self.utmp), self.fptr(self.vtmp),

@@ -32,8 +32,9 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_default_params():
     from euler_b200 import gpu as G
-    assert G.abi_version() == 2
+    assert G.abi_version() == 3
     p = G.default_params()
+    assert p.pcg_dtype == G.PCG_FP64 and p.pcg_refresh_every == 10
     # the reference's constants (main.c:58-60, 735-736, 838, 849-851)
     assert (p.h, p.rho, p.gravity) == (1.0, 1.0, -10.0)
     assert abs(p.frame_time - 0.1) < 1e-8 and p.max_substeps == 8 and p.cfl_distance == 0.75
@@ -66,3 +67,26 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "liboracle" not in src and "euler_oracle.h" not in src, f
+
+
+def test_pcg_dtype_parameter_validation():
+    """pcg_dtype = FP32 is a mode of the fused red-black iteration on a single-GPU handle:
+    every other combination is refused before any device work (so this runs without a GPU)."""
+    import numpy as np
+    from euler_b200 import gpu as G
+    z = np.zeros((16, 16), np.uint8)
+    m = np.zeros((0, 2), np.float32)
+    bad = [dict(pcg_dtype=G.PCG_FP32),                                          # default precon is IC(0)
+           dict(pcg_dtype=G.PCG_FP32, precon=G.PRECON_REDBLACK, dot_mode=G.DOT_REFERENCE_ORDER),
+           dict(pcg_dtype=G.PCG_FP32, precon=G.PRECON_REDBLACK, stencil_variant=1),
+           dict(pcg_dtype=G.PCG_FP32, precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST, slab_row0=0, slab_rows=8)]
+    for kw in bad:
+        with pytest.raises(G.EulerGpuError) as e:
+            G.EulerGpu(16, 16, z, z, z, m, **kw)
+        assert e.value.code == -4 and "pcg_dtype=FP32" in str(e.value), kw
+    for kw, code in ((dict(pcg_dtype=7), -1),
+                     (dict(pcg_dtype=G.PCG_FP32, precon=G.PRECON_REDBLACK, pcg_refresh_every=5), -1),
+                     (dict(pcg_dtype=G.PCG_FP32, precon=G.PRECON_REDBLACK, pcg_refresh_every=-2), -1)):
+        with pytest.raises(G.EulerGpuError) as e:
+            G.EulerGpu(16, 16, z, z, z, m, **kw)
+        assert e.value.code == code, kw
