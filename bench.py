@@ -322,8 +322,8 @@ def run_gpu(args):
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tt = json.load(f)
-            if n == 16384 and world == 1 and args.scenario == "basic-fill" and dom and not mixed:
-                traffic = tt.get(dom[0])
+            if n == 16384 and world == 1 and args.scenario == "basic-fill" and dom:
+                traffic = (tt.get("fp32", {}) if mixed else tt).get(dom[0])
         except (OSError, ValueError):
             pass
         if dom and kernels[dom[0]]["gbs"]:

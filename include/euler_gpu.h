@@ -69,7 +69,7 @@ enum euler_pcg_dtype {
   EULER_PCG_FP32 = 1  /* NOT in the reference.  r, z, s, q, A s and the preconditioner diagonal
                          are stored and combined in fp32; the pressure p, the dot products and
                          alpha / beta / sigma stay fp64, and every `pcg_refresh_every` iterations
-                         r is replaced by the true residual b - A p evaluated in fp64.  73 instead
+                         r is replaced by the true residual b - A p evaluated in fp64.  75 instead
                          of 132 B/cell per iteration.  Converged solves agree with the fp64 solve
                          to fp32 rounding of u, v (measured <= 1e-7 relative on the shipped
                          scenarios); a solve cut off at max_iterations is a different, equally

@@ -18,6 +18,12 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Reference-parity suites first; the opt-in modes that are not in the reference (mixed-
+    precision PCG) after them, so that `-x` reports a parity failure before anything else."""
+    items.sort(key=lambda it: 1 if "mixed" in it.nodeid.split("::")[0] else 0)
+
+
 @pytest.fixture(scope="session")
 def known_answers():
     with open(os.path.join(GOLDEN, "known_answers.json")) as f:

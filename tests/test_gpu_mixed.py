@@ -91,22 +91,20 @@ def test_mixed_solve_pieces_and_whole_solve(name, nx, ny, frames):
     g.close()
 
 
-@pytest.mark.parametrize("name", ["block", "waterfall", "filter"])
-def test_mixed_frames_follow_the_mirror(name):
+@pytest.mark.parametrize("name,frames", [("block", 22), ("waterfall", 10), ("filter", 10)])
+def test_mixed_frames_follow_the_mirror(name, frames):
     """Whole frames (odd and even iteration counts exercise the deferred p update and its
     fix-up, every 10th iteration the residual replacement): classification bit-exact,
-    velocities within 1e-5 of the CPU mirror."""
+    velocities within 1e-5 of the CPU mirror.  (block.txt is in free fall — solve skipped,
+    main.c:742 — until its fluid reaches the floor around frame 12.)"""
     o, g, G = _mixed_pair(shipped_text(name), 100, 40)
-    its = set()
-    for _ in range(10):
+    for _ in range(frames):
         o.step_frame(); g.step_frame()
-        its.add(g.stats().last_iterations & 1)
     assert same_bits(g.get(G.F_COUNT), o.count)
     for fld, ref in ((G.F_U, o.u), (G.F_V, o.v)):
         assert float(np.abs(g.get(fld) - ref).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
-    assert g.stats().pcg_iterations > 0
-    prof_names = g.kernel_profile()          # empty unless profiling: only checks the call
-    assert isinstance(prof_names, dict)
+    st = g.stats()
+    assert st.pcg_iterations > 0 and st.solves == o.c.total_solves
     g.close()
 
 
