@@ -41,6 +41,7 @@ int fail(int code, const char* fmt, ...) {
 }  // namespace
 
 constexpr int SLAB_HALO = 4;     // halo rows kept on each side of the owned rows
+constexpr int NS_MIXED_DEFAULT[3] = {4, 4, 4};   // forward, backward, search+apply (pcg_dtype = FP32)
 static_assert(SLAB_HALO == P2P_HALO_DEPTH, "p2p.cuh halo depth");
 
 struct euler_gpu {
@@ -702,6 +703,17 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.fused = (prm.precon == EULER_PRECON_REDBLACK && prm.dot_mode == EULER_DOT_TREE && prm.stencil_variant != 1)
                 ? (prm.stencil_variant == 2 ? 2 : 1) : 0;
   c.mixed = mixed ? 1 : 0;
+  {
+    // ring depths of the fp32 pipe kernels (A/B knobs: EULER_NS_MIXED for all three, or
+    // EULER_NS_MIXED_F / _B / _KA), read once per handle
+    static const char* const names[3] = {"EULER_NS_MIXED_F", "EULER_NS_MIXED_B", "EULER_NS_MIXED_KA"};
+    const char* all = getenv("EULER_NS_MIXED");
+    for (int i = 0; i < 3; ++i) {
+      const char* e = getenv(names[i]);
+      const int v = e ? atoi(e) : all ? atoi(all) : NS_MIXED_DEFAULT[i];
+      c.ns_mixed[i] = (v == 6 || v == 8) ? v : 4;
+    }
+  }
   if (mixed) {
     // fp64: p and b (in the r plane) only; everything the iteration streams is fp32
     TRY(alloc_plane(h, &c.p)); TRY(alloc_plane(h, &c.r));

@@ -71,6 +71,7 @@ struct Ctx {
   // ping-pong), q and the preconditioner diagonal; p stays fp64 and the fp64 r plane keeps b
   int mixed;
   float *r32, *z32, *s32, *s32b, *q32, *pc32;
+  int ns_mixed[3];                // TMA ring depth of the fp32 forward / backward / search+apply kernels
   int fused;                      // red-black: two fused kernels per iteration
   uint8_t* tile_active;           // per PCG tile: contains fluid (pcg_kernels.cu)
   int* tile_list;                 // ordered compact list of those tiles

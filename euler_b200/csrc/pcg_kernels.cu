@@ -1133,8 +1133,10 @@ __global__ void __launch_bounds__(TW / C) k_fused_axpy_forward(
 
 constexpr int NS_KA = 4, NS_KB = 4;
 constexpr int CPT_F = 2, CPT_B = 2, CPT_KA = 4;   // cells per thread of the pipe kernels
-// mixed-precision (fp32 storage) instantiations: 4 cells = one 16 B vector per thread and plane
-constexpr int NS_MIXED = 4, CPT_MIXED = 4;
+// mixed-precision (fp32 storage) instantiations: 4 cells = one 16 B vector per thread and plane;
+// ring depth per kernel in Ctx::ns_mixed (4, 6 or 8: a row segment is half the bytes of an fp64
+// one, so the same bytes in flight need a deeper ring)
+constexpr int CPT_MIXED = 4;
 
 // persistent grid: resident blocks per SM (occupancy of that kernel) x SM count, capped by
 // the number of tiles
@@ -1316,9 +1318,11 @@ void launch_rb_forward(Ctx& c) {
   const PV v = pview(c);
   if (c.mixed) {
     constexpr int C = CPT_MIXED;
-    constexpr int sf = pipe::smem_bytes<2, 1, NS_MIXED, float>();
-    launch_pdl(k_rb_forward_pipe<NS_MIXED, C, float>, pcg_blocks(c, k_rb_forward_pipe<NS_MIXED, C, float>, sf, TW / C),
-               TW / C, sf, c.stream, v.g, TL, v.r32, v.fluid, v.pc32, v.q32, c.sc);
+#define FWD32(N) { constexpr int sf = pipe::smem_bytes<2, 1, N, float>(); \
+    launch_pdl(k_rb_forward_pipe<N, C, float>, pcg_blocks(c, k_rb_forward_pipe<N, C, float>, sf, TW / C), \
+               TW / C, sf, c.stream, v.g, TL, v.r32, v.fluid, v.pc32, v.q32, c.sc); }
+    if (c.ns_mixed[0] == 8) FWD32(8) else if (c.ns_mixed[0] == 6) FWD32(6) else FWD32(4)
+#undef FWD32
   } else if (c.use_pipe) {
     static const int ns = env_int("EULER_NS_F", NS_F);
     static const int cpt = env_int("EULER_CPT_F", CPT_F);
@@ -1339,12 +1343,14 @@ void launch_rb_backward(Ctx& c, bool init) {
   const PV v = pview(c);
   if (c.mixed) {
     constexpr int C = CPT_MIXED;
-    constexpr int sb = pipe::smem_bytes<3, 1, NS_MIXED, float>();
     DistArgs d;
     memset(&d, 0, sizeof d);
-    launch_pdl(k_rb_backward_pipe<NS_MIXED, C, float>, pcg_blocks(c, k_rb_backward_pipe<NS_MIXED, C, float>, sb, TW / C),
-               TW / C, sb, c.stream, v.g, TL, v.q32, v.r32, v.fluid, v.pc32, v.z32, c.partials, c.sc, init ? 1 : 0, 0,
-               v.a0, v.a1, c.tol, d);
+#define BWD32(N) { constexpr int sb = pipe::smem_bytes<3, 1, N, float>(); \
+    launch_pdl(k_rb_backward_pipe<N, C, float>, pcg_blocks(c, k_rb_backward_pipe<N, C, float>, sb, TW / C), \
+               TW / C, sb, c.stream, v.g, TL, v.q32, v.r32, v.fluid, v.pc32, v.z32, c.partials, c.sc, init ? 1 : 0, 0, \
+               v.a0, v.a1, c.tol, d); }
+    if (c.ns_mixed[1] == 8) BWD32(8) else if (c.ns_mixed[1] == 6) BWD32(6) else BWD32(4)
+#undef BWD32
   } else if (c.use_pipe) {
     static const int ns = env_int("EULER_NS_B", NS_B);
     static const int cpt = env_int("EULER_CPT_B", CPT_B);
@@ -1397,11 +1403,13 @@ void launch_fused_search_apply(Ctx& c, bool init) {
   memset(&d, 0, sizeof d);
   if (c.mixed) {
     constexpr int C = CPT_MIXED;
-    constexpr int smem = pipe::smem_bytes<2, 2, NS_MIXED, float>();
-    launch_pdl(k_fused_search_apply<NS_MIXED, C, float>,
-               pcg_blocks(c, k_fused_search_apply<NS_MIXED, C, float>, smem, TW / C), TW / C, smem, c.stream,
-               v.g, TL, v.z32, v.s32, v.fluid, v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0,
-               v.a0, v.a1, d);
+#define KA32(N) { constexpr int smem = pipe::smem_bytes<2, 2, N, float>(); \
+    launch_pdl(k_fused_search_apply<N, C, float>, \
+               pcg_blocks(c, k_fused_search_apply<N, C, float>, smem, TW / C), TW / C, smem, c.stream, \
+               v.g, TL, v.z32, v.s32, v.fluid, v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0, \
+               v.a0, v.a1, d); }
+    if (c.ns_mixed[2] == 8) KA32(8) else if (c.ns_mixed[2] == 6) KA32(6) else KA32(4)
+#undef KA32
     c.launches += 1;
     float* t32 = c.s32; c.s32 = c.s32b; c.s32b = t32;
     return;
