@@ -74,12 +74,67 @@ ALG_BYTES_PER_CELL_FP32 = {
 }
 
 
+NOMINAL_HBM_GBS = 8000.0     # north_star's "~8 TB/s" (DGX B200 figure); reported beside the measured peak
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roofline_report(prof, alg_bytes, active_cells, cells_local, n_markers, headline, mixed):
+    """Per-kernel achieved GB/s of ALGORITHMIC bytes and the `roofline` object of the dominant
+    kernel.  `prof` = {kernel class: (summed ms, launches)} from the library's CUDA-event timers;
+    PCG kernels stream only the tiles that contain fluid (like the reference, which touches
+    only is_fluid cells): their unit count is `active_cells`; grid stages stream every stored
+    cell (`cells_local`), marker kernels every marker.  `headline`: the workload the committed
+    ncu capture (profiles/ncu_traffic.json) was taken on."""
+    peak, peak_src = peaks()
+    total_ms = sum(v[0] for v in prof.values())
+    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
+    roof = None
+    kernels = {}
+    for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        if name in PCG_KERNELS and name in alg_bytes:
+            b = alg_bytes[name] * active_cells
+        elif name in alg_bytes:
+            b = alg_bytes[name] * cells_local
+        elif name in ALG_BYTES_PER_MARKER:
+            b = ALG_BYTES_PER_MARKER[name] * n_markers
+        else:
+            b = None
+        avg = kms / cnt
+        kernels[name] = {"ms_avg": round(avg, 4), "launches": cnt, "share": round(kms / total_ms, 4),
+                         "gbs": round(b / avg / 1e6, 1) if b else None,
+                         "frac": round(b / avg / 1e6 / peak, 4) if b else None,
+                         "frac_nominal": round(b / avg / 1e6 / NOMINAL_HBM_GBS, 4) if b else None}
+        if name in DRY_BYTES_PER_CELL:
+            wet = min(active_cells, cells_local)
+            bt = alg_bytes[name] * wet + DRY_BYTES_PER_CELL[name] * (cells_local - wet)
+            kernels[name]["gbs_touched"] = round(bt / avg / 1e6, 1)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tt = json.load(f)
+        if headline and dom:
+            traffic = (tt.get("fp32", {}) if mixed else tt).get(dom[0])
+    except (OSError, ValueError):
+        pass
+    if dom and kernels[dom[0]]["gbs"]:
+        k = kernels[dom[0]]
+        units = active_cells if dom[0] in PCG_KERNELS else cells_local
+        roof = {"kernel": dom[0], "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": k["frac"], "traffic": traffic, "peak_source": peak_src,
+                "peak_nominal": NOMINAL_HBM_GBS, "frac_nominal": k["frac_nominal"],
+                "traffic_source": "ncu capture committed under profiles/ (same workload)" if traffic else None,
+                "alg_bytes_per_launch": alg_bytes[dom[0]] * units,
+                "units_per_launch": units,
+                "bytes_per_unit": alg_bytes[dom[0]],
+                "ms_per_launch": k["ms_avg"], "share_of_step": k["share"]}
+    return kernels, roof
 
 
 class ClockSampler:
@@ -294,47 +349,9 @@ def run_gpu(args):
     iters_all, launches_all = iters, int(it[0])      # one global solve: every rank counts the same iterations
 
     if rank == 0:
-        peak, peak_src = peaks()
-        total_ms = sum(v[0] for v in prof.values())
-        dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
-        roof = None
-        kernels = {}
-        for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-            if name in PCG_KERNELS:
-                # PCG kernels stream only the tiles that contain fluid (like the reference,
-                # which touches only is_fluid cells): units = cells of those tiles
-                b = alg_bytes[name] * active_cells
-            elif name in alg_bytes:
-                b = alg_bytes[name] * cells_local
-            elif name in ALG_BYTES_PER_MARKER:
-                b = ALG_BYTES_PER_MARKER[name] * n_markers
-            else:
-                b = None
-            avg = kms / cnt
-            kernels[name] = {"ms_avg": round(avg, 4), "launches": cnt, "share": round(kms / total_ms, 4),
-                             "gbs": round(b / avg / 1e6, 1) if b else None,
-                             "frac": round(b / avg / 1e6 / peak, 4) if b else None}
-            if name in DRY_BYTES_PER_CELL:
-                wet = min(active_cells, cells_local)
-                bt = alg_bytes[name] * wet + DRY_BYTES_PER_CELL[name] * (cells_local - wet)
-                kernels[name]["gbs_touched"] = round(bt / avg / 1e6, 1)
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                tt = json.load(f)
-            if n == 16384 and world == 1 and args.scenario == "basic-fill" and dom:
-                traffic = (tt.get("fp32", {}) if mixed else tt).get(dom[0])
-        except (OSError, ValueError):
-            pass
-        if dom and kernels[dom[0]]["gbs"]:
-            k = kernels[dom[0]]
-            roof = {"kernel": dom[0], "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": k["frac"], "traffic": traffic, "peak_source": peak_src,
-                    "traffic_source": "ncu capture committed under profiles/ (same workload)" if traffic else None,
-                    "alg_bytes_per_launch": alg_bytes[dom[0]] * (active_cells if dom[0] in PCG_KERNELS else cells_local),
-                    "units_per_launch": active_cells if dom[0] in PCG_KERNELS else cells_local,
-                    "bytes_per_unit": alg_bytes[dom[0]],
-                    "ms_per_launch": k["ms_avg"], "share_of_step": k["share"]}
+        kernels, roof = roofline_report(prof, alg_bytes, active_cells, cells_local, n_markers,
+                                        headline=(n == 16384 and world == 1 and args.scenario == "basic-fill"),
+                                        mixed=mixed)
         value = cells * args.steps / (ms_max * 1e-3)
         line = {
             "metric": "MAC cell-updates/s", "value": value, "unit": "cell-updates/s",
