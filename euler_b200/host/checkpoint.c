@@ -20,6 +20,15 @@ typedef struct plane_desc { int field; size_t elem; } plane_desc;
 static const plane_desc BASE[] = {{EULER_F_U, 4}, {EULER_F_V, 4}, {EULER_F_COUNT, 1}, {EULER_F_PREV_COUNT, 1},
                                   {EULER_F_PRECON, 8}};
 static const plane_desc COLOR[] = {{EULER_F_CR, 4}, {EULER_F_CG, 4}, {EULER_F_CB, 4}};
+enum { FLAG_COLOR = 1u, FLAG_NO_PRECON = 2u };
+
+/* A handle created with pcg_dtype = FP32 has no fp64 g_precon plane (its red-black factor is
+ * rebuilt from scratch every solve, nothing persists): get/set(EULER_F_PRECON) answer
+ * EULER_E_INVALID there.  The file keeps its fixed layout — zeros are written in that case —
+ * and bit 1 of the flags says so. */
+static int has_precon_plane(const euler_ckpt_api *a, euler_gpu *sim, void *buf, size_t cells) {
+  return a->get(sim, EULER_F_PRECON, buf, cells * 8) == 0;
+}
 
 int euler_checkpoint_save(const euler_ckpt_api *a, euler_gpu *sim, int nx, int ny, int rainbow, const char *path) {
   euler_stats st;
@@ -28,17 +37,21 @@ int euler_checkpoint_save(const euler_ckpt_api *a, euler_gpu *sim, int nx, int n
   header h;
   memset(&h, 0, sizeof h);
   memcpy(h.magic, MAGIC, 8);
-  h.nx = nx; h.ny = ny; h.flags = rainbow ? 1u : 0u;
+  h.nx = nx; h.ny = ny; h.flags = rainbow ? FLAG_COLOR : 0u;
   h.n_markers = st.n_markers; h.rng_state = st.rng_state; h.frames = st.frames;
   h.source_exhausted = st.source_exhausted;
   const size_t cells = (size_t)nx * ny;
   size_t big = cells * 8 > h.n_markers * 8 ? cells * 8 : (size_t)h.n_markers * 8;
   void *buf = malloc(big ? big : 1);
+  if (!buf) return -1;
+  const int precon = has_precon_plane(a, sim, buf, cells);
+  if (!precon) h.flags |= FLAG_NO_PRECON;
   FILE *f = fopen(path, "wb");
-  if (!buf || !f) { free(buf); if (f) fclose(f); return -1; }
+  if (!f) { free(buf); return -1; }
   int err = fwrite(&h, sizeof h, 1, f) != 1;
   for (size_t i = 0; !err && i < sizeof BASE / sizeof BASE[0]; ++i) {
-    if ((rc = a->get(sim, BASE[i].field, buf, cells * BASE[i].elem))) break;
+    if (BASE[i].field == EULER_F_PRECON && !precon) memset(buf, 0, cells * 8);
+    else if ((rc = a->get(sim, BASE[i].field, buf, cells * BASE[i].elem))) break;
     err = fwrite(buf, BASE[i].elem, cells, f) != cells;
   }
   for (size_t i = 0; !err && !rc && rainbow && i < 3; ++i) {
@@ -59,15 +72,18 @@ int euler_checkpoint_load(const euler_ckpt_api *a, euler_gpu *sim, int nx, int n
   if (!f) return -1;
   header h;
   if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, MAGIC, 8)) { fclose(f); return -1; }
-  if (h.nx != nx || h.ny != ny || ((h.flags & 1u) != 0) != (rainbow != 0) ||
+  if (h.nx != nx || h.ny != ny || ((h.flags & FLAG_COLOR) != 0) != (rainbow != 0) ||
       h.n_markers > 4ull * (uint64_t)nx * (uint64_t)ny) { fclose(f); return -2; }
   const size_t cells = (size_t)nx * ny;
   size_t big = cells * 8 > h.n_markers * 8 ? cells * 8 : (size_t)h.n_markers * 8;
   void *buf = malloc(big ? big : 1);
   if (!buf) { fclose(f); return -1; }
   int rc = 0, err = 0;
+  /* the plane is restored when both the file and the handle have it */
+  const int precon = !(h.flags & FLAG_NO_PRECON) && has_precon_plane(a, sim, buf, cells);
   for (size_t i = 0; !err && !rc && i < sizeof BASE / sizeof BASE[0]; ++i) {
     err = fread(buf, BASE[i].elem, cells, f) != cells;
+    if (BASE[i].field == EULER_F_PRECON && !precon) continue;
     if (!err) rc = a->set(sim, BASE[i].field, buf, cells * BASE[i].elem);
   }
   for (size_t i = 0; !err && !rc && rainbow && i < 3; ++i) {

@@ -6,7 +6,8 @@
  * persistent g_precon plane (:577), g_frame_count (:89) and, with --rainbow,
  * g_r g_g g_b (:77-79).  Everything else is recomputed every sub-step.
  *
- * File: "EULERCK1" | nx ny (i32) | flags (u32, bit 0 = colour planes) | n_markers (u64) |
+ * File: "EULERCK1" | nx ny (i32) | flags (u32, bit 0 = colour planes, bit 1 = the handle had no
+ * fp64 g_precon plane (pcg_dtype = FP32): zeros in its place) | n_markers (u64) |
  * rng_state (u64) | frames (u64) | source_exhausted (i32) | pad (i32) | u v (f32 planes) |
  * count prev_count (u8 planes) | precon (f64 plane) | [r g b (f32 planes)] | markers (f32 x 2).
  * Little-endian, planes row-major [ny][nx]. */
