@@ -84,15 +84,21 @@ int comm_exchange(Ctx& c, Comm& cm, const void* to_dn, size_t n_to_dn, void* fro
   ncclComm_t comm = (ncclComm_t)cm.nccl;
   const int dn = cm.rank - 1, up = cm.rank + 1;
   NC(api.GroupStart());
+  // a failed call must not leave the group open: remember the first error, always close
+  int bad = 0;
+#define NCG(call) do { if (!bad && nerr((call), #call)) bad = 1; } while (0)
   if (dn >= 0) {
-    if (n_to_dn) NC(api.Send(to_dn, n_to_dn, ncclChar, dn, comm, c.stream));
-    if (n_from_dn) NC(api.Recv(from_dn, n_from_dn, ncclChar, dn, comm, c.stream));
+    if (n_to_dn) NCG(api.Send(to_dn, n_to_dn, ncclChar, dn, comm, c.stream));
+    if (n_from_dn) NCG(api.Recv(from_dn, n_from_dn, ncclChar, dn, comm, c.stream));
   }
   if (up < cm.nranks) {
-    if (n_to_up) NC(api.Send(to_up, n_to_up, ncclChar, up, comm, c.stream));
-    if (n_from_up) NC(api.Recv(from_up, n_from_up, ncclChar, up, comm, c.stream));
+    if (n_to_up) NCG(api.Send(to_up, n_to_up, ncclChar, up, comm, c.stream));
+    if (n_from_up) NCG(api.Recv(from_up, n_from_up, ncclChar, up, comm, c.stream));
   }
-  NC(api.GroupEnd());
+#undef NCG
+  const ncclResult_t end = api.GroupEnd();
+  if (bad) return -1;
+  NC(end);
   return 0;
 }
 
