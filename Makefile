@@ -18,8 +18,11 @@ CU_OBJS  := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 HDRS     := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/euler_gpu.h
 HOST     := euler_b200/host
 
-.PHONY: all gpu host oracle clean
-all: gpu host oracle
+CXX      ?= g++
+CUDA_INC ?= $(dir $(NVCC))../include
+
+.PHONY: all gpu host oracle hostops clean
+all: gpu host oracle hostops
 
 gpu: $(LIBDIR)/libeuler_gpu.so
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
@@ -42,6 +45,14 @@ bin/euler-gpu: $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c $(HOST)/checkp
 
 oracle:
 	$(MAKE) -C oracle all
+
+# TEST INFRASTRUCTURE: the row operators of the PCG kernels (csrc/pcg_ops.cuh) compiled for the
+# host, same no-contraction arithmetic as the oracle (tests/test_pcg_ops_host.py)
+hostops: build/libpcg_ops_host.so
+build/libpcg_ops_host.so: tests/csrc/pcg_ops_host.cpp $(CSRC)/pcg_ops.cuh $(CSRC)/pcg_pipe.cuh $(CSRC)/common.cuh
+	@mkdir -p build
+	$(CXX) -std=c++17 -O2 -ffp-contract=off -Wall -Wextra -Wno-unknown-pragmas -Wno-unused-function -fPIC -shared \
+	  -I$(CUDA_INC) -I$(CSRC) $< -o $@
 
 clean:
 	rm -rf build bin $(LIBDIR)/*.so

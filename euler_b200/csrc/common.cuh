@@ -76,6 +76,8 @@ __device__ __forceinline__ float div_h(float a, float h) { return h == 1.f ? a :
 
 #define EULER_FULL_MASK 0xffffffffu
 
+#ifdef __CUDACC__   // device-only from here on (the host build of pcg_ops.cuh stops above)
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(EULER_FULL_MASK, v, o);
@@ -180,5 +182,6 @@ __device__ __forceinline__ bool grid_reduce_last_block_all(double block_value, d
   total = total_sh;
   return true;
 }
+#endif  // __CUDACC__
 
 }  // namespace euler

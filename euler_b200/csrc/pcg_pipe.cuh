@@ -34,6 +34,7 @@ template <class T> struct Elem {
   static constexpr int ROW = (TW + 2 * HX) * (int)sizeof(T);   // bytes of one row segment in smem
 };
 
+#ifdef __CUDACC__   // mbarrier / bulk-copy PTX: device compilation only
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -70,6 +71,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
+#endif  // __CUDACC__
+
 struct Tiles { int tx, ty, n; };
 __host__ __device__ inline Tiles tiles_of(const Grid& g, int th) {
   Tiles t;
@@ -94,6 +97,7 @@ __host__ __device__ inline Tiles tiles_of(const Grid& g, int th) {
 // of one tile and needs its own halo rows.
 struct Piece { int x0, y0, y1, w; };
 
+#ifdef __CUDACC__   // the work split reads blockIdx / gridDim
 struct ChunkIter {
   int k, q;                        // next round robin round, number of full rounds
   int cur, end;                    // row-split tail, in strip rows from the start of the list;
@@ -160,6 +164,8 @@ struct JobIter {
   }
 };
 
+#endif  // __CUDACC__
+
 // One stage of the ring, as seen by the consumers: pointers are biased so that index i is tile
 // column i (value planes valid for i in [-HX, TW+HX), u8 planes for i in [-16, TW+16)).
 template <int ND, int NB, class T = double>
@@ -188,6 +194,7 @@ struct Planes {
   const uint8_t* b[NB];
 };
 
+#ifdef __CUDACC__
 // The pipeline driver.  `Op::row(dn, ce, up, t4, x, y, live)` is called by every thread for
 // each output row of each active tile of the block: t4 = 4*threadIdx.x is the tile column of
 // the thread's first cell, x its global column; `live` is false for threads past the row end.
@@ -321,6 +328,8 @@ __device__ __forceinline__ void run_radius(const Grid& g, const int* __restrict_
     cons.next(g, T, th, list);
   }
 }
+
+#endif  // __CUDACC__
 
 template <int ND, int NB, int NS, class T = double>
 constexpr int smem_bytes() { return NS * Layout<ND, NB, T>::stage_bytes + 2 * NS * 8; }

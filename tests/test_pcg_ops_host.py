@@ -1,0 +1,164 @@
+"""The row operators of the pressure-solve kernels (euler_b200/csrc/pcg_ops.cuh — the SAME source
+the GPU kernels instantiate) compiled for the host and checked BIT FOR BIT against the oracle,
+without a GPU: red-black forward / backward solves, the fused search-direction update + A·s,
+the unfused A·s and the mixed-precision residual replacement, for both storage types and both
+cells-per-thread variants.  What is not covered here is the machinery that feeds the operators
+on the device (TMA ring, work split, grid reductions): tests/test_gpu_*.py.
+
+The fused dot products are accumulated by one operator instance in row-major order here, which
+is the oracle's sequential dot(): they must match exactly too."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, same_bits
+from euler_b200 import shipped_text, resample
+from oracle.oracle import Oracle, PRECON_REDBLACK
+
+GUARD = 4
+LIB = os.path.join(ROOT, "build", "libpcg_ops_host.so")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    subprocess.run(["make", "-C", ROOT, "hostops"], check=True, capture_output=True)
+    L = C.CDLL(LIB)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    L.ops_rb_forward_f64.argtypes = L.ops_rb_forward_f32.argtypes = [i, i, i, i, vp, vp, vp, vp]
+    L.ops_rb_backward_f64.argtypes = L.ops_rb_backward_f32.argtypes = [i, i, i, i, vp, vp, vp, vp, vp]
+    L.ops_rb_backward_f64.restype = L.ops_rb_backward_f32.restype = d
+    L.ops_fused_search_apply_f64.argtypes = L.ops_fused_search_apply_f32.argtypes = [i, i, i, i, vp, vp, vp, vp, d, i, vp, vp]
+    L.ops_fused_search_apply_f64.restype = L.ops_fused_search_apply_f32.restype = d
+    L.ops_apply_a_f64.argtypes = [i, i, i, vp, vp, vp, vp]
+    L.ops_apply_a_f64.restype = d
+    L.ops_true_residual.argtypes = [i, i, i, vp, vp, vp, vp, vp]
+    return L
+
+
+class Planes:
+    """Device layout on the host: pitch = nx rounded up to 32, GUARD zero rows above and below."""
+
+    def __init__(self, nx, ny):
+        self.nx, self.ny, self.pitch = nx, ny, (nx + 31) // 32 * 32
+        self.keep = []
+
+    def put(self, a):
+        buf = np.zeros((self.ny + 2 * GUARD, self.pitch), dtype=a.dtype)
+        buf[GUARD:GUARD + self.ny, :self.nx] = a
+        self.keep.append(buf)
+        return buf
+
+    def ptr(self, buf):
+        return buf.ctypes.data + GUARD * self.pitch * buf.itemsize
+
+    def get(self, buf):
+        return buf[GUARD:GUARD + self.ny, :self.nx]
+
+
+def _state(name, nx, ny, frames):
+    """An oracle in red-black mode a few frames in, with rhs and a_diag of the next solve built."""
+    text = shipped_text(name) if (nx, ny) == (100, 40) else resample(shipped_text(name), nx - 2, ny - 2)
+    o = Oracle(nx, ny, text)
+    o.c.precon_mode = PRECON_REDBLACK
+    o.c.quirk_marker_dt_leak = 0
+    for _ in range(frames):
+        o.step_frame()
+    dt = o.calculate_timestep(0.1)
+    o.substep(dt)
+    o.build_rhs(o.calculate_timestep(0.1))
+    assert (o.count != 0).sum() > 50 and np.abs(o.b).max() > 0
+    return o
+
+
+CASES = [("block", 100, 40, 14), ("waterfall", 100, 40, 20), ("weird-edges", 100, 40, 15),
+         ("filter", 160, 90, 12), ("waterfall", 600, 70, 10)]      # 600 wide: two 512-cell tiles per row
+
+
+@pytest.mark.parametrize("cpt", [2, 4])
+@pytest.mark.parametrize("name,nx,ny,frames", CASES)
+def test_fp64_operators_bit_exact(ops, name, nx, ny, frames, cpt):
+    o = _state(name, nx, ny, frames)
+    fl = o.count != 0
+    P = Planes(nx, ny)
+    fluid, adiag = P.put(o.count), P.put(o.adiag)
+    # z = M^-1 r: forward and backward solves, z.r
+    o.r[:] = o.b
+    o.apply_preconditioner(o.r, o.z)
+    r, pc = P.put(o.r), P.put(np.where(fl, o.precon, 0.0))
+    q, z = P.put(np.zeros_like(o.r)), P.put(np.zeros_like(o.r))
+    ops.ops_rb_forward_f64(nx, ny, P.pitch, cpt, P.ptr(r), P.ptr(pc), P.ptr(fluid), P.ptr(q))
+    assert same_bits(P.get(q)[fl], o.q[fl])
+    zr = ops.ops_rb_backward_f64(nx, ny, P.pitch, cpt, P.ptr(q), P.ptr(pc), P.ptr(r), P.ptr(fluid), P.ptr(z))
+    assert same_bits(P.get(z)[fl], o.z[fl])
+    assert zr == o.dot(o.z, o.r)
+    # s' = z + beta s ; A s' ; (A s').s'
+    rng = np.random.default_rng(3)
+    s_old = rng.standard_normal((ny, nx))
+    beta = 0.8125 + 1e-3 * rng.random()
+    for init in (1, 0):
+        s_ref = np.where(fl, o.z if init else o.z + beta * s_old, s_old)
+        as_ref = np.zeros_like(s_ref)
+        o.apply_a(np.ascontiguousarray(s_ref), as_ref)
+        s_in, s_new, a_s = P.put(s_old), P.put(np.zeros_like(s_old)), P.put(np.zeros_like(s_old))
+        acc = ops.ops_fused_search_apply_f64(nx, ny, P.pitch, cpt, P.ptr(z), P.ptr(s_in), P.ptr(fluid), P.ptr(adiag),
+                                             beta, init, P.ptr(s_new), P.ptr(a_s))
+        assert same_bits(P.get(s_new)[fl], s_ref[fl])
+        assert same_bits(P.get(a_s)[fl], as_ref[fl])
+        assert acc == o.dot(as_ref, np.ascontiguousarray(s_ref))
+    # the unfused operator
+    out, out_ref = P.put(np.zeros_like(s_old)), np.zeros_like(s_old)
+    o.apply_a(s_old, out_ref)
+    acc = ops.ops_apply_a_f64(nx, ny, P.pitch, P.ptr(P.put(s_old)), P.ptr(fluid), P.ptr(adiag), P.ptr(out))
+    assert same_bits(P.get(out)[fl], out_ref[fl]) and acc == o.dot(out_ref, s_old)
+
+
+@pytest.mark.parametrize("cpt", [2, 4])
+@pytest.mark.parametrize("name,nx,ny,frames", CASES)
+def test_fp32_operators_bit_exact(ops, name, nx, ny, frames, cpt):
+    o = _state(name, nx, ny, frames)
+    fl = o.count != 0
+    P = Planes(nx, ny)
+    fluid, adiag = P.put(o.count), P.put(o.adiag)
+    o.r32[:] = o.b.astype(np.float32)
+    o.rb_build32()
+    o.rb_apply32(o.r32, o.z32)
+    r, pc = P.put(o.r32), P.put(np.where(fl, o.pc32, np.float32(0)))
+    q, z = P.put(np.zeros_like(o.r32)), P.put(np.zeros_like(o.r32))
+    ops.ops_rb_forward_f32(nx, ny, P.pitch, cpt, P.ptr(r), P.ptr(pc), P.ptr(fluid), P.ptr(q))
+    assert same_bits(P.get(q)[fl], o.q32[fl])
+    zr = ops.ops_rb_backward_f32(nx, ny, P.pitch, cpt, P.ptr(q), P.ptr(pc), P.ptr(r), P.ptr(fluid), P.ptr(z))
+    assert same_bits(P.get(z)[fl], o.z32[fl])
+    # fp64 products of the fp32 values, summed sequentially in row-major order (cumsum is sequential)
+    assert zr == float((o.z32[fl].astype(np.float64) * o.r32[fl].astype(np.float64)).cumsum()[-1])
+    rng = np.random.default_rng(4)
+    s_old = rng.standard_normal((ny, nx)).astype(np.float32)
+    beta = 0.8125 + 1e-3 * rng.random()
+    for init in (1, 0):
+        s_ref = np.where(fl, o.z32 if init else o.z32 + np.float32(beta) * s_old, s_old).astype(np.float32)
+        as_ref = np.zeros_like(s_ref)
+        o.apply_a32(np.ascontiguousarray(s_ref), as_ref)
+        s_in, s_new, a_s = P.put(s_old), P.put(np.zeros_like(s_old)), P.put(np.zeros_like(s_old))
+        acc = ops.ops_fused_search_apply_f32(nx, ny, P.pitch, cpt, P.ptr(z), P.ptr(s_in), P.ptr(fluid), P.ptr(adiag),
+                                             beta, init, P.ptr(s_new), P.ptr(a_s))
+        assert same_bits(P.get(s_new)[fl], s_ref[fl])
+        assert same_bits(P.get(a_s)[fl], as_ref[fl])
+        seq = (as_ref[fl].astype(np.float64) * s_ref[fl].astype(np.float64)).cumsum()[-1]
+        assert acc == float(seq)
+
+
+def test_true_residual_bit_exact(ops):
+    o = _state("waterfall", 100, 40, 25)
+    fl = o.count != 0
+    P = Planes(100, 40)
+    p = np.where(fl, np.random.default_rng(9).standard_normal(o.p.shape) * 300.0, 0.0)
+    ap = np.zeros_like(p)
+    o.apply_a(p, ap)
+    ref = (o.b - ap).astype(np.float32)
+    r = P.put(np.zeros((40, 100), np.float32))
+    ops.ops_true_residual(100, 40, P.pitch, P.ptr(P.put(p)), P.ptr(P.put(o.b)), P.ptr(P.put(o.count)),
+                          P.ptr(P.put(o.adiag)), P.ptr(r))
+    assert same_bits(P.get(r)[fl], ref[fl])
+    assert not P.get(r)[~fl].any()
