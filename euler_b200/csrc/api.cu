@@ -713,6 +713,10 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
       const int v = e ? atoi(e) : all ? atoi(all) : NS_MIXED_DEFAULT[i];
       c.ns_mixed[i] = (v == 6 || v == 8) ? v : 4;
     }
+    // EULER_MIXED_BLOCKS=8: the fp32 pipe kernels compiled for 8 resident blocks per SM (64
+    // registers; the backward solve spills 16 B) instead of 7 — unmeasured, off by default
+    const char* mb = getenv("EULER_MIXED_BLOCKS");
+    c.mixed_blocks = (mb && atoi(mb) == 8) ? 8 : 0;
   }
   if (mixed) {
     // fp64: p and b (in the r plane) only; everything the iteration streams is fp32

@@ -72,6 +72,7 @@ struct Ctx {
   int mixed;
   float *r32, *z32, *s32, *s32b, *q32, *pc32;
   int ns_mixed[3];                // TMA ring depth of the fp32 forward / backward / search+apply kernels
+  int mixed_blocks;               // 8: the 64-register fp32 instantiations (8 resident blocks per SM); 0: default
   int fused;                      // red-black: two fused kernels per iteration
   uint8_t* tile_active;           // per PCG tile: contains fluid (pcg_kernels.cu)
   int* tile_list;                 // ordered compact list of those tiles

@@ -620,8 +620,10 @@ __global__ void __launch_bounds__(TT) k_apply_a_pipe(
   });
 }
 
-template <int NS, int C, class T = double>
-__global__ void __launch_bounds__(TW / C, C == 2 ? 4 : 5) k_rb_forward_pipe(
+// MB: minimum resident blocks per SM asked of the compiler (0 = the tuned default of the fp64
+// kernels); MB = 8 caps the fp32 instantiations at 64 registers (A/B knob EULER_MIXED_BLOCKS)
+template <int NS, int C, class T = double, int MB = 0>
+__global__ void __launch_bounds__(TW / C, MB ? MB : (C == 2 ? 4 : 5)) k_rb_forward_pipe(
     Grid g, TileList active, const T* __restrict__ r,
     const uint8_t* __restrict__ fluid, const T* __restrict__ precon, T* __restrict__ q,
     const DevScalars* sc) {
@@ -633,8 +635,8 @@ __global__ void __launch_bounds__(TW / C, C == 2 ? 4 : 5) k_rb_forward_pipe(
   pipe::run<2, 1, NS, TH, RbForwardPipe<C, T>, C, T>(g, active.list, (int)*active.count, in, op);
 }
 
-template <int NS, int C, class T = double>
-__global__ void __launch_bounds__(TW / C) k_rb_backward_pipe(
+template <int NS, int C, class T = double, int MB = 0>
+__global__ void __launch_bounds__(TW / C, MB) k_rb_backward_pipe(
     Grid g, TileList active, const T* __restrict__ q,
     const T* __restrict__ r, const uint8_t* __restrict__ fluid,
     const T* __restrict__ precon, T* __restrict__ z, double* partials, DevScalars* sc,
@@ -717,8 +719,8 @@ static int env_int(const char* name, int dflt) {
 // the new s / r cannot be written in place: s and r ping-pong between two planes each.
 // =========================================================================================
 
-template <int NS, int C, class T = double>
-__global__ void __launch_bounds__(TW / C) k_fused_search_apply(
+template <int NS, int C, class T = double, int MB = 0>
+__global__ void __launch_bounds__(TW / C, MB) k_fused_search_apply(
     Grid g, TileList active, const T* __restrict__ z, const T* __restrict__ s,
     const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, T* __restrict__ s_new,
     T* __restrict__ as, double* partials, DevScalars* sc, int init, int exact, int acc0, int acc1,
@@ -785,7 +787,7 @@ constexpr int CPT_MIXED = 4;
 // persistent grid: resident blocks per SM (occupancy of that kernel) x SM count, capped by
 // the number of tiles
 template <class K>
-int pcg_blocks(const Ctx& c, K kernel, int smem = 0, int threads = TT) {
+int pcg_blocks(const Ctx& c, K kernel, int smem = 0, int threads = TT, bool max_carveout = false) {
   // occupancy is a property of (kernel, threads, smem) on this architecture: asked once per
   // kernel and host thread, not on every launch (two driver calls per launch were a visible
   // share of the host time per PCG iteration on thin slabs)
@@ -801,6 +803,8 @@ int pcg_blocks(const Ctx& c, K kernel, int smem = 0, int threads = TT) {
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (max_carveout)             // 8 blocks x ~28 KB need (nearly) all of the SM's shared memory
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
       per_sm = 1;
     cache[key] = per_sm;
@@ -965,7 +969,11 @@ void launch_rb_forward(Ctx& c) {
 #define FWD32(N) { constexpr int sf = pipe::smem_bytes<2, 1, N, float>(); \
     launch_pdl(k_rb_forward_pipe<N, C, float>, pcg_blocks(c, k_rb_forward_pipe<N, C, float>, sf, TW / C), \
                TW / C, sf, c.stream, v.g, TL, v.r32, v.fluid, v.pc32, v.q32, c.sc); }
-    if (c.ns_mixed[0] == 8) FWD32(8) else if (c.ns_mixed[0] == 6) FWD32(6) else FWD32(4)
+    if (c.mixed_blocks == 8) {      // 64-register instantiation, 8 resident blocks (ring depth 4)
+      constexpr int sf = pipe::smem_bytes<2, 1, 4, float>();
+      auto k = k_rb_forward_pipe<4, C, float, 8>;
+      launch_pdl(k, pcg_blocks(c, k, sf, TW / C, true), TW / C, sf, c.stream, v.g, TL, v.r32, v.fluid, v.pc32, v.q32, c.sc);
+    } else if (c.ns_mixed[0] == 8) FWD32(8) else if (c.ns_mixed[0] == 6) FWD32(6) else FWD32(4)
 #undef FWD32
   } else if (c.use_pipe) {
     static const int ns = env_int("EULER_NS_F", NS_F);
@@ -993,7 +1001,12 @@ void launch_rb_backward(Ctx& c, bool init) {
     launch_pdl(k_rb_backward_pipe<N, C, float>, pcg_blocks(c, k_rb_backward_pipe<N, C, float>, sb, TW / C), \
                TW / C, sb, c.stream, v.g, TL, v.q32, v.r32, v.fluid, v.pc32, v.z32, c.partials, c.sc, init ? 1 : 0, 0, \
                v.a0, v.a1, c.tol, d); }
-    if (c.ns_mixed[1] == 8) BWD32(8) else if (c.ns_mixed[1] == 6) BWD32(6) else BWD32(4)
+    if (c.mixed_blocks == 8) {
+      constexpr int sb = pipe::smem_bytes<3, 1, 4, float>();
+      auto k = k_rb_backward_pipe<4, C, float, 8>;
+      launch_pdl(k, pcg_blocks(c, k, sb, TW / C, true), TW / C, sb, c.stream, v.g, TL, v.q32, v.r32, v.fluid, v.pc32,
+                 v.z32, c.partials, c.sc, init ? 1 : 0, 0, v.a0, v.a1, c.tol, d);
+    } else if (c.ns_mixed[1] == 8) BWD32(8) else if (c.ns_mixed[1] == 6) BWD32(6) else BWD32(4)
 #undef BWD32
   } else if (c.use_pipe) {
     static const int ns = env_int("EULER_NS_B", NS_B);
@@ -1052,7 +1065,12 @@ void launch_fused_search_apply(Ctx& c, bool init) {
                pcg_blocks(c, k_fused_search_apply<N, C, float>, smem, TW / C), TW / C, smem, c.stream, \
                v.g, TL, v.z32, v.s32, v.fluid, v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0, \
                v.a0, v.a1, d); }
-    if (c.ns_mixed[2] == 8) KA32(8) else if (c.ns_mixed[2] == 6) KA32(6) else KA32(4)
+    if (c.mixed_blocks == 8) {
+      constexpr int smem = pipe::smem_bytes<2, 2, 4, float>();
+      auto k = k_fused_search_apply<4, C, float, 8>;
+      launch_pdl(k, pcg_blocks(c, k, smem, TW / C, true), TW / C, smem, c.stream, v.g, TL, v.z32, v.s32, v.fluid,
+                 v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0, v.a0, v.a1, d);
+    } else if (c.ns_mixed[2] == 8) KA32(8) else if (c.ns_mixed[2] == 6) KA32(6) else KA32(4)
 #undef KA32
     c.launches += 1;
     float* t32 = c.s32; c.s32 = c.s32b; c.s32b = t32;
