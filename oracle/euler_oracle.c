@@ -214,7 +214,7 @@ void orc_advect_p(const orc_sim *o, const float *q, const float *u, const float 
 /* ref :276-298.  Argument evaluation order of
  * v2f(x+randf(), y+randf()) is unspecified in C; gcc 13 on x86-64 (the build that the
  * parity oracle oracle/_ref is made with) evaluates the SECOND argument first, i.e. the
- * y jitter takes the earlier draw.  tests/test_oracle_vs_ref.py pins this. */
+ * y jitter takes the earlier draw.  tests/test_oracle.py pins this. */
 void orc_update_fluid_sources(orc_sim *o) {
   const size_t cap = o->max_markers - 1;
   o->source_exhausted |= (o->n_markers == cap);

@@ -7,7 +7,7 @@
  *
  * Parity status: PINNED against the reference itself.  The reference has no tests or
  * golden vectors, but it compiles here unmodified (oracle/build_ref.sh →
- * oracle/_ref/ libraries); tests/test_oracle_vs_ref.py checks that every plane and the marker
+ * oracle/_ref/ libraries); tests/test_oracle.py checks that every plane and the marker
  * array of this restatement are bit-identical to the reference's after whole frames and
  * after each individual stage, on all five shipped scenarios and on resampled ones.
  *
