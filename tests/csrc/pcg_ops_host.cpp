@@ -119,4 +119,17 @@ void ops_true_residual(int nx, int ny, int pitch, const double* p, const double*
   sweep<1, 2, 4, double>(g, d, b, op);
 }
 
+// stencil_variant 2 (kept for A/B): p += alpha s, r' = r - alpha A s, ||r'||inf and q = L^-1 r'
+// in one pass (k_fused_axpy_forward); returns ||r'||inf
+double ops_fused_axpy_forward_f64(int nx, int ny, int pitch, const double* r, const double* as, const double* pc,
+                                  const uint8_t* fluid, const double* s, double alpha, double* p, double* r_new,
+                                  double* q) {
+  const Grid g = make_grid(nx, ny, pitch);
+  FusedAxpyForward<2> op{g, s, p, r_new, q, alpha, 0.0, 0, ny, {}, {}, ~(size_t)0};
+  const double* const d[3] = {r, as, pc};
+  const uint8_t* const b[1] = {fluid};
+  sweep<3, 1, 2, double>(g, d, b, op);
+  return op.mx;
+}
+
 }  // extern "C"

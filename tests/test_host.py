@@ -69,3 +69,23 @@ def test_row_major_marker_order_is_a_permutation():
     assert same_bits(key(a.markers), key(b.markers))
     cells = (np.floor(b.markers[:, 1]).astype(np.int64) * 100 + np.floor(b.markers[:, 0]).astype(np.int64))
     assert (np.diff(cells) >= 0).all()          # row-major, 4 per cell
+
+
+def test_parser_fuzz_against_oracle():
+    """Random scenario texts over the format's alphabet plus junk, ragged and over-long lines,
+    empty lines, no trailing newline; random grid sizes: masks, seeded markers and the RNG state
+    equal the oracle's restatement of sim_init (main.c:209-274)."""
+    from hypothesis import given, settings, strategies as st
+
+    line = st.text(alphabet="X0?= ab\t", min_size=0, max_size=40)
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(line, min_size=0, max_size=30), st.booleans(), st.integers(4, 48), st.integers(4, 36))
+    def run(lines, trailing, nx, ny):
+        text = "\n".join(lines) + ("\n" if trailing else "")
+        s, o = Scenario(text, nx, ny), Oracle(nx, ny, text)
+        assert np.array_equal(s.solid, o.solid) and np.array_equal(s.source, o.source)
+        assert np.array_equal(s.sink, o.sink)
+        assert same_bits(s.markers, o.markers) and s.rng_state == int(o.c.rng_state)
+
+    run()

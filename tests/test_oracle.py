@@ -214,3 +214,23 @@ def test_rainbow_planes_bit_identical_to_reference(name):
     o.colorize(); r.L.colorize()
     for a, b in ((o.cr, r.cr), (o.cg, r.cg), (o.cb, r.cb)):
         assert same_bits(a, b)
+
+
+@pytest.mark.skipif(not (ref_available(100, 40) and ref_available(64, 48)), reason="oracle/_ref not built")
+def test_sim_init_fuzz_against_reference():
+    """The parser / ring of sinks / marker seeding of sim_init (main.c:209-274) on random texts —
+    junk characters, ragged, over-long and empty lines, missing final newline — and the first
+    frames that follow: the restatement equals the unmodified reference bit for bit."""
+    rng = np.random.default_rng(20261017)
+    alphabet = np.array(list("X0?=   ab"))
+    for case in range(24):
+        nx, ny = ((100, 40), (64, 48))[case % 2]
+        lines = ["".join(rng.choice(alphabet, size=int(rng.integers(0, nx + 30)))) for _ in range(int(rng.integers(0, ny + 8)))]
+        text = "\n".join(lines) + ("\n" if case % 3 else "")
+        o, r = Oracle(nx, ny, text), Reference(nx, ny)
+        r.init_from_text(text)
+        _assert_same_state(o, r, "fuzz %d init" % case)
+        for f in range(8):
+            o.step_frame()
+            r.step_frame()
+            _assert_same_state(o, r, "fuzz %d frame %d" % (case, f + 1))

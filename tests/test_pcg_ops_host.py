@@ -35,6 +35,8 @@ def ops():
     L.ops_apply_a_f64.argtypes = [i, i, i, vp, vp, vp, vp]
     L.ops_apply_a_f64.restype = d
     L.ops_true_residual.argtypes = [i, i, i, vp, vp, vp, vp, vp]
+    L.ops_fused_axpy_forward_f64.argtypes = [i, i, i, vp, vp, vp, vp, vp, d, vp, vp, vp]
+    L.ops_fused_axpy_forward_f64.restype = d
     return L
 
 
@@ -162,3 +164,85 @@ def test_true_residual_bit_exact(ops):
                           P.ptr(P.put(o.adiag)), P.ptr(r))
     assert same_bits(P.get(r)[fl], ref[fl])
     assert not P.get(r)[~fl].any()
+
+
+def _random_state(nx, ny, seed, density):
+    """Arbitrary ragged masks: random fluid (never on the border ring), random solids, a_diag as
+    build_rhs would leave it — isolated cells, cells on both sides of the 512-column tile edges,
+    rows that end inside the pitch padding."""
+    rng = np.random.default_rng(seed)
+    o = Oracle(nx, ny, "")
+    o.c.precon_mode = PRECON_REDBLACK
+    solid = (rng.random((ny, nx)) < 0.08).astype(np.uint8)
+    cnt = ((rng.random((ny, nx)) < density) & (solid == 0)).astype(np.uint8) * rng.integers(1, 5, (ny, nx)).astype(np.uint8)
+    cnt[0] = cnt[-1] = 0; cnt[:, 0] = cnt[:, -1] = 0
+    o.solid[:] = solid; o.count[:] = cnt
+    s = solid.astype(np.int32)
+    a = np.zeros((ny, nx), np.int32)
+    a[1:-1, 1:-1] = 4 - s[1:-1, :-2] - s[1:-1, 2:] - s[:-2, 1:-1] - s[2:, 1:-1]
+    o.adiag[:] = np.where(cnt != 0, a, 0).astype(np.int8)
+    return o, rng
+
+
+@pytest.mark.parametrize("nx,ny,density,seed", [(1030, 37, 0.55, 1), (513, 20, 0.15, 2), (96, 70, 0.9, 3), (544, 9, 0.5, 4)])
+def test_operators_on_random_ragged_masks(ops, nx, ny, density, seed):
+    o, rng = _random_state(nx, ny, seed, density)
+    fl = o.count != 0
+    P = Planes(nx, ny)
+    fluid, adiag = P.put(o.count), P.put(o.adiag)
+    scale = 10.0 ** rng.integers(-3, 4, (ny, nx))
+    # fp64
+    o.r[:] = np.where(fl, rng.standard_normal((ny, nx)) * scale, 0.0)
+    o.apply_preconditioner(o.r, o.z)
+    r, pc = P.put(o.r), P.put(np.where(fl, o.precon, 0.0))
+    q, z = P.put(np.zeros((ny, nx))), P.put(np.zeros((ny, nx)))
+    for cpt in (2, 4):
+        ops.ops_rb_forward_f64(nx, ny, P.pitch, cpt, P.ptr(r), P.ptr(pc), P.ptr(fluid), P.ptr(q))
+        zr = ops.ops_rb_backward_f64(nx, ny, P.pitch, cpt, P.ptr(q), P.ptr(pc), P.ptr(r), P.ptr(fluid), P.ptr(z))
+        assert same_bits(P.get(q)[fl], o.q[fl]) and same_bits(P.get(z)[fl], o.z[fl]) and zr == o.dot(o.z, o.r)
+    # fp32
+    o.r32[:] = o.r.astype(np.float32)
+    o.rb_build32(); o.rb_apply32(o.r32, o.z32)
+    r, pc = P.put(o.r32), P.put(np.where(fl, o.pc32, np.float32(0)))
+    q, z = P.put(np.zeros((ny, nx), np.float32)), P.put(np.zeros((ny, nx), np.float32))
+    for cpt in (2, 4):
+        ops.ops_rb_forward_f32(nx, ny, P.pitch, cpt, P.ptr(r), P.ptr(pc), P.ptr(fluid), P.ptr(q))
+        ops.ops_rb_backward_f32(nx, ny, P.pitch, cpt, P.ptr(q), P.ptr(pc), P.ptr(r), P.ptr(fluid), P.ptr(z))
+        assert same_bits(P.get(q)[fl], o.q32[fl]) and same_bits(P.get(z)[fl], o.z32[fl])
+    # fused search + apply, both types
+    for dt, fn, apply in ((np.float64, ops.ops_fused_search_apply_f64, o.apply_a), (np.float32, ops.ops_fused_search_apply_f32, o.apply_a32)):
+        zz = (rng.standard_normal((ny, nx)) * scale).astype(dt)
+        ss = (rng.standard_normal((ny, nx)) * scale).astype(dt)
+        beta = 1.37
+        s_ref = np.where(fl, zz + dt(beta) * ss, ss).astype(dt)
+        as_ref = np.zeros((ny, nx), dt)
+        apply(np.ascontiguousarray(s_ref), as_ref)
+        s_new, a_s = P.put(np.zeros((ny, nx), dt)), P.put(np.zeros((ny, nx), dt))
+        fn(nx, ny, P.pitch, 4, P.ptr(P.put(zz)), P.ptr(P.put(ss)), P.ptr(fluid), P.ptr(adiag), beta, 0, P.ptr(s_new), P.ptr(a_s))
+        assert same_bits(P.get(s_new)[fl], s_ref[fl]) and same_bits(P.get(a_s)[fl], as_ref[fl])
+
+
+def test_fused_axpy_forward_variant_bit_exact(ops):
+    """stencil_variant 2: p, r', ||r'||inf and q = L^-1 r' in one pass equal the separate
+    fmadd (main.c:753-754), inf_norm (:756) and forward solve."""
+    o = _state("waterfall", 160, 90, 18)
+    nx, ny = 160, 90
+    fl = o.count != 0
+    rng = np.random.default_rng(12)
+    o.r[:] = o.b
+    o.apply_preconditioner(o.r, o.z)                       # builds o.precon
+    s = np.where(fl, rng.standard_normal((ny, nx)), 0.0)
+    a_s = np.zeros((ny, nx)); o.apply_a(s, a_s)
+    p0 = np.where(fl, rng.standard_normal((ny, nx)) * 50.0, 0.0)
+    alpha = 0.3731
+    p_ref = np.where(fl, p0 + s * alpha, p0)
+    r_ref = np.where(fl, o.b + a_s * -alpha, o.b)
+    zz = np.zeros((ny, nx)); o.apply_preconditioner(np.ascontiguousarray(r_ref), zz)    # o.q = L^-1 r'
+    P = Planes(nx, ny)
+    p, r_new, q = P.put(p0), P.put(np.zeros((ny, nx))), P.put(np.zeros((ny, nx)))
+    mx = ops.ops_fused_axpy_forward_f64(nx, ny, P.pitch, P.ptr(P.put(o.b)), P.ptr(P.put(a_s)),
+                                        P.ptr(P.put(np.where(fl, o.precon, 0.0))), P.ptr(P.put(o.count)),
+                                        P.ptr(P.put(s)), alpha, P.ptr(p), P.ptr(r_new), P.ptr(q))
+    assert same_bits(P.get(p)[fl], p_ref[fl]) and same_bits(P.get(r_new)[fl], r_ref[fl])
+    assert same_bits(P.get(q)[fl], o.q[fl])
+    assert mx == float(np.abs(r_ref[fl]).max())
