@@ -19,9 +19,13 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    """Reference-parity suites first; the opt-in modes that are not in the reference (mixed-
-    precision PCG) after them, so that `-x` reports a parity failure before anything else."""
-    items.sort(key=lambda it: 1 if "mixed" in it.nodeid.split("::")[0] else 0)
+    """The reference-parity suites on the shipped scenarios first; then the random-scenario fuzz,
+    then the opt-in modes that are not in the reference (mixed-precision PCG) — so that `-x`
+    reports a failure of the core suites before anything else."""
+    def rank(item):
+        module = item.nodeid.split("::")[0]
+        return 2 if "mixed" in module else 1 if "fuzz" in module else 0
+    items.sort(key=rank)
 
 
 @pytest.fixture(scope="session")
