@@ -263,72 +263,6 @@ __device__ __forceinline__ void run(const Grid& g, const int* __restrict__ list,
   }
 }
 
-// Same pipeline with a window of 2R+1 rows: `Op::rows(w, t4, x, y, live)` gets w[0..2R], w[R]
-// being the output row's own row.  Used by the fused axpy + red-black solve (R = 2).
-template <int ND, int NB, int NS, int TH, int R, class Op>
-__device__ __forceinline__ void run_radius(const Grid& g, const int* __restrict__ list, int n_active,
-                                           const Planes<ND, NB>& in, Op& op) {
-  using L = Layout<ND, NB>;
-  constexpr int ROW8 = L::ROWT, HX8 = L::HXT;
-  constexpr int W = 2 * R + 1;
-  constexpr int PF = NS - W;
-  static_assert(PF >= 1, "ring too short for the window");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* stages = smem_raw;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NS * L::stage_bytes);
-  uint64_t* empty = full + NS;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, TT / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
-  const int th = g.th;                             // run-time tile height (TH is the default)
-  const Tiles T = tiles_of(g, th);
-  JobIter cons, prod;
-  cons.rad = R;
-  cons.start(g, T, th, list, n_active);
-  prod = cons;
-  int issued = 0;
-
-  auto issue = [&]() {          // thread 0 only
-    const int s = issued % NS, use = issued / NS;
-    mbar_wait(empty + s, (use & 1) ^ 1);
-    unsigned char* st = stages + s * L::stage_bytes;
-    const uint32_t b8 = (uint32_t)(prod.p.w + 2 * HX8) * 8u, b1 = (uint32_t)(prod.p.w + 2 * HX1);
-    mbar_expect_tx(full + s, ND * b8 + NB * b1);
-    const long row = (long)prod.yy * g.pitch + prod.p.x0;
-#pragma unroll
-    for (int i = 0; i < ND; ++i) bulk_g2s(st + i * ROW8, in.d[i] + row - HX8, b8, full + s);
-#pragma unroll
-    for (int i = 0; i < NB; ++i) bulk_g2s(st + ND * ROW8 + i * ROW1, in.b[i] + row - HX1, b1, full + s);
-    ++issued;
-    prod.next(g, T, th, list);
-  };
-
-  for (int j = 0; cons.valid; ++j) {
-    if (threadIdx.x == 0)
-      while (prod.valid && issued <= j + PF) issue();
-    mbar_wait(full + (j % NS), (j / NS) & 1);
-    if (cons.yy >= cons.p.y0 + R) {
-      RowView<ND, NB> w[W];
-#pragma unroll
-      for (int k = 0; k < W; ++k) w[k] = L::view(stages + ((j + NS - (W - 1) + k) % NS) * L::stage_bytes);
-      const int t4 = threadIdx.x * 4;
-      op.rows(w, t4, cons.p.x0 + t4, cons.yy - R, t4 < cons.p.w);
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(empty + ((j + NS - (W - 1)) % NS));
-        if (cons.yy == cons.p.y1 - 1 + R)
-          for (int k = 1; k < W; ++k) mbar_arrive(empty + ((j + NS - (W - 1) + k) % NS));
-      }
-    }
-    cons.next(g, T, th, list);
-  }
-}
-
 #endif  // __CUDACC__
 
 template <int ND, int NB, int NS, class T = double>
