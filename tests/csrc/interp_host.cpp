@@ -1,0 +1,34 @@
+// tests/csrc/interp_host.cpp — TEST INFRASTRUCTURE: the masked bilinear sampler of the advection
+// kernels (euler_b200/csrc/interp.cuh, reference main.c:301-364) compiled for the host and called
+// on padded host planes, for a bit-for-bit comparison with the oracle's orc_interpolate
+// (tests/test_pcg_ops_host.py).  Same source as the device code; g++ -ffp-contract=off.
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+using std::max;
+using std::min;
+
+#include "interp.cuh"
+
+using namespace euler;
+
+extern "C" {
+
+// out[i] = interpolate<type>(q, fluid, ix[i], iy[i]); planes in device layout (pitch, guard rows),
+// pointers given for row 0.  type: 0 = P cell, 1 = U face, 2 = V face (celltype_t, main.c:46-50)
+void ops_interpolate(int nx, int ny, int pitch, int type, const float* q, const uint8_t* fluid, int n,
+                     const float* ix, const float* iy, float* out) {
+  Grid g;
+  g.nx = nx; g.ny = ny; g.pitch = pitch; g.yoff = 0; g.gny = ny; g.th = 32;
+  InterpLimits lim;
+  lim.u_x = nextafterf((float)(nx - 2), 0.f); lim.u_y = nextafterf((float)(ny - 1), 0.f);   // main.c:339-340
+  lim.v_x = nextafterf((float)(nx - 1), 0.f); lim.v_y = nextafterf((float)(ny - 2), 0.f);
+  lim.p_x = nextafterf((float)(nx - 1), 0.f); lim.p_y = nextafterf((float)(ny - 1), 0.f);
+  for (int i = 0; i < n; ++i)
+    out[i] = type == FACE_U ? interpolate<FACE_U>(q, fluid, g, lim, ix[i], iy[i])
+           : type == FACE_V ? interpolate<FACE_V>(q, fluid, g, lim, ix[i], iy[i])
+                            : interpolate<CELL_P>(q, fluid, g, lim, ix[i], iy[i]);
+}
+
+}  // extern "C"

@@ -1,6 +1,7 @@
-"""The row operators of the pressure-solve kernels (euler_b200/csrc/pcg_ops.cuh — the SAME source
-the GPU kernels instantiate) compiled for the host and checked BIT FOR BIT against the oracle,
-without a GPU: red-black forward / backward solves, the fused search-direction update + A·s,
+"""Device arithmetic checked on the CPU.  The row operators of the pressure-solve kernels
+(euler_b200/csrc/pcg_ops.cuh) and the masked bilinear sampler of the advection kernels
+(csrc/interp.cuh) — the SAME source the GPU kernels instantiate — are compiled for the host and
+checked BIT FOR BIT against the oracle, without a GPU: red-black forward / backward solves, the fused search-direction update + A·s,
 the unfused A·s and the mixed-precision residual replacement, for both storage types and both
 cells-per-thread variants.  What is not covered here is the machinery that feeds the operators
 on the device (TMA ring, work split, grid reductions): tests/test_gpu_*.py.
@@ -246,3 +247,30 @@ def test_fused_axpy_forward_variant_bit_exact(ops):
     assert same_bits(P.get(p)[fl], p_ref[fl]) and same_bits(P.get(r_new)[fl], r_ref[fl])
     assert same_bits(P.get(q)[fl], o.q[fl])
     assert mx == float(np.abs(r_ref[fl]).max())
+
+
+@pytest.mark.parametrize("nx,ny,seed", [(100, 40, 1), (37, 53, 2), (257, 19, 3)])
+def test_masked_bilinear_sampler_bit_exact(ops, nx, ny, seed):
+    """interp.cuh's interpolate<P|U|V> (the sampler of advect_u/v, advect_markers, advect_p)
+    against the oracle's restatement of main.c:301-364 on random planes, ragged fluid masks and
+    sample positions that include exact grid lines, the clamped range ends and far outliers."""
+    ops.ops_interpolate.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(seed)
+    o = Oracle(nx, ny, "")
+    cnt = (rng.random((ny, nx)) < 0.6).astype(np.uint8) * rng.integers(1, 5, (ny, nx)).astype(np.uint8)
+    cnt[0] = cnt[-1] = 0; cnt[:, 0] = cnt[:, -1] = 0
+    o.count[:] = cnt
+    q = rng.uniform(-30, 30, (ny, nx)).astype(np.float32)
+    n = 4000
+    ix = rng.uniform(-3, nx + 3, n).astype(np.float32)
+    iy = rng.uniform(-3, ny + 3, n).astype(np.float32)
+    ix[:400] = np.floor(ix[:400]); iy[200:600] = np.floor(iy[200:600])          # on grid lines
+    special = np.array([0, -0.0, nx - 1, nx - 2, ny - 1, ny - 2, 1e9, -1e9, 0.5, nx - 1.5], np.float32)
+    ix[600:610] = special; iy[605:615] = special
+    P = Planes(nx, ny)
+    qp, fp = P.put(q), P.put(cnt)
+    for t in (0, 1, 2):
+        out = np.empty(n, np.float32)
+        ops.ops_interpolate(nx, ny, P.pitch, t, P.ptr(qp), P.ptr(fp), n, ix.ctypes.data, iy.ctypes.data, out.ctypes.data)
+        ref = np.array([o.interpolate(q, float(a), float(b), t) for a, b in zip(ix, iy)], np.float32)
+        assert same_bits(out, ref), "type %d: %d samples differ" % (t, int((out.view(np.uint32) != ref.view(np.uint32)).sum()))
