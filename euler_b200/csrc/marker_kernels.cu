@@ -14,6 +14,7 @@
 // re-basing: SURVEY §7 hard part 8); all arithmetic is fp32 without FMA contraction in the
 // reference's order, so positions — and therefore cell classification — are bit-exact.
 #include "kernels.h"
+#include "rng.cuh"
 
 #include <float.h>
 
@@ -592,30 +593,6 @@ __global__ void k_sources_prep(DevScalars* sc, const double* __restrict__ gather
 
 // ------------------------------------------------------------------- sources ----
 
-// xorshift64 state transition is linear over GF(2) (misc/rng.c:7-9); jump[j] holds the 64
-// columns of T^(2^j), so any number of draws can be skipped in O(64 log k).
-__device__ __forceinline__ unsigned long long rng_jump(const unsigned long long* __restrict__ jump,
-                                                       unsigned long long s, unsigned long long k) {
-  for (int j = 0; k != 0; ++j, k >>= 1) {
-    if (k & 1ull) {
-      const unsigned long long* col = jump + (size_t)j * 64;
-      unsigned long long out = 0;
-      for (int b = 0; b < 64; ++b)
-        if ((s >> b) & 1ull) out ^= col[b];
-      s = out;
-    }
-  }
-  return s;
-}
-__device__ __forceinline__ unsigned long long rng_step(unsigned long long s) {
-  s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
-  return s;
-}
-__device__ __forceinline__ float rng_float(unsigned long long s) {
-  const unsigned int bits = (unsigned int)((s * 0x2545F4914F6CDD1Dull) >> 32);
-  return (float)((double)bits / (double)0xFFFFFFFFu);        // main.c:206
-}
-
 // Row-major over source cells; the k-th cell that needs a marker uses draws 2k and 2k+1 of
 // the stream (y jitter first: gcc evaluates v2f's second argument first, see oracle).
 __global__ void __launch_bounds__(1024) k_sources(
@@ -685,24 +662,7 @@ __global__ void __launch_bounds__(1024) k_sources(
 
 }  // namespace
 
-void init_rng_jump_table(unsigned long long* t) {
-  // column b of T: image of the basis vector e_b under one xorshift64 step
-  for (int b = 0; b < 64; ++b) {
-    unsigned long long s = 1ull << b;
-    s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
-    t[b] = s;
-  }
-  for (int j = 1; j < 64; ++j) {
-    const unsigned long long* prev = t + (size_t)(j - 1) * 64;
-    unsigned long long* cur = t + (size_t)j * 64;
-    for (int b = 0; b < 64; ++b) {
-      unsigned long long s = prev[b], out = 0;
-      for (int k = 0; k < 64; ++k)
-        if ((s >> k) & 1ull) out ^= prev[k];
-      cur[b] = out;
-    }
-  }
-}
+void init_rng_jump_table(unsigned long long* t) { rng_build_jump_table(t); }
 
 void launch_advect_markers(Ctx& c, float dt, int mode) {
   ProfScope ps(c, KC_ADVECT_MARKERS);

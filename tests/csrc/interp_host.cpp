@@ -32,3 +32,23 @@ void ops_interpolate(int nx, int ny, int pitch, int type, const float* q, const 
 }
 
 }  // extern "C"
+
+// ---- the reference's random stream with jump-ahead (csrc/rng.cuh) -----------------------------
+#include "rng.cuh"
+
+extern "C" {
+
+// state after k draws, by jump-ahead (GF(2) matrix powers)
+unsigned long long ops_rng_jump(unsigned long long state, unsigned long long k) {
+  static unsigned long long table[64 * 64];
+  static bool built = false;
+  if (!built) { rng_build_jump_table(table); built = true; }
+  return rng_jump(table, state, k);
+}
+// n sequential draws as the kernels form them: step, then randf() of the new state; returns the state
+unsigned long long ops_rng_draws(unsigned long long state, int n, float* out) {
+  for (int i = 0; i < n; ++i) { state = rng_step(state); out[i] = rng_float(state); }
+  return state;
+}
+
+}  // extern "C"

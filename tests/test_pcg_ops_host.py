@@ -274,3 +274,31 @@ def test_masked_bilinear_sampler_bit_exact(ops, nx, ny, seed):
         ops.ops_interpolate(nx, ny, P.pitch, t, P.ptr(qp), P.ptr(fp), n, ix.ctypes.data, iy.ctypes.data, out.ctypes.data)
         ref = np.array([o.interpolate(q, float(a), float(b), t) for a, b in zip(ix, iy)], np.float32)
         assert same_bits(out, ref), "type %d: %d samples differ" % (t, int((out.view(np.uint32) != ref.view(np.uint32)).sum()))
+
+
+def test_rng_jump_ahead_equals_sequential_draws(ops):
+    """csrc/rng.cuh: jumping k draws ahead (what gives every source cell its own slice of the
+    stream) lands on the state k sequential xorshift64 steps reach, and the floats are the host
+    program's randf() (euler_b200/host/scenario.c == reference main.c:203-207, misc/rng.c)."""
+    from euler_b200 import scenario as S
+    ops.ops_rng_jump.restype = C.c_uint64
+    ops.ops_rng_jump.argtypes = [C.c_uint64, C.c_uint64]
+    ops.ops_rng_draws.restype = C.c_uint64
+    ops.ops_rng_draws.argtypes = [C.c_uint64, C.c_int, C.c_void_p]
+    seed = 0x9bd185c449534b91
+    n = 5000
+    out = np.empty(n, np.float32)
+    end = ops.ops_rng_draws(seed, n, out.ctypes.data)
+    host_state = C.c_uint64(seed)
+    host = np.array([S._lib().euler_randf(C.byref(host_state)) for _ in range(n)], np.float32)
+    assert same_bits(out, host) and host_state.value == end
+    assert ops.ops_rng_jump(seed, 0) == seed and ops.ops_rng_jump(seed, n) == end
+    # composition and large strides: jump(a + b) == jump(jump(a), b); 2^40 draws in one go
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        a, b = int(rng.integers(0, 2 ** 40)), int(rng.integers(0, 2 ** 40))
+        s = int(rng.integers(1, 2 ** 63))
+        assert ops.ops_rng_jump(ops.ops_rng_jump(s, a), b) == ops.ops_rng_jump(s, a + b)
+    k = 123457
+    tmp = np.empty(k, np.float32)
+    assert ops.ops_rng_jump(seed, k) == ops.ops_rng_draws(seed, k, tmp.ctypes.data)
