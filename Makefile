@@ -50,7 +50,7 @@ oracle:
 # host, same no-contraction arithmetic as the oracle (tests/test_pcg_ops_host.py)
 hostops: build/libpcg_ops_host.so
 build/libpcg_ops_host.so: tests/csrc/pcg_ops_host.cpp tests/csrc/interp_host.cpp $(CSRC)/pcg_ops.cuh $(CSRC)/pcg_pipe.cuh \
-                          $(CSRC)/common.cuh $(CSRC)/interp.cuh $(CSRC)/rng.cuh
+                          $(CSRC)/common.cuh $(CSRC)/interp.cuh $(CSRC)/rng.cuh $(CSRC)/marker_walk.cuh
 	@mkdir -p build
 	$(CXX) -std=c++17 -O2 -ffp-contract=off -Wall -Wextra -Wno-unknown-pragmas -Wno-unused-function -fPIC -shared \
 	  -I$(CUDA_INC) -I$(CSRC) tests/csrc/pcg_ops_host.cpp tests/csrc/interp_host.cpp -o $@

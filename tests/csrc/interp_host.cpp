@@ -52,3 +52,31 @@ unsigned long long ops_rng_draws(unsigned long long state, int n, float* out) {
 }
 
 }  // extern "C"
+
+// ---- one marker: RK1 step with the grid-line walk, and the marker -> cell map -----------------
+#include "marker_walk.cuh"
+
+extern "C" {
+
+// dst[i] = walk_marker(src[i], dt) for n markers (x, y pairs); every marker gets the full dt
+// (EULER_MARKERS_FAST; the oracle's quirk_marker_dt_leak = 0).  cells[i] = the flat cell index
+// refresh_marker_counts bins the MOVED marker into.
+void ops_walk_markers(int nx, int ny, int pitch, const float* u, const float* v, const uint8_t* fluid,
+                      const uint8_t* solid, float h, float dt, int n, const float* src, float* dst,
+                      long long* cells) {
+  Grid g;
+  g.nx = nx; g.ny = ny; g.pitch = pitch; g.yoff = 0; g.gny = ny; g.th = 32;
+  InterpLimits lim;
+  lim.u_x = nextafterf((float)(nx - 2), 0.f); lim.u_y = nextafterf((float)(ny - 1), 0.f);
+  lim.v_x = nextafterf((float)(nx - 1), 0.f); lim.v_y = nextafterf((float)(ny - 2), 0.f);
+  lim.p_x = nextafterf((float)(nx - 1), 0.f); lim.p_y = nextafterf((float)(ny - 1), 0.f);
+  for (int i = 0; i < n; ++i) {
+    const float2 p = walk_marker<false>(g, lim, u, v, fluid, solid, h, make_float2(src[2 * i], src[2 * i + 1]), dt);
+    dst[2 * i] = p.x; dst[2 * i + 1] = p.y;
+    size_t c = 0;
+    marker_cell(g, h, p, &c);
+    cells[i] = (long long)(c / (size_t)pitch) * nx + (long long)(c % (size_t)pitch);   // back to [ny][nx] indexing
+  }
+}
+
+}  // extern "C"

@@ -302,3 +302,45 @@ def test_rng_jump_ahead_equals_sequential_draws(ops):
     k = 123457
     tmp = np.empty(k, np.float32)
     assert ops.ops_rng_jump(seed, k) == ops.ops_rng_draws(seed, k, tmp.ctypes.data)
+
+
+@pytest.mark.parametrize("name,nx,ny,frames,dt", [("block", 100, 40, 16, None), ("waterfall", 100, 40, 30, None),
+                                                   ("weird-edges", 100, 40, 20, 0.3), ("filter", 160, 90, 15, 0.25)])
+def test_marker_walk_bit_exact(ops, name, nx, ny, frames, dt):
+    """csrc/marker_walk.cuh: the RK1 step with the reference's grid-line walk and solid rewind
+    (main.c:464-537) and the marker -> cell map (main.c:106-107), marker by marker, against the
+    oracle (per-marker dt): positions bit-exact, cells equal.  With `dt` given the markers are
+    re-sprinkled over the whole domain and pushed with an over-long step through random
+    velocities, so that walks cross many cells and run into solids."""
+    ops.ops_walk_markers.argtypes = [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_float, C.c_float, C.c_int] + [C.c_void_p] * 3
+    text = shipped_text(name) if (nx, ny) == (100, 40) else resample(shipped_text(name), nx - 2, ny - 2)
+    o = Oracle(nx, ny, text)
+    o.c.quirk_marker_dt_leak = 0
+    for _ in range(frames):
+        o.step_frame()
+    rng = np.random.default_rng(8)
+    if dt is None:
+        dt = o.calculate_timestep(0.1)
+    else:
+        k = 12000                                            # < MAX_MARKER_COUNT = 4 nx ny
+        m = np.stack([rng.uniform(1.01, nx - 1.01, k), rng.uniform(1.01, ny - 1.01, k)], 1).astype(np.float32)
+        o.set_markers(m)
+        o.u[:] = rng.uniform(-3, 3, (ny, nx)).astype(np.float32)
+        o.v[:] = rng.uniform(-3, 3, (ny, nx)).astype(np.float32)
+    src = o.markers.copy()
+    n = len(src)
+    assert n > 300
+    P = Planes(nx, ny)
+    u, v, fluid, solid = P.put(o.u), P.put(o.v), P.put(o.count), P.put(o.solid)
+    dst = np.empty_like(src)
+    cells = np.empty(n, np.int64)
+    ops.ops_walk_markers(nx, ny, P.pitch, P.ptr(u), P.ptr(v), P.ptr(fluid), P.ptr(solid), 1.0, dt, n,
+                         src.ctypes.data, dst.ctypes.data, cells.ctypes.data)
+    o.advect_markers(dt)
+    ref = o.markers
+    ok = np.isfinite(ref).all(1)
+    assert ok.sum() > 0.9 * n
+    assert same_bits(dst[ok], ref[ok])
+    ref_cells = np.floor(ref[ok, 1]).astype(np.int64) * nx + np.floor(ref[ok, 0]).astype(np.int64)
+    inside = (ref[ok, 0] >= 0) & (ref[ok, 0] < nx) & (ref[ok, 1] >= 0) & (ref[ok, 1] < ny)
+    assert np.array_equal(cells[ok][inside], ref_cells[inside])
