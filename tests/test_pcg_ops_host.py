@@ -344,3 +344,66 @@ def test_marker_walk_bit_exact(ops, name, nx, ny, frames, dt):
     ref_cells = np.floor(ref[ok, 1]).astype(np.int64) * nx + np.floor(ref[ok, 0]).astype(np.int64)
     inside = (ref[ok, 0] >= 0) & (ref[ok, 0] < nx) & (ref[ok, 1] >= 0) & (ref[ok, 1] < ny)
     assert np.array_equal(cells[ok][inside], ref_cells[inside])
+
+
+def _nan_equal_bits(a, b):
+    """bit-exact except that NaNs (0/0 means of extrapolate, assert off) only have to coincide"""
+    return np.array_equal(np.isnan(a), np.isnan(b)) and same_bits(np.nan_to_num(a), np.nan_to_num(b))
+
+
+GRID_CASES = [("block", 100, 40, 16), ("waterfall", 100, 40, 30), ("weird-edges", 100, 40, 20),
+              ("filter", 160, 90, 15), ("waterfall", 333, 129, 12)]
+
+
+@pytest.mark.parametrize("name,nx,ny,frames", GRID_CASES)
+def test_grid_stage_quads_bit_exact(ops, name, nx, ny, frames):
+    """csrc/grid_ops.cuh (the per-quad arithmetic of k_extrapolate_bounds, k_advect_velocity,
+    k_build_rhs, k_pressure_update) in sim_step order from an oracle state: every output plane
+    bit-exact against the oracle's stages (main.c:865-889, 713-733, 769-805)."""
+    vp, i, f, d = C.c_void_p, C.c_int, C.c_float, C.c_double
+    ops.ops_extrapolate_bounds.argtypes = [i, i, i] + [vp] * 7
+    ops.ops_advect_velocity.argtypes = [i, i, i] + [vp] * 4 + [f, f, f, vp, vp]
+    ops.ops_build_rhs.argtypes = [i, i, i] + [vp] * 4 + [f, d, vp, vp]
+    ops.ops_build_rhs.restype = i
+    ops.ops_pressure_update.argtypes = [i, i, i] + [vp] * 5 + [f, f, vp, vp]
+    text = shipped_text(name) if (nx, ny) == (100, 40) else resample(shipped_text(name), nx - 2, ny - 2)
+    o = Oracle(nx, ny, text)
+    o.c.precon_mode = PRECON_REDBLACK
+    o.c.quirk_marker_dt_leak = 0
+    for _ in range(frames):
+        o.step_frame()
+    # the marker half of a sub-step on the oracle, then the grid stages on both sides
+    dt = o.calculate_timestep(0.1)
+    o.advect_markers(dt); o.refresh_marker_counts(); o.update_fluid_sources()
+    P = Planes(nx, ny)
+    fluid, prev, solid = P.put(o.count), P.put(o.prev_count), P.put(o.solid)
+    u, v = P.put(o.u), P.put(o.v)
+    ue, ve = P.put(np.zeros_like(o.u)), P.put(np.zeros_like(o.u))
+    ops.ops_extrapolate_bounds(nx, ny, P.pitch, P.ptr(u), P.ptr(v), P.ptr(fluid), P.ptr(prev), P.ptr(solid), P.ptr(ue), P.ptr(ve))
+    o.extrapolate(o.u, 1); o.extrapolate(o.v, 2); o.zero_bounds(o.u, 1); o.zero_bounds(o.v, 2)
+    assert _nan_equal_bits(P.get(ue), o.u) and _nan_equal_bits(P.get(ve), o.v)
+    o.u[:] = np.nan_to_num(o.u); o.v[:] = np.nan_to_num(o.v)
+    u, v = P.put(o.u), P.put(o.v)
+    ut, vt = P.put(np.zeros_like(o.u)), P.put(np.zeros_like(o.u))
+    ops.ops_advect_velocity(nx, ny, P.pitch, P.ptr(u), P.ptr(v), P.ptr(fluid), P.ptr(solid), dt, 1.0, -10.0, P.ptr(ut), P.ptr(vt))
+    o.advect_u(dt); o.advect_v(dt); o.apply_body_forces(dt); o.zero_bounds(o.utmp, 1); o.zero_bounds(o.vtmp, 2)
+    assert same_bits(P.get(ut), o.utmp) and same_bits(P.get(vt), o.vtmp)
+    # rhs + a_diag
+    fl = o.count != 0
+    scale = float(np.float32(np.float32(1.0) * np.float32(1.0) * np.float32(1.0) / np.float32(dt)))   # main.c:713, fp32
+    b, adiag = P.put(np.zeros((ny, nx))), P.put(o.adiag.copy())
+    nonzero = ops.ops_build_rhs(nx, ny, P.pitch, P.ptr(ut), P.ptr(vt), P.ptr(fluid), P.ptr(solid), 1.0, scale, P.ptr(b), P.ptr(adiag))
+    o.build_rhs(dt)
+    assert same_bits(P.get(b), o.b) and np.array_equal(P.get(adiag)[fl], o.adiag[fl])
+    assert bool(nonzero) == bool(np.any(o.b[fl] != 0))
+    # pressure update from the oracle's own solve
+    o.project(dt)                                     # leaves the CLAMPED p; redo with an unclamped one
+    rng = np.random.default_rng(2)
+    p_raw = np.where(fl, o.p - rng.random((ny, nx)) * 0.3 * (rng.random((ny, nx)) < 0.2), 0.0)   # some negatives
+    o.p[:] = p_raw
+    o.pressure_update(dt)
+    p = P.put(p_raw)
+    uo, vo = P.put(np.zeros_like(o.u)), P.put(np.zeros_like(o.u))
+    ops.ops_pressure_update(nx, ny, P.pitch, P.ptr(p), P.ptr(ut), P.ptr(vt), P.ptr(fluid), P.ptr(solid), dt, 1.0, P.ptr(uo), P.ptr(vo))
+    assert same_bits(P.get(uo), o.u) and same_bits(P.get(vo), o.v)
+    assert same_bits(P.get(p)[fl], o.p[fl]) and float(P.get(p)[fl].min()) >= 0.0
