@@ -817,7 +817,7 @@ int euler_gpu_step_frame(euler_gpu* h, int* substeps) {
   float frame_time = h->prm.frame_time;                      // main.c:849-851
   int step = 0;
   for (; frame_time > 0.f && step < h->prm.max_substeps; ++step) {
-    float dt;
+    float dt = 0.f;
     int rc = compute_dt(h, frame_time, &dt);
     if (rc) return rc;
     frame_time -= dt;
