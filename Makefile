@@ -47,10 +47,10 @@ oracle:
 	$(MAKE) -C oracle all
 
 # TEST INFRASTRUCTURE: the row operators of the PCG kernels (csrc/pcg_ops.cuh) compiled for the
-# host, same no-contraction arithmetic as the oracle (tests/test_pcg_ops_host.py)
-hostops: build/libpcg_ops_host.so
+# host, same no-contraction arithmetic as the oracle (tests/test_kernel_arith_host.py)
+hostops: build/libkernels_host.so
 HOSTOPS_SRC := tests/csrc/pcg_ops_host.cpp tests/csrc/interp_host.cpp tests/csrc/grid_ops_host.cpp
-build/libpcg_ops_host.so: $(HOSTOPS_SRC) $(CSRC)/pcg_ops.cuh $(CSRC)/pcg_pipe.cuh $(CSRC)/common.cuh $(CSRC)/interp.cuh \
+build/libkernels_host.so: $(HOSTOPS_SRC) $(CSRC)/pcg_ops.cuh $(CSRC)/pcg_pipe.cuh $(CSRC)/common.cuh $(CSRC)/interp.cuh \
                           $(CSRC)/rng.cuh $(CSRC)/marker_walk.cuh $(CSRC)/grid_ops.cuh
 	@mkdir -p build
 	$(CXX) -std=c++17 -O2 -ffp-contract=off -Wall -Wextra -Wno-unknown-pragmas -Wno-unused-function -fPIC -shared \

@@ -2,7 +2,7 @@
 // quad of four consecutive cells: extrapolate + zero_bounds, advect_u/v + gravity + bounds, rhs +
 // a_diag, pressure clamp + gradient.  The kernels add the addressing, the warp-level mask exchange
 // and the reductions; the arithmetic lives here so that the same source also compiles for the
-// host, where tests/test_pcg_ops_host.py checks it bit for bit against the oracle without a GPU.
+// host, where tests/test_kernel_arith_host.py checks it bit for bit against the oracle without a GPU.
 // Reference lines: main.c:158-185, 382-422, 539-545, 713-733, 769-805, 822-832.
 #pragma once
 #include <math.h>

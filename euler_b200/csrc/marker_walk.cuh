@@ -2,7 +2,7 @@
 // the reference's grid-line walk and solid rewind (advect_markers + velocity_at + time_to,
 // main.c:440-537) and the marker -> cell map of refresh_marker_counts (main.c:106-107).  fp32,
 // no FMA contraction, the reference's operation order: positions are bit-exact.  The same
-// source compiles for the host, where tests/test_pcg_ops_host.py checks it against the oracle.
+// source compiles for the host, where tests/test_kernel_arith_host.py checks it against the oracle.
 #pragma once
 #include <float.h>
 #include <math.h>

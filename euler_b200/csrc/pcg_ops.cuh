@@ -7,7 +7,7 @@
 // (pcg_pipe.cuh run()); the same code compiles for the HOST (tests/csrc/pcg_ops_host.cpp,
 // g++ -ffp-contract=off), where the row views point straight into padded host planes — that is
 // how the arithmetic of these kernels is checked bit for bit against the oracle on a machine
-// without a GPU (tests/test_pcg_ops_host.py).  Reference lines: main.c:669-691 (update_search,
+// without a GPU (tests/test_kernel_arith_host.py).  Reference lines: main.c:669-691 (update_search,
 // apply_a), :694-702/:753-754 (fmadd), the red-black IC(0) of oracle/euler_oracle.c
 // precon_redblack (not in the reference).
 #pragma once

@@ -1,7 +1,7 @@
 // euler_b200/csrc/rng.cuh — the reference's random stream (misc/rng.c:5-20 xorshift64* keeping
 // the high 32 bits; randf() main.c:203-207) with JUMP-AHEAD, so that every marker a source cell
 // appends gets exactly the draws the reference's sequential loop (main.c:284-291) would give it.
-// Host and device: the same functions are checked on the CPU in tests/test_pcg_ops_host.py.
+// Host and device: the same functions are checked on the CPU in tests/test_kernel_arith_host.py.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>

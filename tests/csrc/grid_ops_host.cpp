@@ -1,6 +1,6 @@
 // tests/csrc/grid_ops_host.cpp — TEST INFRASTRUCTURE: the per-quad arithmetic of the MAC-grid
 // stage kernels (euler_b200/csrc/grid_ops.cuh) compiled for the host and swept over padded host
-// planes, for a bit-for-bit comparison with the oracle (tests/test_pcg_ops_host.py).  The wrappers
+// planes, for a bit-for-bit comparison with the oracle (tests/test_kernel_arith_host.py).  The wrappers
 // below repeat only what the kernels add around a quad: zero-initialised results, the
 // "neighbourhood holds fluid" test, the stores.  The fluid mask of a quad comes from
 // load_quad_mask (plain loads) instead of the kernels' warp shuffle — same three words.

@@ -1,7 +1,7 @@
 // tests/csrc/interp_host.cpp — TEST INFRASTRUCTURE: the masked bilinear sampler of the advection
 // kernels (euler_b200/csrc/interp.cuh, reference main.c:301-364) compiled for the host and called
 // on padded host planes, for a bit-for-bit comparison with the oracle's orc_interpolate
-// (tests/test_pcg_ops_host.py).  Same source as the device code; g++ -ffp-contract=off.
+// (tests/test_kernel_arith_host.py).  Same source as the device code; g++ -ffp-contract=off.
 #include <math.h>
 #include <stdint.h>
 

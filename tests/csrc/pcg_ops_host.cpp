@@ -1,7 +1,7 @@
 // tests/csrc/pcg_ops_host.cpp — TEST INFRASTRUCTURE: the row operators of the pressure-solve
 // kernels (euler_b200/csrc/pcg_ops.cuh), compiled for the HOST with g++ -ffp-contract=off and
 // driven row by row over padded host planes, so that their arithmetic can be compared bit for
-// bit with the oracle on a machine without a GPU (tests/test_pcg_ops_host.py).
+// bit with the oracle on a machine without a GPU (tests/test_kernel_arith_host.py).
 //
 // What runs here is the SAME source the GPU kernels instantiate; what is emulated is only the
 // feeding: on the GPU the three input rows of a call are stages of the TMA ring in shared

@@ -20,7 +20,7 @@ from euler_b200 import shipped_text, resample
 from oracle.oracle import Oracle, PRECON_REDBLACK
 
 GUARD = 4
-LIB = os.path.join(ROOT, "build", "libpcg_ops_host.so")
+LIB = os.path.join(ROOT, "build", "libkernels_host.so")
 
 
 @pytest.fixture(scope="module")
