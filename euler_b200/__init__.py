@@ -6,6 +6,6 @@ package is only a thin ctypes mirror of that C-ABI for tests and benchmarks; it 
 compute and no CPU fallback — if the CUDA library is missing, importing `euler_b200.gpu`
 raises.
 """
-from .scenario import Scenario, resample, synthetic, shipped_text  # noqa: F401
+from .scenario import Scenario, resample, synthetic, shipped_text, export_text  # noqa: F401
 
-__all__ = ["Scenario", "resample", "synthetic", "shipped_text"]
+__all__ = ["Scenario", "resample", "synthetic", "shipped_text", "export_text"]

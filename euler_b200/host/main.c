@@ -23,6 +23,7 @@
  *   --device D          CUDA device
  *   --print             in --headless: print the final picture (plain ASCII)
  *   --load / --save F   restore / write a checkpoint of the dynamic state (checkpoint.c)
+ *   --export F          write the final state as a scenario file (X 0 ? =; scenario.h)
  */
 #define _POSIX_C_SOURCE 200809L
 #include <dlfcn.h>
@@ -120,12 +121,12 @@ static void usage(const char *argv0) {
           "usage: %s [--rainbow] [--headless] [--frames N] [--grid WxH] [--synthetic NAME]\n"
           "       [--precon ic0|rb] [--markers ref|fast] [--exact-dot] [--pcg-dtype fp64|fp32]\n"
           "       [--device D] [--print]\n"
-          "       [--load CHECKPOINT] [--save CHECKPOINT] <scenario>\n",
+          "       [--load CHECKPOINT] [--save CHECKPOINT] [--export SCENARIO] <scenario>\n",
           argv0);
 }
 
 int main(int argc, char **argv) {
-  const char *file = NULL, *synthetic = NULL, *load_path = NULL, *save_path = NULL;
+  const char *file = NULL, *synthetic = NULL, *load_path = NULL, *save_path = NULL, *export_path = NULL;
   int headless = 0, frames = -1, nx = 100, ny = 40, do_print = 0;
   api a; memset(&a, 0, sizeof a);
   if (bind_api(&a, argv[0])) return 1;
@@ -143,6 +144,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(s, "--synthetic") && i + 1 < argc) synthetic = argv[++i];
     else if (!strcmp(s, "--load") && i + 1 < argc) load_path = argv[++i];
     else if (!strcmp(s, "--save") && i + 1 < argc) save_path = argv[++i];
+    else if (!strcmp(s, "--export") && i + 1 < argc) export_path = argv[++i];
     else if (!strcmp(s, "--grid") && i + 1 < argc) {
       if (sscanf(argv[++i], "%dx%d", &nx, &ny) != 2 || nx < 4 || ny < 4) { usage(argv[0]); return 1; }
     } else if (!strcmp(s, "--precon") && i + 1 < argc) {
@@ -296,6 +298,18 @@ int main(int argc, char **argv) {
   if (save_path) {
     int src = euler_checkpoint_save(&a.ck, sim, nx, ny, prm.rainbow, save_path);
     if (src) { fprintf(stderr, "cannot save checkpoint %s (%d): %s\n", save_path, src, src > 0 ? a.last_error() : "I/O"); return 1; }
+  }
+  if (export_path) {            /* the state the last frame left, in the scenario-file format */
+    long len = 0;
+    char *text = NULL;
+    FILE *f = NULL;
+    int bad = a.read_marker_count(sim, count) != 0;
+    if (!bad) bad = !(text = euler_scenario_export(nx, ny, scn.solid, scn.source, scn.sink, count, &len));
+    if (!bad) bad = !(f = fopen(export_path, "wb"));
+    if (!bad) bad = len && fwrite(text, (size_t)len, 1, f) != 1;
+    if (f && fclose(f)) bad = 1;
+    free(text);
+    if (bad) { fprintf(stderr, "cannot export scenario %s\n", export_path); return 1; }
   }
   free(count);
   a.destroy(sim);

@@ -137,6 +137,26 @@ char *euler_scenario_resample(const char *text, long length, int out_w, int out_
   return out;
 }
 
+char *euler_scenario_export(int nx, int ny, const uint8_t *solid, const uint8_t *source, const uint8_t *sink,
+                            const uint8_t *count, long *out_len) {
+  if (nx < 3 || ny < 3) return NULL;
+  const int w = nx - 2, h = ny - 2;
+  char *out = malloc((size_t)(w + 1) * h + 1);
+  if (!out) return NULL;
+  char *p = out;
+  for (int r = 0; r < h; ++r) {
+    const int y = ny - 2 - r;
+    for (int i = 0; i < w; ++i) {
+      const size_t c = (size_t)y * nx + (size_t)(1 + i);
+      *p++ = solid[c] ? 'X' : source[c] ? '?' : sink[c] ? '=' : count[c] ? '0' : ' ';
+    }
+    *p++ = '\n';
+  }
+  *p = '\0';
+  if (out_len) *out_len = p - out;
+  return out;
+}
+
 char *euler_scenario_synthetic(const char *name, int nx, int ny, long *out_len) {
   const int w = nx - 2, h = ny - 2;
   int mode;

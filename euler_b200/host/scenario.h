@@ -45,6 +45,17 @@ int  euler_scenario_markers_row_major(euler_scenario *s);
  * caller frees the result with free().  *out_len receives the length. */
 char *euler_scenario_resample(const char *text, long length, int out_w, int out_h, long *out_len);
 
+/* The CURRENT state written back in the scenario-file format: text row r is grid
+ * row ny-2-r, column i is x = 1+i (the inverse of main.c:220-241); 'X' solid, '?' source, '='
+ * sink, '0' a cell that holds markers now (count > 0), ' ' anything else.  The outer ring of
+ * sinks is implicit — sim_init adds it (main.c:244-252).  Parsing the result on the same grid
+ * size reproduces the static masks exactly and makes fluid exactly the source cells plus the
+ * other non-solid, non-sink cells that hold markers now; markers are re-seeded 4 per cell and
+ * velocities start from rest (the format has no finer state — euler_checkpoint_save keeps all
+ * of it).  The caller frees the result. */
+char *euler_scenario_export(int nx, int ny, const uint8_t *solid, const uint8_t *source, const uint8_t *sink,
+                            const uint8_t *count, long *out_len);
+
 /* Synthetic scenario text for an nx x ny grid (interior (nx-2) x (ny-2) characters):
  *   "basic-fill"  walled box, fluid block resting on the floor (left 40 %, lower 50 %):
  *                 the pressure solve is active from the first sub-step

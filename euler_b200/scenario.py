@@ -31,6 +31,9 @@ def _lib():
         L.euler_scenario_resample.argtypes = [C.c_char_p, C.c_long, C.c_int, C.c_int, C.POINTER(C.c_long)]
         L.euler_scenario_synthetic.restype = C.c_void_p
         L.euler_scenario_synthetic.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_long)]
+        L.euler_scenario_export.restype = C.c_void_p
+        L.euler_scenario_export.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_long)]
         L.euler_randf.restype = C.c_float
         L.euler_randf.argtypes = [C.POINTER(C.c_uint64)]
         _LIB = L
@@ -64,6 +67,20 @@ def synthetic(name, nx, ny):
     p = _lib().euler_scenario_synthetic(name.encode(), nx, ny, C.byref(n))
     if not p:
         raise ValueError("unknown synthetic scenario %r" % name)
+    return _take(p, n.value)
+
+
+def export_text(solid, source, sink, count):
+    """The current state in the scenario-file format (euler_scenario_export): static masks plus
+    '0' for every cell that holds markers.  Arrays are [ny][nx] uint8."""
+    planes = [np.ascontiguousarray(a, dtype=np.uint8) for a in (solid, source, sink, count)]
+    ny, nx = planes[0].shape
+    if any(a.shape != (ny, nx) for a in planes):
+        raise ValueError("planes must have the same [ny][nx] shape")
+    n = C.c_long(0)
+    p = _lib().euler_scenario_export(nx, ny, *(a.ctypes.data for a in planes), C.byref(n))
+    if not p:
+        raise ValueError("grid too small to export")
     return _take(p, n.value)
 
 

@@ -58,3 +58,31 @@ def test_random_scenarios_red_black(case):
     for fld, ref in ((G.F_U, o.u), (G.F_V, o.v)):
         assert float(np.abs(g.get(fld) - ref).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
     g.close()
+
+
+def test_host_program_exports_its_final_state_as_a_scenario(tmp_path):
+    """bin/euler-gpu --export: the file is the final state in the scenario format —
+    parsing it gives the static masks back and, as fluid, the cells the count plane marks wet
+    (hash of the count plane printed by the same run == hash of the oracle's)."""
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT
+    from euler_b200 import shipped_text
+    from oracle.oracle import Oracle, fnv1a
+    exe = os.path.join(ROOT, "bin", "euler-gpu")
+    assert os.path.exists(exe), "run `make host`"
+    src = tmp_path / "waterfall.txt"
+    src.write_bytes(shipped_text("waterfall"))
+    dst = tmp_path / "exported.txt"
+    out = subprocess.run([exe, "--headless", "--frames", "20", "--exact-dot", "--export", str(dst), str(src)],
+                         check=True, capture_output=True, text=True, cwd=ROOT).stdout
+    res = json.loads(out.strip().splitlines()[-1])
+    o = Oracle(100, 40, shipped_text("waterfall"))          # reference-faithful defaults, like the CLI
+    for _ in range(20):
+        o.step_frame()
+    assert res["fnv_count"] == "%016x" % fnv1a(o.count)
+    s = Scenario(dst.read_bytes(), 100, 40)
+    assert np.array_equal(s.solid, o.solid) and np.array_equal(s.source, o.source) and np.array_equal(s.sink, o.sink)
+    expect = ((o.count != 0) & (o.solid == 0) & (o.sink == 0)) | (o.source != 0)
+    assert np.array_equal(s.fluid != 0, expect)

@@ -89,3 +89,44 @@ def test_parser_fuzz_against_oracle():
         assert same_bits(s.markers, o.markers) and s.rng_state == int(o.c.rng_state)
 
     run()
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_scenario_export_round_trip(name):
+    """euler_scenario_export is the inverse of the parser: exporting the initial
+    state and parsing it again reproduces masks, fluid cells, seeded markers and RNG state;
+    exporting a LATER state gives a scenario whose fluid cells are the cells holding markers."""
+    from euler_b200 import export_text
+    text = shipped_text(name)
+    s0 = Scenario(text, 100, 40)
+    out = export_text(s0.solid, s0.source, s0.sink, s0.fluid)
+    rows = out.decode().split("\n")
+    assert len(rows) == 39 and rows[-1] == "" and all(len(r) == 98 for r in rows[:-1])
+    assert set(out.decode()) <= set("X0?= \n")
+    s1 = Scenario(out, 100, 40)
+    for f in ("solid", "source", "sink", "fluid"):
+        assert np.array_equal(getattr(s0, f), getattr(s1, f)), f
+    assert same_bits(s0.markers, s1.markers) and s0.rng_state == s1.rng_state
+    assert export_text(s1.solid, s1.source, s1.sink, s1.fluid) == out          # idempotent
+    # a later state (from the oracle): fluid of the re-parsed export == cells with markers
+    o = Oracle(100, 40, text)
+    for _ in range(25):
+        o.step_frame()
+    s2 = Scenario(export_text(o.solid, o.source, o.sink, o.count), 100, 40)
+    assert np.array_equal(s2.solid, o.solid) and np.array_equal(s2.source, o.source) and np.array_equal(s2.sink, o.sink)
+    expect = ((o.count != 0) & (o.solid == 0) & (o.sink == 0)) | (o.source != 0)
+    assert np.array_equal(s2.fluid != 0, expect)
+    assert len(s2.markers) == 4 * int(expect.sum())
+
+
+def test_scenario_export_other_sizes_and_errors():
+    from euler_b200 import export_text
+    text = resample(shipped_text("weird-edges"), 62, 46)
+    s0 = Scenario(text, 64, 48)
+    s1 = Scenario(export_text(s0.solid, s0.source, s0.sink, s0.fluid), 64, 48)
+    assert np.array_equal(s0.solid, s1.solid) and np.array_equal(s0.fluid, s1.fluid) and same_bits(s0.markers, s1.markers)
+    z = np.zeros((2, 2), np.uint8)
+    with pytest.raises(ValueError):
+        export_text(z, z, z, z)
+    with pytest.raises(ValueError):
+        export_text(np.zeros((5, 5), np.uint8), z, z, z)
