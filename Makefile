@@ -33,14 +33,16 @@ $(LIBDIR)/libeuler_gpu.so: $(CU_OBJS)
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^ -ldl
 
 host: $(LIBDIR)/libeuler_host.so bin/euler-gpu
-$(LIBDIR)/libeuler_host.so: $(HOST)/scenario.c $(HOST)/scenario.h $(HOST)/checkpoint.c $(HOST)/checkpoint.h include/euler_gpu.h
+$(LIBDIR)/libeuler_host.so: $(HOST)/scenario.c $(HOST)/scenario.h $(HOST)/checkpoint.c $(HOST)/checkpoint.h \
+                            $(HOST)/rendezvous.c $(HOST)/rendezvous.h include/euler_gpu.h
 	@mkdir -p $(LIBDIR)
-	$(CC) -std=gnu99 -O2 -ffp-contract=off -Wall -Wextra -fPIC -shared -Iinclude $(HOST)/scenario.c $(HOST)/checkpoint.c -lm -o $@
-bin/euler-gpu: $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c $(HOST)/checkpoint.c $(HOST)/scenario.h $(HOST)/render.h \
-               $(HOST)/checkpoint.h include/euler_gpu.h
+	$(CC) -std=gnu99 -O2 -ffp-contract=off -Wall -Wextra -fPIC -shared -Iinclude $(HOST)/scenario.c $(HOST)/checkpoint.c \
+	  $(HOST)/rendezvous.c -lm -o $@
+bin/euler-gpu: $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c $(HOST)/checkpoint.c $(HOST)/rendezvous.c \
+               $(HOST)/scenario.h $(HOST)/render.h $(HOST)/checkpoint.h $(HOST)/rendezvous.h include/euler_gpu.h
 	@mkdir -p bin
 	$(CC) -std=gnu99 -O2 -ffp-contract=off -Wall -Wextra -Iinclude $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c \
-	  $(HOST)/checkpoint.c \
+	  $(HOST)/checkpoint.c $(HOST)/rendezvous.c \
 	  -ldl -lm -o $@
 
 oracle:

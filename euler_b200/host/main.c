@@ -24,6 +24,13 @@
  *   --print             in --headless: print the final picture (plain ASCII)
  *   --load / --save F   restore / write a checkpoint of the dynamic state (checkpoint.c)
  *   --export F          write the final state as a scenario file (X 0 ? =; scenario.h)
+ *   --ranks N --rank R --rendezvous DIR [--no-p2p]
+ *                       one of N processes of a row-slab decomposed run: this
+ *                       process drives GPU R (or --device) and owns a slab of rows balanced by
+ *                       fluid cells; the NCCL id and the NVLink peer handles are exchanged
+ *                       through files in DIR (fresh per run, rendezvous.h).  --headless only;
+ *                       implies --precon rb --markers fast.  Rank 0 prints the statistics of
+ *                       the whole grid.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <dlfcn.h>
@@ -34,6 +41,7 @@
 
 #include "checkpoint.h"
 #include "euler_gpu.h"
+#include "rendezvous.h"
 #include "render.h"
 #include "scenario.h"
 
@@ -50,6 +58,12 @@ typedef struct api {
   euler_ckpt_api ck;
   int (*stats)(euler_gpu *, euler_stats *);
   const char *(*last_error)(void);
+  /* row slabs (only bound when --ranks is given) */
+  int (*slab_partition_weighted)(const uint64_t *, int, int, int, int *, int *);
+  int (*comm_unique_id)(void *);
+  int (*comm_init)(euler_gpu *, int, int, const void *);
+  int (*comm_p2p_export)(euler_gpu *, void *);
+  int (*comm_p2p_import)(euler_gpu *, const void *);
 } api;
 
 /* What draw_rows() looks at (main.c:917-920): the top `rows` text rows and the left `cols`
@@ -106,6 +120,11 @@ static int bind_api(api *a, const char *argv0) {
   BIND(ck.set_frame_count, "euler_gpu_set_frame_count");
   BIND(stats, "euler_gpu_stats");
   BIND(last_error, "euler_gpu_last_error");
+  BIND(slab_partition_weighted, "euler_gpu_slab_partition_weighted");
+  BIND(comm_unique_id, "euler_gpu_comm_unique_id");
+  BIND(comm_init, "euler_gpu_comm_init");
+  BIND(comm_p2p_export, "euler_gpu_comm_p2p_export");
+  BIND(comm_p2p_import, "euler_gpu_comm_p2p_import");
 #undef BIND
   return 0;
 }
@@ -121,13 +140,16 @@ static void usage(const char *argv0) {
           "usage: %s [--rainbow] [--headless] [--frames N] [--grid WxH] [--synthetic NAME]\n"
           "       [--precon ic0|rb] [--markers ref|fast] [--exact-dot] [--pcg-dtype fp64|fp32]\n"
           "       [--device D] [--print]\n"
-          "       [--load CHECKPOINT] [--save CHECKPOINT] [--export SCENARIO] <scenario>\n",
+          "       [--load CHECKPOINT] [--save CHECKPOINT] [--export SCENARIO]\n"
+          "       [--ranks N --rank R --rendezvous DIR [--no-p2p]] <scenario>\n",
           argv0);
 }
 
 int main(int argc, char **argv) {
   const char *file = NULL, *synthetic = NULL, *load_path = NULL, *save_path = NULL, *export_path = NULL;
   int headless = 0, frames = -1, nx = 100, ny = 40, do_print = 0;
+  int ranks = 1, rank = 0, no_p2p = 0, device_given = 0;
+  const char *rdv = NULL;
   api a; memset(&a, 0, sizeof a);
   if (bind_api(&a, argv[0])) return 1;
   euler_params prm;
@@ -140,7 +162,11 @@ int main(int argc, char **argv) {
     else if (!strcmp(s, "--print")) do_print = 1;
     else if (!strcmp(s, "--exact-dot")) prm.dot_mode = EULER_DOT_REFERENCE_ORDER;
     else if (!strcmp(s, "--frames") && i + 1 < argc) frames = atoi(argv[++i]);
-    else if (!strcmp(s, "--device") && i + 1 < argc) prm.device = atoi(argv[++i]);
+    else if (!strcmp(s, "--device") && i + 1 < argc) { prm.device = atoi(argv[++i]); device_given = 1; }
+    else if (!strcmp(s, "--ranks") && i + 1 < argc) ranks = atoi(argv[++i]);
+    else if (!strcmp(s, "--rank") && i + 1 < argc) rank = atoi(argv[++i]);
+    else if (!strcmp(s, "--rendezvous") && i + 1 < argc) rdv = argv[++i];
+    else if (!strcmp(s, "--no-p2p")) no_p2p = 1;
     else if (!strcmp(s, "--synthetic") && i + 1 < argc) synthetic = argv[++i];
     else if (!strcmp(s, "--load") && i + 1 < argc) load_path = argv[++i];
     else if (!strcmp(s, "--save") && i + 1 < argc) save_path = argv[++i];
@@ -169,6 +195,15 @@ int main(int argc, char **argv) {
   }
   if (!file && !synthetic) { usage(argv[0]); return 1; }    /* as main.c:986-989 */
   if (headless && frames < 0) frames = 100;
+  if (ranks > 1) {
+    if (!headless || !rdv || rank < 0 || rank >= ranks || load_path || save_path || prm.rainbow) {
+      fprintf(stderr, "--ranks needs --headless, --rank 0..N-1 and --rendezvous DIR (no --load/--save/--rainbow)\n");
+      return 1;
+    }
+    prm.precon = EULER_PRECON_REDBLACK;                       /* the only modes that decompose */
+    prm.marker_mode = EULER_MARKERS_FAST;
+    if (!device_given) prm.device = rank;
+  }
 
   /* scenario text -> masks + seeded markers (host, reference format and RNG stream) */
   euler_scenario scn;
@@ -199,13 +234,47 @@ int main(int argc, char **argv) {
   if (rc) { fprintf(stderr, "Could not load %s!\n", file ? file : synthetic); return 1; }  /* main.c:213 */
 
   prm.rng_state = scn.rng_state;
+  if (ranks > 1) {
+    /* slabs balanced by work: the PCG streams the cells that hold fluid, the grid stages every
+     * cell (the weights bench.py uses) */
+    uint64_t *weight = malloc((size_t)ny * sizeof *weight);
+    if (!weight) return 1;
+    for (int y = 0; y < ny; ++y) {
+      uint64_t wet = 0;
+      for (int x = 0; x < nx; ++x) wet += scn.fluid[(size_t)y * nx + x] ? 1 : 0;
+      weight[y] = wet * 100 + (uint64_t)nx;
+    }
+    const int prc = a.slab_partition_weighted(weight, ny, ranks, rank, &prm.slab_row0, &prm.slab_rows);
+    free(weight);
+    if (prc) { fprintf(stderr, "slab partition: %s\n", a.last_error()); return 1; }
+  }
   euler_gpu *sim = NULL;
   if (a.create(&sim, nx, ny, scn.solid, scn.source, scn.sink, scn.markers, scn.n_markers, &prm)) {
     fprintf(stderr, "euler_gpu_create: %s\n", a.last_error());
     return 1;
   }
-  uint8_t *count = malloc((size_t)nx * ny);
+  uint8_t *count = calloc((size_t)nx * ny, 1);     /* a slab handle fills in only the rows it owns */
   if (!count) return 1;
+  if (ranks > 1) {
+    /* communicator id from rank 0, then (NVLink path) everybody's peer handles, through DIR */
+    unsigned char uid[128];
+    if (rank == 0 && (a.comm_unique_id(uid) || euler_rdv_publish(rdv, "uid", 0, uid, sizeof uid))) {
+      fprintf(stderr, "cannot publish the communicator id: %s\n", a.last_error());
+      return 1;
+    }
+    if (euler_rdv_fetch(rdv, "uid", 0, uid, sizeof uid, 120)) { fprintf(stderr, "rank 0 never published the communicator id in %s\n", rdv); return 1; }
+    if (a.comm_init(sim, rank, ranks, uid)) { fprintf(stderr, "comm_init: %s\n", a.last_error()); return 1; }
+    if (!no_p2p) {
+      unsigned char *blobs = malloc((size_t)ranks * 256);
+      if (!blobs) return 1;
+      int bad = a.comm_p2p_export(sim, blobs + (size_t)rank * 256) != 0;
+      if (!bad) bad = euler_rdv_publish(rdv, "blob", rank, blobs + (size_t)rank * 256, 256) != 0;
+      for (int r = 0; r < ranks && !bad; ++r) bad = euler_rdv_fetch(rdv, "blob", r, blobs + (size_t)r * 256, 256, 120) != 0;
+      if (!bad) bad = a.comm_p2p_import(sim, blobs) != 0;
+      free(blobs);
+      if (bad) { fprintf(stderr, "peer-to-peer set-up failed: %s\n", a.last_error()); return 1; }
+    }
+  }
   if (load_path) {            /* state of an earlier run; the scenario still supplies the static masks */
     int lrc = euler_checkpoint_load(&a.ck, sim, nx, ny, prm.rainbow, load_path);
     if (lrc) { fprintf(stderr, "cannot load checkpoint %s (%d): %s\n", load_path, lrc, lrc > 0 ? a.last_error() : "bad file"); return 1; }
@@ -264,6 +333,26 @@ int main(int argc, char **argv) {
 
   euler_stats st;
   a.stats(sim, &st);
+  if (ranks > 1) {
+    /* every rank publishes the rows it owns; rank 0 assembles the whole count plane and the
+     * global marker count, the others are done */
+    const size_t row0 = (size_t)prm.slab_row0 * nx, nrow = (size_t)prm.slab_rows * nx;
+    struct { int32_t row0, rows; uint64_t markers; } info = {prm.slab_row0, prm.slab_rows, st.n_markers};
+    if (euler_rdv_publish(rdv, "info", rank, &info, sizeof info) || euler_rdv_publish(rdv, "count", rank, count + row0, nrow)) {
+      fprintf(stderr, "cannot publish the results of rank %d\n", rank);
+      return 1;
+    }
+    if (rank != 0) { free(count); a.destroy(sim); euler_scenario_free(&scn); return 0; }
+    for (int r = 1; r < ranks; ++r) {
+      if (euler_rdv_fetch(rdv, "info", r, &info, sizeof info, 600) ||
+          info.row0 < 0 || info.rows < 0 || info.row0 + info.rows > ny ||
+          euler_rdv_fetch(rdv, "count", r, count + (size_t)info.row0 * nx, (size_t)info.rows * nx, 600)) {
+        fprintf(stderr, "rank %d never delivered its rows\n", r);
+        return 1;
+      }
+      st.n_markers += info.markers;
+    }
+  }
   if (do_print) {
     size_t cap = (size_t)(nx + 1) * ny + 1;
     char *pic = malloc(cap);

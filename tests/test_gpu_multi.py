@@ -169,3 +169,33 @@ def test_large_grids_two_slabs(kind, n, steps):
     if kind == "basic-fill":
         assert int(st.pcg_iterations) == 100 * steps          # the solve ran, at the reference's cap
     ref.close()
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("no_p2p", [False, True])
+def test_host_program_two_ranks_match_one(no_p2p, tmp_path):
+    """bin/euler-gpu --ranks 2 (two processes of the host C program, one GPU each, file
+    rendezvous for the NCCL id and the NVLink peer handles) against the single-process run in
+    the same modes: identical count plane (hash), marker total, sub-step and iteration counts.
+    (Written after round 1's GPU budget was spent: not yet run on hardware.)"""
+    import json
+    import subprocess
+    exe = os.path.join(ROOT, "bin", "euler-gpu")
+    assert os.path.exists(exe), "run `make host`"
+    src = tmp_path / "waterfall.txt"
+    src.write_bytes(shipped_text("waterfall"))
+    common = [exe, "--headless", "--frames", "25", "--grid", "160x96", "--precon", "rb", "--markers", "fast"]
+    one = subprocess.run(common + [str(src)], check=True, capture_output=True, text=True, cwd=ROOT, timeout=300).stdout
+    want = json.loads(one.strip().splitlines()[-1])
+    rdv = tmp_path / "rdv"
+    rdv.mkdir()
+    procs = [subprocess.Popen(common + ["--ranks", "2", "--rank", str(r), "--rendezvous", str(rdv)] +
+                              (["--no-p2p"] if no_p2p else []) + [str(src)],
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT) for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert [p.returncode for p in procs] == [0, 0], [o[1] for o in outs]
+    got = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert outs[1][0].strip() == ""                       # only rank 0 reports
+    for key in ("fnv_count", "markers", "substeps", "rng_state", "solves"):
+        assert got[key] == want[key], key
+    assert abs(got["pcg_iterations"] - want["pcg_iterations"]) <= got["solves"]    # +-1 per solve at the tolerance

@@ -130,3 +130,50 @@ def test_scenario_export_other_sizes_and_errors():
         export_text(z, z, z, z)
     with pytest.raises(ValueError):
         export_text(np.zeros((5, 5), np.uint8), z, z, z)
+
+
+def test_file_rendezvous(tmp_path):
+    """euler_b200/host/rendezvous.c: the side channel of the multi-process host runs — atomic
+    publish, blocking fetch, size check, timeout."""
+    import ctypes as C
+    import os
+    import threading
+    import time
+    from euler_b200.scenario import _lib
+    L = _lib()
+    L.euler_rdv_publish.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t]
+    L.euler_rdv_fetch.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+    d = str(tmp_path).encode()
+    payload = bytes(range(256)) * 3
+    assert L.euler_rdv_publish(d, b"blob", 3, payload, len(payload)) == 0
+    assert sorted(os.listdir(tmp_path)) == ["blob3.bin"]                      # no temporary left behind
+    buf = C.create_string_buffer(len(payload))
+    assert L.euler_rdv_fetch(d, b"blob", 3, buf, len(payload), 1) == 0 and buf.raw == payload
+    assert L.euler_rdv_fetch(d, b"blob", 3, buf, len(payload) - 1, 1) == -1   # size mismatch
+    t0 = time.time()
+    assert L.euler_rdv_fetch(d, b"blob", 4, buf, 8, 1) == -2                  # nobody publishes: timeout
+    assert 0.9 <= time.time() - t0 < 3.0
+    assert L.euler_rdv_publish(str(tmp_path / "missing").encode(), b"x", 0, payload, 4) == -1
+    # a fetch that starts before the publish
+    def late():
+        time.sleep(0.3)
+        L.euler_rdv_publish(d, b"uid", 0, payload, 128)
+    th = threading.Thread(target=late)
+    th.start()
+    got = C.create_string_buffer(128)
+    assert L.euler_rdv_fetch(d, b"uid", 0, got, 128, 10) == 0 and got.raw == payload[:128]
+    th.join()
+    assert L.euler_rdv_publish(d, b"empty", 1, None, 0) == 0 and L.euler_rdv_fetch(d, b"empty", 1, None, 0, 1) == 0
+
+
+def test_host_program_rank_arguments():
+    """bin/euler-gpu refuses an incomplete --ranks set-up before it touches a GPU."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "bin", "euler-gpu")
+    assert os.path.exists(exe), "run `make host`"
+    for args in (["--ranks", "2", "--rank", "0", "x"], ["--headless", "--ranks", "2", "--rank", "2", "--rendezvous", "/tmp", "x"],
+                 ["--headless", "--ranks", "2", "--rank", "0", "x"]):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, cwd=ROOT)
+        assert r.returncode == 1 and "--ranks needs" in r.stderr, args
