@@ -270,6 +270,10 @@ __global__ void __launch_bounds__(TT) k_apply_a(
 // completed by k_p_fixup.
 // T = storage type of s, A s and r (p is fp64 in both modes; with T = float alpha is narrowed
 // once for the r update and s is widened for the p update).
+// (The per-quad body stays inline on purpose: moved into a function of pcg_ops.cuh like the row
+// operators, nvcc 12.9 stopped using the read-only path for these loads and re-ordered the
+// memory operations of this, the dominant kernel — checked with cuobjdump, not measured, so not
+// taken.  The arithmetic is three fmadds per cell; the GPU suite covers it.)
 template <class T>
 __global__ void __launch_bounds__(TT) k_axpy(
     Grid g, TileList active, const T* __restrict__ s, const T* __restrict__ s_prev,
