@@ -816,6 +816,10 @@ int pcg_blocks(const Ctx& c, K kernel, int smem = 0, int threads = TT, bool max_
   // at most one block per 8 rows of a tile column, so that tiny grids do not pay two halo
   // rows per output row
   const Tiles T = tiles_of(c.g);
+  // A/B knob for thin slabs: EULER_PCG_MAX_BLOCKS_PER_SM caps the resident
+  // blocks of every persistent PCG kernel, i.e. fewer, longer row ranges per block
+  static const int max_per_sm = env_int("EULER_PCG_MAX_BLOCKS_PER_SM", 0);
+  if (max_per_sm > 0 && per_sm > max_per_sm) per_sm = max_per_sm;
   const long want = (long)c.sm_count * per_sm, cap = (long)T.n * c.g.th / 8;
   return (int)(cap < 1 ? 1 : (cap < want ? cap : want));
 }
