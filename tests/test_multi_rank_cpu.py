@@ -91,3 +91,35 @@ def test_weighted_slab_partition():
     z = np.zeros(64, np.uint64)
     rows = [G.slab_partition_weighted(z, 4, r) for r in range(4)]
     assert rows[0][0] == 0 and sum(k for _, k in rows) == 64 and all(k >= 8 for _, k in rows)
+
+
+def test_weighted_slab_partition_properties():
+    """Any weights (zeros, spikes, all the work in one row): the slabs tile [0, ny) in rank order
+    and every slab keeps at least 2 x halo = 8 rows, which create() requires."""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st
+    from euler_b200 import gpu as G
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 8), st.integers(0, 300), st.integers(0, 2 ** 32 - 1), st.sampled_from(["flat", "spike", "zeros", "random"]))
+    def run(n, extra, seed, kind):
+        ny = 8 * n + extra
+        rng = np.random.default_rng(seed)
+        if kind == "flat":
+            w = np.ones(ny, np.uint64)
+        elif kind == "zeros":
+            w = np.zeros(ny, np.uint64)
+        elif kind == "spike":
+            w = np.zeros(ny, np.uint64); w[int(rng.integers(0, ny))] = 10 ** 12
+        else:
+            w = rng.integers(0, 10 ** 6, ny).astype(np.uint64)
+        nxt = 0
+        for r in range(n):
+            r0, k = G.slab_partition_weighted(w, n, r)
+            assert r0 == nxt and k >= 8
+            nxt = r0 + k
+        assert nxt == ny
+
+    run()
+    with pytest.raises(G.EulerGpuError):
+        G.slab_partition_weighted(np.ones(15, np.uint64), 2, 0)       # too short for two slabs
