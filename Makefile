@@ -34,10 +34,10 @@ $(LIBDIR)/libeuler_gpu.so: $(CU_OBJS)
 
 host: $(LIBDIR)/libeuler_host.so bin/euler-gpu
 $(LIBDIR)/libeuler_host.so: $(HOST)/scenario.c $(HOST)/scenario.h $(HOST)/checkpoint.c $(HOST)/checkpoint.h \
-                            $(HOST)/rendezvous.c $(HOST)/rendezvous.h include/euler_gpu.h
+                            $(HOST)/rendezvous.c $(HOST)/rendezvous.h $(HOST)/render.c $(HOST)/render.h include/euler_gpu.h
 	@mkdir -p $(LIBDIR)
 	$(CC) -std=gnu99 -O2 -ffp-contract=off -Wall -Wextra -fPIC -shared -Iinclude $(HOST)/scenario.c $(HOST)/checkpoint.c \
-	  $(HOST)/rendezvous.c -lm -o $@
+	  $(HOST)/rendezvous.c $(HOST)/render.c -lm -o $@
 bin/euler-gpu: $(HOST)/main.c $(HOST)/scenario.c $(HOST)/render.c $(HOST)/checkpoint.c $(HOST)/rendezvous.c \
                $(HOST)/scenario.h $(HOST)/render.h $(HOST)/checkpoint.h $(HOST)/rendezvous.h include/euler_gpu.h
 	@mkdir -p bin

@@ -78,7 +78,9 @@ void euler_draw(euler_screen *s, int nx, int ny, const uint8_t *solid, const uin
     for (int x = 1; x < nx - 1 && x < s->cols + 1; ++x) {
       const size_t c = (size_t)y * nx + x;
       if (solid[c]) { if (wet) PUTS(s, "\x1b[0m"); PUTS(s, "X"); wet = 0; }
-      else if (sink[c]) { if (wet) PUTS(s, "\x1b[0m"); PUTS(s, "="); wet = 0; }
+      /* like main.c:928-932 a sink resets the colour but NOT prev_water: water right after a sink
+       * is drawn without a new blue escape.  Kept: the bytes equal the reference's. */
+      else if (sink[c]) { if (wet) PUTS(s, "\x1b[0m"); PUTS(s, "="); }
       else {
         const int level = count[c] < 3 ? count[c] : 3;
         if (level && !wet) PUTS(s, "\x1b[34m");
@@ -115,7 +117,7 @@ static void draw_frame(euler_screen *s, int nx, int ny, const uint8_t *solid, co
     for (int x = 1; x < nx - 1 && x < s->cols + 1; ++x) {
       const size_t c = (size_t)y * nx + x;
       if (solid[c]) { if (wet) PUTS(s, "\x1b[0m"); PUTS(s, "X"); wet = 0; }
-      else if (sink[c]) { if (wet) PUTS(s, "\x1b[0m"); PUTS(s, "="); wet = 0; }
+      else if (sink[c]) { if (wet) PUTS(s, "\x1b[0m"); PUTS(s, "="); }   /* prev_water kept, main.c:928-932 */
       else {
         const int level = count[c] < 3 ? count[c] : 3;
         if (level) {
