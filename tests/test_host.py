@@ -177,3 +177,22 @@ def test_host_program_rank_arguments():
                  ["--headless", "--ranks", "2", "--rank", "0", "x"]):
         r = subprocess.run([exe] + args, capture_output=True, text=True, cwd=ROOT)
         assert r.returncode == 1 and "--ranks needs" in r.stderr, args
+
+
+def test_host_program_cli_errors_like_the_reference():
+    """parse_args / sim_init error behaviour (main.c:982-999, 213-214): usage line and exit 1
+    without arguments, "Unrecognized input: X" for an unknown option, "Could not load F!" for a
+    missing scenario — all before any GPU work."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "bin", "euler-gpu")
+    run = lambda *a: subprocess.run([exe] + list(a), capture_output=True, text=True, cwd=ROOT)
+    r = run()
+    assert r.returncode == 1 and r.stderr.startswith("usage: %s [--rainbow]" % exe) and "<scenario>" in r.stderr
+    r = run("--bogus", "x.txt")
+    assert r.returncode == 1 and r.stderr == "Unrecognized input: --bogus\n"
+    r = run("--headless", "/nonexistent/scenario.txt")
+    assert r.returncode == 1 and r.stderr == "Could not load /nonexistent/scenario.txt!\n"
+    r = run("--precon", "nope", "x.txt")
+    assert r.returncode == 1 and r.stderr.startswith("usage:")
