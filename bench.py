@@ -185,6 +185,25 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# Workloads: BASELINE.json `configs` plus the worst-case-traffic full-fluid box.
+# name -> (scenario, grid, what it is)
+CONFIGS = {
+    "c5": ("basic-fill", 16384, "BASELINE config 5: 16384^2 synthetic basic-fill (the headline workload)"),
+    "c3": ("waterfall", 4096, "BASELINE config 3: waterfall source/sink scenario resampled to 4096^2"),
+    "c4": ("weird-edges", 8192, "BASELINE config 4: weird-edges irregular solid mask resampled to 8192^2"),
+    "full": ("full", 16384, "full-fluid interior at 16384^2 (SURVEY 8d: worst-case traffic, every tile active)"),
+}
+
+
+def scenario_text(kind, nx, ny):
+    """Scenario text at nx x ny: the two synthetic generators, or a shipped scenario file
+    resampled nearest-neighbour, in the reference's scenario-file format."""
+    from euler_b200 import synthetic, shipped_text, resample
+    if kind in ("basic-fill", "full"):
+        return synthetic(kind, nx, ny)
+    return resample(shipped_text(kind), nx - 2, ny - 2)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,7 +216,7 @@ def dist_env():
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from euler_b200 import Scenario, synthetic
+    from euler_b200 import Scenario
     from euler_b200 import gpu as G
 
     rank, world, local = dist_env()
@@ -212,7 +231,7 @@ def run_gpu(args):
     alg_bytes = dict(ALG_BYTES_PER_CELL, **ALG_BYTES_PER_CELL_FP32) if mixed else ALG_BYTES_PER_CELL
 
     t_host0 = time.perf_counter()
-    text = synthetic(args.scenario, n, n)
+    text = scenario_text(args.scenario, n, n)
     # FAST marker mode: array order is free, store the seeded markers in row-major cell order
     scn = Scenario(text, n, n, row_major_markers=True)
     del text
@@ -314,7 +333,23 @@ def run_gpu(args):
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
-    keep = [pinned(scn.solid), pinned(scn.source), pinned(scn.sink), pinned(scn.markers)]
+    # Slab handles accept any superset of their own markers (include/euler_gpu.h): with the
+    # markers in row-major cell order a slab's markers are one contiguous range of the global
+    # array, so each rank ships ~1/N of it over PCIe.  The range is found from the marker rows
+    # (host-side scenario preparation, like the parse itself; robust to any order: first / last
+    # marker within one row of the slab, since init jitter can round a marker into the next row).
+    markers_local = scn.markers
+    if world > 1 and len(scn.markers):
+        mrow = np.floor(scn.markers[:, 1]).astype(np.int32)
+        inside = (mrow >= row0 - 1) & (mrow <= row0 + rows)
+        if inside.any():
+            lo_i = int(np.argmax(inside))
+            hi_i = len(inside) - int(np.argmax(inside[::-1]))
+            markers_local = scn.markers[lo_i:hi_i]
+        else:
+            markers_local = scn.markers[:0]
+        del mrow, inside
+    keep = [pinned(scn.solid), pinned(scn.source), pinned(scn.sink), pinned(markers_local)]
     (_, solid_h), (_, source_h), (_, sink_h), (_, markers_h) = keep
     count_host = torch.empty((n, n), dtype=torch.uint8, pin_memory=True).numpy()
     barrier()
@@ -325,19 +360,27 @@ def run_gpu(args):
         sim.read_marker_count(count_host)
     sim.synchronize()
     t_e2e = time.perf_counter() - t0
-    rows_stored = n if world == 1 else rows + 8
-    h2d_rank = 3 * n * rows_stored + scn.markers.nbytes      # every rank streams the global marker array
+    rows_stored = n if world == 1 else min(n, row0 + rows + 4) - max(0, row0 - 4)
+    h2d_rank = 3 * n * rows_stored + markers_local.nbytes
     d2h_rank = n * (n if world == 1 else rows)
+    # ---- invariants of the state K sub-steps after sim_init (outside every timed region) ----
+    # the e2e leg started from euler_gpu_reinit, so this state does not depend on the warm-up:
+    # runs on 1, 2, 4, 8 slabs with the same --steps must agree (integers exactly, sums to the
+    # tolerance the unconverged solve allows — see DESIGN.md)
+    chk = sim.check()
+    st_end = sim.stats()
+    migrated = int(st_end.markers_migrated)
     sim.close()
     del sim, keep
 
     t = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
-    it = torch.tensor([launches, h2d_rank, d2h_rank], dtype=torch.float64, device="cuda")
+    it = torch.tensor([launches, h2d_rank, d2h_rank, active_cells], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(it, op=dist.ReduceOp.SUM)
     h2d = float(it[1]) / args.steps
     d2h = float(it[2])
+    active_cells_all = int(it[3])     # halo-row tiles are counted by both neighbours: slightly above the N=1 figure
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
     ksum = torch.tensor([sum(v[0] for v in prof.values()) / args.steps], dtype=torch.float64, device="cuda")
     ksums = [torch.zeros_like(ksum) for _ in range(world)]
@@ -347,6 +390,25 @@ def run_gpu(args):
         ksums = [ksum]
     per_rank_kernel_ms = [round(float(k[0]), 3) for k in ksums]
     iters_all, launches_all = iters, int(it[0])      # one global solve: every rank counts the same iterations
+    # check object: integer fields add up over ranks modulo 2^64 (int64 wrap-around add), sums add, maxima max
+    ci = torch.tensor([np.array([getattr(chk, k)], dtype=np.uint64).view(np.int64)[0]
+                       for k in ("n_markers", "fluid_cells", "count_sum", "count_hash")] + [migrated],
+                      dtype=torch.int64, device="cuda")
+    cs = torch.tensor([chk.sum_abs_u, chk.sum_abs_v, chk.sum_p], dtype=torch.float64, device="cuda")
+    cmx = torch.tensor([chk.max_abs_div, chk.max_abs_u, chk.max_abs_v], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ci, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cmx, op=dist.ReduceOp.MAX)
+    ci = ci.cpu().numpy().view(np.uint64)
+    check = {"state": "%d sub-steps after sim_init (end of the e2e leg)" % args.steps,
+             "n_markers": int(ci[0]), "fluid_cells": int(ci[1]), "count_sum": int(ci[2]),
+             "count_hash": "%016x" % int(ci[3]),
+             "sum_abs_u": float(cs[0]), "sum_abs_v": float(cs[1]), "sum_p": float(cs[2]),
+             "max_abs_div": float(cmx[0]), "max_abs_u": float(cmx[1]), "max_abs_v": float(cmx[2]),
+             "pcg_iterations_last_solve": int(st_end.last_iterations), "last_residual": float(st_end.last_residual),
+             "rng_state": "%016x" % int(st_end.rng_state), "substeps": int(st_end.substeps),
+             "markers_migrated_total": int(ci[4])}
 
     if rank == 0:
         kernels, roof = roofline_report(prof, alg_bytes, active_cells, cells_local, n_markers,
@@ -367,7 +429,10 @@ def run_gpu(args):
                                    % (args.scenario, n, n, "red-black IC(0)" if args.precon == "rb" else "IC(0) wavefront",
                                       "fp32 PCG vectors + fp64 p, residual replacement every 10 iterations "
                                       "(NOT the reference's precision: opt-in mode)" if mixed else "fp64 PCG vectors"),
+                       "preset": args.config if (args.scenario, n) == CONFIGS[args.config][:2] else None,
                        "grid": [n, n], "markers": n_markers, "active_cells": active_cells,
+                       "active_fraction": round(active_cells_all / cells, 4),
+                       "markers_migrated_per_step": round(check["markers_migrated_total"] / max(1, int(st_end.substeps)), 1),
                        "parallelism": "single GPU" if world == 1 else
                                       "%d row slabs balanced by fluid cells (rank 0: %d rows), NCCL halo exchange + marker migration, %s" % (world, rows, "NCCL per-iteration exchanges" if args.no_p2p else "per-iteration exchanges by NVLink peer stores (CUDA IPC)"),
                        "l2_policy": "inputs >> L2: every plane is %.0f MB..%.0f MB vs 126 MB L2, no flush needed"
@@ -383,6 +448,7 @@ def run_gpu(args):
             "roofline": roof,
             "kernels": kernels,
             "per_rank_kernel_ms_per_step": per_rank_kernel_ms,
+            "check": check,
             "clocks": clocks,
         }
         if not args.no_cpu and world >= 1:
@@ -397,10 +463,9 @@ def run_gpu(args):
 def cpu_sample(args, steps, warmup):
     """Times the UNMODIFIED reference (oracle/_ref, its own -O3 -ffast-math flags) on one host
     core, same synthetic scenario resampled to the sample grid."""
-    from euler_b200 import synthetic
     from oracle.oracle import Reference, ref_available, Oracle
     n = args.cpu_grid
-    text = synthetic(args.scenario, n, n)
+    text = scenario_text(args.scenario, n, n)
     if ref_available(n, n, fast=True):
         sim = Reference(n, n, fast=True)
         sim.init_from_text(text)
@@ -466,8 +531,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
-    ap.add_argument("--grid", type=int, default=16384)
-    ap.add_argument("--scenario", default="basic-fill")
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS),
+                    help="workload preset (BASELINE.json configs 3-5, or the full-fluid worst case); "
+                         "--scenario / --grid override its parts")
+    ap.add_argument("--grid", type=int, default=None)
+    ap.add_argument("--scenario", default=None,
+                    help="basic-fill | full (synthetic) or a shipped scenario name (resampled to --grid)")
     ap.add_argument("--precon", default="rb", choices=["rb", "ic0"])
     ap.add_argument("--check-every", type=int, default=25)
     ap.add_argument("--pcg-dtype", default="fp64", choices=["fp64", "fp32"],
@@ -480,6 +549,10 @@ def main():
                          "measures what the events themselves cost")
     ap.add_argument("--no-p2p", action="store_true", help="N>1: NCCL for every exchange (no CUDA-IPC fast path)")
     args = ap.parse_args()
+    if args.scenario is None:
+        args.scenario = CONFIGS[args.config][0]
+    if args.grid is None:
+        args.grid = CONFIGS[args.config][1]
     if args.impl == "reference":
         run_reference(args)
     else:

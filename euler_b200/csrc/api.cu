@@ -62,7 +62,7 @@ struct euler_gpu {
   size_t device_bytes;
   bool max_valid;                // sc.max_*_bits describe the current u, v
   // stats
-  uint64_t frames, substeps, solves, solves_skipped, pcg_iterations;
+  uint64_t frames, substeps, solves, solves_skipped, pcg_iterations, markers_migrated;
   int last_iterations;
   double last_residual;
   float last_dt;
@@ -167,6 +167,19 @@ int zero_plane(euler_gpu* h, T* plane) {
   return 0;
 }
 
+// Slab handles scan only their own rows for source cells; the sources step is a collective
+// (cross-rank prefix of the RNG draws), so every rank must know whether ANY rank has one.
+int agree_on_sources(euler_gpu* h) {
+  Ctx& c = h->c;
+  int flag = c.n_source_cells_global ? 1 : 0;
+  CU(cudaMemcpyAsync(&c.sc->pad1, &flag, sizeof flag, cudaMemcpyHostToDevice, c.stream));
+  if (comm_allreduce_max_i32(c, h->cm, &c.sc->pad1, 1)) return fail(EULER_E_COMM, "%s", comm_last_error());
+  CU(cudaMemcpyAsync(&flag, &c.sc->pad1, sizeof flag, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  if (flag && !c.n_source_cells_global) c.n_source_cells_global = 1;   // used as a boolean on slabs
+  return 0;
+}
+
 // The state hand-over at the end of sim_init (main.c:209-274) into an existing handle: the
 // three static masks, the seeded markers and the RNG state go to the device, every dynamic
 // plane starts from zero (the reference's globals are zero-initialised: main.c:64-100, 577),
@@ -221,10 +234,12 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
   }
 
   // static row-major list of source cells (main.c:284-286 visits them in this order); rows
-  // are scanned a machine word at a time: almost all of them hold no source
+  // are scanned a machine word at a time: almost all of them hold no source.  A slab handle
+  // looks only at the rows it stores; whether ANY rank has a source is agreed on below.
   std::vector<unsigned int> cells;
   size_t n_src_global = 0;
-  for (int y = 0; y < ny; ++y) {
+  const int scan0 = h->slab ? h->lo : 0, scan1 = h->slab ? h->lo + c.g.ny : ny;
+  for (int y = scan0; y < scan1; ++y) {
     const uint8_t* row = source + (size_t)y * nx;
     const bool mine = y >= h->row0 && y < h->row0 + h->rows;
     for (int x = 0; x < nx;) {
@@ -255,6 +270,8 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
   launch_refresh_counts(c);                                  // sim_init, main.c:268
   launch_colorize(c);                                        // --rainbow, main.c:271-273
   if (h->slab && h->comm_ready) {
+    int grc = agree_on_sources(h);
+    if (grc) return grc;
     // halo rows of the initial classification (only the owned markers were binned)
     if (comm_halo(c, h->cm, c.count, 1, SLAB_HALO)) return fail(EULER_E_COMM, "%s", comm_last_error());
   }
@@ -486,6 +503,7 @@ int migrate_markers(euler_gpu* h) {
   CU(cudaMemcpyAsync(&host[4], h->n_keep, 8, cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
   const unsigned long long to_dn = host[0], to_up = host[1], from_dn = host[2], from_up = host[3], keep = host[4];
+  h->markers_migrated += to_dn + to_up;
   if (to_dn > cm.send_cap || to_up > cm.send_cap)
     return fail(EULER_E_UNSUPPORTED, "more than %zu markers cross a slab boundary in one sub-step", cm.send_cap);
   if (keep + from_dn + from_up > c.max_markers)
@@ -654,7 +672,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   memset(&h->cm, 0, sizeof h->cm); h->comm_ready = false; h->n_keep = nullptr;
   memset(&h->pp, 0, sizeof h->pp); h->z_raw = nullptr; h->source_cap = 0;
   h->host_sc = nullptr; h->device_bytes = 0; h->max_valid = false;
-  h->frames = h->substeps = h->solves = h->solves_skipped = h->pcg_iterations = 0;
+  h->frames = h->substeps = h->solves = h->solves_skipped = h->pcg_iterations = h->markers_migrated = 0;
   h->last_iterations = 0; h->last_residual = 0; h->last_dt = 0; h->profiling = false;
   h->ms_markers = h->ms_grid = h->ms_project = 0;
   for (int i = 0; i < 4; ++i) h->ev[i] = nullptr;
@@ -786,6 +804,7 @@ int euler_gpu_reinit(euler_gpu* h, const uint8_t* solid, const uint8_t* source, 
   if (h->slab && !h->comm_ready) return fail(EULER_E_COMM, "slab handle: call euler_gpu_comm_init first");
   CU(cudaStreamSynchronize(h->c.stream));
   h->prm.rng_state = rng_state;
+  h->frames = 0;                 // g_frame_count (main.c:89) is simulation state: the source hue restarts at t = 0
   return load_state(h, solid, source, sink, markers_xy, n_markers, rng_state, false);
 }
 
@@ -1010,8 +1029,36 @@ int euler_gpu_stats(euler_gpu* h, euler_stats* out) {
   out->device_bytes = h->device_bytes;
   out->ms_markers = h->ms_markers; out->ms_grid = h->ms_grid; out->ms_project = h->ms_project;
   out->active_cells = (uint64_t)h->host_sc->active_tiles * (uint64_t)pcg_tile_cells(h->c);
+  out->markers_migrated = h->markers_migrated;
+  out->grid_cells = (uint64_t)h->c.g.ny * (uint64_t)h->c.g.pitch;
   for (int i = 0; i < KC__COUNT; ++i) { out->kernel_ms[i] = h->c.prof.ms[i]; out->kernel_count[i] = h->c.prof.count[i]; }
   return 0;
+}
+
+int euler_gpu_check(euler_gpu* h, euler_check* out) {
+  ENTER(h);
+  if (!out) return fail(EULER_E_INVALID, "out is NULL");
+  Ctx& c = h->c;
+  const int blocks = 1024;                       // c.partials holds >= 65536 doubles
+  unsigned long long* ints = reinterpret_cast<unsigned long long*>(c.partials + 6 * blocks);
+  launch_check(c, ints, c.partials, blocks);
+  std::vector<double> parts(6 * blocks);
+  unsigned long long hi[3];
+  CU(cudaMemcpyAsync(parts.data(), c.partials, parts.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaMemcpyAsync(hi, ints, sizeof hi, cudaMemcpyDeviceToHost, c.stream));
+  int rc = pull_scalars(h);                      // synchronises the stream
+  if (rc) return rc;
+  memset(out, 0, sizeof *out);
+  out->n_markers = h->host_sc->n_markers;
+  out->fluid_cells = hi[0]; out->count_sum = hi[1]; out->count_hash = hi[2];
+  for (int b = 0; b < blocks; ++b) {
+    const double* q = &parts[6 * b];
+    out->sum_abs_u += q[0]; out->sum_abs_v += q[1]; out->sum_p += q[2];
+    if (q[3] > out->max_abs_div) out->max_abs_div = q[3];
+    if (q[4] > out->max_abs_u) out->max_abs_u = q[4];
+    if (q[5] > out->max_abs_v) out->max_abs_v = q[5];
+  }
+  return check_launch("check");
 }
 
 int euler_gpu_set_profiling(euler_gpu* h, int enabled) {
@@ -1075,6 +1122,7 @@ int euler_gpu_comm_init(euler_gpu* h, int rank, int n_ranks, const void* unique_
   h->device_bytes += 2 * h->cm.send_cap * 8;
   c.distributed = 1;
   h->comm_ready = true;
+  { int grc = agree_on_sources(h); if (grc) return grc; }
   // halo rows of the initial classification (create() binned only the owned markers)
   CM(comm_halo(c, h->cm, c.count, 1, SLAB_HALO));
   CU(cudaStreamSynchronize(c.stream));

@@ -429,9 +429,64 @@ __global__ void __launch_bounds__(BX* BY) k_advect_color(
   bo[c] = interpolate<CELL_P>(cb, fluid, g, lim, px, py);
 }
 
+// ------------------------------------------------------------------ invariants ----
+// euler_gpu_check: size-independent invariants of the state over the OWNED rows (one pass).
+// Integer results by 64-bit atomics (exact, order-free); floating sums as one partial per block,
+// added up by the host in block order (deterministic for a given grid).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+__global__ void __launch_bounds__(256) k_check(Grid g, int r0, int r1, const float* __restrict__ u,
+                                                const float* __restrict__ v, const double* __restrict__ p,
+                                                const uint8_t* __restrict__ count, float h,
+                                                unsigned long long* __restrict__ ints /*3*/,
+                                                double* __restrict__ parts /*6 x gridDim.x*/) {
+  unsigned long long n_fluid = 0, c_sum = 0, c_hash = 0;
+  double su = 0.0, sv = 0.0, sp = 0.0, mdiv = 0.0, mu = 0.0, mv = 0.0;
+  const size_t total = (size_t)g.nx * (r1 - r0);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int y = r0 + (int)(i / g.nx), x = (int)(i % g.nx);
+    const size_t c = gidx(g, x, y);
+    const unsigned cnt = count[c];
+    const double au = fabs((double)u[c]), av = fabs((double)v[c]);
+    if (au == au) { su += au; mu = fmax(mu, au); }
+    if (av == av) { sv += av; mv = fmax(mv, av); }
+    if (cnt) {
+      n_fluid += 1; c_sum += cnt;
+      c_hash += cnt * mix64((unsigned long long)(y + g.yoff) * (unsigned long long)g.nx + x + 1);
+      if (p) sp += p[c];
+      const float div = div_h(u[c] - u[c - 1] + v[c] - v[c - g.pitch], h);   // main.c:720
+      const double ad = fabs((double)div);
+      if (ad == ad) mdiv = fmax(mdiv, ad);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_fluid += __shfl_xor_sync(EULER_FULL_MASK, n_fluid, o);
+    c_sum += __shfl_xor_sync(EULER_FULL_MASK, c_sum, o);
+    c_hash += __shfl_xor_sync(EULER_FULL_MASK, c_hash, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(ints + 0, n_fluid); atomicAdd(ints + 1, c_sum); atomicAdd(ints + 2, c_hash); }
+  double* out = parts + (size_t)blockIdx.x * 6;
+  double r;
+  r = block_reduce<false>(su); if (threadIdx.x == 0) out[0] = r;
+  r = block_reduce<false>(sv); if (threadIdx.x == 0) out[1] = r;
+  r = block_reduce<false>(sp); if (threadIdx.x == 0) out[2] = r;
+  r = block_reduce<true>(mdiv); if (threadIdx.x == 0) out[3] = r;
+  r = block_reduce<true>(mu); if (threadIdx.x == 0) out[4] = r;
+  r = block_reduce<true>(mv); if (threadIdx.x == 0) out[5] = r;
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------- launchers ----
+
+void launch_check(Ctx& c, unsigned long long* ints3, double* parts, int blocks) {
+  cudaMemsetAsync(ints3, 0, 3 * sizeof(unsigned long long), c.stream);
+  k_check<<<blocks, 256, 0, c.stream>>>(c.g, c.own0, c.own1, c.u, c.v, c.p, c.count, c.h, ints3, parts);
+  c.launches += 1;
+}
 
 void launch_maxsq(Ctx& c) {
   ProfScope ps(c, KC_MAXSQ);

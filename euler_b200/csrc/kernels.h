@@ -117,6 +117,9 @@ void launch_extrapolate(Ctx& c);                             // (u,v) -> (uext,v
 void launch_advect_velocity(Ctx& c, float dt);               // (u,v) -> (utmp,vtmp)
 void launch_build_rhs(Ctx& c, float dt);                     // -> r, p=0, adiag, sc.nonzero_rhs
 void launch_pressure_update(Ctx& c, float dt);               // p,utmp,vtmp -> u,v (+max u2,v2)
+// euler_gpu_check: invariants over the owned rows; ints3 = {fluid cells, sum count, count hash},
+// parts = 6 doubles per block {sum|u|, sum|v|, sum p, max|div|, max|u|, max|v|}
+void launch_check(Ctx& c, unsigned long long* ints3, double* parts, int blocks);
 // --rainbow colour transport; all four return at once when the colour planes do not exist
 void launch_colorize(Ctx& c);                                // colorize(), main.c:187-201
 void launch_extrapolate_color(Ctx& c);                       // extrapolate(r|g|b, P), main.c:859-863

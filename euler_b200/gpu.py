@@ -56,7 +56,21 @@ class Stats(C.Structure):
                 ("device_bytes", C.c_uint64),
                 ("ms_markers", C.c_double), ("ms_grid", C.c_double), ("ms_project", C.c_double),
                 ("active_cells", C.c_uint64),
-                ("kernel_ms", C.c_double * 24), ("kernel_count", C.c_uint64 * 24)]
+                ("kernel_ms", C.c_double * 24), ("kernel_count", C.c_uint64 * 24),
+                ("markers_migrated", C.c_uint64), ("grid_cells", C.c_uint64)]
+
+
+class Check(C.Structure):
+    """euler_check: invariants over the rows the handle owns (additive / max-combinable over slabs)."""
+    _fields_ = [("n_markers", C.c_uint64), ("fluid_cells", C.c_uint64), ("count_sum", C.c_uint64),
+                ("count_hash", C.c_uint64), ("sum_abs_u", C.c_double), ("sum_abs_v", C.c_double),
+                ("sum_p", C.c_double), ("max_abs_div", C.c_double), ("max_abs_u", C.c_double),
+                ("max_abs_v", C.c_double)]
+    SUMS = ("n_markers", "fluid_cells", "count_sum", "count_hash", "sum_abs_u", "sum_abs_v", "sum_p")
+    MAXES = ("max_abs_div", "max_abs_u", "max_abs_v")
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class EulerGpuError(RuntimeError):
@@ -85,6 +99,7 @@ _L.euler_gpu_colorize.argtypes = [_H]
 _L.euler_gpu_set_source_exhausted.argtypes = [_H, C.c_int]
 _L.euler_gpu_set_frame_count.argtypes = [_H, C.c_uint64]
 _L.euler_gpu_stats.argtypes = [_H, C.POINTER(Stats)]
+_L.euler_gpu_check.argtypes = [_H, C.POINTER(Check)]
 _L.euler_gpu_set_profiling.argtypes = [_H, C.c_int]
 _L.euler_gpu_synchronize.argtypes = [_H]
 _L.euler_gpu_reset_profile.argtypes = [_H]
@@ -239,6 +254,11 @@ class EulerGpu:
         s = Stats()
         _ck(_L.euler_gpu_stats(self._h, C.byref(s)))
         return s
+
+    def check(self):
+        c = Check()
+        _ck(_L.euler_gpu_check(self._h, C.byref(c)))
+        return c
 
     def read_marker_count(self, out=None):
         if out is None:

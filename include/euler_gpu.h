@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define EULER_GPU_ABI_VERSION 3
+#define EULER_GPU_ABI_VERSION 4
 
 enum euler_error {
   EULER_OK            =  0,
@@ -203,7 +203,30 @@ typedef struct euler_stats {
                                        cells the PCG kernels actually stream */
   double   kernel_ms[EULER_KERNEL_CLASSES];
   uint64_t kernel_count[EULER_KERNEL_CLASSES];
+  uint64_t markers_migrated;        /* slab handles: markers this rank handed to a neighbouring slab
+                                       since create (advect_markers moved them across the boundary) */
+  uint64_t grid_cells;              /* cells the grid-stage kernels streamed in the last sub-step */
 } euler_stats;
+
+/* Size-independent invariants of the current state (euler_gpu_check): what a run on N row slabs
+ * must reproduce from a run on one GPU.  Counted over the rows the handle OWNS, so the integer
+ * fields of all ranks ADD UP (modulo 2^64) to the single-GPU values exactly, the sums add up to
+ * within fp64 summation order (and whatever the solve itself differs by), the maxima combine by
+ * max.  Reference quantities: g_markers_length (main.c:93), g_marker_count (main.c:96), the
+ * divergence of main.c:720 evaluated on the projected u, v (SURVEY north_star: "matching
+ * post-projection divergence norms"). */
+typedef struct euler_check {
+  uint64_t n_markers;       /* markers held by this handle */
+  uint64_t fluid_cells;     /* owned cells with marker count > 0 */
+  uint64_t count_sum;       /* sum of the owned count plane */
+  uint64_t count_hash;      /* sum over owned cells of count * mix(global cell index), mod 2^64:
+                               position-sensitive, additive over slabs */
+  double   sum_abs_u;       /* sum |u| over owned rows */
+  double   sum_abs_v;
+  double   sum_p;           /* sum of p over owned fluid cells (p >= 0 after the clamp, main.c:773) */
+  double   max_abs_div;     /* max over owned fluid cells of |(u - u[x-1] + v - v[y-1]) / h| */
+  double   max_abs_u, max_abs_v;
+} euler_check;
 
 typedef struct euler_gpu euler_gpu;
 
@@ -223,9 +246,15 @@ int euler_gpu_destroy(euler_gpu *h);
 /* sim_init() again on an existing handle (same grid, same params): the hand-over of create()
  * without the allocation — new masks, markers and RNG state go to the device, every dynamic
  * plane (u, v, counts, the persistent g_precon, the PCG vectors) restarts from zero like the
- * reference's zero-initialised globals (main.c:64-100, 577), refresh_marker_counts runs once
- * (main.c:268).  Statistics keep counting.  On slab handles: collective (halo exchange of the
- * count plane), after euler_gpu_comm_init. */
+ * reference's zero-initialised globals (main.c:64-100, 577), g_frame_count restarts at 0
+ * (main.c:89), refresh_marker_counts runs once (main.c:268).  The launch / iteration statistics
+ * keep counting.  On slab handles: collective (halo exchange of the count plane), after
+ * euler_gpu_comm_init.
+ * Slab handles (create and reinit): `markers_xy` may be ANY superset of the markers whose cell row
+ * the slab owns — the whole global array, or just the slab's own markers (with markers stored in
+ * row-major cell order that is one contiguous range of the global array, so each rank ships
+ * 1/N of it over PCIe instead of all of it); the handle keeps the ones it owns.  The mask
+ * pointers are global-shaped [ny][nx]; only the rows the handle stores are read. */
 int euler_gpu_reinit(euler_gpu *h, const uint8_t *solid, const uint8_t *source, const uint8_t *sink,
                      const float *markers_xy, size_t n_markers, uint64_t rng_state);
 
@@ -264,6 +293,9 @@ int euler_gpu_set_source_exhausted(euler_gpu *h, int exhausted);
 int euler_gpu_set_frame_count(euler_gpu *h, uint64_t frames);
 
 int euler_gpu_stats(euler_gpu *h, euler_stats *out);
+/* Invariants of the current state, reduced on the device (one pass over the owned rows; a few
+ * hundred bytes come back).  Synchronises the stream. */
+int euler_gpu_check(euler_gpu *h, euler_check *out);
 /* Toggle per-stage-group CUDA-event timing (adds synchronisation; off by default). */
 int euler_gpu_set_profiling(euler_gpu *h, int enabled);
 /* Name of kernel class i (0 <= i < EULER_KERNEL_CLASSES), or NULL. */

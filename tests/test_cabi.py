@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_default_params():
     from euler_b200 import gpu as G
-    assert G.abi_version() == 3
+    assert G.abi_version() == 4
     p = G.default_params()
     assert p.pcg_dtype == G.PCG_FP64 and p.pcg_refresh_every == 10
     # the reference's constants (main.c:58-60, 735-736, 838, 849-851)

@@ -1,6 +1,9 @@
-"""Row-slab decomposition across 2 GPUs against the single-GPU run of the same
-scenario: NCCL halo exchange, cross-slab marker migration, distributed PCG scalars, the
-cross-rank order of the source RNG draws.  Needs 2 visible GPUs (skipped otherwise)."""
+"""Row-slab decomposition across 2, 4 and 8 GPUs against the single-GPU run of the
+same scenario and against the oracle: NCCL halo exchange, cross-slab marker migration
+(reference semantics at stake: main.c:464-537), distributed PCG scalars (main.c:629-667), the
+cross-rank order of the source RNG draws (main.c:284-291).  Each case needs as many visible GPUs
+as it has slabs (skipped otherwise); the logs of the 2-, 4- and 8-GPU runs on hardware are kept
+under profiles/."""
 import os
 import sys
 
@@ -40,11 +43,15 @@ def _exchange_blobs(out_dir, rank, nranks, blob):
     return blobs
 
 
-def _worker(rank, nranks, uid, text, nx, ny, frames, out_dir, p2p=False, reinit=False):
+def _worker(rank, nranks, uid, text, nx, ny, frames, out_dir, p2p=False, reinit=False, weighted=False):
     sys.path.insert(0, ROOT)
     from euler_b200 import gpu as G
     scn = Scenario(text, nx, ny)
-    row0, rows = G.slab_partition(ny, nranks, rank)
+    if weighted:
+        weight = scn.fluid.sum(axis=1, dtype=np.uint64) * 100 + np.uint64(nx)
+        row0, rows = G.slab_partition_weighted(weight, nranks, rank)
+    else:
+        row0, rows = G.slab_partition(ny, nranks, rank)
     g = G.EulerGpu.from_scenario(scn, precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST,
                                  device=rank, slab_row0=row0, slab_rows=rows)
     g.comm_init(rank, nranks, uid)
@@ -59,26 +66,46 @@ def _worker(rank, nranks, uid, text, nx, ny, frames, out_dir, p2p=False, reinit=
     it0 = g.stats().pcg_iterations
     subs = [g.step_frame() for _ in range(frames)]
     st = g.stats()
+    chk = g.check()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), row0=row0, rows=rows,
              count=g.get(G.F_COUNT), u=g.get(G.F_U), v=g.get(G.F_V), p=g.get(G.F_P),
              markers=g.get(G.F_MARKERS), subs=np.array(subs), iters=st.pcg_iterations - it0,
-             rng=np.uint64(st.rng_state))
+             rng=np.uint64(st.rng_state),
+             chk_int=np.array([chk.n_markers, chk.fluid_cells, chk.count_sum, chk.count_hash], dtype=np.uint64),
+             chk_sum=np.array([chk.sum_abs_u, chk.sum_abs_v, chk.sum_p]),
+             chk_max=np.array([chk.max_abs_div, chk.max_abs_u, chk.max_abs_v]))
     g.close()
 
 
-@pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("p2p,reinit", [(False, False), (True, False), (True, True)])
-@pytest.mark.parametrize("name,nx,ny,frames", [("block", 100, 40, 12), ("waterfall", 160, 96, 30),
-                                               ("weird-edges", 256, 256, 5)])
-def test_two_slabs_match_single_gpu(name, nx, ny, frames, p2p, reinit, tmp_path):
+# (slabs, scenario, nx, ny, frames): 8 slabs of 100x64 / 4 of 100x40 are the degenerate geometry —
+# 8 and 10 rows per slab, the minimum (2 x 4 halo rows) the decomposition accepts
+_GRIDS = {2: [("block", 100, 40, 12), ("waterfall", 160, 96, 30), ("weird-edges", 256, 256, 5)],
+          4: [("block", 100, 40, 12), ("waterfall", 160, 96, 30), ("weird-edges", 256, 256, 5)],
+          8: [("block", 100, 64, 12), ("waterfall", 160, 96, 30), ("weird-edges", 256, 256, 5)]}
+# (p2p, reinit, weighted): NCCL-only path, NVLink peer path, reinit into a used handle, weighted split.
+# 2 slabs run the full matrix; 4 and 8 slabs (charged 4x / 8x on the GPU pool) the NVLink path on
+# every grid plus one case each of the other modes.
+_MODES_ALL = [(False, False, False), (True, False, False), (True, True, False), (True, False, True)]
+_SLAB_CASES = [(2,) + g + m for g in _GRIDS[2] for m in _MODES_ALL]
+for _n in (4, 8):
+    _SLAB_CASES += [(_n,) + g + (True, False, False) for g in _GRIDS[_n]]
+    _SLAB_CASES += [(_n,) + _GRIDS[_n][1] + (True, False, True), (_n,) + _GRIDS[_n][0] + (False, False, False),
+                    (_n,) + _GRIDS[_n][2] + (True, True, False)]
+
+
+@pytest.mark.parametrize("nranks,name,nx,ny,frames,p2p,reinit,weighted", _SLAB_CASES)
+def test_slabs_match_single_gpu(nranks, name, nx, ny, frames, p2p, reinit, weighted, tmp_path):
+    if _gpu_count() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
     import torch.multiprocessing as mp
     from euler_b200 import gpu as G
     text = shipped_text(name)
     if (nx, ny) != (100, 40):
         text = resample(text, nx - 2, ny - 2)
     uid = G.comm_unique_id()
-    mp.spawn(_worker, args=(2, uid, text, nx, ny, frames, str(tmp_path), p2p, reinit), nprocs=2, join=True)
-    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(2)]
+    mp.spawn(_worker, args=(nranks, uid, text, nx, ny, frames, str(tmp_path), p2p, reinit, weighted),
+             nprocs=nranks, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(nranks)]
 
     ref = G.EulerGpu.from_scenario(Scenario(text, nx, ny), precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST)
     subs = [ref.step_frame() for _ in range(frames)]
@@ -89,7 +116,8 @@ def test_two_slabs_match_single_gpu(name, nx, ny, frames, p2p, reinit, tmp_path)
             r0, n = int(p["row0"]), int(p["rows"])
             out[r0:r0 + n] = p[field][r0:r0 + n]
         return out
-    assert list(parts[0]["subs"]) == subs == list(parts[1]["subs"])
+    assert all(list(p["subs"]) == subs for p in parts)
+    assert sum(int(p["rows"]) for p in parts) == ny
     # cell classification: bit-exact
     assert same_bits(merged("count", np.uint8), ref.get(G.F_COUNT))
     # markers: same multiset (order across slabs is unspecified)
@@ -99,10 +127,23 @@ def test_two_slabs_match_single_gpu(name, nx, ny, frames, p2p, reinit, tmp_path)
     key = lambda a: a[np.lexsort((a[:, 0], a[:, 1]))]
     assert np.abs(key(m) - key(rm)).max() <= 1e-4
     # the RNG stream advanced identically on every rank and as on one GPU
-    assert int(parts[0]["rng"]) == int(parts[1]["rng"]) == int(ref.stats().rng_state)
+    assert all(int(p["rng"]) == int(ref.stats().rng_state) for p in parts)
     for f, fld in (("u", G.F_U), ("v", G.F_V)):
         a, b = merged(f, np.float32), ref.get(fld)
         assert float(np.abs(a - b).max()) <= 1e-5 * max(1.0, float(np.abs(b).max())), f
+    # euler_gpu_check (what bench.py prints at every N): integers add up exactly modulo 2^64,
+    # sums / maxima agree to the tolerance of the fields themselves
+    want = ref.check()
+    got_int = np.zeros(4, dtype=np.uint64)
+    for p in parts:
+        got_int += p["chk_int"]
+    assert [int(x) for x in got_int] == [want.n_markers, want.fluid_cells, want.count_sum, want.count_hash]
+    got_sum = sum(p["chk_sum"] for p in parts)
+    got_max = np.max([p["chk_max"] for p in parts], axis=0)
+    for a, b in zip(got_sum, (want.sum_abs_u, want.sum_abs_v, want.sum_p)):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b))
+    for a, b in zip(got_max[1:], (want.max_abs_u, want.max_abs_v)):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b))
     ref.close()
 
 
