@@ -61,6 +61,7 @@ struct euler_gpu {
   DevScalars* host_sc;           // pinned mirror
   size_t device_bytes;
   bool max_valid;                // sc.max_*_bits describe the current u, v
+  bool use_tail;                 // fused red-black iteration: axpy + forward + backward as one kernel
   // stats
   uint64_t frames, substeps, solves, solves_skipped, pcg_iterations, markers_migrated;
   int last_iterations;
@@ -330,6 +331,11 @@ int run_project(euler_gpu* h, float dt) {
           launch_fused_search_apply(c, first);              // s = z (+ beta s), A s -> c.q, alpha
           if (c.fused >= 2) {
             launch_fused_axpy_forward(c, h->prm.tol);       // p, r, ||r||inf, q = L^-1 r
+          } else if (h->use_tail) {
+            // r, (p), ||r||inf, q = L^-1 r, z = L^-T q, z.r, beta: one kernel (pcg_tail.cuh)
+            launch_fused_tail(c, h->prm.tol, (it & 1) ? 0 : 1);
+            first = false;
+            continue;
           } else {
             launch_axpy(c, h->prm.tol, true, (it & 1) ? 0 : 1);  // r, ||r||inf; p every 2nd iteration
             // mixed precision: r <- b - A p in fp64 (p is complete after an even iteration)
@@ -392,12 +398,20 @@ int run_substep(euler_gpu* h, float dt) {
 // ---- row-slab mode: same stages, plus the exchange steps ---------------------
 #define CM(call) do { if ((call)) return fail(EULER_E_COMM, "%s: %s", #call, comm_last_error()); } while (0)
 
+int dist_after_backward(euler_gpu* h, bool init);
+
 int dist_precon_apply(euler_gpu* h, bool init) {
   Ctx& c = h->c;
   // no exchange: r is kept consistent on the halo rows by redundant updates (pcg_kernels.cu
   // pview), q and z are recomputed there
   launch_rb_forward(c);
   launch_rb_backward(c, init);
+  return dist_after_backward(h, init);
+}
+
+// the exchanges that follow z = M^-1 r on a slab: halo rows of z, {z.r, ||r||inf} across ranks
+int dist_after_backward(euler_gpu* h, bool init) {
+  Ctx& c = h->c;
   if (c.p2p_mode == 2) return 0;   // NVLink: halo stores + scalars happened inside k_rb_backward_pipe
   if (c.p2p_mode == 1) {
     // the same exchanges as two separate small kernels (A/B: EULER_P2P_SEPARATE=1)
@@ -433,6 +447,12 @@ int dist_iteration(euler_gpu* h, bool first, int it) {
   } else {
     CM(comm_gather_scalars(c, h->cm, c.sc->part));  // {z.s partial}
     launch_dist_alpha(c, h->cm.gather, h->cm.nranks);
+  }
+  if (h->use_tail) {
+    launch_fused_tail(c, h->prm.tol, (it & 1) ? 0 : 1);
+    int trc = dist_after_backward(h, false);
+    if (trc) return trc;
+    return 0;
   }
   launch_axpy(c, h->prm.tol, c.fused != 0, c.fused == 1 ? ((it & 1) ? 0 : 1) : 2);
   int rc = dist_precon_apply(h, false);
@@ -722,6 +742,11 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
                 ? (prm.stencil_variant == 2 ? 2 : 1) : 0;
   c.mixed = mixed ? 1 : 0;
   {
+    // EULER_TAIL=0: the three separate kernels (k_axpy, k_rb_forward_pipe, k_rb_backward_pipe) for A/B runs
+    const char* te = getenv("EULER_TAIL");
+    h->use_tail = c.fused == 1 && !mixed && !(te && atoi(te) == 0);
+  }
+  {
     // ring depths of the fp32 pipe kernels (A/B knobs: EULER_NS_MIXED for all three, or
     // EULER_NS_MIXED_F / _B / _KA), read once per handle
     static const char* const names[3] = {"EULER_NS_MIXED_F", "EULER_NS_MIXED_B", "EULER_NS_MIXED_KA"};
@@ -876,6 +901,13 @@ int euler_gpu_run_stage(euler_gpu* h, int stage, float dt) {
       if (c.mixed) return fail(EULER_E_UNSUPPORTED, "pcg_dtype=FP32 has no stand-alone apply_a (fused into the search update)");
       launch_pcg_reset(c); launch_tile_flags(c); launch_apply_a(c, false); break;
     case EULER_S_PRESSURE_UPDATE: launch_pressure_update(c, dt); h->max_valid = true; break;
+    case EULER_S_FUSED_TAIL:
+      if (c.fused != 1 || c.mixed)
+        return fail(EULER_E_UNSUPPORTED, "the fused tail is part of the fp64 fused red-black iteration (precon=REDBLACK, dot_mode=TREE, stencil_variant=0)");
+      launch_pcg_reset(c); launch_tile_flags(c); launch_rb_build(c);
+      launch_set_alpha(c, (double)dt);
+      launch_fused_tail(c, h->prm.tol, 2);
+      break;
     case EULER_S_EXTRAPOLATE_COLOR:
     case EULER_S_ADVECT_COLOR:
       if (!c.cr) return fail(EULER_E_INVALID, "handle was created without params.rainbow");
@@ -1087,7 +1119,7 @@ const char* euler_gpu_kernel_class_name(int i) {
       "maxsq", "advect_markers", "refresh_counts", "sources", "extrapolate_bounds",
       "advect_velocity", "build_rhs", "precon_build", "precon_apply", "apply_a", "axpy_norm",
       "update_search", "pressure_update", "misc", "fused_search_apply_a", "fused_axpy_forward",
-      "rb_forward", "rb_backward", "color_transport", "true_residual"};
+      "rb_forward", "rb_backward", "color_transport", "true_residual", "fused_tail"};
   return (i >= 0 && i < KC__COUNT) ? names[i] : nullptr;
 }
 

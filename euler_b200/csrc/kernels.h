@@ -13,7 +13,7 @@ enum KernelClass {
   KC_MAXSQ = 0, KC_ADVECT_MARKERS, KC_REFRESH_COUNTS, KC_SOURCES, KC_EXTRAPOLATE,
   KC_ADVECT_VELOCITY, KC_BUILD_RHS, KC_PRECON_BUILD, KC_PRECON_APPLY, KC_APPLY_A, KC_AXPY,
   KC_UPDATE_SEARCH, KC_PRESSURE_UPDATE, KC_MISC, KC_FUSED_A, KC_FUSED_B,
-  KC_PRECON_FWD, KC_PRECON_BWD, KC_COLOR, KC_RESIDUAL, KC__COUNT
+  KC_PRECON_FWD, KC_PRECON_BWD, KC_COLOR, KC_RESIDUAL, KC_FUSED_TAIL, KC__COUNT
 };
 
 struct Prof {
@@ -148,6 +148,10 @@ void launch_rb_forward(Ctx& c);                              //   q = L^-1 r
 void launch_rb_backward(Ctx& c, bool init);                  //   z = L^-T q (+ z.r)
 void launch_fused_search_apply(Ctx& c, bool init);            // s' = z + beta s ; A s' ; alpha
 void launch_fused_axpy_forward(Ctx& c, double tol);           // p, r', ||r'||inf, q = L^-1 r'
+// r' = r - alpha A s, p, ||r'||inf, q = L^-1 r', z = L^-T q, z.r', beta: one kernel (pcg_tail.cuh);
+// mode as launch_axpy
+void launch_fused_tail(Ctx& c, double tol, int mode);
+void launch_set_alpha(Ctx& c, double alpha);                 // parity hook: alpha = given, alpha_prev = 0, sigma = 1
 void launch_dist_alpha(Ctx& c, const double* gathered, int nranks);
 void launch_dist_beta(Ctx& c, const double* gathered, int nranks, bool init, double tol);
 void launch_copy_search(Ctx& c);                             // s = z

@@ -781,6 +781,8 @@ __global__ void __launch_bounds__(TW / C) k_fused_axpy_forward(
   });
 }
 
+#include "pcg_tail.cuh"
+
 constexpr int NS_KA = 4, NS_KB = 4;
 constexpr int CPT_F = 2, CPT_B = 2, CPT_KA = 4;   // cells per thread of the pipe kernels
 // mixed-precision (fp32 storage) instantiations: 4 cells = one 16 B vector per thread and plane;
@@ -1108,6 +1110,42 @@ void launch_fused_axpy_forward(Ctx& c, double tol) {
   c.launches += 1;
   double* t = c.r; c.r = c.r2; c.r2 = t;
   t = c.z; c.z = c.q; c.q = t;
+}
+
+// axpy + forward + backward of the fused red-black iteration as one kernel (pcg_tail.cuh):
+// reads r, A s (c.q), pc, s (, s_prev), p; writes r' into the twin plane (swapped in), p, z
+void launch_fused_tail(Ctx& c, double tol, int mode) {
+  ProfScope ps(c, KC_FUSED_TAIL);
+  const PV v = pview(c);
+  const size_t o = (size_t)(v.r - c.r);
+  DistArgs d;
+  memset(&d, 0, sizeof d);
+  if (c.p2p_mode == 2) {          // NVLink path: edge rows of z go straight into the neighbours' halo rows
+    d = c.dist;
+    d.depth = P2P_HALO_DEPTH;
+    const long lo = (long)((v.z - c.z) / c.g.pitch);
+    if (d.z_dn) d.z_dn += (lo + c.p2p_dn_own1 - c.own0) * (long)c.g.pitch;
+    if (d.z_up) d.z_up += (lo + c.p2p_up_own0 - c.own1) * (long)c.g.pitch;
+  }
+  static const int cpt = env_int("EULER_CPT_TAIL", 2);
+  static const int ns = env_int("EULER_NS_TAIL", 3);
+#define TAIL(N, C) { constexpr int smem = tail::smem_bytes<N>(); constexpr int threads = TW / C + 32; \
+    k_fused_tail<N, C><<<pcg_blocks(c, k_fused_tail<N, C>, smem, threads), threads, smem, c.stream>>>( \
+        v.g, TL, v.r, v.q, v.precon, v.fluid, v.s, c.s2 + o, v.p, c.r2 + o, v.z, c.partials, c.sc, tol, mode, \
+        dotflag(c), v.a0, v.a1, d); }
+  if (cpt == 4) { if (ns == 4) TAIL(4, 4) else TAIL(3, 4) }
+  else { if (ns == 4) TAIL(4, 2) else TAIL(3, 2) }
+#undef TAIL
+  c.launches += 1;
+  double* t = c.r; c.r = c.r2; c.r2 = t;
+}
+
+__global__ void k_set_alpha(DevScalars* sc, double alpha) {
+  sc->alpha = alpha; sc->alpha_prev = 0.0; sc->sigma = 1.0;
+}
+void launch_set_alpha(Ctx& c, double alpha) {
+  k_set_alpha<<<1, 1, 0, c.stream>>>(c.sc, alpha);
+  c.launches += 1;
 }
 
 void launch_dot_zr_exact(Ctx& c, bool init) {

@@ -261,8 +261,12 @@ static int wf_dbg() { static int v = -1; if (v < 0) { const char* e = getenv("EU
 // head start of a strip over the next one, in columns (see k_ic0_sweep); EULER_WF_LAG overrides
 static int wf_lag() { static int v = -1; if (v < 0) { const char* e = getenv("EULER_WF_LAG"); v = e ? atoi(e) : 64; } return v; }
 
+// progress flags AND the strip tickets restart at 0 for every sweep: a ticket that kept counting
+// would lose its alignment with n_strips when it wraps at 2^32 (n_strips is not a power of two),
+// and a strip could then be handed out before the one below it
 static void reset_wavefront(Ctx& c) {
   cudaMemsetAsync(c.wf_progress, 0, sizeof(unsigned int) * (size_t)c.n_strips, c.stream);
+  cudaMemsetAsync(c.sc->ticket, 0, sizeof(c.sc->ticket), c.stream);
 }
 
 void launch_ic0_build(Ctx& c) {

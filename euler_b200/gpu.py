@@ -24,7 +24,7 @@ PCG_FP64, PCG_FP32 = 0, 1
  F_R32, F_Z32, F_S32, F_Q32, F_PRECON32) = range(25)
 (S_ADVECT_MARKERS, S_REFRESH_COUNTS, S_SOURCES, S_EXTRAPOLATE, S_ADVECT_VELOCITY, S_PROJECT,
  S_BUILD_RHS, S_PRECONDITION, S_APPLY_A, S_PRESSURE_UPDATE, S_EXTRAPOLATE_COLOR,
- S_ADVECT_COLOR) = range(12)
+ S_ADVECT_COLOR, S_FUSED_TAIL) = range(13)
 
 _DTYPES = {F_U: np.float32, F_V: np.float32, F_UTMP: np.float32, F_VTMP: np.float32,
            F_SOLID: np.uint8, F_SOURCE: np.uint8, F_SINK: np.uint8, F_COUNT: np.uint8,

@@ -11,9 +11,10 @@ typedef struct header {
   char magic[8];
   int32_t nx, ny;
   uint32_t flags;
-  uint32_t pad0;
+  uint32_t mask_hash_lo;         /* FNV-1a 64 of the solid, source and sink planes the state belongs to */
   uint64_t n_markers, rng_state, frames;
-  int32_t source_exhausted, pad1;
+  int32_t source_exhausted;
+  uint32_t mask_hash_hi;         /* (0/0 in files written before the hash existed: not checked) */
 } header;
 
 typedef struct plane_desc { int field; size_t elem; } plane_desc;
@@ -28,6 +29,21 @@ enum { FLAG_COLOR = 1u, FLAG_NO_PRECON = 2u };
  * and bit 1 of the flags says so. */
 static int has_precon_plane(const euler_ckpt_api *a, euler_gpu *sim, void *buf, size_t cells) {
   return a->get(sim, EULER_F_PRECON, buf, cells * 8) == 0;
+}
+
+/* The dynamic state only makes sense on the static masks it was computed with (markers inside
+ * another scenario's solids, sources elsewhere): the header carries their hash. */
+static int mask_hash(const euler_ckpt_api *a, euler_gpu *sim, void *buf, size_t cells, uint64_t *out) {
+  static const int planes[3] = {EULER_F_SOLID, EULER_F_SOURCE, EULER_F_SINK};
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (int i = 0; i < 3; ++i) {
+    const int rc = a->get(sim, planes[i], buf, cells);
+    if (rc) return rc;
+    const unsigned char *b = buf;
+    for (size_t k = 0; k < cells; ++k) { h ^= b[k]; h *= 0x100000001b3ull; }
+  }
+  *out = h ? h : 1;
+  return 0;
 }
 
 int euler_checkpoint_save(const euler_ckpt_api *a, euler_gpu *sim, int nx, int ny, int rainbow, const char *path) {
@@ -46,6 +62,9 @@ int euler_checkpoint_save(const euler_ckpt_api *a, euler_gpu *sim, int nx, int n
   if (!buf) return -1;
   const int precon = has_precon_plane(a, sim, buf, cells);
   if (!precon) h.flags |= FLAG_NO_PRECON;
+  uint64_t mh = 0;
+  if ((rc = mask_hash(a, sim, buf, cells, &mh))) { free(buf); return -rc; }
+  h.mask_hash_lo = (uint32_t)mh; h.mask_hash_hi = (uint32_t)(mh >> 32);
   FILE *f = fopen(path, "wb");
   if (!f) { free(buf); return -1; }
   int err = fwrite(&h, sizeof h, 1, f) != 1;
@@ -79,11 +98,23 @@ int euler_checkpoint_load(const euler_ckpt_api *a, euler_gpu *sim, int nx, int n
   void *buf = malloc(big ? big : 1);
   if (!buf) { fclose(f); return -1; }
   int rc = 0, err = 0;
-  /* the plane is restored when both the file and the handle have it */
-  const int precon = !(h.flags & FLAG_NO_PRECON) && has_precon_plane(a, sim, buf, cells);
+  const uint64_t want = ((uint64_t)h.mask_hash_hi << 32) | h.mask_hash_lo;
+  if (want) {                                  /* a state of another scenario of the same size: refuse */
+    uint64_t mh = 0;
+    if ((rc = mask_hash(a, sim, buf, cells, &mh))) { free(buf); fclose(f); return -rc; }
+    if (mh != want) { free(buf); fclose(f); return -2; }
+  }
+  /* the plane is restored when both the file and the handle have it; a handle that has it while
+   * the file does not starts from the zero-initialised g_precon of a fresh run (main.c:577): the
+   * IC(0) iterates depend on what the plane holds at non-fluid cells */
+  const int handle_precon = has_precon_plane(a, sim, buf, cells);
+  const int precon = !(h.flags & FLAG_NO_PRECON) && handle_precon;
   for (size_t i = 0; !err && !rc && i < sizeof BASE / sizeof BASE[0]; ++i) {
     err = fread(buf, BASE[i].elem, cells, f) != cells;
-    if (BASE[i].field == EULER_F_PRECON && !precon) continue;
+    if (BASE[i].field == EULER_F_PRECON && !precon) {
+      if (!err && handle_precon) { memset(buf, 0, cells * 8); rc = a->set(sim, EULER_F_PRECON, buf, cells * 8); }
+      continue;
+    }
     if (!err) rc = a->set(sim, BASE[i].field, buf, cells * BASE[i].elem);
   }
   for (size_t i = 0; !err && !rc && rainbow && i < 3; ++i) {

@@ -145,7 +145,36 @@ static void usage(const char *argv0) {
           argv0);
 }
 
+/* Argument syntax, checked BEFORE the CUDA library is bound (usage and "Unrecognized input" errors
+ * must not need a loadable libeuler_gpu.so): unknown options, options without their value and
+ * more than one scenario file are errors, like the reference's parse_args (main.c:982-1002), which
+ * rejects every token it does not know. */
+static int check_args(int argc, char **argv) {
+  static const char *const flags[] = {"--rainbow", "--headless", "--print", "--exact-dot", "--no-p2p", NULL};
+  static const char *const valued[] = {"--frames", "--device", "--ranks", "--rank", "--rendezvous", "--synthetic",
+                                       "--load", "--save", "--export", "--grid", "--precon", "--pcg-dtype",
+                                       "--markers", NULL};
+  int files = 0, synthetic = 0;
+  for (int i = 1; i < argc; ++i) {
+    const char *s = argv[i];
+    int known = 0;
+    for (int k = 0; flags[k] && !known; ++k) known = !strcmp(s, flags[k]);
+    for (int k = 0; valued[k] && !known; ++k)
+      if (!strcmp(s, valued[k])) {
+        if (i + 1 >= argc) { usage(argv[0]); return 1; }
+        if (!strcmp(s, "--synthetic")) synthetic = 1;
+        ++i; known = 1;
+      }
+    if (known) continue;
+    if (s[0] == '-' && s[1] == '-') { fprintf(stderr, "Unrecognized input: %s\n", s); return 1; }   /* main.c:995 */
+    if (++files > 1) { fprintf(stderr, "Unrecognized input: %s\n", s); return 1; }
+  }
+  if (!files && !synthetic) { usage(argv[0]); return 1; }                                            /* main.c:986-989 */
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (check_args(argc, argv)) return 1;
   const char *file = NULL, *synthetic = NULL, *load_path = NULL, *save_path = NULL, *export_path = NULL;
   int headless = 0, frames = -1, nx = 100, ny = 40, do_print = 0;
   int ranks = 1, rank = 0, no_p2p = 0, device_given = 0;
@@ -220,8 +249,9 @@ int main(int argc, char **argv) {
     FILE *f = fopen(file, "rb");
     rc = -2;
     if (f) {
-      fseek(f, 0, SEEK_END); long len = ftell(f); fseek(f, 0, SEEK_SET);
-      char *raw = malloc((size_t)len + 1);
+      long len = -1;
+      if (fseek(f, 0, SEEK_END) == 0) len = ftell(f);
+      char *raw = (len >= 0 && fseek(f, 0, SEEK_SET) == 0) ? malloc((size_t)len + 1) : NULL;
       if (raw && (len == 0 || fread(raw, (size_t)len, 1, f) == 1)) {
         long rlen = 0;
         char *text = euler_scenario_resample(raw, len, nx - 2, ny - 2, &rlen);
@@ -254,22 +284,25 @@ int main(int argc, char **argv) {
     return 1;
   }
   uint8_t *count = calloc((size_t)nx * ny, 1);     /* a slab handle fills in only the rows it owns */
+  uint64_t run_key = 0;                             /* of this run's rendezvous files */
   if (!count) return 1;
   if (ranks > 1) {
     /* communicator id from rank 0, then (NVLink path) everybody's peer handles, through DIR */
     unsigned char uid[128];
-    if (rank == 0 && (a.comm_unique_id(uid) || euler_rdv_publish(rdv, "uid", 0, uid, sizeof uid))) {
-      fprintf(stderr, "cannot publish the communicator id: %s\n", a.last_error());
+    if (rank == 0 && a.comm_unique_id(uid)) { fprintf(stderr, "cannot make the communicator id: %s\n", a.last_error()); return 1; }
+    /* token-echo handshake (rendezvous.h): DIR may hold files of earlier runs */
+    const int hrc = euler_rdv_handshake(rdv, rank, ranks, uid, sizeof uid, &run_key, 120);
+    if (hrc) {
+      fprintf(stderr, hrc == -2 ? "rendezvous in %s timed out: not all %d ranks showed up\n" : "rendezvous in %s failed (I/O)\n", rdv, ranks);
       return 1;
     }
-    if (euler_rdv_fetch(rdv, "uid", 0, uid, sizeof uid, 120)) { fprintf(stderr, "rank 0 never published the communicator id in %s\n", rdv); return 1; }
     if (a.comm_init(sim, rank, ranks, uid)) { fprintf(stderr, "comm_init: %s\n", a.last_error()); return 1; }
     if (!no_p2p) {
       unsigned char *blobs = malloc((size_t)ranks * 256);
       if (!blobs) return 1;
       int bad = a.comm_p2p_export(sim, blobs + (size_t)rank * 256) != 0;
-      if (!bad) bad = euler_rdv_publish(rdv, "blob", rank, blobs + (size_t)rank * 256, 256) != 0;
-      for (int r = 0; r < ranks && !bad; ++r) bad = euler_rdv_fetch(rdv, "blob", r, blobs + (size_t)r * 256, 256, 120) != 0;
+      if (!bad) bad = euler_rdv_publish_keyed(rdv, "blob", rank, run_key, blobs + (size_t)rank * 256, 256) != 0;
+      for (int r = 0; r < ranks && !bad; ++r) bad = euler_rdv_fetch_keyed(rdv, "blob", r, run_key, blobs + (size_t)r * 256, 256, 120) != 0;
       if (!bad) bad = a.comm_p2p_import(sim, blobs) != 0;
       free(blobs);
       if (bad) { fprintf(stderr, "peer-to-peer set-up failed: %s\n", a.last_error()); return 1; }
@@ -338,15 +371,16 @@ int main(int argc, char **argv) {
      * global marker count, the others are done */
     const size_t row0 = (size_t)prm.slab_row0 * nx, nrow = (size_t)prm.slab_rows * nx;
     struct { int32_t row0, rows; uint64_t markers; } info = {prm.slab_row0, prm.slab_rows, st.n_markers};
-    if (euler_rdv_publish(rdv, "info", rank, &info, sizeof info) || euler_rdv_publish(rdv, "count", rank, count + row0, nrow)) {
+    if (euler_rdv_publish_keyed(rdv, "info", rank, run_key, &info, sizeof info) ||
+        euler_rdv_publish_keyed(rdv, "count", rank, run_key, count + row0, nrow)) {
       fprintf(stderr, "cannot publish the results of rank %d\n", rank);
       return 1;
     }
     if (rank != 0) { free(count); a.destroy(sim); euler_scenario_free(&scn); return 0; }
     for (int r = 1; r < ranks; ++r) {
-      if (euler_rdv_fetch(rdv, "info", r, &info, sizeof info, 600) ||
+      if (euler_rdv_fetch_keyed(rdv, "info", r, run_key, &info, sizeof info, 600) ||
           info.row0 < 0 || info.rows < 0 || info.row0 + info.rows > ny ||
-          euler_rdv_fetch(rdv, "count", r, count + (size_t)info.row0 * nx, (size_t)info.rows * nx, 600)) {
+          euler_rdv_fetch_keyed(rdv, "count", r, run_key, count + (size_t)info.row0 * nx, (size_t)info.rows * nx, 600)) {
         fprintf(stderr, "rank %d never delivered its rows\n", r);
         return 1;
       }

@@ -134,6 +134,10 @@ enum euler_stage {
   EULER_S_PRESSURE_UPDATE,    /* clamp p, subtract gradient    main.c:769-805 */
   EULER_S_EXTRAPOLATE_COLOR,  /* --rainbow: extrapolate(g_r|g_g|g_b, P)   main.c:859-863 */
   EULER_S_ADVECT_COLOR,       /* --rainbow: advect_p x3 + plane copies    main.c:873-882 */
+  EULER_S_FUSED_TAIL,         /* parity hook of the fused red-black iteration's second kernel (not a
+                                 reference stage): with alpha = `dt`, from R = r, Q = A s, S = s, P = p
+                                 and the current count plane: R <- r - alpha A s, P <- p + alpha s
+                                 (main.c:753-754), Z <- M^-1 R (red-black IC(0)) in ONE launch */
   EULER_S__COUNT
 };
 

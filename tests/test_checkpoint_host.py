@@ -28,8 +28,10 @@ class FakeSim:
     DT = {G.F_U: np.float32, G.F_V: np.float32, G.F_COUNT: np.uint8, G.F_PREV_COUNT: np.uint8,
           G.F_PRECON: np.float64, G.F_CR: np.float32, G.F_CG: np.float32, G.F_CB: np.float32}
 
-    def __init__(self, nx, ny, seed, rainbow=False, precon=True, n_markers=37):
+    def __init__(self, nx, ny, seed, rainbow=False, precon=True, n_markers=37, mask_seed=0):
         rng = np.random.default_rng(seed)
+        mrng = np.random.default_rng(1000 + mask_seed)      # the static masks = "the scenario"
+        self.masks = {f: (mrng.random((ny, nx)) < 0.2).astype(np.uint8) for f in (G.F_SOLID, G.F_SOURCE, G.F_SINK)}
         fields = [G.F_U, G.F_V, G.F_COUNT, G.F_PREV_COUNT] + ([G.F_PRECON] if precon else []) + \
                  ([G.F_CR, G.F_CG, G.F_CB] if rainbow else [])
         self.planes = {}
@@ -47,6 +49,8 @@ class FakeSim:
             src = self.markers
         elif field in self.planes:
             src = self.planes[field]
+        elif field in self.masks:
+            src = self.masks[field]
         else:
             return -1                                   # EULER_E_INVALID: no such plane on this handle
         if n != src.nbytes:
@@ -112,6 +116,8 @@ def test_refusals(lib, tmp_path):
     bad = tmp_path / "bad.ck"
     bad.write_bytes(b"NOTEULER" + b"\0" * 64)
     assert lib.euler_checkpoint_load(C.byref(a.api), None, nx, ny, 0, str(bad).encode()) == -1
+    # same size, another scenario (other static masks): the dynamic state does not belong there
+    assert lib.euler_checkpoint_load(C.byref(FakeSim(nx, ny, 4, mask_seed=1).api), None, nx, ny, 0, path) == -2
     cut = tmp_path / "cut.ck"
     cut.write_bytes(open(path.decode(), "rb").read()[:200])       # truncated planes
     assert lib.euler_checkpoint_load(C.byref(FakeSim(nx, ny, 5).api), None, nx, ny, 0, str(cut).encode()) == -1
@@ -127,11 +133,11 @@ def test_handles_without_the_fp64_precon_plane(lib, tmp_path):
     assert lib.euler_checkpoint_save(C.byref(mixed.api), None, nx, ny, 0, p_mixed) == 0
     assert lib.euler_checkpoint_save(C.byref(full.api), None, nx, ny, 0, p_full) == 0
     assert os.path.getsize(p_mixed) == os.path.getsize(p_full)       # fixed layout (same marker count)
-    # mixed file -> fp64 handle: its own precon plane is left alone
+    # mixed file -> fp64 handle: the handle's g_precon restarts from zero like a fresh run's
+    # (main.c:577) instead of keeping whatever it held (the IC(0) iterates depend on it)
     tgt = FakeSim(nx, ny, 8)
-    keep = tgt.planes[G.F_PRECON].copy()
     assert lib.euler_checkpoint_load(C.byref(tgt.api), None, nx, ny, 0, p_mixed) == 0
-    assert _same(mixed, tgt) and np.array_equal(tgt.planes[G.F_PRECON], keep)
+    assert _same(mixed, tgt) and not tgt.planes[G.F_PRECON].any()
     # fp64 file -> mixed handle
     tgt = FakeSim(nx, ny, 9, precon=False)
     assert lib.euler_checkpoint_load(C.byref(tgt.api), None, nx, ny, 0, p_full) == 0

@@ -279,3 +279,33 @@ def test_advect_markers_reference_mode_stage():
     o2.advect_markers(0.3)
     assert not same_bits(o2.markers, o.markers)
     g.close()
+
+
+@pytest.mark.parametrize("name,nx,ny,how", CASES + [("block", 1100, 300, 3), ("waterfall", 2000, 200, 4)])
+def test_fused_tail_bit_exact(name, nx, ny, how):
+    """The second kernel of the fused red-black iteration (pcg_tail.cuh: r' = r - alpha A s,
+    p += alpha s, z = M^-1 r' in ONE launch, intermediates in shared memory) against the CPU
+    mirror's three separate steps, from identical planes: r', p and z bit for bit.  The wide cases
+    span several 512-column tiles and tile rows (halo columns / rows between blocks)."""
+    o, g, G = _prepare(name, nx, ny, how, 1)
+    dt = o.calculate_timestep(0.1)
+    o.substep(dt); g.substep(dt)
+    g.set(G.F_COUNT, o.count)
+    fl = o.count != 0
+    rng = np.random.default_rng(7)
+    r = rng.standard_normal((ny, nx)); a_s = rng.standard_normal((ny, nx))
+    s = rng.standard_normal((ny, nx)); p = rng.standard_normal((ny, nx))
+    alpha = 0.3125 + 2.0 ** -20                       # exactly representable in fp32 (the hook's dt argument)
+    # a_diag of the current classification (the factor is built from it)
+    g.set(G.F_UTMP, o.utmp); g.set(G.F_VTMP, o.vtmp)
+    o.build_rhs(dt); g.run_stage(G.S_BUILD_RHS, dt)
+    g.set(G.F_R, r); g.set(G.F_Q, a_s); g.set(G.F_S, s); g.set(G.F_P, p)
+    g.run_stage(G.S_FUSED_TAIL, alpha)
+    r_new = np.where(fl, r + a_s * -alpha, r)         # fmadd(z, -alpha, r), main.c:754 (no FMA contraction)
+    p_new = np.where(fl, p + s * alpha, p)            # fmadd(s, alpha, p), main.c:753
+    z = np.zeros_like(r)
+    o.apply_preconditioner(np.ascontiguousarray(r_new), z)
+    assert same_bits(g.get(G.F_R)[fl], r_new[fl])
+    assert same_bits(g.get(G.F_P)[fl], p_new[fl])
+    assert same_bits(g.get(G.F_Z)[fl], z[fl])
+    g.close()

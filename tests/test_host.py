@@ -166,6 +166,59 @@ def test_file_rendezvous(tmp_path):
     assert L.euler_rdv_publish(d, b"empty", 1, None, 0) == 0 and L.euler_rdv_fetch(d, b"empty", 1, None, 0, 1) == 0
 
 
+def _handshake_proc(d, rank, ranks, uid, delay, out):
+    import ctypes as C
+    import time
+    from euler_b200.scenario import _lib
+    L = _lib()
+    L.euler_rdv_handshake.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_int]
+    time.sleep(delay)
+    buf = C.create_string_buffer(uid if rank == 0 else b"\0" * 128, 128)
+    key = C.c_uint64(0)
+    rc = L.euler_rdv_handshake(d.encode(), rank, ranks, buf, 128, C.byref(key), 20)
+    out.put((rank, rc, buf.raw, key.value))
+
+
+def test_rendezvous_handshake_ignores_a_stale_directory(tmp_path):
+    """Two runs, one after the other, in the SAME directory (a reused DIR let ranks
+    pick up the previous run's communicator id and hang in ncclCommInitRank): in the second run the
+    non-zero ranks start BEFORE rank 0, with the first run's answer / hello / ack files still there,
+    and must end up with the second run's id and key; keyed files of the first run are ignored."""
+    import ctypes as C
+    import multiprocessing as mp
+    from euler_b200.scenario import _lib
+    L = _lib()
+    L.euler_rdv_publish_keyed.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint64, C.c_void_p, C.c_size_t]
+    L.euler_rdv_fetch_keyed.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint64, C.c_void_p, C.c_size_t, C.c_int]
+    d = str(tmp_path)
+    ctx = mp.get_context("spawn")
+    keys = []
+    for run, delays in enumerate([(0.0, 0.1, 0.2), (0.6, 0.0, 0.0)]):
+        uid = bytes([run + 1]) * 128
+        out = ctx.Queue()
+        procs = [ctx.Process(target=_handshake_proc, args=(d, r, 3, uid, delays[r], out)) for r in range(3)]
+        for p in procs:
+            p.start()
+        res = sorted(out.get(timeout=60) for _ in procs)
+        for p in procs:
+            p.join()
+        assert [x[1] for x in res] == [0, 0, 0]
+        assert all(x[2] == uid for x in res), "a rank accepted another run's communicator id"
+        assert len({x[3] for x in res}) == 1
+        keys.append(res[0][3])
+        payload = bytes([0x40 + run]) * 16
+        assert L.euler_rdv_publish_keyed(d.encode(), b"info", 1, keys[-1], payload, 16) == 0
+    assert keys[0] != keys[1]
+    buf = C.create_string_buffer(16)
+    assert L.euler_rdv_fetch_keyed(d.encode(), b"info", 1, keys[1], buf, 16, 1) == 0 and buf.raw == b"\x41" * 16
+    assert L.euler_rdv_fetch_keyed(d.encode(), b"info", 1, keys[0], buf, 16, 1) == -2     # first run's file is gone / not ours
+    # a rank that never shows up: timeout, not a hang
+    L.euler_rdv_handshake.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_int]
+    key = C.c_uint64(0)
+    lone = C.create_string_buffer(b"\x07" * 128, 128)
+    assert L.euler_rdv_handshake(str(tmp_path / ".").encode(), 0, 4, lone, 128, C.byref(key), 1) == -2
+
+
 def test_host_program_rank_arguments():
     """bin/euler-gpu refuses an incomplete --ranks set-up before it touches a GPU."""
     import os
