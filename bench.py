@@ -47,6 +47,8 @@ ALG_BYTES_PER_CELL = {
     "rb_backward": 33.0,        # R q,pc,r 24 + fluid 1 + W z 8 (fused with z.r)
     "fused_search_apply_a": 34.0,  # R z,s 16 + fluid,a_diag 2 + W s',A s' 16
     "fused_axpy_forward": 65.0,    # R s,As,p,r,pc 40 + fluid 1 + W p,r',q 24
+    "fused_tail": 57.0,            # axpy + forward + backward in one kernel (pcg_tail.cuh): odd launches
+                                   # R r,As,pc 24 + fluid 1 + W r',z 16 = 41, even ones + R s',s,p 24 + W p 8 = 73
     "update_search": 24.0,      # R z,s 16 + W s 8
     "build_rhs": 27.0,          # R utmp,vtmp 8 + fluid,solid 2, W b 8 + a_diag 1 + p=0 8 (main.c:739)
     "pressure_update": 26.0,
@@ -62,7 +64,7 @@ DRY_BYTES_PER_CELL = {"build_rhs": 17.0, "pressure_update": 9.0, "extrapolate_bo
                       "advect_velocity": 9.0}
 ALG_BYTES_PER_MARKER = {"advect_markers": 16.0}
 PCG_KERNELS = ("apply_a", "axpy_norm", "precon_apply", "update_search", "rb_forward", "rb_backward",
-               "fused_search_apply_a", "fused_axpy_forward", "true_residual")
+               "fused_search_apply_a", "fused_axpy_forward", "true_residual", "fused_tail")
 # --pcg-dtype fp32 (euler_params.pcg_dtype = FP32, not the headline configuration): r, z, s, q,
 # A s and the preconditioner diagonal are fp32 planes, p stays fp64 — DESIGN.md §9 row 4
 ALG_BYTES_PER_CELL_FP32 = {
@@ -85,25 +87,41 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def roofline_report(prof, alg_bytes, active_cells, cells_local, n_markers, headline, mixed):
+def roofline_report(prof, alg_bytes, active_cells, cells_local, n_markers, headline, mixed,
+                    grid_cells=None, wet_cells=None):
     """Per-kernel achieved GB/s of ALGORITHMIC bytes and the `roofline` object of the dominant
-    kernel.  `prof` = {kernel class: (summed ms, launches)} from the library's CUDA-event timers;
-    PCG kernels stream only the tiles that contain fluid (like the reference, which touches
-    only is_fluid cells): their unit count is `active_cells`; grid stages stream every stored
-    cell (`cells_local`), marker kernels every marker.  `headline`: the workload the committed
-    ncu capture (profiles/ncu_traffic.json) was taken on."""
+    kernel.  `prof` = {kernel class: (summed ms, launches)} from the library's CUDA-event timers.
+    Units per launch: PCG kernels stream the tiles that contain fluid (like the reference, which
+    touches only is_fluid cells): `active_cells`; marker kernels every marker; the grid stages the
+    tiles of their list (`grid_cells`: tiles with fluid in or next to them within three sub-steps),
+    where a quad without fluid in its neighbourhood moves only the fluid mask and the zeros it
+    writes — so their bytes are B/cell x wet cells + (mask + zero store) x the other streamed
+    cells, what the kernel really has to move (`frac`); the dense figure SURVEY 8d defines
+    (B/cell x every stored cell, moved or not) is kept as `frac_dense` for reference only.
+    `headline`: the workload the committed ncu capture (profiles/ncu_traffic.json) was taken on."""
     peak, peak_src = peaks()
     total_ms = sum(v[0] for v in prof.values())
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
     roof = None
     kernels = {}
+    grid_cells = cells_local if grid_cells is None else grid_cells
+    wet = min(active_cells if wet_cells is None else wet_cells, grid_cells)
+    units_of = {}
     for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        b_dense = None
         if name in PCG_KERNELS and name in alg_bytes:
             b = alg_bytes[name] * active_cells
+            units_of[name] = active_cells
+        elif name in DRY_BYTES_PER_CELL:
+            b = alg_bytes[name] * wet + DRY_BYTES_PER_CELL[name] * (grid_cells - wet)
+            b_dense = alg_bytes[name] * cells_local
+            units_of[name] = grid_cells
         elif name in alg_bytes:
             b = alg_bytes[name] * cells_local
+            units_of[name] = cells_local
         elif name in ALG_BYTES_PER_MARKER:
             b = ALG_BYTES_PER_MARKER[name] * n_markers
+            units_of[name] = n_markers
         else:
             b = None
         avg = kms / cnt
@@ -111,10 +129,9 @@ def roofline_report(prof, alg_bytes, active_cells, cells_local, n_markers, headl
                          "gbs": round(b / avg / 1e6, 1) if b else None,
                          "frac": round(b / avg / 1e6 / peak, 4) if b else None,
                          "frac_nominal": round(b / avg / 1e6 / NOMINAL_HBM_GBS, 4) if b else None}
-        if name in DRY_BYTES_PER_CELL:
-            wet = min(active_cells, cells_local)
-            bt = alg_bytes[name] * wet + DRY_BYTES_PER_CELL[name] * (cells_local - wet)
-            kernels[name]["gbs_touched"] = round(bt / avg / 1e6, 1)
+        if b_dense:
+            kernels[name]["frac_dense"] = round(b_dense / avg / 1e6 / peak, 4)
+            kernels[name]["bytes_per_launch"] = b
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
@@ -125,7 +142,7 @@ def roofline_report(prof, alg_bytes, active_cells, cells_local, n_markers, headl
         pass
     if dom and kernels[dom[0]]["gbs"]:
         k = kernels[dom[0]]
-        units = active_cells if dom[0] in PCG_KERNELS else cells_local
+        units = units_of[dom[0]]
         roof = {"kernel": dom[0], "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": k["frac"], "traffic": traffic, "peak_source": peak_src,
                 "peak_nominal": NOMINAL_HBM_GBS, "frac_nominal": k["frac_nominal"],
@@ -324,6 +341,7 @@ def run_gpu(args):
     n_markers = int(st1.n_markers)
     dev_bytes = int(st1.device_bytes)
     active_cells = int(st1.active_cells)
+    grid_cells = int(st1.grid_cells)
     # ---- end to end through the C-ABI from host buffers (e2e) ------------------------
     # timed region: euler_gpu_reinit (== sim_init's hand-over: H2D of the three masks and the
     # seeded markers from pinned host arrays into the existing handle), K sub-steps, and after
@@ -413,7 +431,7 @@ def run_gpu(args):
     if rank == 0:
         kernels, roof = roofline_report(prof, alg_bytes, active_cells, cells_local, n_markers,
                                         headline=(n == 16384 and world == 1 and args.scenario == "basic-fill"),
-                                        mixed=mixed)
+                                        mixed=mixed, grid_cells=grid_cells, wet_cells=int(chk.fluid_cells))
         value = cells * args.steps / (ms_max * 1e-3)
         line = {
             "metric": "MAC cell-updates/s", "value": value, "unit": "cell-updates/s",
@@ -432,6 +450,8 @@ def run_gpu(args):
                        "preset": args.config if (args.scenario, n) == CONFIGS[args.config][:2] else None,
                        "grid": [n, n], "markers": n_markers, "active_cells": active_cells,
                        "active_fraction": round(active_cells_all / cells, 4),
+                       "fluid_cells": check["fluid_cells"], "fluid_fraction": round(check["fluid_cells"] / cells, 4),
+                       "grid_stage_cells_rank0": grid_cells,
                        "markers_migrated_per_step": round(check["markers_migrated_total"] / max(1, int(st_end.substeps)), 1),
                        "parallelism": "single GPU" if world == 1 else
                                       "%d row slabs balanced by fluid cells (rank 0: %d rows), NCCL halo exchange + marker migration, %s" % (world, rows, "NCCL per-iteration exchanges" if args.no_p2p else "per-iteration exchanges by NVLink peer stores (CUDA IPC)"),
@@ -451,11 +471,44 @@ def run_gpu(args):
             "check": check,
             "clocks": clocks,
         }
+        if world == 1 and not args.no_tol_study:
+            ts = tol_study(G, Scenario, [int(x) for x in args.tol_study.split(",") if x], local)
+            line["iters_to_tol"] = {k: {m: v[m]["iters"] for m in v} for k, v in ts.items()}
+            line["ms_to_tol"] = {k: {m: v[m]["ms"] for m in v} for k, v in ts.items()}
+            line["tol_study"] = {"what": "first projection of basic-fill NxN, iteration cap raised until ||r||inf <= 1e-6f "
+                                         "(main.c:736): ic0 = the reference's natural-order IC(0) (wavefront kernels), "
+                                         "rb = red-black IC(0); wall-clock ms of the whole solve on this GPU",
+                                 "detail": ts}
         if not args.no_cpu and world >= 1:
             line["cpu_baseline"] = cpu_baseline(args, seconds=args.cpu_seconds)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def tol_study(G, Scenario, sizes, device):
+    """Time-to-tolerance of both preconditioners (PCG iters/s is not time-to-solution):
+    the first projection of basic-fill (hydrostatic column) with the iteration cap raised until
+    ||r||inf <= 1e-6f (main.c:736, 756), natural-order IC(0) by wavefront (the reference's algorithm)
+    and red-black IC(0); iterations and wall-clock milliseconds of the solve on this GPU."""
+    out = {}
+    for n in sizes:
+        scn = Scenario(scenario_text("basic-fill", n, n), n, n, row_major_markers=True)
+        res = {}
+        for name, precon, every in (("rb", G.PRECON_REDBLACK, 50), ("ic0", G.PRECON_IC0_WAVEFRONT, 16)):
+            sim = G.EulerGpu.from_scenario(scn, precon=precon, marker_mode=G.MARKERS_FAST, device=device,
+                                           max_iterations=100000, pcg_check_every=every)
+            dt = sim.calculate_timestep(0.1)
+            for st in (G.S_ADVECT_MARKERS, G.S_REFRESH_COUNTS, G.S_SOURCES, G.S_EXTRAPOLATE, G.S_ADVECT_VELOCITY):
+                sim.run_stage(st, dt)
+            t0 = time.perf_counter()
+            sim.run_stage(G.S_PROJECT, dt)
+            ms = (time.perf_counter() - t0) * 1e3
+            stt = sim.stats()
+            res[name] = {"iters": int(stt.last_iterations), "ms": round(ms, 2), "residual": float(stt.last_residual)}
+            sim.close()
+        out[str(n)] = res
+    return out
 
 
 # ------------------------------------------------------------------- reference arm ----
@@ -544,6 +597,8 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=1024)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tol-study", default="1024,4096", help="grid sizes of the time-to-tolerance study (N=1 only)")
+    ap.add_argument("--no-tol-study", action="store_true")
     ap.add_argument("--no-kernel-timers", action="store_true",
                     help="no per-launch CUDA events inside the timed region (no roofline/kernels objects): "
                          "measures what the events themselves cost")

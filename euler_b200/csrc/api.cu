@@ -210,6 +210,7 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
   if ((rc = upload_plane(h, c.source, source, 1))) return rc;
   if ((rc = upload_plane(h, c.sink, sink, 1))) return rc;
 
+  c.gt_hist = c.gt_sparse = c.gt_prev_sparse = 0;           // the grid stages start over all tiles
   memset(h->host_sc, 0, sizeof(DevScalars));
   h->host_sc->n_markers = h->slab ? 0 : n_markers;
   h->host_sc->rng_state = rng_state;
@@ -372,6 +373,7 @@ int run_substep(euler_gpu* h, float dt) {
   launch_extrapolate_color(c);                               // main.c:859-863 (--rainbow)
   launch_sources(c);                                         // main.c:864
   launch_source_colors(c, (unsigned int)h->frames);          // main.c:283, 292-294 (--rainbow)
+  launch_grid_tiles(c);                                      // which tiles the grid stages stream
   prof_mark(h, 1);
   launch_extrapolate(c);                                     // main.c:865-868
   { float* t = c.u; c.u = c.uext; c.uext = t; t = c.v; c.v = c.vext; c.vext = t; }
@@ -382,6 +384,7 @@ int run_substep(euler_gpu* h, float dt) {
   if (rc) return rc;
   prof_mark(h, 3);
   h->substeps++;
+  c.gt_prev_sparse = c.gt_sparse;
   if (h->profiling) {
     CU(cudaEventSynchronize(h->ev[3]));
     CU(cudaStreamSynchronize(c.stream));
@@ -551,6 +554,7 @@ int run_substep_dist(euler_gpu* h, float dt) {
     launch_sources(c);
   }
   CM(comm_halo(c, h->cm, c.count, 1, SLAB_HALO));    // classification of the neighbours' edge rows
+  launch_grid_tiles(c);
   prof_mark(h, 1);
   launch_extrapolate(c);
   { float* t = c.u; c.u = c.uext; c.uext = t; t = c.v; c.v = c.vext; c.vext = t; }
@@ -560,6 +564,7 @@ int run_substep_dist(euler_gpu* h, float dt) {
   if (rc) return rc;
   prof_mark(h, 3);
   h->substeps++;
+  c.gt_prev_sparse = c.gt_sparse;
   if (h->profiling) {
     CU(cudaEventSynchronize(h->ev[3]));
     CU(cudaStreamSynchronize(c.stream));
@@ -794,6 +799,10 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   c.n_strips = (ny_loc - 2 + 31) / 32;
   c.n_partials = 65536 > (size_t)c.n_strips ? 65536 : (size_t)c.n_strips;
   (void)nblk2d;
+  c.gt_tx = (c.g.pitch + GT_W - 1) / GT_W; c.gt_ty = (c.g.ny + GT_H - 1) / GT_H;
+  for (int i = 0; i < 3; ++i) TRY(alloc_array(h, &c.gt_flags[i], (size_t)c.gt_tx * c.gt_ty));
+  TRY(alloc_array(h, &c.gt_list, (size_t)c.gt_tx * c.gt_ty));
+  c.gt_hist = c.gt_sparse = c.gt_prev_sparse = 0;
   TRY(alloc_array(h, &c.tile_active, (size_t)pcg_tile_count(c.g)));
   TRY(alloc_array(h, &c.tile_list, (size_t)pcg_tile_count(c.g)));
   TRY(alloc_array(h, &c.partials, c.n_partials));
@@ -878,6 +887,7 @@ int euler_gpu_run_stage(euler_gpu* h, int stage, float dt) {
   ENTER(h);
   if (h->slab) return fail(EULER_E_UNSUPPORTED, "run_stage is a single-GPU parity hook");
   Ctx& c = h->c;
+  c.gt_hist = c.gt_sparse = c.gt_prev_sparse = 0;            // single stages always stream every tile
   switch (stage) {
     case EULER_S_ADVECT_MARKERS: launch_advect_markers(c, dt, h->prm.marker_mode); break;
     case EULER_S_REFRESH_COUNTS: launch_refresh_counts(c); break;
@@ -989,6 +999,9 @@ int euler_gpu_set(euler_gpu* h, int field, const void* src, size_t bytes) {
   ENTER(h);
   if (!src && bytes) return fail(EULER_E_INVALID, "src is NULL");
   const Grid& g = h->c.g;
+  // the caller may put values (or markers) where the grid stages' tile list assumes zeros: the
+  // next sub-steps stream every tile again until the list's memory is rebuilt
+  h->c.gt_hist = h->c.gt_sparse = h->c.gt_prev_sparse = 0;
   if (field == EULER_F_MARKERS) {
     if (bytes % sizeof(float2)) return fail(EULER_E_INVALID, "markers: size not a multiple of 8");
     const size_t n = bytes / sizeof(float2);
@@ -1062,7 +1075,8 @@ int euler_gpu_stats(euler_gpu* h, euler_stats* out) {
   out->ms_markers = h->ms_markers; out->ms_grid = h->ms_grid; out->ms_project = h->ms_project;
   out->active_cells = (uint64_t)h->host_sc->active_tiles * (uint64_t)pcg_tile_cells(h->c);
   out->markers_migrated = h->markers_migrated;
-  out->grid_cells = (uint64_t)h->c.g.ny * (uint64_t)h->c.g.pitch;
+  out->grid_cells = h->c.gt_prev_sparse ? (uint64_t)h->host_sc->grid_tiles * (uint64_t)(GT_W * GT_H)
+                                        : (uint64_t)h->c.g.ny * (uint64_t)h->c.g.pitch;
   for (int i = 0; i < KC__COUNT; ++i) { out->kernel_ms[i] = h->c.prof.ms[i]; out->kernel_count[i] = h->c.prof.count[i]; }
   return 0;
 }

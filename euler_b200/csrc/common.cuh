@@ -68,7 +68,20 @@ struct DevScalars {
   unsigned long long n_send_dn, n_send_up;   // markers leaving towards the lower/upper slab
   unsigned long long src_base, n_markers_global;
   int comm_timeout, pad3;                    // a peer never showed up in a P2P exchange
+  unsigned int grid_tiles, pad4;             // tiles the grid stages stream this sub-step (GridTiles)
 };
+
+// The MAC-grid stage kernels (grid_kernels.cu) stream only the 512 x 32-cell tiles that can hold a
+// nonzero value: tiles with fluid in them or next to them now or in one of the two previous
+// sub-steps (everything else is zero in every plane and stays zero).  `list == nullptr` means all
+// tx * ty tiles (the first sub-steps after create / reinit / a set() call, and the parity stages).
+struct GridTiles {
+  const int* list;
+  const unsigned int* count;
+  int tx, ty;
+};
+constexpr int GT_W = 512, GT_H = 32;         // tile size in cells
+constexpr int GT_SUB = 16;                   // a tile is 4 x 4 thread blocks of 128 cells x 8 rows
 
 // a / h in fp32; the reference's h is 1 (k_side_length, main.c:58) and a / 1.f == a exactly, so
 // the common case skips the IEEE division sequence without changing a bit

@@ -219,7 +219,12 @@ __global__ void __launch_bounds__(BX* BY) k_pressure_update_scalar(
 // ============================================================== 4 cells per thread ====
 
 constexpr int QX = 32, QY = 8;           // threads per block: 32 quads (128 cells) x 8 rows
-inline dim3 grid4(const Grid& g) { return dim3((g.pitch / 4 + QX - 1) / QX, (g.ny + QY - 1) / QY); }
+// persistent launch of the 4-cells-per-thread kernels: enough blocks to fill the machine, never
+// more than there are pieces
+inline int grid4(const Ctx& c) {
+  const long pieces = (long)c.gt_tx * c.gt_ty * GT_SUB, want = (long)c.sm_count * 8;
+  return (int)(pieces < want ? pieces : want);
+}
 
 // The fluid plane, read by every quad: ALL 32 lanes of the warp must call this (the byte right
 // of the quad is the next lane's first byte; lane 31 loads it).
@@ -234,105 +239,175 @@ __device__ __forceinline__ QuadMask load_quad_mask_warp(const uint8_t* __restric
 // Quad addressing shared by the four kernels.  A warp is one row of 32 quads; lanes past the
 // row end keep a clamped, harmless address so that they can take part in the shuffle.
 struct QuadPos { int x0, y; size_t c; bool row_ok, inside; };
-__device__ __forceinline__ QuadPos quad_pos(const Grid& g) {
+__device__ __forceinline__ QuadPos quad_pos(const Grid& g, int bx, int by) {
   QuadPos q;
-  q.x0 = (blockIdx.x * QX + threadIdx.x) * 4;
-  q.y = blockIdx.y * QY + threadIdx.y;
+  q.x0 = (bx * QX + threadIdx.x) * 4;
+  q.y = by * QY + threadIdx.y;
   q.row_ok = q.y < g.ny;                         // uniform per warp
   q.inside = q.row_ok && q.x0 < g.pitch;
   q.c = gidx(g, q.x0 < g.pitch ? q.x0 : g.pitch - 4, q.row_ok ? q.y : 0);
   return q;
 }
 
+// The kernels below are persistent: a block walks the 128-cell x 8-row pieces (16 per tile) of the
+// tiles in the list, `body(bx, by)` once per piece with the piece's block coordinates.
+static_assert(GT_W == 4 * QX * 4 && GT_H == 4 * QY && GT_SUB == 16, "a tile is 4 x 4 blocks");
+template <class Body>
+__device__ __forceinline__ void for_each_piece(const GridTiles& gt, Body body) {
+  const unsigned int n = gt.list ? *gt.count : (unsigned int)(gt.tx * gt.ty);
+  for (unsigned int i = blockIdx.x; i < n * GT_SUB; i += gridDim.x) {
+    const int tile = gt.list ? gt.list[i / GT_SUB] : (int)(i / GT_SUB);
+    const int sub = (int)(i % GT_SUB);
+    body((tile % gt.tx) * 4 + (sub & 3), (tile / gt.tx) * 4 + (sub >> 2));
+  }
+}
+
+// ---- which tiles the grid stages have to stream -----------------------------------------------
+// k_gt_flags: per tile "holds fluid now".  k_gt_compact: a tile is streamed when it or one of its 8
+// neighbours held fluid in this or one of the two previous sub-steps — every value a stage could
+// produce or would have to clear lies within one cell of such a tile (faces touching fluid,
+// main.c:128-138, 827), and planes written one or two sub-steps ago (the u/uext ping-pong) are
+// still cleared where the fluid has left; everywhere else every plane is, and stays, zero.
+__global__ void __launch_bounds__(128) k_gt_flags(Grid g, int tx, int ty, const uint8_t* __restrict__ fluid,
+                                                   uint8_t* __restrict__ flags) {
+  for (int tile = blockIdx.x; tile < tx * ty; tile += gridDim.x) {
+    const int x0 = (tile % tx) * GT_W + threadIdx.x * 4, y0 = (tile / tx) * GT_H;
+    const int y1 = min(y0 + GT_H, g.ny);
+    unsigned any = 0;
+    if (x0 < g.pitch)
+      for (int y = y0; y < y1; ++y) any |= ld_u8x4(fluid + gidx(g, x0, y));
+    const int has = __syncthreads_or(any != 0);
+    if (threadIdx.x == 0) flags[tile] = has ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_gt_compact(int tx, int ty, const uint8_t* __restrict__ f0,
+                                                     const uint8_t* __restrict__ f1, const uint8_t* __restrict__ f2,
+                                                     int* __restrict__ list, DevScalars* sc) {
+  __shared__ int sh[1024];
+  const int n = tx * ty;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, per * (int)threadIdx.x), hi = min(n, lo + per);
+  auto wanted = [&](int t) {
+    const int x = t % tx, y = t / tx;
+    for (int yy = max(y - 1, 0); yy <= min(y + 1, ty - 1); ++yy)
+      for (int xx = max(x - 1, 0); xx <= min(x + 1, tx - 1); ++xx) {
+        const int k = yy * tx + xx;
+        if (f0[k] | f1[k] | f2[k]) return true;
+      }
+    return false;
+  };
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) cnt += wanted(i) ? 1 : 0;
+  sh[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int v = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = sh[threadIdx.x] - cnt;
+  for (int i = lo; i < hi; ++i)
+    if (wanted(i)) list[run++] = i;
+  if (threadIdx.x == 1023) sc->grid_tiles = (unsigned int)sh[1023];
+}
+
 // Out of place: a face that stops being wet is zeroed here while a neighbour may still need
 // its old value for the 3x3 mean (in the reference the two passes are sequential).
 __global__ void __launch_bounds__(QX* QY) k_extrapolate_bounds(
-    Grid g, const float* __restrict__ u, const float* __restrict__ v,
+    Grid g, GridTiles gt, const float* __restrict__ u, const float* __restrict__ v,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ prev,
     const uint8_t* __restrict__ solid, float* __restrict__ uo, float* __restrict__ vo) {
-  const QuadPos q = quad_pos(g);
-  if (!q.row_ok) return;
-  const QuadMask f = load_quad_mask_warp(fluid, g, q.c);
-  if (!q.inside) return;
-  F4 ru, rv;
+  for_each_piece(gt, [&](int bx, int by) {
+    const QuadPos q = quad_pos(g, bx, by);
+    if (!q.row_ok) return;
+    const QuadMask f = load_quad_mask_warp(fluid, g, q.c);
+    if (!q.inside) return;
+    F4 ru, rv;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) ru.v[k] = rv.v[k] = 0.f;
-  if (f.any()) extrapolate_quad(g, f, q.x0, q.y, q.c, u, v, prev, solid, ru, rv);
-  st_f4(uo + q.c, ru);
-  st_f4(vo + q.c, rv);
+    for (int k = 0; k < 4; ++k) ru.v[k] = rv.v[k] = 0.f;
+    if (f.any()) extrapolate_quad(g, f, q.x0, q.y, q.c, u, v, prev, solid, ru, rv);
+    st_f4(uo + q.c, ru);
+    st_f4(vo + q.c, rv);
+  });
 }
 
 // ---- advect_u, advect_v + gravity + zero_bounds ---------------------------------------
 template <int MINB>
 __global__ void __launch_bounds__(QX* QY, MINB) k_advect_velocity(
-    Grid g, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
+    Grid g, GridTiles gt, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
     float* __restrict__ uo, float* __restrict__ vo, float dt, float h, float gravity) {
-  const QuadPos q = quad_pos(g);
-  if (!q.row_ok) return;
-  const QuadMask f = load_quad_mask_warp(fluid, g, q.c);
-  if (!q.inside) return;
-  F4 ru, rv;
+  for_each_piece(gt, [&](int bx, int by) {
+    const QuadPos q = quad_pos(g, bx, by);
+    if (!q.row_ok) return;
+    const QuadMask f = load_quad_mask_warp(fluid, g, q.c);
+    if (!q.inside) return;
+    F4 ru, rv;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) ru.v[k] = rv.v[k] = 0.f;
-  if (f.any()) advect_quad(g, lim, f, q.x0, q.y, q.c, u, v, fluid, solid, dt, h, gravity, ru, rv);
-  st_f4(uo + q.c, ru);
-  st_f4(vo + q.c, rv);
+    for (int k = 0; k < 4; ++k) ru.v[k] = rv.v[k] = 0.f;
+    if (f.any()) advect_quad(g, lim, f, q.x0, q.y, q.c, u, v, fluid, solid, dt, h, gravity, ru, rv);
+    st_f4(uo + q.c, ru);
+    st_f4(vo + q.c, rv);
+  });
 }
 
 // ---- rhs build --------------------------------------------------------------------------
 __global__ void __launch_bounds__(QX* QY) k_build_rhs(
-    Grid g, const float* __restrict__ u, const float* __restrict__ v,
+    Grid g, GridTiles gt, const float* __restrict__ u, const float* __restrict__ v,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
     double* __restrict__ r, double* __restrict__ p, int8_t* __restrict__ adiag, float h,
     double scale, DevScalars* sc, int own0, int own1, float* __restrict__ r32) {
-  const QuadPos q = quad_pos(g);
   bool nz = false;
-  if (q.inside) {
+  for_each_piece(gt, [&](int bx, int by) {
+    const QuadPos q = quad_pos(g, bx, by);
+    if (!q.inside) return;
     const unsigned mf = ld_u8x4(fluid + q.c);
     D4g b, zero;
 #pragma unroll
     for (int k = 0; k < 4; ++k) b.v[k] = zero.v[k] = 0.0;
     if (mf) {
       const bool owned = q.y >= own0 && q.y < own1;      // halo rows are the neighbour slab's business
-      nz = rhs_quad(g, mf, q.c, u, v, solid, adiag, h, scale, owned, b);
+      nz |= rhs_quad(g, mf, q.c, u, v, solid, adiag, h, scale, owned, b);
     }
     st_d4(r + q.c, b);
     st_d4(p + q.c, zero);                                 // p = 0, main.c:739
     if (r32)                                              // mixed-precision PCG: r starts as fp32(b)
       *reinterpret_cast<float4*>(r32 + q.c) = make_float4((float)b.v[0], (float)b.v[1], (float)b.v[2], (float)b.v[3]);
-  }
+  });
   if (__any_sync(EULER_FULL_MASK, nz) && (threadIdx.x & 31) == 0) atomicOr(&sc->nonzero_rhs, 1);
 }
 
 // ---- pressure update ----------------------------------------------------------------------
 __global__ void __launch_bounds__(QX* QY) k_pressure_update(
-    Grid g, double* __restrict__ p, const float* __restrict__ ut, const float* __restrict__ vt,
+    Grid g, GridTiles gt, double* __restrict__ p, const float* __restrict__ ut, const float* __restrict__ vt,
     const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid,
     float* __restrict__ uo, float* __restrict__ vo, float dt, float kk, DevScalars* sc,
     int own0, int own1) {
-  const QuadPos q = quad_pos(g);
   float mu = 0.f, mv = 0.f;
-  if (q.row_ok) {
+  for_each_piece(gt, [&](int bx, int by) {
+    const QuadPos q = quad_pos(g, bx, by);
+    if (!q.row_ok) return;
     const QuadMask f = load_quad_mask_warp(fluid, g, q.c);
-    if (q.inside) {
-      F4 ru, rv;
+    if (!q.inside) return;
+    F4 ru, rv;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) ru.v[k] = rv.v[k] = 0.f;
-      if (f.any()) pressure_quad(g, f, q.x0, q.y, q.c, p, ut, vt, solid, dt, kk, ru, rv);
-      st_f4(uo + q.c, ru);
-      st_f4(vo + q.c, rv);
-      // fused max u^2 / max v^2 for the next calculate_timestep (main.c:808-820)
-      if (q.y >= own0 && q.y < own1) {
+    for (int k = 0; k < 4; ++k) ru.v[k] = rv.v[k] = 0.f;
+    if (f.any()) pressure_quad(g, f, q.x0, q.y, q.c, p, ut, vt, solid, dt, kk, ru, rv);
+    st_f4(uo + q.c, ru);
+    st_f4(vo + q.c, rv);
+    // fused max u^2 / max v^2 for the next calculate_timestep (main.c:808-820); cells outside
+    // the streamed tiles are zero and cannot raise a maximum
+    if (q.y >= own0 && q.y < own1) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float a = ru.v[k] * ru.v[k], b = rv.v[k] * rv.v[k];
-          if (a > mu) mu = a;                    // drops NaN like the reference's `value > max`
-          if (b > mv) mv = b;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const float a = ru.v[k] * ru.v[k], b = rv.v[k] * rv.v[k];
+        if (a > mu) mu = a;                    // drops NaN like the reference's `value > max`
+        if (b > mv) mv = b;
       }
     }
-  }
+  });
   mu = warp_maxf(mu);
   mv = warp_maxf(mv);
   if ((threadIdx.x & 31) == 0) {
@@ -488,6 +563,25 @@ void launch_check(Ctx& c, unsigned long long* ints3, double* parts, int blocks) 
   c.launches += 1;
 }
 
+// The tile list of this sub-step, from the final count plane (after the sources and, on a slab,
+// the halo exchange of the classification).  Until two earlier flag planes exist the stages run
+// over all tiles (and thereby bring every plane into the "zero outside the list" state).
+void launch_grid_tiles(Ctx& c) {
+  ProfScope ps(c, KC_MISC);
+  uint8_t* now = c.gt_flags[2];                 // rotate: [0] = now, [1], [2] = the two previous
+  c.gt_flags[2] = c.gt_flags[1]; c.gt_flags[1] = c.gt_flags[0]; c.gt_flags[0] = now;
+  const int n = c.gt_tx * c.gt_ty;
+  k_gt_flags<<<n < c.sm_count * 16 ? n : c.sm_count * 16, 128, 0, c.stream>>>(c.g, c.gt_tx, c.gt_ty, c.count, now);
+  c.launches += 1;
+  static const int off = getenv("EULER_GRID_DENSE") ? atoi(getenv("EULER_GRID_DENSE")) : 0;   // A/B knob
+  c.gt_sparse = (c.gt_hist >= 2 && !off) ? 1 : 0;
+  if (c.gt_sparse) {
+    k_gt_compact<<<1, 1024, 0, c.stream>>>(c.gt_tx, c.gt_ty, c.gt_flags[0], c.gt_flags[1], c.gt_flags[2], c.gt_list, c.sc);
+    c.launches += 1;
+  }
+  if (c.gt_hist < 2) c.gt_hist++;
+}
+
 void launch_maxsq(Ctx& c) {
   ProfScope ps(c, KC_MAXSQ);
   cudaMemsetAsync(&c.sc->max_u2_bits, 0, 2 * sizeof(unsigned int), c.stream);
@@ -515,8 +609,8 @@ void launch_extrapolate(Ctx& c) {
     k_extrapolate_bounds_scalar<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
         c.g, c.u, c.v, c.count, c.prev_count, c.solid, c.uext, c.vext);
   else
-    k_extrapolate_bounds<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
-        c.g, c.u, c.v, c.count, c.prev_count, c.solid, c.uext, c.vext);
+    k_extrapolate_bounds<<<grid4(c), dim3(QX, QY), 0, c.stream>>>(
+        c.g, grid_tiles_of(c, c.gt_sparse), c.u, c.v, c.count, c.prev_count, c.solid, c.uext, c.vext);
   c.launches += 1;
 }
 
@@ -533,8 +627,8 @@ void launch_advect_velocity(Ctx& c, float dt) {
     // (quad-wide mask/value loads instead of 10 loads per sample) was tried as well: same time at
     // equal occupancy, so the simpler kernel stays.
     static const int minb = getenv("EULER_ADV_MINB") ? atoi(getenv("EULER_ADV_MINB")) : 8;
-#define ADV(M) k_advect_velocity<M><<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>( \
-        c.g, c.lim, c.u, c.v, c.count, c.solid, c.utmp, c.vtmp, dt, c.h, c.gravity)
+#define ADV(M) k_advect_velocity<M><<<grid4(c), dim3(QX, QY), 0, c.stream>>>( \
+        c.g, grid_tiles_of(c, c.gt_sparse), c.lim, c.u, c.v, c.count, c.solid, c.utmp, c.vtmp, dt, c.h, c.gravity)
     if (minb == 4) ADV(4); else if (minb == 6) ADV(6); else ADV(8);
 #undef ADV
   }
@@ -550,9 +644,9 @@ void launch_build_rhs(Ctx& c, float dt) {
         c.g, c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc, c.own0, c.own1,
         c.mixed ? c.r32 : nullptr);
   else
-    k_build_rhs<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
-        c.g, c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc, c.own0, c.own1,
-        c.mixed ? c.r32 : nullptr);
+    k_build_rhs<<<grid4(c), dim3(QX, QY), 0, c.stream>>>(
+        c.g, grid_tiles_of(c, c.gt_sparse), c.utmp, c.vtmp, c.count, c.solid, c.r, c.p, c.adiag, c.h, scale, c.sc,
+        c.own0, c.own1, c.mixed ? c.r32 : nullptr);
   c.launches += 1;
 }
 
@@ -564,8 +658,8 @@ void launch_pressure_update(Ctx& c, float dt) {
     k_pressure_update_scalar<<<grid2d(c.g), dim3(BX, BY), 0, c.stream>>>(
         c.g, c.p, c.utmp, c.vtmp, c.count, c.solid, c.u, c.v, dt, k, c.sc, c.own0, c.own1);
   else
-    k_pressure_update<<<grid4(c.g), dim3(QX, QY), 0, c.stream>>>(
-        c.g, c.p, c.utmp, c.vtmp, c.count, c.solid, c.u, c.v, dt, k, c.sc, c.own0, c.own1);
+    k_pressure_update<<<grid4(c), dim3(QX, QY), 0, c.stream>>>(
+        c.g, grid_tiles_of(c, c.gt_sparse), c.p, c.utmp, c.vtmp, c.count, c.solid, c.u, c.v, dt, k, c.sc, c.own0, c.own1);
   c.launches += 1;
 }
 

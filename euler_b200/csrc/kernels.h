@@ -80,6 +80,15 @@ struct Ctx {
   size_t n_partials;
   unsigned int* wf_progress;      // wavefront strip progress flags
   int n_strips;
+  // tiles the grid stages stream (common.cuh GridTiles): "has fluid" flags of this and the two
+  // previous sub-steps (ring), the compact list, how many previous flag planes are valid, and
+  // whether this sub-step's launches use the list
+  uint8_t* gt_flags[3];
+  int* gt_list;
+  int gt_tx, gt_ty;
+  int gt_hist;                    // valid previous flag planes (0..2); the list needs 2
+  int gt_sparse;                  // this sub-step's grid stages go by the list
+  int gt_prev_sparse;             // last sub-step's list is valid (the count fold uses it)
   DevScalars* sc;                 // device scalars
   // row slabs, NVLink path (p2p.cuh): 0 = exchanges by NCCL, 1 = separate exchange kernels,
   // 2 = exchanges fused into the producing kernels' epilogues (default when peers are mapped)
@@ -111,6 +120,14 @@ inline void prof_collect(Ctx& c) {
 }
 
 // ---- grid stages (grid_kernels.cu)
+void launch_grid_tiles(Ctx& c);                              // count plane -> the tile list of this sub-step
+inline GridTiles grid_tiles_of(const Ctx& c, bool sparse) {
+  GridTiles gt;
+  gt.list = sparse ? c.gt_list : nullptr;
+  gt.count = &c.sc->grid_tiles;
+  gt.tx = c.gt_tx; gt.ty = c.gt_ty;
+  return gt;
+}
 void launch_maxsq(Ctx& c);                                   // -> sc.max_u2_bits/max_v2_bits
 void launch_timestep(Ctx& c, float frame_time, float cfl);   // -> sc.dt (uses sc.max_*)
 void launch_extrapolate(Ctx& c);                             // (u,v) -> (uext,vext); caller swaps

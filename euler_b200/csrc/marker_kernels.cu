@@ -379,20 +379,27 @@ __global__ void __launch_bounds__(1024) k_fill_holes(
   }
 }
 
-__global__ void __launch_bounds__(256) k_fold_counts(Grid g, unsigned int* __restrict__ count32,
+// Over the tiles of the LAST sub-step's list (common.cuh GridTiles; all tiles when there is none):
+// a marker moves less than one cell per sub-step (CFL 0.75, main.c:838), so every cell that was
+// binned into, and every stale cell of the count plane being recycled (the one of two sub-steps
+// ago), lies in a tile that held or bordered fluid within the list's three-sub-step memory.
+__global__ void __launch_bounds__(256) k_fold_counts(Grid g, GridTiles gt, unsigned int* __restrict__ count32,
                                                      uint8_t* __restrict__ count) {
-  const int quads = g.pitch >> 2;
-  const size_t total = (size_t)quads * g.ny;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int y = (int)(i / quads);
-    const int x0 = (int)(i % quads) << 2;
-    const size_t c = gidx(g, x0, y);
-    uint4 v = *reinterpret_cast<uint4*>(count32 + c);
-    uchar4 o = make_uchar4((unsigned char)v.x, (unsigned char)v.y, (unsigned char)v.z,
-                           (unsigned char)v.w);            // uint8 wrap, main.c:96,114
-    *reinterpret_cast<uchar4*>(count + c) = o;
-    *reinterpret_cast<uint4*>(count32 + c) = make_uint4(0, 0, 0, 0);
+  const unsigned int n = gt.list ? *gt.count : (unsigned int)(gt.tx * gt.ty);
+  constexpr int QPT = GT_W / 4;                               // quads per tile row
+  for (unsigned int t = blockIdx.x; t < n; t += gridDim.x) {
+    const int tile = gt.list ? gt.list[t] : (int)t;
+    const int x00 = (tile % gt.tx) * GT_W, y0 = (tile / gt.tx) * GT_H;
+    for (int i = threadIdx.x; i < QPT * GT_H; i += blockDim.x) {
+      const int y = y0 + i / QPT, x0 = x00 + (i % QPT) * 4;
+      if (y >= g.ny || x0 >= g.pitch) continue;
+      const size_t c = gidx(g, x0, y);
+      uint4 v = *reinterpret_cast<uint4*>(count32 + c);
+      uchar4 o = make_uchar4((unsigned char)v.x, (unsigned char)v.y, (unsigned char)v.z,
+                             (unsigned char)v.w);            // uint8 wrap, main.c:96,114
+      *reinterpret_cast<uchar4*>(count + c) = o;
+      if (v.x | v.y | v.z | v.w) *reinterpret_cast<uint4*>(count32 + c) = make_uint4(0, 0, 0, 0);
+    }
   }
 }
 
@@ -613,7 +620,7 @@ void launch_refresh_counts(Ctx& c) {
   k_list_deleted<<<blocks, MTHREADS, 0, c.stream>>>(c.g, c.h, c.markers, c.sink, c.solid,
                                                     c.seg_count, c.seg_offset, del_list, c.sc);
   k_fill_holes<<<1, 1024, 0, c.stream>>>(c.g, c.h, c.markers, c.sink, c.solid, del_list, c.sc);
-  k_fold_counts<<<blocks, 256, 0, c.stream>>>(c.g, c.count32, c.count);
+  k_fold_counts<<<blocks, 256, 0, c.stream>>>(c.g, grid_tiles_of(c, c.gt_prev_sparse), c.count32, c.count);
   c.launches += 5;
 }
 

@@ -396,28 +396,35 @@ __device__ __forceinline__ double rb_e_red(const int8_t* __restrict__ adiag, siz
 // when none of them is fluid (most of a free-surface scene).
 template <class T>
 __global__ void __launch_bounds__(256) k_rb_build(
-    Grid g, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
+    Grid g, GridTiles gt, const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag,
     T* __restrict__ precon) {
-  const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
-  if (x0 >= g.pitch || y >= g.ny || y + g.yoff < 1 || y + g.yoff >= g.gny - 1) return;
-  const unsigned mf = ldmask(fluid + gidx(g, x0, y));
-  if (!mf) return;
+  // persistent over the 128-cell x 8-row pieces of the grid-stage tile list (common.cuh GridTiles)
+  const unsigned int n = gt.list ? *gt.count : (unsigned int)(gt.tx * gt.ty);
+  for (unsigned int i = blockIdx.x; i < n * GT_SUB; i += gridDim.x) {
+    const int tile = gt.list ? gt.list[i / GT_SUB] : (int)(i / GT_SUB);
+    const int sub = (int)(i % GT_SUB);
+    const int x0 = (((tile % gt.tx) * 4 + (sub & 3)) * 32 + threadIdx.x) * 4;
+    const int y = ((tile / gt.tx) * 4 + (sub >> 2)) * 8 + threadIdx.y;
+    if (x0 >= g.pitch || y >= g.ny || y + g.yoff < 1 || y + g.yoff >= g.gny - 1) continue;
+    const unsigned mf = ldmask(fluid + gidx(g, x0, y));
+    if (!mf) continue;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int x = x0 + k;
-    if (!mbit(mf, k) || x < 1 || x >= g.nx - 1) continue;
-    const size_t c = gidx(g, x, y);
-    if (((x + y + g.yoff) & 1) == 0) { precon[c] = (T)(1.0 / sqrt(rb_e_red(adiag, c))); continue; }
-    const double a = (double)adiag[c];
-    double e = a;
-    const long off[4] = {-1, 1, -(long)g.pitch, (long)g.pitch};
+    for (int k = 0; k < 4; ++k) {
+      const int x = x0 + k;
+      if (!mbit(mf, k) || x < 1 || x >= g.nx - 1) continue;
+      const size_t c = gidx(g, x, y);
+      if (((x + y + g.yoff) & 1) == 0) { precon[c] = (T)(1.0 / sqrt(rb_e_red(adiag, c))); continue; }
+      const double a = (double)adiag[c];
+      double e = a;
+      const long off[4] = {-1, 1, -(long)g.pitch, (long)g.pitch};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const size_t nb = c + off[j];
-      if (fluid[nb]) e = e - 1.0 / rb_e_red(adiag, nb);
+      for (int j = 0; j < 4; ++j) {
+        const size_t nb = c + off[j];
+        if (fluid[nb]) e = e - 1.0 / rb_e_red(adiag, nb);
+      }
+      if (e < 0.25 * a) e = a != 0.0 ? a : 1.0;
+      precon[c] = (T)(1.0 / sqrt(e));                        // fp64 factor, narrowed once for T = float
     }
-    if (e < 0.25 * a) e = a != 0.0 ? a : 1.0;
-    precon[c] = (T)(1.0 / sqrt(e));                          // fp64 factor, narrowed once for T = float
   }
 }
 
@@ -965,9 +972,12 @@ void launch_copy_search(Ctx& c) {
 void launch_rb_build(Ctx& c) {
   // over ALL locally stored rows: halo rows get their own (identical) factor, no exchange
   ProfScope ps(c, KC_PRECON_BUILD);
-  const dim3 grid((c.g.pitch / 4 + 31) / 32, (c.g.ny + 7) / 8), block(32, 8);
-  if (c.mixed) k_rb_build<float><<<grid, block, 0, c.stream>>>(c.g, c.count, c.adiag, c.pc32);
-  else k_rb_build<double><<<grid, block, 0, c.stream>>>(c.g, c.count, c.adiag, c.precon);
+  const dim3 block(32, 8);
+  const long pieces = (long)c.gt_tx * c.gt_ty * GT_SUB, want = (long)c.sm_count * 8;
+  const int grid = (int)(pieces < want ? pieces : want);
+  const GridTiles gt = grid_tiles_of(c, c.gt_sparse);
+  if (c.mixed) k_rb_build<float><<<grid, block, 0, c.stream>>>(c.g, gt, c.count, c.adiag, c.pc32);
+  else k_rb_build<double><<<grid, block, 0, c.stream>>>(c.g, gt, c.count, c.adiag, c.precon);
   c.launches += 1;
 }
 
@@ -1129,12 +1139,17 @@ void launch_fused_tail(Ctx& c, double tol, int mode) {
   }
   static const int cpt = env_int("EULER_CPT_TAIL", 2);
   static const int ns = env_int("EULER_NS_TAIL", 3);
-#define TAIL(N, C) { constexpr int smem = tail::smem_bytes<N>(); constexpr int threads = TW / C + 32; \
-    k_fused_tail<N, C><<<pcg_blocks(c, k_fused_tail<N, C>, smem, threads), threads, smem, c.stream>>>( \
+  // resident blocks per SM the compiler must allow.  Measured at 16384^2 (same box, profiles/r02a):
+  // 3 blocks = 72 registers with 48 B of spills inside the row loop, 1.12 ms per launch; 2 blocks =
+  // 96 registers, no spill, 0.636 ms (ring depth 3 / 4 / 5: 0.636 / 0.639 / 0.648 ms)
+  static const int mb = env_int("EULER_TAIL_MINB", 2);
+#define TAIL(N, C, MB) { constexpr int smem = tail::smem_bytes<N>(); constexpr int threads = TW / C + 32; \
+    k_fused_tail<N, C, MB><<<pcg_blocks(c, k_fused_tail<N, C, MB>, smem, threads), threads, smem, c.stream>>>( \
         v.g, TL, v.r, v.q, v.precon, v.fluid, v.s, c.s2 + o, v.p, c.r2 + o, v.z, c.partials, c.sc, tol, mode, \
         dotflag(c), v.a0, v.a1, d); }
-  if (cpt == 4) { if (ns == 4) TAIL(4, 4) else TAIL(3, 4) }
-  else { if (ns == 4) TAIL(4, 2) else TAIL(3, 2) }
+  if (cpt == 4) { if (ns == 4) TAIL(4, 4, 3) else TAIL(3, 4, 3) }
+  else if (mb == 2) { if (ns == 5) TAIL(5, 2, 2) else if (ns == 4) TAIL(4, 2, 2) else TAIL(3, 2, 2) }
+  else { if (ns == 4) TAIL(4, 2, 3) else TAIL(3, 2, 3) }
 #undef TAIL
   c.launches += 1;
   double* t = c.r; c.r = c.r2; c.r2 = t;

@@ -17,7 +17,8 @@
 //     four neighbours — w = pc (r' pc) of a red neighbour for the forward solve, zb = q pc of a
 //     black neighbour for the backward solve — goes through ONE rolling shared-memory row buffer
 //     (red cells hold w, black cells zb: a cell is never asked for the other one); a thread's own
-//     r', pc and q of the two previous rows stay in registers;
+//     r', pc and q of the two previous rows stay in registers, and so do the fluid masks of its
+//     cells and their neighbours (one bit word per row);
 //   * a row range needs r' on its +-2 rows / columns and q on +-1 (red z <- black q <- red r'):
 //     the 4 + 2 halo rows are recomputed (their inputs are L2 hits: the neighbouring block loads
 //     the same rows), the 4 halo columns are the job of an extra warp that also runs the ring;
@@ -38,20 +39,30 @@ namespace tail {
 
 constexpr int HALO = 2;                 // halo columns of the value planes (== pipe::Elem<double>::HX)
 constexpr int ABW = TW + 2 * HALO;      // doubles per row of the rolling neighbour buffer
-constexpr int MW = TW + 2 * pipe::HX1;  // bytes per row of the rolling mask buffer
 constexpr int NSLOT = 5;                // steps j-3 .. j are live; a fast warp may already write step j+1
 
 template <int NS>
 constexpr int smem_bytes() {
-  return NS * pipe::Layout<3, 1>::stage_bytes + 2 * NS * 8 + NSLOT * ABW * 8 + NSLOT * MW;
+  return NS * pipe::Layout<3, 1>::stage_bytes + 2 * NS * 8 + NSLOT * ABW * 8;
 }
 
 }  // namespace tail
 
+// Per-thread state of the row pipeline, NC cells per thread (C for the main threads, 1 for a lane
+// of the halo warp).  Masks travel as bit words: bit i of mw* = cell (col - 1 + i) is fluid, one
+// word per row, shifted along with the register window.
+template <int NC>
+struct TailLane {
+  double r1[NC], pc1[NC], r2[NC], pc2[NC], q2[NC];    // r', pc of rows yy-1 / yy-2, q of row yy-2
+  unsigned mw0, mw1, mw2, mw3;                        // rows yy, yy-1, yy-2, yy-3
+};
+
+__device__ __forceinline__ bool tbit(unsigned w, int i) { return (w >> i) & 1u; }
+
 // mode: 0 = r only (odd iterations), 1 = r and both pending p updates (even iterations),
-//       2 = r and this iteration's p update (every iteration; not used by the fused solve)
-template <int NS, int C>
-__global__ void __launch_bounds__(TW / C + 32, 3) k_fused_tail(
+//       2 = r and this iteration's p update (every iteration; the parity hook)
+template <int NS, int C, int MB = 3>
+__global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     Grid g, TileList active, const double* __restrict__ r, const double* __restrict__ as,
     const double* __restrict__ precon, const uint8_t* __restrict__ fluid, const double* __restrict__ s,
     const double* __restrict__ s_prev, double* __restrict__ p, double* __restrict__ r_new,
@@ -65,8 +76,7 @@ __global__ void __launch_bounds__(TW / C + 32, 3) k_fused_tail(
   unsigned char* stages = smem_raw;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NS * L::stage_bytes);
   uint64_t* empty = full + NS;
-  double* ab = reinterpret_cast<double*>(empty + NS);                       // [NSLOT][ABW], index col + HALO
-  uint8_t* mk = reinterpret_cast<uint8_t*>(ab + tail::NSLOT * tail::ABW);   // [NSLOT][MW], index col + HX1
+  double* ab = reinterpret_cast<double*>(empty + NS) + tail::HALO;          // [NSLOT][ABW], index slot*ABW + col
 
   const int tid = threadIdx.x, lane = tid & 31;
   const bool is_main = tid < NMAIN;
@@ -81,188 +91,211 @@ __global__ void __launch_bounds__(TW / C + 32, 3) k_fused_tail(
   const double alpha = sc->alpha, alpha_prev = sc->alpha_prev;
   const double neg_alpha = -alpha;
   const int th = g.th;
+  const size_t pitch = (size_t)g.pitch;
   const pipe::Tiles T = pipe::tiles_of(g, th);
-  pipe::JobIter cons, prod;
+  pipe::JobIter cons;
   cons.rad = 2;
   cons.start(g, T, th, active.list, (int)*active.count);
-  prod = cons;
-  int issued = 0;
+  // the producer's own walk over the same rows (NS-1 rows ahead) lives in shared memory: one lane
+  // uses it, but registers would be reserved in all 288 threads
+  __shared__ pipe::JobIter prod_sh;
+  __shared__ int pstage_sh, pphase_sh;           // next stage to fill, parity its `empty` must have passed
+  if (producer) { prod_sh = cons; pstage_sh = 0; pphase_sh = 1; }
 
   auto issue = [&]() {                           // producer lane only
-    const int st = issued % NS, use = issued / NS;
-    pipe::mbar_wait(empty + st, (use & 1) ^ 1);
-    unsigned char* dst = stages + st * L::stage_bytes;
+    pipe::JobIter prod = prod_sh;
+    int pstage = pstage_sh, pphase = pphase_sh;
+    pipe::mbar_wait(empty + pstage, (uint32_t)pphase);
+    unsigned char* dst = stages + pstage * L::stage_bytes;
     const uint32_t b8 = (uint32_t)(prod.p.w + 2 * tail::HALO) * 8u, b1 = (uint32_t)(prod.p.w + 2 * pipe::HX1);
-    pipe::mbar_expect_tx(full + st, 3 * b8 + b1);
+    pipe::mbar_expect_tx(full + pstage, 3 * b8 + b1);
     const long row = (long)prod.yy * g.pitch + prod.p.x0;
-    pipe::bulk_g2s(dst, r + row - tail::HALO, b8, full + st);
-    pipe::bulk_g2s(dst + ROWT, as + row - tail::HALO, b8, full + st);
-    pipe::bulk_g2s(dst + 2 * ROWT, precon + row - tail::HALO, b8, full + st);
-    pipe::bulk_g2s(dst + 3 * ROWT, fluid + row - pipe::HX1, b1, full + st);
-    ++issued;
+    pipe::bulk_g2s(dst, r + row - tail::HALO, b8, full + pstage);
+    pipe::bulk_g2s(dst + ROWT, as + row - tail::HALO, b8, full + pstage);
+    pipe::bulk_g2s(dst + 2 * ROWT, precon + row - tail::HALO, b8, full + pstage);
+    pipe::bulk_g2s(dst + 3 * ROWT, fluid + row - pipe::HX1, b1, full + pstage);
+    if (++pstage == NS) { pstage = 0; pphase ^= 1; }
     prod.next(g, T, th, active.list);
+    prod_sh = prod; pstage_sh = pstage; pphase_sh = pphase;
   };
+  if (producer)
+    for (int i = 0; i < NS - 1 && prod_sh.valid; ++i) issue();   // NS-1 rows ahead from here on
 
-  // columns this thread works on, relative to the piece: main threads C cells from tid*C; the
-  // extra warp's lanes 0..3 one halo column each (-2, -1, w, w+1: set per piece)
-  const int t0 = tid * C;
-  double r1[C], pc1[C], r2[C], pc2[C], q1[C], q2[C];      // rows yy-1 / yy-2 of this thread's columns
+  TailLane<C> t;
+#pragma unroll
+  for (int k = 0; k < C; ++k) t.r1[k] = t.pc1[k] = t.r2[k] = t.pc2[k] = t.q2[k] = 0.0;
+  t.mw0 = t.mw1 = t.mw2 = t.mw3 = 0u;
   double acc = 0.0, mx = 0.0;
   bool peer_stored = false;
   double* __restrict__ z_dn = dist.z_dn;
   double* __restrict__ z_up = dist.z_up;
-#pragma unroll
-  for (int k = 0; k < C; ++k) r1[k] = pc1[k] = r2[k] = pc2[k] = q1[k] = q2[k] = 0.0;
+  const bool has_peer = z_dn || z_up;
+  // rolling row slots of the neighbour buffer, as element offsets: steps j, j-1, j-2, j-3 and the
+  // free one.  No barrier separates stage 3 of one step from stage 1 of the next: with 5 slots the
+  // one a fast warp already overwrites (step j-4's) is one nobody still reads.
+  int o0 = 0, o1 = tail::ABW, o2 = 2 * tail::ABW, o3 = 3 * tail::ABW, of = 4 * tail::ABW;
+  int cstage = 0, cphase = 0;                    // consumer: ring stage of this step, its parity
+  // per piece: this thread's first column / cell count, global parity base, element offset of
+  // (x0 + col, yy) in the planes
+  int col = 0, ncol = 0, par_base = 0;
+  size_t rowp = 0;
 
-  for (int j = 0; cons.valid; ++j) {
-    if (producer)
-      while (prod.valid && issued <= j + NS - 1) issue();
-    const pipe::Piece pz = cons.p;
+  while (cons.valid) {
+    if (producer && prod_sh.valid) issue();
+    const pipe::Piece& pz = cons.p;
     const int yy = cons.yy;                      // row whose inputs arrive in this step
-    // slots of the rolling buffers go by STEP, not by row (rows jump at a piece boundary).  No
-    // barrier separates stage 3 of one step from stage 1 of the next: with 5 slots the one a fast
-    // warp overwrites (step j-5's) is one nobody still reads (stage 3 reads steps j-3 .. j-1)
-    const int s0 = j % tail::NSLOT, sm1 = (j + 4) % tail::NSLOT, sm2 = (j + 3) % tail::NSLOT,
-              sm3 = (j + 2) % tail::NSLOT;
-    double* ab0 = ab + s0 * tail::ABW + tail::HALO;     // rows yy, yy-1, yy-2, yy-3 of the neighbour buffer
-    double* ab1 = ab + sm1 * tail::ABW + tail::HALO;
-    double* ab2 = ab + sm2 * tail::ABW + tail::HALO;
-    double* ab3 = ab + sm3 * tail::ABW + tail::HALO;
-    uint8_t* mk0 = mk + s0 * tail::MW + pipe::HX1;
-    const uint8_t* mk1 = mk + sm1 * tail::MW + pipe::HX1;
-    const uint8_t* mk2 = mk + sm2 * tail::MW + pipe::HX1;
-    const uint8_t* mk3 = mk + sm3 * tail::MW + pipe::HX1;
-    // first column and number of columns of this thread in this piece
-    int col, ncol;
-    if (is_main) { col = t0; ncol = t0 < pz.w ? C : 0; }
-    else { col = lane < 2 ? lane - 2 : pz.w + lane - 2; ncol = lane < 4 ? 1 : 0; }
-    const bool own_cols = is_main && ncol > 0;
-    const int gx = pz.x0 + col;                  // global column (the red/black parity needs it)
-    const int gyy = yy + g.yoff;
+    const int rel = yy - pz.y0;                  // -2 at the first row of a piece
+    if (rel == -2) {
+      if (is_main) { col = tid * C; ncol = col < pz.w ? C : 0; }
+      else { col = lane < 2 ? lane - 2 : pz.w + lane - 2; ncol = lane < 4 ? 1 : 0; }
+      par_base = pz.x0 + col + g.yoff;
+      rowp = (size_t)yy * pitch + (size_t)(pz.x0 + col);
+    }
+    const int par0 = (par_base + yy) & 1;        // parity of (col, yy): 0 = red
+    const bool own_row = (unsigned)rel < (unsigned)(pz.y1 - pz.y0);
+    const bool acc_row = yy >= acc0 && yy < acc1;
 
     // the element-wise operands of the p update, issued before the wait on the ring
-    double sv[C], spv[C], pv[C];
-    const bool own_row = yy >= pz.y0 && yy < pz.y1;
-    const size_t c0 = gidx(g, pz.x0 + t0, yy);
-    const bool do_p = mode != 0 && own_row && own_cols;
+    const bool do_p = mode != 0 && own_row && is_main && ncol > 0;
+    DV<C> sv, spv, pv;
     if (do_p) {
-      const DV<C> a = ldg_v<C>(s + c0), b = ldg_v<C>(p + c0);
-#pragma unroll
-      for (int k = 0; k < C; ++k) { sv[k] = a.v[k]; pv[k] = b.v[k]; }
-      if (mode == 1) {
-        const DV<C> d = ldg_v<C>(s_prev + c0);
-#pragma unroll
-        for (int k = 0; k < C; ++k) spv[k] = d.v[k];
-      }
+      sv = ldg_v<C>(s + rowp); pv = ldg_v<C>(p + rowp);
+      if (mode == 1) spv = ldg_v<C>(s_prev + rowp);
     }
 
     // ---- stage 1: r'(yy), w(yy) ---------------------------------------------------------
-    pipe::mbar_wait(full + (j % NS), (j / NS) & 1);
+    pipe::mbar_wait(full + cstage, (uint32_t)cphase);
     double r0[C], pc0[C];
     {
-      const pipe::RowView<3, 1> in = L::view(stages + (j % NS) * L::stage_bytes);
+      const pipe::RowView<3, 1> in = L::view(stages + cstage * L::stage_bytes);
+      unsigned mw = 0u;
+      if (is_main) {
+        if (ncol) {
+          const DV<C> rr = ldsv<C>(in.d[0] + col), aa = ldsv<C>(in.d[1] + col), pp = ldsv<C>(in.d[2] + col);
 #pragma unroll
-      for (int k = 0; k < C; ++k) {
-        r0[k] = pc0[k] = 0.0;
-        if (k >= ncol) continue;
-        const uint8_t m = in.b[0][col + k];
-        mk0[col + k] = m;
-        const double rr = in.d[0][col + k], aa = in.d[1][col + k], pp = in.d[2][col + k];
-        const double rn = m ? rr + aa * neg_alpha : rr;            // fmadd(z, -alpha, r), main.c:754
-        r0[k] = rn; pc0[k] = pp;
-        if (((gx + k + gyy) & 1) == 0) ab0[col + k] = pp * (rn * pp);   // red: what a black neighbour adds
-        if (own_row && own_cols && m) {
-          if (mode == 1) pv[k] = pv[k] + spv[k] * alpha_prev;      // the previous iteration's main.c:753
-          if (mode) pv[k] = pv[k] + sv[k] * alpha;                 // fmadd(s, alpha, p), main.c:753
-          const double a = fabs(rn);
-          if (a > mx && yy >= acc0 && yy < acc1) mx = a;           // NaN-dropping max, main.c:659-662
+          for (int i = 0; i < C + 2; ++i) mw |= (in.b[0][col - 1 + i] ? 1u : 0u) << i;
+#pragma unroll
+          for (int k = 0; k < C; ++k) {
+            const bool m = tbit(mw, k + 1);
+            const double rn = m ? rr.v[k] + aa.v[k] * neg_alpha : rr.v[k];      // fmadd(z, -alpha, r), main.c:754
+            r0[k] = rn; pc0[k] = pp.v[k];
+            if (((par0 + k) & 1) == 0) ab[o0 + col + k] = pp.v[k] * (rn * pp.v[k]);   // red: what a black neighbour adds
+            if (own_row && m) {
+              if (mode == 1) pv.v[k] = pv.v[k] + spv.v[k] * alpha_prev;         // the previous iteration's main.c:753
+              if (mode) pv.v[k] = pv.v[k] + sv.v[k] * alpha;                    // fmadd(s, alpha, p), main.c:753
+              const double a = fabs(rn);
+              if (a > mx && acc_row) mx = a;                                     // NaN-dropping max, main.c:659-662
+            }
+          }
+          if (own_row) {
+            DV<C> o;
+#pragma unroll
+            for (int k = 0; k < C; ++k) o.v[k] = r0[k];
+            stv<C>(r_new + rowp, o);
+            if (do_p) stv<C>(p + rowp, pv);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < C; ++k) r0[k] = pc0[k] = 0.0;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < C; ++k) r0[k] = pc0[k] = 0.0;
+        if (ncol) {                              // one halo column per lane
+#pragma unroll
+          for (int i = 0; i < 3; ++i) mw |= (in.b[0][col - 1 + i] ? 1u : 0u) << i;
+          const double rr = in.d[0][col], aa = in.d[1][col], pp = in.d[2][col];
+          const double rn = tbit(mw, 1) ? rr + aa * neg_alpha : rr;
+          r0[0] = rn; pc0[0] = pp;
+          if (par0 == 0) ab[o0 + col] = pp * (rn * pp);
         }
       }
-      // the mask bytes left and right of the value halo are never read; the ring stage is free
+      t.mw0 = mw;
+      // the ring stage is free again
       __syncwarp();
-      if (lane == 0) pipe::mbar_arrive(empty + (j % NS));
-      if (own_row && own_cols) {
-        DV<C> o;
-#pragma unroll
-        for (int k = 0; k < C; ++k) o.v[k] = r0[k];
-        stv<C>(r_new + c0, o);
-        if (do_p) {
-#pragma unroll
-          for (int k = 0; k < C; ++k) o.v[k] = pv[k];
-          stv<C>(p + c0, o);
-        }
-      }
+      if (lane == 0) pipe::mbar_arrive(empty + cstage);
+      if (++cstage == NS) { cstage = 0; cphase ^= 1; }
     }
     __syncthreads();
 
-    // ---- stage 2: q(yy-1), zb(yy-1) -----------------------------------------------------
-    const int y1r = yy - 1;
-    double q0[C];
+    // ---- stage 2: q(yy-1), zb(yy-1): rows y0-1 .. y1 ----------------------------------------
+    double q1[C];
 #pragma unroll
-    for (int k = 0; k < C; ++k) q0[k] = 0.0;
-    if (y1r >= pz.y0 - 1 && y1r <= pz.y1 && yy >= pz.y0 - 1) {
-      // (the extra warp: only the inner halo columns -1 and w)
-      const bool active2 = is_main ? ncol > 0 : (lane == 1 || lane == 2);
-      if (active2) {
+    for (int k = 0; k < C; ++k) q1[k] = 0.0;
+    if (rel >= 0 && ncol) {
+      if (is_main) {
 #pragma unroll
         for (int k = 0; k < C; ++k) {
-          if (k >= ncol) continue;
+          if (!tbit(t.mw1, k + 1)) continue;
           const int cc = col + k;
-          if (!mk1[cc]) continue;
-          double t = r1[k];
-          const bool black = ((gx + k + gyy - 1) & 1) != 0;
-          if (black) {                                             // + red neighbours: l, r, d, u
-            if (mk1[cc - 1]) t = t + ab1[cc - 1];
-            if (mk1[cc + 1]) t = t + ab1[cc + 1];
-            if (mk2[cc]) t = t + ab2[cc];
-            if (mk0[cc]) t = t + ab0[cc];
+          double v = t.r1[k];
+          const bool black = ((par0 + k) & 1) == 0;                  // row yy-1: the colours of row yy swapped
+          if (black) {                                               // + red neighbours: l, r, d, u
+            if (tbit(t.mw1, k)) v = v + ab[o1 + cc - 1];
+            if (tbit(t.mw1, k + 2)) v = v + ab[o1 + cc + 1];
+            if (tbit(t.mw2, k + 1)) v = v + ab[o2 + cc];
+            if (tbit(t.mw0, k + 1)) v = v + ab[o0 + cc];
           }
-          const double q = t * pc1[k];
-          q0[k] = q;
-          if (black) ab1[cc] = q * pc1[k];                         // what a red neighbour adds (times its pc)
+          const double q = v * t.pc1[k];
+          q1[k] = q;
+          if (black) ab[o1 + cc] = q * t.pc1[k];                     // what a red neighbour adds (times its pc)
         }
+      } else if ((lane == 1 || lane == 2) && tbit(t.mw1, 1) && par0 == 0) {
+        // inner halo columns -1 and w: only a black cell's zb is ever asked for
+        double v = t.r1[0];
+        if (tbit(t.mw1, 0)) v = v + ab[o1 + col - 1];
+        if (tbit(t.mw1, 2)) v = v + ab[o1 + col + 1];
+        if (tbit(t.mw2, 1)) v = v + ab[o2 + col];
+        if (tbit(t.mw0, 1)) v = v + ab[o0 + col];
+        ab[o1 + col] = (v * t.pc1[0]) * t.pc1[0];
       }
     }
     __syncthreads();
 
-    // ---- stage 3: z(yy-2), z.r' -----------------------------------------------------------
-    const int y2r = yy - 2;
-    if (is_main && ncol > 0 && y2r >= pz.y0 && y2r < pz.y1 && yy >= pz.y0 + 2) {
+    // ---- stage 3: z(yy-2), z.r': rows y0 .. y1-1 -------------------------------------------
+    if (is_main && ncol && rel >= 2) {
+      const int y2r = yy - 2;
+      const bool acc2 = y2r >= acc0 && y2r < acc1;
       DV<C> out;
-      bool any = false;
+      const unsigned any = t.mw2 & (((1u << C) - 1u) << 1);
 #pragma unroll
       for (int k = 0; k < C; ++k) {
         out.v[k] = 0.0;
+        if (!tbit(t.mw2, k + 1)) continue;
         const int cc = col + k;
-        if (!mk2[cc]) continue;
-        any = true;
-        const double pk = pc2[k];
+        const double pk = t.pc2[k];
         double zc;
-        if ((gx + k + gyy - 2) & 1) {
-          zc = q2[k] * pk;                                         // black: q*pc
+        if ((par0 + k) & 1) {                                        // row yy-2 has the colours of row yy
+          zc = t.q2[k] * pk;                                         // black: q*pc
         } else {
-          double t = q2[k];
-          if (mk2[cc - 1]) t = t + pk * ab2[cc - 1];
-          if (mk2[cc + 1]) t = t + pk * ab2[cc + 1];
-          if (mk3[cc]) t = t + pk * ab3[cc];
-          if (mk1[cc]) t = t + pk * ab1[cc];
-          zc = t * pk;
+          double v = t.q2[k];
+          if (tbit(t.mw2, k)) v = v + pk * ab[o2 + cc - 1];
+          if (tbit(t.mw2, k + 2)) v = v + pk * ab[o2 + cc + 1];
+          if (tbit(t.mw3, k + 1)) v = v + pk * ab[o3 + cc];
+          if (tbit(t.mw1, k + 1)) v = v + pk * ab[o1 + cc];
+          zc = v * pk;
         }
         out.v[k] = zc;
-        if (y2r >= acc0 && y2r < acc1) acc += zc * r2[k];
+        if (acc2) acc += zc * t.r2[k];
       }
       // only the owned rows are stored: the halo rows of z belong to the neighbouring slabs
-      if (any && y2r >= acc0 && y2r < acc1) {
-        const size_t c2 = gidx(g, pz.x0 + t0, y2r);
+      if (any && acc2) {
+        const size_t c2 = rowp - 2 * pitch;
         stv<C>(z + c2, out);
-        if (z_dn && y2r < acc0 + dist.depth) { stv<C>(z_dn + c2, out); peer_stored = true; }
-        if (z_up && y2r >= acc1 - dist.depth) { stv<C>(z_up + c2, out); peer_stored = true; }
+        if (has_peer) {
+          if (z_dn && y2r < acc0 + dist.depth) { stv<C>(z_dn + c2, out); peer_stored = true; }
+          if (z_up && y2r >= acc1 - dist.depth) { stv<C>(z_up + c2, out); peer_stored = true; }
+        }
       }
     }
-    // shift the register window
+    // shift the register window and the row slots
 #pragma unroll
-    for (int k = 0; k < C; ++k) { r2[k] = r1[k]; pc2[k] = pc1[k]; q2[k] = q0[k]; r1[k] = r0[k]; pc1[k] = pc0[k]; }
-    (void)q1;
+    for (int k = 0; k < C; ++k) {
+      t.r2[k] = t.r1[k]; t.pc2[k] = t.pc1[k]; t.q2[k] = q1[k]; t.r1[k] = r0[k]; t.pc1[k] = pc0[k];
+    }
+    t.mw3 = t.mw2; t.mw2 = t.mw1; t.mw1 = t.mw0;
+    { const int f = o3; o3 = o2; o2 = o1; o1 = o0; o0 = of; of = f; }
+    rowp += pitch;
     cons.next(g, T, th, active.list);
   }
 
