@@ -258,8 +258,10 @@ def run_gpu(args):
 
     if world > 1 and args.precon != "rb":
         raise SystemExit("row slabs need --precon rb")
-    # slabs balanced by work: the PCG streams only tiles with fluid, the grid stages every cell
-    weight = scn.fluid.sum(axis=1, dtype=np.uint64) * 100 + np.uint64(n)
+    # slabs balanced by work: the PCG and (since the tile list, common.cuh GridTiles) the grid stages
+    # stream only tiles with fluid in or next to them, markers live in fluid cells; a dry row costs
+    # one pass over its count bytes
+    weight = scn.fluid.sum(axis=1, dtype=np.uint64) * 4096 + np.uint64(max(1, n // 256))
     row0, rows = G.slab_partition_weighted(weight, world, rank) if world > 1 else (0, 0)
 
     def make():

@@ -265,14 +265,15 @@ int main(int argc, char **argv) {
 
   prm.rng_state = scn.rng_state;
   if (ranks > 1) {
-    /* slabs balanced by work: the PCG streams the cells that hold fluid, the grid stages every
-     * cell (the weights bench.py uses) */
+    /* slabs balanced by work: the PCG and the grid stages stream the tiles that hold or border
+     * fluid, markers live in fluid cells; a dry row costs one pass over its count bytes (the
+     * weights bench.py uses) */
     uint64_t *weight = malloc((size_t)ny * sizeof *weight);
     if (!weight) return 1;
     for (int y = 0; y < ny; ++y) {
       uint64_t wet = 0;
       for (int x = 0; x < nx; ++x) wet += scn.fluid[(size_t)y * nx + x] ? 1 : 0;
-      weight[y] = wet * 100 + (uint64_t)nx;
+      weight[y] = wet * 4096 + (uint64_t)(nx / 256 > 0 ? nx / 256 : 1);
     }
     const int prc = a.slab_partition_weighted(weight, ny, ranks, rank, &prm.slab_row0, &prm.slab_rows);
     free(weight);
