@@ -62,6 +62,8 @@ struct euler_gpu {
   size_t device_bytes;
   bool max_valid;                // sc.max_*_bits describe the current u, v
   bool use_tail;                 // fused red-black iteration: axpy + forward + backward as one kernel
+  bool split;                    // slab solve over NVLink: split-phase scalar exchange (p2p.cuh)
+  int poll_hint;                 // iterations of the previous solve (first_poll_chunk)
   // stats
   uint64_t frames, substeps, solves, solves_skipped, pcg_iterations, markers_migrated;
   int last_iterations;
@@ -297,6 +299,17 @@ void enqueue_iteration(euler_gpu* h) {
   launch_update_search(h->c);
 }
 
+// How many iterations to enqueue before the host looks at the stop flag.  Consecutive solves of a
+// run need about the same number of iterations (at scale they all end at the cap, main.c:735), so
+// the first poll of a solve waits for as many iterations as the previous solve took: one host
+// round trip per solve instead of one per `pcg_check_every` iterations.  Later polls go by
+// `every`.  Iterations enqueued past convergence return at once (the stop flag is on the device).
+int first_poll_chunk(const euler_gpu* h, int remaining, int every, bool first) {
+  int chunk = every;
+  if (first && h->poll_hint > every) chunk = h->poll_hint;
+  return chunk < remaining ? chunk : remaining;
+}
+
 int run_project(euler_gpu* h, float dt) {
   Ctx& c = h->c;
   launch_build_rhs(c, dt);
@@ -319,12 +332,14 @@ int run_project(euler_gpu* h, float dt) {
     if (!c.fused) launch_copy_search(c);                    // s = z                    (:746)
     int remaining = h->prm.max_iterations;
     const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
+    bool first_chunk = true;
     // where iteration 1 leaves its s
     const void* s_odd = c.mixed ? static_cast<const void*>(c.s32b) : static_cast<const void*>(c.s2);
     const int refresh = c.mixed ? h->prm.pcg_refresh_every : 0;
     int it = 0;
     while (remaining > 0) {
-      const int chunk = remaining < every ? remaining : every;
+      const int chunk = first_poll_chunk(h, remaining, every, first_chunk);
+      first_chunk = false;
       for (int i = 0; i < chunk; ++i) {
         ++it;
         if (c.fused) {
@@ -358,6 +373,7 @@ int run_project(euler_gpu* h, float dt) {
     h->last_iterations = h->host_sc->iters;
     h->last_residual = h->host_sc->resid;
     h->pcg_iterations += (uint64_t)h->host_sc->iters;
+    h->poll_hint = h->host_sc->iters;
   }
   launch_pressure_update(c, dt);
   h->max_valid = true;
@@ -438,7 +454,7 @@ int dist_iteration(euler_gpu* h, bool first, int it) {
     // the one exchange per iteration: z = M^-1 r, 4 rows deep; s' = z + beta s is then formed
     // redundantly on the halo rows (s itself was formed the same way one iteration earlier)
     // (z was exchanged together with the scalars at the end of the previous preconditioner)
-    launch_fused_search_apply(c, first);            // s', A s' -> c.q, z.s partial
+    launch_fused_search_apply(c, first, h->split ? it : 0);   // s', A s' -> c.q, z.s partial
   } else {
     CM(comm_halo(c, h->cm, c.s, 8, SLAB_HALO));
     launch_apply_a(c, true);
@@ -452,7 +468,7 @@ int dist_iteration(euler_gpu* h, bool first, int it) {
     launch_dist_alpha(c, h->cm.gather, h->cm.nranks);
   }
   if (h->use_tail) {
-    launch_fused_tail(c, h->prm.tol, (it & 1) ? 0 : 1);
+    launch_fused_tail(c, h->prm.tol, (it & 1) ? 0 : 1, h->split ? it : 0);
     int trc = dist_after_backward(h, false);
     if (trc) return trc;
     return 0;
@@ -487,20 +503,32 @@ int run_project_dist(euler_gpu* h, float dt) {
     const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
     const double* s_odd = c.s2;                      // where iteration 1 leaves its s
     int it = 0;
+    bool first_chunk = true;
     while (remaining > 0) {
-      const int chunk = remaining < every ? remaining : every;
+      const int chunk = first_poll_chunk(h, remaining, every, first_chunk);
+      first_chunk = false;
       for (int i = 0; i < chunk; ++i) { rc = dist_iteration(h, first, ++it); if (rc) return rc; first = false; }
       remaining -= chunk;
+      // split-phase exchange: the last tail kernel's {z.r, ||r||inf} has no consumer yet — a
+      // one-block kernel reads it for the host, and applies it when this was the last batch
+      if (h->split) launch_dist_peek(c, remaining == 0);
       rc = pull_scalars(h);
       if (rc) return rc;
       if (h->host_sc->comm_timeout)
         return fail(EULER_E_COMM, "peer-to-peer exchange timed out (a rank stopped participating)");
       if (h->host_sc->done) break;
+      if (h->split && h->host_sc->peek_done) {
+        launch_dist_peek(c, true);
+        rc = pull_scalars(h);
+        if (rc) return rc;
+        break;
+      }
     }
-    if (c.fused == 1) launch_p_fixup(c, s_odd);      // pending p update of an odd last iteration
+    if (c.fused == 1) launch_p_fixup(c, s_odd, h->split ? 1 : 0);   // pending p update of an odd last iteration
     h->last_iterations = h->host_sc->iters;
     h->last_residual = h->host_sc->resid;
     h->pcg_iterations += (uint64_t)h->host_sc->iters;
+    h->poll_hint = h->host_sc->iters;
   }
   // p[y+1] of the last owned row (main.c:800) is already there: p was updated redundantly on
   // the halo rows.  (When the solve was skipped p == 0 everywhere.)
@@ -512,30 +540,29 @@ int run_project_dist(euler_gpu* h, float dt) {
   return check_launch("project");
 }
 
-// markers that crossed into a neighbouring slab (displacement < 1 cell per sub-step)
+// markers that crossed into a neighbouring slab (displacement < 1 cell per sub-step): the advection
+// kernel has put them into the staging buffers and turned the local copies into sink-column
+// positions that the next refresh_marker_counts deletes; what the neighbours hand over is appended
 int migrate_markers(euler_gpu* h) {
   Ctx& c = h->c;
   Comm& cm = h->cm;
-  launch_partition_markers(c, h->row0, h->row0 + h->rows, cm.send_dn, cm.send_up, cm.send_cap, h->n_keep);
   // counts first: what I send down/up, what the neighbours send me
   CU(cudaMemsetAsync(cm.mig, 0, 2 * sizeof(unsigned long long), c.stream));
   CM(comm_exchange(c, cm, &c.sc->n_send_dn, 8, &cm.mig[0], 8, &c.sc->n_send_up, 8, &cm.mig[1], 8));
   unsigned long long host[5];
   CU(cudaMemcpyAsync(&host[0], &c.sc->n_send_dn, 16, cudaMemcpyDeviceToHost, c.stream));
   CU(cudaMemcpyAsync(&host[2], cm.mig, 16, cudaMemcpyDeviceToHost, c.stream));
-  CU(cudaMemcpyAsync(&host[4], h->n_keep, 8, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaMemcpyAsync(&host[4], &c.sc->n_markers, 8, cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
-  const unsigned long long to_dn = host[0], to_up = host[1], from_dn = host[2], from_up = host[3], keep = host[4];
+  const unsigned long long to_dn = host[0], to_up = host[1], from_dn = host[2], from_up = host[3], have = host[4];
   h->markers_migrated += to_dn + to_up;
   if (to_dn > cm.send_cap || to_up > cm.send_cap)
     return fail(EULER_E_UNSUPPORTED, "more than %zu markers cross a slab boundary in one sub-step", cm.send_cap);
-  if (keep + from_dn + from_up > c.max_markers)
+  if (have + from_dn + from_up > c.max_markers)
     return fail(EULER_E_UNSUPPORTED, "slab marker capacity exceeded");
-  CM(comm_exchange(c, cm, cm.send_dn, (size_t)to_dn * 8, c.markers + keep, (size_t)from_dn * 8,
-                   cm.send_up, (size_t)to_up * 8, c.markers + keep + from_dn, (size_t)from_up * 8));
-  const unsigned long long n_new = keep + from_dn + from_up;
-  CU(cudaMemcpyAsync(&c.sc->n_markers, &n_new, 8, cudaMemcpyHostToDevice, c.stream));
-  CU(cudaStreamSynchronize(c.stream));               // n_new is a stack variable
+  CM(comm_exchange(c, cm, cm.send_dn, (size_t)to_dn * 8, c.markers + have, (size_t)from_dn * 8,
+                   cm.send_up, (size_t)to_up * 8, c.markers + have + from_dn, (size_t)from_up * 8));
+  if (from_dn + from_up) launch_add_markers(c, from_dn + from_up);
   return 0;
 }
 
@@ -543,7 +570,8 @@ int run_substep_dist(euler_gpu* h, float dt) {
   Ctx& c = h->c;
   h->last_dt = dt;
   prof_mark(h, 0);
-  launch_advect_markers(c, dt, EULER_MARKERS_FAST);
+  launch_advect_markers_slab(c, dt, h->row0, h->row0 + h->rows, h->cm.rank > 0 ? h->cm.send_dn : nullptr,
+                             h->cm.rank + 1 < h->cm.nranks ? h->cm.send_up : nullptr, h->cm.send_cap);
   int rc = migrate_markers(h);
   if (rc) return rc;
   launch_refresh_counts(c);
@@ -698,7 +726,8 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   memset(&h->pp, 0, sizeof h->pp); h->z_raw = nullptr; h->source_cap = 0;
   h->host_sc = nullptr; h->device_bytes = 0; h->max_valid = false;
   h->frames = h->substeps = h->solves = h->solves_skipped = h->pcg_iterations = h->markers_migrated = 0;
-  h->last_iterations = 0; h->last_residual = 0; h->last_dt = 0; h->profiling = false;
+  h->last_iterations = 0; h->last_residual = 0; h->last_dt = 0; h->profiling = false; h->poll_hint = 0;
+  h->split = false;
   h->ms_markers = h->ms_grid = h->ms_project = 0;
   for (int i = 0; i < 4; ++i) h->ev[i] = nullptr;
   Ctx& c = h->c;
@@ -1192,6 +1221,10 @@ int euler_gpu_comm_p2p_import(euler_gpu* h, const void* blobs) {
   if (h->c.fused == 1) {
     const char* e = getenv("EULER_P2P_SEPARATE");
     h->c.p2p_mode = (e && atoi(e)) ? 1 : 2;
+    // EULER_P2P_SPLIT=1: split-phase scalar exchange (post in the producing kernel, collect in every
+    // block of the consuming one); needs the fused tail kernel
+    const char* sp = getenv("EULER_P2P_SPLIT");
+    h->split = h->c.p2p_mode == 2 && h->use_tail && sp && atoi(sp) != 0;
   }
   return 0;
 }

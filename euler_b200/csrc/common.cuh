@@ -69,6 +69,12 @@ struct DevScalars {
   unsigned long long src_base, n_markers_global;
   int comm_timeout, pad3;                    // a peer never showed up in a P2P exchange
   unsigned int grid_tiles, pad4;             // tiles the grid stages stream this sub-step (GridTiles)
+  // split-phase scalar exchange of the slab solve (p2p.cuh): sigma / alpha by iteration parity (a
+  // kernel's block 0 writes the next value while its other blocks still read the current one),
+  // and what the host sees of an exchange that has been posted but not consumed yet
+  double sigma_s[2], alpha_s[2];
+  double peek_resid;
+  int peek_done, peek_iters;
 };
 
 // The MAC-grid stage kernels (grid_kernels.cu) stream only the 512 x 32-cell tiles that can hold a

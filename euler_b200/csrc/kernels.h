@@ -149,6 +149,11 @@ void launch_refresh_counts(Ctx& c);                          // prev<-cur, re-bi
 void launch_sources(Ctx& c);                                 // update_fluid_sources
 void launch_sources_count(Ctx& c);
 void launch_sources_prep(Ctx& c, const double* gathered, int rank, int nranks);
+// slab mode: advect + hand the markers that left rows [own_lo, own_hi) to the staging buffers
+// (null = no neighbour on that side); they are deleted locally by the next refresh_marker_counts
+void launch_advect_markers_slab(Ctx& c, float dt, int own_lo_global, int own_hi_global, float2* send_dn,
+                                float2* send_up, size_t send_cap);
+void launch_add_markers(Ctx& c, unsigned long long n);       // sc.n_markers += n (markers received)
 void launch_partition_markers(Ctx& c, int own_lo_global, int own_hi_global, float2* send_dn,
                               float2* send_up, size_t send_cap, unsigned long long* n_keep);
 // slab create/reinit: append the staged markers of rows [lo, hi) to c.markers at sc->n_markers
@@ -163,11 +168,13 @@ void launch_rb_build(Ctx& c);                                // red-black E^-1
 void launch_rb_apply(Ctx& c, bool init);                     // z = M^-1 r (+ z.r, sigma/beta)
 void launch_rb_forward(Ctx& c);                              //   q = L^-1 r
 void launch_rb_backward(Ctx& c, bool init);                  //   z = L^-T q (+ z.r)
-void launch_fused_search_apply(Ctx& c, bool init);            // s' = z + beta s ; A s' ; alpha
+// split_it: 0, or the 1-based iteration number when the slab solve uses the split-phase exchange
+void launch_fused_search_apply(Ctx& c, bool init, int split_it = 0);   // s' = z + beta s ; A s' ; alpha
 void launch_fused_axpy_forward(Ctx& c, double tol);           // p, r', ||r'||inf, q = L^-1 r'
 // r' = r - alpha A s, p, ||r'||inf, q = L^-1 r', z = L^-T q, z.r', beta: one kernel (pcg_tail.cuh);
 // mode as launch_axpy
-void launch_fused_tail(Ctx& c, double tol, int mode);
+void launch_fused_tail(Ctx& c, double tol, int mode, int split_it = 0);
+void launch_dist_peek(Ctx& c, bool apply);                   // split-phase: the pending {z.r, ||r||inf} for the host
 void launch_set_alpha(Ctx& c, double alpha);                 // parity hook: alpha = given, alpha_prev = 0, sigma = 1
 void launch_dist_alpha(Ctx& c, const double* gathered, int nranks);
 void launch_dist_beta(Ctx& c, const double* gathered, int nranks, bool init, double tol);
@@ -179,7 +186,7 @@ void launch_apply_a(Ctx& c, bool with_alpha);                // z = A s (+ z.s, 
 void launch_axpy(Ctx& c, double tol, bool as_in_q = false, int mode = 2);
 // completes p after a fused solve that stopped on an odd iteration; s_odd_plane = the plane
 // the first iteration wrote its search direction to (Ctx::s2 at the start of the solve)
-void launch_p_fixup(Ctx& c, const void* s_odd_plane);
+void launch_p_fixup(Ctx& c, const void* s_odd_plane, int split = 0);
 // mixed-precision mode: r32 <- b - A p evaluated in fp64 (residual replacement)
 void launch_true_residual(Ctx& c);
 void launch_update_search(Ctx& c);                           // s = z + beta s

@@ -39,6 +39,34 @@ __global__ void __launch_bounds__(MTHREADS) k_advect_markers(
   }
 }
 
+// Row-slab mode: the same step, and a marker whose new cell row lies outside the rows this rank
+// owns is handed to the neighbouring slab right here — appended to the staging buffer NCCL sends
+// (displacement per sub-step is < 1 cell, CFL 0.75, main.c:838, so only to an ADJACENT slab; a
+// handful of markers per boundary column, so one atomic each is cheap) and replaced in place by
+// a position in the sink column x = 0 (main.c:244-252), where refresh_marker_counts' ordinary
+// swap-delete removes it.  No separate partition pass over all markers.
+__global__ void __launch_bounds__(MTHREADS) k_advect_markers_slab(
+    Grid g, InterpLimits lim, const float* __restrict__ u, const float* __restrict__ v,
+    const uint8_t* __restrict__ fluid, const uint8_t* __restrict__ solid, float h,
+    const float2* __restrict__ src, float2* __restrict__ dst, DevScalars* sc, float dt,
+    int own_lo, int own_hi, float2* __restrict__ send_dn, float2* __restrict__ send_up, size_t send_cap) {
+  const size_t n = sc->n_markers;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float2 p = walk_marker<false>(g, lim, u, v, fluid, solid, h, src[i], dt);
+    const int gy = (int)floorf(div_h(p.y, h));
+    float2* out = gy < own_lo ? send_dn : (gy >= own_hi ? send_up : nullptr);   // null at the grid's ends too
+    if (out) {
+      const unsigned long long pos = atomicAdd(gy < own_lo ? &sc->n_send_dn : &sc->n_send_up, 1ull);
+      if (pos < send_cap) out[pos] = p; else sc->marker_overflow = 1;
+      p = make_float2(-1.f, -1.f);
+    }
+    dst[i] = p;
+  }
+}
+
+__global__ void k_add_markers(DevScalars* sc, unsigned long long n) { sc->n_markers += n; }
+
 // ---- reference marker mode: the `dt -= t_prev` carry-over (main.c:464, 501, 518) ---------
 // In the reference `dt` is advect_markers' PARAMETER, so what one marker's rewind takes off
 // it is also missing for every later marker of the array.  A walk with a smaller dt is a
@@ -450,9 +478,13 @@ __global__ void __launch_bounds__(MTHREADS) k_partition_markers(
 __global__ void __launch_bounds__(MTHREADS) k_filter_markers(
     float h, int own_lo, int own_hi, const float2* __restrict__ src, size_t n,
     float2* __restrict__ dst, size_t cap, DevScalars* sc) {
+  // one atomic per BLOCK and round (a warp-level cursor on one address serialises: 3 ms for 10^8
+  // markers): warp ballots, block scan of the warp counts, thread 0 reserves the block's range
   const size_t per = (size_t)gridDim.x * blockDim.x;
   const size_t rounds = (n + per - 1) / per;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __shared__ unsigned int wcount[MTHREADS / 32];
+  __shared__ unsigned long long base_sh;
   for (size_t rd = 0; rd < rounds; ++rd) {
     const size_t i = rd * per + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     bool mine = false;
@@ -463,14 +495,20 @@ __global__ void __launch_bounds__(MTHREADS) k_filter_markers(
       mine = gy >= own_lo && gy < own_hi;
     }
     const unsigned bal = __ballot_sync(EULER_FULL_MASK, mine);
-    if (!bal) continue;
-    unsigned long long base = 0;
-    if (lane == __ffs(bal) - 1) base = atomicAdd(&sc->n_markers, (unsigned long long)__popc(bal));
-    base = __shfl_sync(EULER_FULL_MASK, base, __ffs(bal) - 1);
+    if (lane == 0) wcount[wid] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int tot = 0;
+#pragma unroll
+      for (int k = 0; k < MTHREADS / 32; ++k) { const unsigned int t = wcount[k]; wcount[k] = tot; tot += t; }
+      base_sh = tot ? atomicAdd(&sc->n_markers, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
     if (mine) {
-      const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+      const unsigned long long pos = base_sh + wcount[wid] + __popc(bal & ((1u << lane) - 1u));
       if (pos < cap) dst[pos] = m;
     }
+    __syncthreads();
   }
 }
 
@@ -639,6 +677,22 @@ void launch_sources_count(Ctx& c) {
 }
 void launch_sources_prep(Ctx& c, const double* gathered, int rank, int nranks) {
   k_sources_prep<<<1, 1, 0, c.stream>>>(c.sc, gathered, rank, nranks);
+  c.launches += 1;
+}
+
+// slab mode: advection + hand-over of the leavers in one pass (k_advect_markers_slab)
+void launch_advect_markers_slab(Ctx& c, float dt, int own_lo_global, int own_hi_global, float2* send_dn,
+                                float2* send_up, size_t send_cap) {
+  ProfScope ps(c, KC_ADVECT_MARKERS);
+  cudaMemsetAsync(&c.sc->n_send_dn, 0, 2 * sizeof(unsigned long long), c.stream);
+  k_advect_markers_slab<<<c.sm_count * 8, MTHREADS, 0, c.stream>>>(
+      c.g, c.lim, c.u, c.v, c.count, c.solid, c.h, c.markers, c.markers_alt, c.sc, dt, own_lo_global,
+      own_hi_global, send_dn, send_up, send_cap);
+  c.launches += 1;
+  float2* t = c.markers; c.markers = c.markers_alt; c.markers_alt = t;
+}
+void launch_add_markers(Ctx& c, unsigned long long n) {
+  k_add_markers<<<1, 1, 0, c.stream>>>(c.sc, n);
   c.launches += 1;
 }
 

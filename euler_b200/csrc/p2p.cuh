@@ -109,4 +109,60 @@ __device__ __forceinline__ void p2p_finish(const DistArgs& d, DevScalars* sc, in
   sc->sigma = sum;
 }
 
+// ---- split-phase form of the same exchange (EULER_P2P_SPLIT=1) ---------------------------------
+// p2p_finish makes the PRODUCING kernel's last block wait for every rank's partial: an NVLink
+// round trip plus the skew between ranks, serialised with the kernel's tail and the next launch.
+// Here the last block only POSTS (stores + release, no wait) and every block of the NEXT kernel
+// COLLECTS at its start: the wait overlaps the launch gap and the next kernel's ramp, and the
+// scalar step (alpha, or the stop test and beta) is repeated identically by every block.
+// Reuse of a mailbox slot (parity of the sequence number) is safe for the same reason as before:
+// a peer posts exchange n+2 only after it collected n+1, which needs my post of n+1, which my
+// last block makes after all my blocks collected n.
+__device__ __forceinline__ void p2p_post(const DistArgs& d, double part0, double part1, bool halo) {
+  const int t = threadIdx.x;
+  Mailbox* mine = d.mine;
+  const unsigned long long seq = mine->seq_ctr;
+  const unsigned long long hseq = mine->halo_ctr + 1;
+  const int par = (int)(seq & 1ull);
+  if (halo) {
+    if (t == 32 && d.mb_dn) { __threadfence_system(); st_release_sys(&d.mb_dn->halo_flag[1], hseq); }
+    if (t == 33 && d.mb_up) { __threadfence_system(); st_release_sys(&d.mb_up->halo_flag[0], hseq); }
+  }
+  if (t < d.nranks) {
+    Mailbox* dst = d.peer[t];
+    dst->pay[par][d.rank][0] = part0;
+    dst->pay[par][d.rank][1] = part1;
+    st_release_sys(&dst->flag[par][d.rank], seq + 1);       // release orders the two stores before it
+  }
+  __syncthreads();
+  if (t == 0) { mine->seq_ctr = seq + 1; if (halo) mine->halo_ctr = hseq; }
+}
+
+// All threads of a block (>= 64).  false: a peer never showed up (bounded poll).
+__device__ __forceinline__ bool p2p_collect(const DistArgs& d, bool wait_halo, double& sum, double& mx) {
+  const int t = threadIdx.x;
+  __shared__ int ok_c;
+  __shared__ double res_c[2];
+  Mailbox* mine = d.mine;
+  const unsigned long long seq = mine->seq_ctr;             // posted by my own rank's previous kernel
+  const int par = (int)((seq - 1ull) & 1ull);
+  if (t == 0) ok_c = 1;
+  __syncthreads();
+  if (t < d.nranks && !wait_flag(&mine->flag[par][t], seq)) ok_c = 0;
+  if (wait_halo) {
+    const unsigned long long hseq = mine->halo_ctr;
+    if (t == 34 && d.mb_dn && !wait_flag(&mine->halo_flag[0], hseq)) ok_c = 0;
+    if (t == 35 && d.mb_up && !wait_flag(&mine->halo_flag[1], hseq)) ok_c = 0;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double a = 0.0, m = 0.0;
+    for (int r = 0; r < d.nranks; ++r) { a += mine->pay[par][r][0]; m = fmax(m, mine->pay[par][r][1]); }
+    res_c[0] = a; res_c[1] = m;
+  }
+  __syncthreads();
+  sum = res_c[0]; mx = res_c[1];
+  return ok_c != 0;
+}
+
 }  // namespace euler

@@ -325,10 +325,10 @@ __global__ void __launch_bounds__(TT) k_axpy(
 template <class T>
 __global__ void __launch_bounds__(TT) k_p_fixup(Grid g, TileList active, const T* __restrict__ s_odd,
                                                 const uint8_t* __restrict__ fluid, double* __restrict__ p,
-                                                const DevScalars* sc) {
+                                                const DevScalars* sc, int split) {
   using V4 = typename Vec4<T>::type;
   if (!(sc->iters & 1)) return;
-  const double alpha = sc->alpha;
+  const double alpha = split ? sc->alpha_s[1] : sc->alpha;   // split-phase exchange: alpha of an odd iteration
   for_each_tile(g, active, [&](int x0, int y0, int y1, bool live) {
     if (!live) return;
     size_t c = gidx(g, x0, y0);
@@ -735,10 +735,27 @@ __global__ void __launch_bounds__(TW / C, MB) k_fused_search_apply(
     Grid g, TileList active, const T* __restrict__ z, const T* __restrict__ s,
     const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, T* __restrict__ s_new,
     T* __restrict__ as, double* partials, DevScalars* sc, int init, int exact, int acc0, int acc1,
-    const __grid_constant__ DistArgs dist) {
+    const __grid_constant__ DistArgs dist, int split_it, double tol) {
   pdl_prologue();
   if (sc->done) return;
-  FusedSearchApply<C, T> op{g, s_new, as, (T)sc->beta, init != 0, 0.0, acc0, acc1};
+  double beta = sc->beta;
+  if (split_it) {
+    // split-phase exchange (p2p.cuh): this kernel's blocks consume {z.r, ||r||inf} that the
+    // previous iteration's tail kernel posted — the stop test and beta of main.c:756-765
+    if (split_it == 1) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) sc->sigma_s[0] = sc->sigma;   // z.r of the initial application
+    } else {
+      double zr, nm;
+      const bool ok = p2p_collect(dist, true, zr, nm);
+      const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
+      if (!ok) { if (writer) { sc->comm_timeout = 1; sc->done = 1; } return; }
+      if (writer) { sc->resid = nm; sc->iters += 1; }
+      if (nm <= tol) { if (writer) sc->done = 1; return; }                   // main.c:756-758
+      beta = zr / sc->sigma_s[split_it & 1];                                // main.c:762-765
+      if (writer) { sc->beta = beta; sc->sigma_s[(split_it + 1) & 1] = zr; }
+    }
+  }
+  FusedSearchApply<C, T> op{g, s_new, as, (T)beta, init != 0, 0.0, acc0, acc1};
   pipe::Planes<2, 2, T> in;
   in.d[0] = z; in.d[1] = s; in.b[0] = fluid; in.b[1] = reinterpret_cast<const uint8_t*>(adiag);
   pipe::run<2, 2, NS, TH, FusedSearchApply<C, T>, C, T>(g, active.list, (int)*active.count, in, op);
@@ -746,7 +763,8 @@ __global__ void __launch_bounds__(TW / C, MB) k_fused_search_apply(
   double total;
   if (!grid_reduce_last_block_all<false>(bsum, partials, &sc->ctr[CTR_ZS], total)) return;
   if (dist.mine) {                                           // {z.s} over NVLink -> alpha
-    p2p_finish(dist, sc, 0, 0, 0.0, total, false);
+    if (split_it) p2p_post(dist, total, 0.0, false);
+    else p2p_finish(dist, sc, 0, 0, 0.0, total, false);
     return;
   }
   if (threadIdx.x != 0) return;
@@ -931,16 +949,16 @@ void launch_axpy(Ctx& c, double tol, bool as_in_q, int mode) {
   c.launches += 1;
 }
 
-void launch_p_fixup(Ctx& c, const void* s_odd_plane) {
+void launch_p_fixup(Ctx& c, const void* s_odd_plane, int split) {
   ProfScope ps(c, KC_MISC);
   const PV v = pview(c);
   const size_t o = (size_t)(v.s - c.s);
   if (c.mixed)
     k_p_fixup<float><<<pcg_blocks(c, k_p_fixup<float>), TT, 0, c.stream>>>(
-        v.g, TL, static_cast<const float*>(s_odd_plane) + o, v.fluid, v.p, c.sc);
+        v.g, TL, static_cast<const float*>(s_odd_plane) + o, v.fluid, v.p, c.sc, split);
   else
     k_p_fixup<double><<<pcg_blocks(c, k_p_fixup<double>), TT, 0, c.stream>>>(
-        v.g, TL, static_cast<const double*>(s_odd_plane) + o, v.fluid, v.p, c.sc);
+        v.g, TL, static_cast<const double*>(s_odd_plane) + o, v.fluid, v.p, c.sc, split);
   c.launches += 1;
 }
 
@@ -1070,7 +1088,7 @@ void launch_rb_apply(Ctx& c, bool init) {
 //   axpy_forward : reads A s' (c.q), r, pc writes p, r' (twin, swapped in), q -> c.z; then
 //                  c.z <-> c.q so that the ordinary k_rb_backward reads q from c.q and leaves
 //                  the new M^-1 r' in c.z
-void launch_fused_search_apply(Ctx& c, bool init) {
+void launch_fused_search_apply(Ctx& c, bool init, int split_it) {
   ProfScope ps(c, KC_FUSED_A);
   const PV v = pview(c);
   const size_t o = (size_t)(v.s - c.s);
@@ -1084,12 +1102,12 @@ void launch_fused_search_apply(Ctx& c, bool init) {
     launch_pdl(k_fused_search_apply<N, C, float>, \
                pcg_blocks(c, k_fused_search_apply<N, C, float>, smem, TW / C), TW / C, smem, c.stream, \
                v.g, TL, v.z32, v.s32, v.fluid, v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0, \
-               v.a0, v.a1, d); }
+               v.a0, v.a1, d, 0, 0.0); }
     if (c.mixed_blocks == 8) {
       constexpr int smem = pipe::smem_bytes<2, 2, 4, float>();
       auto k = k_fused_search_apply<4, C, float, 8>;
       launch_pdl(k, pcg_blocks(c, k, smem, TW / C, true), TW / C, smem, c.stream, v.g, TL, v.z32, v.s32, v.fluid,
-                 v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0, v.a0, v.a1, d);
+                 v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0, v.a0, v.a1, d, 0, 0.0);
     } else if (c.ns_mixed[2] == 8) KA32(8) else if (c.ns_mixed[2] == 6) KA32(6) else KA32(4)
 #undef KA32
     c.launches += 1;
@@ -1100,7 +1118,7 @@ void launch_fused_search_apply(Ctx& c, bool init) {
 #define KA(N, C) { constexpr int smem = pipe::smem_bytes<2, 2, N>(); \
   launch_pdl(k_fused_search_apply<N, C>, pcg_blocks(c, k_fused_search_apply<N, C>, smem, TW / C), TW / C, smem, c.stream, \
              v.g, TL, v.z, v.s, v.fluid, v.adiag, c.s2 + o, v.q, c.partials, c.sc, init ? 1 : 0, \
-             c.distributed ? 2 : 0, v.a0, v.a1, d); }
+             c.distributed ? 2 : 0, v.a0, v.a1, d, split_it, c.tol); }
   if (cpt == 2) { if (ns == 6) KA(6, 2) else if (ns == 5) KA(5, 2) else KA(4, 2) }
   else { if (ns == 6) KA(6, 4) else if (ns == 5) KA(5, 4) else KA(4, 4) }
 #undef KA
@@ -1124,7 +1142,7 @@ void launch_fused_axpy_forward(Ctx& c, double tol) {
 
 // axpy + forward + backward of the fused red-black iteration as one kernel (pcg_tail.cuh):
 // reads r, A s (c.q), pc, s (, s_prev), p; writes r' into the twin plane (swapped in), p, z
-void launch_fused_tail(Ctx& c, double tol, int mode) {
+void launch_fused_tail(Ctx& c, double tol, int mode, int split_it) {
   ProfScope ps(c, KC_FUSED_TAIL);
   const PV v = pview(c);
   const size_t o = (size_t)(v.r - c.r);
@@ -1146,7 +1164,7 @@ void launch_fused_tail(Ctx& c, double tol, int mode) {
 #define TAIL(N, C, MB) { constexpr int smem = tail::smem_bytes<N>(); constexpr int threads = TW / C + 32; \
     k_fused_tail<N, C, MB><<<pcg_blocks(c, k_fused_tail<N, C, MB>, smem, threads), threads, smem, c.stream>>>( \
         v.g, TL, v.r, v.q, v.precon, v.fluid, v.s, c.s2 + o, v.p, c.r2 + o, v.z, c.partials, c.sc, tol, mode, \
-        dotflag(c), v.a0, v.a1, d); }
+        dotflag(c), v.a0, v.a1, d, split_it); }
   if (cpt == 4) { if (ns == 4) TAIL(4, 4, 3) else TAIL(3, 4, 3) }
   else if (mb == 2) { if (ns == 5) TAIL(5, 2, 2) else if (ns == 4) TAIL(4, 2, 2) else TAIL(3, 2, 2) }
   else { if (ns == 4) TAIL(4, 2, 3) else TAIL(3, 2, 3) }
@@ -1160,6 +1178,24 @@ __global__ void k_set_alpha(DevScalars* sc, double alpha) {
 }
 void launch_set_alpha(Ctx& c, double alpha) {
   k_set_alpha<<<1, 1, 0, c.stream>>>(c.sc, alpha);
+  c.launches += 1;
+}
+
+// Split-phase exchange: what the LAST tail kernel of a batch posted has no consumer yet.  This
+// one-block kernel reads it for the host (peek_*: stop test and iteration count as they will
+// be) and, when the host ends the solve (`apply`), makes it the solve's final state.
+__global__ void __launch_bounds__(64) k_dist_peek(DevScalars* sc, double tol, int apply,
+                                                  const __grid_constant__ DistArgs dist) {
+  if (sc->done) { if (threadIdx.x == 0) { sc->peek_done = 1; sc->peek_iters = sc->iters; sc->peek_resid = sc->resid; } return; }
+  double zr, nm;
+  const bool ok = p2p_collect(dist, true, zr, nm);
+  if (threadIdx.x != 0) return;
+  if (!ok) { sc->comm_timeout = 1; sc->done = 1; return; }
+  sc->peek_resid = nm; sc->peek_iters = sc->iters + 1; sc->peek_done = nm <= tol ? 1 : 0;
+  if (apply) { sc->resid = nm; sc->iters += 1; if (nm <= tol) sc->done = 1; }
+}
+void launch_dist_peek(Ctx& c, bool apply) {
+  k_dist_peek<<<1, 64, 0, c.stream>>>(c.sc, c.tol, apply ? 1 : 0, c.dist);
   c.launches += 1;
 }
 

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     const double* __restrict__ precon, const uint8_t* __restrict__ fluid, const double* __restrict__ s,
     const double* __restrict__ s_prev, double* __restrict__ p, double* __restrict__ r_new,
     double* __restrict__ z, double* partials, DevScalars* sc, double tol, int mode, int exact,
-    int acc0, int acc1, const __grid_constant__ DistArgs dist) {
+    int acc0, int acc1, const __grid_constant__ DistArgs dist, int split_it) {
   using L = pipe::Layout<3, 1>;
   constexpr int NMAIN = TW / C;                  // main threads: C cells each
   constexpr int ROWT = L::ROWT;
@@ -88,7 +88,18 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
   }
   __syncthreads();
 
-  const double alpha = sc->alpha, alpha_prev = sc->alpha_prev;
+  double alpha = sc->alpha, alpha_prev = sc->alpha_prev;
+  if (split_it) {
+    // split-phase exchange (p2p.cuh): every block consumes the {z.s} partials the search/apply
+    // kernel posted and forms alpha itself (main.c:752); block 0 records it
+    double zs, unused;
+    const bool ok = p2p_collect(dist, false, zs, unused);
+    const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
+    if (!ok) { if (writer) { sc->comm_timeout = 1; sc->done = 1; } return; }
+    alpha = sc->sigma_s[(split_it + 1) & 1] / zs;
+    alpha_prev = sc->alpha_s[(split_it + 1) & 1];          // the previous iteration's
+    if (writer) { sc->alpha_s[split_it & 1] = alpha; sc->zs = zs; sc->alpha_prev = alpha_prev; sc->alpha = alpha; }
+  }
   const double neg_alpha = -alpha;
   const int th = g.th;
   const size_t pitch = (size_t)g.pitch;
@@ -326,6 +337,7 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
   __syncthreads();
   const double total = tot_sh[0], norm = tot_sh[1];
   if (dist.mine) {                                           // halo flags + {z.r, ||r||inf} over NVLink
+    if (split_it) { p2p_post(dist, total, norm, true); return; }
     if (tid == 0) sc->part[1] = norm;
     __syncthreads();
     p2p_finish(dist, sc, 1, 0, tol, total, true);

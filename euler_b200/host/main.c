@@ -263,6 +263,9 @@ int main(int argc, char **argv) {
   }
   if (rc) { fprintf(stderr, "Could not load %s!\n", file ? file : synthetic); return 1; }  /* main.c:213 */
 
+  if (prm.precon == EULER_PRECON_IC0_WAVEFRONT && (long)nx * ny > 512l * 512l)
+    fprintf(stderr, "note: --precon ic0 (the default: the reference's natural-order IC(0), solved by a wavefront) is the\n"
+                    "      parity mode and latency-bound; on a %dx%d grid --precon rb (red-black IC(0)) is ~10-100x faster\n", nx, ny);
   prm.rng_state = scn.rng_state;
   if (ranks > 1) {
     /* slabs balanced by work: the PCG and the grid stages stream the tiles that hold or border

@@ -152,14 +152,15 @@ def _big_text(kind, n):
     return synthetic(kind, n, n) if kind == "basic-fill" else resample(shipped_text(kind), n - 2, n - 2)
 
 
-def _worker_big(rank, nranks, uid, kind, n, steps, out_dir):
+def _worker_big(rank, nranks, uid, kind, n, steps, cap, out_dir):
     sys.path.insert(0, ROOT)
     from euler_b200 import gpu as G
     scn = Scenario(_big_text(kind, n), n, n, row_major_markers=True)
-    weight = scn.fluid.sum(axis=1, dtype=np.uint64) * 100 + np.uint64(n)
+    weight = scn.fluid.sum(axis=1, dtype=np.uint64) * 4096 + np.uint64(max(1, n // 256))
     row0, rows = G.slab_partition_weighted(weight, nranks, rank)
     g = G.EulerGpu.from_scenario(scn, precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST,
-                                 device=rank, slab_row0=row0, slab_rows=rows, pcg_check_every=25)
+                                 device=rank, slab_row0=row0, slab_rows=rows, pcg_check_every=50,
+                                 max_iterations=cap)
     g.comm_init(rank, nranks, uid)
     g.comm_p2p_import(_exchange_blobs(out_dir, rank, nranks, g.comm_p2p_export()))
     for _ in range(steps):
@@ -173,41 +174,51 @@ def _worker_big(rank, nranks, uid, kind, n, steps, out_dir):
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("kind,n,steps", [("weird-edges", 8192, 3), ("basic-fill", 4096, 2)])
-def test_large_grids_two_slabs(kind, n, steps):
-    """BASELINE config[3] (weird-edges irregular solid mask at 8192^2 on 2 slabs: halo exchange and
-    marker migration at scale, fluid in free fall) and a resting block at 4096^2 (the capped,
-    unconverged solve across two slabs) against the single-GPU run, weighted split, NVLink
-    exchanges.  Marker totals, iteration counts and RNG state are equal; the count planes are
-    identical up to the handful of markers that sit within one fp32 ulp of a cell edge (the two
-    runs sum their dot products in different orders).  u, v: within 1e-5 of their maximum where
-    the solve is skipped or converges; at 4096^2 the solve stops UNCONVERGED at the reference's
-    100-iteration cap (hard part 2) and CG amplifies the 1e-16 differences of the two
-    summation orders to ~2e-5 of max|u| (measured 1.9e-5), so that case is held to 1e-4."""
+@pytest.mark.parametrize("kind,n,steps,cap", [("weird-edges", 8192, 3, 100), ("basic-fill", 4096, 2, 100),
+                                              ("basic-fill", 4096, 2, 20000)])
+def test_large_grids_two_slabs(kind, n, steps, cap):
+    """BASELINE config[3] geometry (weird-edges irregular solid mask at 8192^2 on 2 slabs: halo exchange and
+    marker migration at scale) and a resting block at 4096^2 against the single-GPU run, weighted split,
+    NVLink exchanges.  Marker totals, iteration counts and RNG state are equal.
+      cap = 20000: both runs CONVERGE (||r||inf <= 1e-6, several thousand iterations) — the comparison
+          that means something: u, v within 1e-5 of their maximum (north_star), count planes identical
+          up to markers within one fp32 ulp of a cell edge.
+      cap = 100 (the reference's, main.c:735): the solve stops far from converged (||r||inf ~ 10^3) and CG
+          amplifies the different summation orders of the two runs' dot products; the iterates are
+          different, equally unconverged ones (measured 2e-5 .. 2e-4 of max|v| depending on the reduction
+          tree), so this case only checks that the runs stay on the same trajectory: 2e-3."""
     import tempfile
     import torch.multiprocessing as mp
     from euler_b200 import gpu as G
     uid = G.comm_unique_id()
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(_worker_big, args=(2, uid, kind, n, steps, tmp), nprocs=2, join=True)
+        mp.spawn(_worker_big, args=(2, uid, kind, n, steps, cap, tmp), nprocs=2, join=True)
         parts = [dict(np.load(os.path.join(tmp, "big%d.npz" % r))) for r in range(2)]
     ref = G.EulerGpu.from_scenario(Scenario(_big_text(kind, n), n, n, row_major_markers=True),
-                                   precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST, pcg_check_every=25)
+                                   precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST, pcg_check_every=50,
+                                   max_iterations=cap)
     for _ in range(steps):
         ref.substep(ref.calculate_timestep(0.1))
     st = ref.stats()
+    converged = cap > 100
+    if converged:
+        assert st.last_residual <= 1e-6 and st.last_iterations < cap
     full, fu, fv = ref.read_marker_count(), ref.get(G.F_U), ref.get(G.F_V)
     mismatched = 0
     for p in parts:
         r0, k = int(p["row0"]), int(p["rows"])
         mismatched += int((p["count"] != full[r0:r0 + k]).sum())
-        assert int(p["iters"]) == int(st.pcg_iterations) and int(p["rng"]) == int(st.rng_state)
-        tol = 1e-4 if kind == "basic-fill" else 1e-5
+        assert int(p["rng"]) == int(st.rng_state)
+        if converged:
+            assert abs(int(p["iters"]) - int(st.pcg_iterations)) <= 2 * steps      # +-1 per solve at the tolerance
+        else:
+            assert int(p["iters"]) == int(st.pcg_iterations)
+        tol = 1e-5 if converged else 2e-3
         for a, b, what in ((p["u"], fu[r0:r0 + k], "u"), (p["v"], fv[r0:r0 + k], "v")):
             assert float(np.abs(a - b).max()) <= tol * max(1.0, float(np.abs(b).max())), what
     assert mismatched <= 8, mismatched
     assert sum(int(p["markers"]) for p in parts) == int(st.n_markers)
-    if kind == "basic-fill":
+    if kind == "basic-fill" and not converged:
         assert int(st.pcg_iterations) == 100 * steps          # the solve ran, at the reference's cap
     ref.close()
 
