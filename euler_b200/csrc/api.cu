@@ -1070,6 +1070,14 @@ int euler_gpu_set_rng_state(euler_gpu* h, uint64_t state) {
   return 0;
 }
 
+int euler_gpu_set_max_iterations(euler_gpu* h, int max_iterations) {
+  ENTER(h);
+  if (max_iterations < 0) return fail(EULER_E_INVALID, "max_iterations %d", max_iterations);
+  h->prm.max_iterations = max_iterations;
+  h->poll_hint = 0;
+  return 0;
+}
+
 int euler_gpu_set_frame_count(euler_gpu* h, uint64_t frames) {
   ENTER(h);
   h->frames = frames;            // g_frame_count (main.c:89): only the source colours read it
@@ -1221,10 +1229,12 @@ int euler_gpu_comm_p2p_import(euler_gpu* h, const void* blobs) {
   if (h->c.fused == 1) {
     const char* e = getenv("EULER_P2P_SEPARATE");
     h->c.p2p_mode = (e && atoi(e)) ? 1 : 2;
-    // EULER_P2P_SPLIT=1: split-phase scalar exchange (post in the producing kernel, collect in every
-    // block of the consuming one); needs the fused tail kernel
+    // split-phase scalar exchange (post in the producing kernel, collect in every block of the
+    // consuming one; needs the fused tail kernel).  Measured on the 16384^2 workload, same boxes,
+    // back to back (profiles/r02b_*): 56.26 -> 55.94 ms at N = 2, 31.39 -> 31.11 at N = 4,
+    // 19.04 -> 18.68 at N = 8, identical results.  EULER_P2P_SPLIT=0 restores the blocking form.
     const char* sp = getenv("EULER_P2P_SPLIT");
-    h->split = h->c.p2p_mode == 2 && h->use_tail && sp && atoi(sp) != 0;
+    h->split = h->c.p2p_mode == 2 && h->use_tail && !(sp && atoi(sp) == 0);
   }
   return 0;
 }

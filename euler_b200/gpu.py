@@ -98,6 +98,7 @@ _L.euler_gpu_set_rng_state.argtypes = [_H, C.c_uint64]
 _L.euler_gpu_colorize.argtypes = [_H]
 _L.euler_gpu_set_source_exhausted.argtypes = [_H, C.c_int]
 _L.euler_gpu_set_frame_count.argtypes = [_H, C.c_uint64]
+_L.euler_gpu_set_max_iterations.argtypes = [_H, C.c_int]
 _L.euler_gpu_stats.argtypes = [_H, C.POINTER(Stats)]
 _L.euler_gpu_check.argtypes = [_H, C.POINTER(Check)]
 _L.euler_gpu_set_profiling.argtypes = [_H, C.c_int]
@@ -245,6 +246,7 @@ class EulerGpu:
     def colorize(self): _ck(_L.euler_gpu_colorize(self._h))
     def set_rng_state(self, s): _ck(_L.euler_gpu_set_rng_state(self._h, s))
     def set_frame_count(self, n): _ck(_L.euler_gpu_set_frame_count(self._h, int(n)))
+    def set_max_iterations(self, n): _ck(_L.euler_gpu_set_max_iterations(self._h, int(n)))
     def set_source_exhausted(self, e): _ck(_L.euler_gpu_set_source_exhausted(self._h, 1 if e else 0))
 
     @property

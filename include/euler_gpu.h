@@ -295,6 +295,10 @@ int euler_gpu_set_source_exhausted(euler_gpu *h, int exhausted);
 /* g_frame_count (main.c:89, incremented per euler_gpu_step_frame; read only by the source
  * colours of --rainbow, main.c:283): restored by a checkpoint load. */
 int euler_gpu_set_frame_count(euler_gpu *h, uint64_t frames);
+/* `max_iterations` of project() (main.c:735) for the solves that follow; 0 = rhs, p = 0 and the
+ * velocity update only (every stage except the PCG iteration: what is bit-determined whatever the
+ * order of the dot products — used by the cross-N invariants of bench.py and the parity tests). */
+int euler_gpu_set_max_iterations(euler_gpu *h, int max_iterations);
 
 int euler_gpu_stats(euler_gpu *h, euler_stats *out);
 /* Invariants of the current state, reduced on the device (one pass over the owned rows; a few
