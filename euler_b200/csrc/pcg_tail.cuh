@@ -34,6 +34,7 @@
 // bit-identical to theirs, checked through the C-ABI stage EULER_S_FUSED_TAIL against the CPU
 // mirror (tests/test_gpu_stages.py).
 #pragma once
+#include <type_traits>
 
 namespace tail {
 
@@ -185,12 +186,20 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
           const DV<C> rr = ldsv<C>(in.d[0] + col), aa = ldsv<C>(in.d[1] + col), pp = ldsv<C>(in.d[2] + col);
 #pragma unroll
           for (int i = 0; i < C + 2; ++i) mw |= (in.b[0][col - 1 + i] ? 1u : 0u) << i;
+          // (main threads start on an even column of a 512-aligned piece: the colour of their cell k
+          // in this row is the same for the whole block, so the two colourings are two straight-line
+          // instantiations instead of per-cell predicates)
+          auto red_w = [&](auto parc) {
+            constexpr int PAR = decltype(parc)::value;
+#pragma unroll
+            for (int k = 0; k < C; ++k)
+              if (((PAR + k) & 1) == 0) ab[o0 + col + k] = pp.v[k] * (r0[k] * pp.v[k]);   // red: what a black neighbour adds
+          };
 #pragma unroll
           for (int k = 0; k < C; ++k) {
             const bool m = tbit(mw, k + 1);
             const double rn = m ? rr.v[k] + aa.v[k] * neg_alpha : rr.v[k];      // fmadd(z, -alpha, r), main.c:754
             r0[k] = rn; pc0[k] = pp.v[k];
-            if (((par0 + k) & 1) == 0) ab[o0 + col + k] = pp.v[k] * (rn * pp.v[k]);   // red: what a black neighbour adds
             if (own_row && m) {
               if (mode == 1) pv.v[k] = pv.v[k] + spv.v[k] * alpha_prev;         // the previous iteration's main.c:753
               if (mode) pv.v[k] = pv.v[k] + sv.v[k] * alpha;                    // fmadd(s, alpha, p), main.c:753
@@ -198,6 +207,7 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
               if (a > mx && acc_row) mx = a;                                     // NaN-dropping max, main.c:659-662
             }
           }
+          if (par0) red_w(std::integral_constant<int, 1>{}); else red_w(std::integral_constant<int, 0>{});
           if (own_row) {
             DV<C> o;
 #pragma unroll
@@ -235,22 +245,26 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     for (int k = 0; k < C; ++k) q1[k] = 0.0;
     if (rel >= 0 && ncol) {
       if (is_main) {
+        auto fwd = [&](auto parc) {
+          constexpr int PAR = decltype(parc)::value;
 #pragma unroll
-        for (int k = 0; k < C; ++k) {
-          if (!tbit(t.mw1, k + 1)) continue;
-          const int cc = col + k;
-          double v = t.r1[k];
-          const bool black = ((par0 + k) & 1) == 0;                  // row yy-1: the colours of row yy swapped
-          if (black) {                                               // + red neighbours: l, r, d, u
-            if (tbit(t.mw1, k)) v = v + ab[o1 + cc - 1];
-            if (tbit(t.mw1, k + 2)) v = v + ab[o1 + cc + 1];
-            if (tbit(t.mw2, k + 1)) v = v + ab[o2 + cc];
-            if (tbit(t.mw0, k + 1)) v = v + ab[o0 + cc];
+          for (int k = 0; k < C; ++k) {
+            if (!tbit(t.mw1, k + 1)) continue;
+            const int cc = col + k;
+            double v = t.r1[k];
+            const bool black = ((PAR + k) & 1) == 0;                 // row yy-1: the colours of row yy swapped (folds after unrolling)
+            if (black) {                                             // + red neighbours: l, r, d, u
+              if (tbit(t.mw1, k)) v = v + ab[o1 + cc - 1];
+              if (tbit(t.mw1, k + 2)) v = v + ab[o1 + cc + 1];
+              if (tbit(t.mw2, k + 1)) v = v + ab[o2 + cc];
+              if (tbit(t.mw0, k + 1)) v = v + ab[o0 + cc];
+            }
+            const double q = v * t.pc1[k];
+            q1[k] = q;
+            if (black) ab[o1 + cc] = q * t.pc1[k];                   // what a red neighbour adds (times its pc)
           }
-          const double q = v * t.pc1[k];
-          q1[k] = q;
-          if (black) ab[o1 + cc] = q * t.pc1[k];                     // what a red neighbour adds (times its pc)
-        }
+        };
+        if (par0) fwd(std::integral_constant<int, 1>{}); else fwd(std::integral_constant<int, 0>{});
       } else if ((lane == 1 || lane == 2) && tbit(t.mw1, 1) && par0 == 0) {
         // inner halo columns -1 and w: only a black cell's zb is ever asked for
         double v = t.r1[0];
@@ -269,26 +283,30 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
       const bool acc2 = y2r >= acc0 && y2r < acc1;
       DV<C> out;
       const unsigned any = t.mw2 & (((1u << C) - 1u) << 1);
+      auto bwd = [&](auto parc) {
+        constexpr int PAR = decltype(parc)::value;
 #pragma unroll
-      for (int k = 0; k < C; ++k) {
-        out.v[k] = 0.0;
-        if (!tbit(t.mw2, k + 1)) continue;
-        const int cc = col + k;
-        const double pk = t.pc2[k];
-        double zc;
-        if ((par0 + k) & 1) {                                        // row yy-2 has the colours of row yy
-          zc = t.q2[k] * pk;                                         // black: q*pc
-        } else {
-          double v = t.q2[k];
-          if (tbit(t.mw2, k)) v = v + pk * ab[o2 + cc - 1];
-          if (tbit(t.mw2, k + 2)) v = v + pk * ab[o2 + cc + 1];
-          if (tbit(t.mw3, k + 1)) v = v + pk * ab[o3 + cc];
-          if (tbit(t.mw1, k + 1)) v = v + pk * ab[o1 + cc];
-          zc = v * pk;
+        for (int k = 0; k < C; ++k) {
+          out.v[k] = 0.0;
+          if (!tbit(t.mw2, k + 1)) continue;
+          const int cc = col + k;
+          const double pk = t.pc2[k];
+          double zc;
+          if ((PAR + k) & 1) {                                       // row yy-2 has the colours of row yy
+            zc = t.q2[k] * pk;                                       // black: q*pc
+          } else {
+            double v = t.q2[k];
+            if (tbit(t.mw2, k)) v = v + pk * ab[o2 + cc - 1];
+            if (tbit(t.mw2, k + 2)) v = v + pk * ab[o2 + cc + 1];
+            if (tbit(t.mw3, k + 1)) v = v + pk * ab[o3 + cc];
+            if (tbit(t.mw1, k + 1)) v = v + pk * ab[o1 + cc];
+            zc = v * pk;
+          }
+          out.v[k] = zc;
+          if (acc2) acc += zc * t.r2[k];
         }
-        out.v[k] = zc;
-        if (acc2) acc += zc * t.r2[k];
-      }
+      };
+      if (par0) bwd(std::integral_constant<int, 1>{}); else bwd(std::integral_constant<int, 0>{});
       // only the owned rows are stored: the halo rows of z belong to the neighbouring slabs
       if (any && acc2) {
         const size_t c2 = rowp - 2 * pitch;
