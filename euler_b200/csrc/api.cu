@@ -183,6 +183,16 @@ int agree_on_sources(euler_gpu* h) {
   return 0;
 }
 
+// --rainbow on slabs: halo rows of the three colour planes from the neighbours' owned rows
+int color_halos(euler_gpu* h) {
+  Ctx& c = h->c;
+  if (!c.cr) return 0;
+  if (comm_halo(c, h->cm, c.cr, 4, SLAB_HALO) || comm_halo(c, h->cm, c.cg, 4, SLAB_HALO) ||
+      comm_halo(c, h->cm, c.cb, 4, SLAB_HALO))
+    return fail(EULER_E_COMM, "%s", comm_last_error());
+  return 0;
+}
+
 // The state hand-over at the end of sim_init (main.c:209-274) into an existing handle: the
 // three static masks, the seeded markers and the RNG state go to the device, every dynamic
 // plane starts from zero (the reference's globals are zero-initialised: main.c:64-100, 577),
@@ -276,6 +286,7 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
   if (h->slab && h->comm_ready) {
     int grc = agree_on_sources(h);
     if (grc) return grc;
+    if ((grc = color_halos(h))) return grc;
     // halo rows of the initial classification (only the owned markers were binned)
     if (comm_halo(c, h->cm, c.count, 1, SLAB_HALO)) return fail(EULER_E_COMM, "%s", comm_last_error());
   }
@@ -582,11 +593,19 @@ int run_substep_dist(euler_gpu* h, float dt) {
     launch_sources(c);
   }
   CM(comm_halo(c, h->cm, c.count, 1, SLAB_HALO));    // classification of the neighbours' edge rows
+  // --rainbow: extrapolate(P) (main.c:859-863) needs the neighbours' classification, so it runs
+  // after the halo exchange instead of before the sources; it reads only colours of cells that were
+  // fluid LAST sub-step and the sources' colour writes (main.c:292-294) still come after it, so the
+  // result is the reference's
+  launch_extrapolate_color(c);
+  launch_source_colors(c, (unsigned int)h->frames);
   launch_grid_tiles(c);
   prof_mark(h, 1);
   launch_extrapolate(c);
   { float* t = c.u; c.u = c.uext; c.uext = t; t = c.v; c.v = c.vext; c.vext = t; }
   launch_advect_velocity(c, dt);
+  launch_advect_color(c, dt);                        // main.c:873-882
+  { int grc = color_halos(h); if (grc) return grc; }
   prof_mark(h, 2);
   rc = run_project_dist(h, dt);
   if (rc) return rc;
@@ -686,8 +705,6 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
       return fail(EULER_E_UNSUPPORTED, "row slabs need precon=REDBLACK, marker_mode=FAST, dot_mode=TREE "
                   "(the IC(0) wavefront and the reference orders are sequential across the whole grid)");
   }
-  if (slab && prm.rainbow)
-    return fail(EULER_E_UNSUPPORTED, "--rainbow colour transport is not decomposed into slabs yet");
   if (prm.pcg_dtype != EULER_PCG_FP64 && prm.pcg_dtype != EULER_PCG_FP32)
     return fail(EULER_E_INVALID, "unknown pcg_dtype %d", prm.pcg_dtype);
   const bool mixed = prm.pcg_dtype == EULER_PCG_FP32;
@@ -1208,6 +1225,7 @@ int euler_gpu_comm_init(euler_gpu* h, int rank, int n_ranks, const void* unique_
   { int grc = agree_on_sources(h); if (grc) return grc; }
   // halo rows of the initial classification (create() binned only the owned markers)
   CM(comm_halo(c, h->cm, c.count, 1, SLAB_HALO));
+  { int grc = color_halos(h); if (grc) return grc; }
   CU(cudaStreamSynchronize(c.stream));
   return 0;
 }

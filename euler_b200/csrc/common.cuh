@@ -75,6 +75,9 @@ struct DevScalars {
   double sigma_s[2], alpha_s[2];
   double peek_resid;
   int peek_done, peek_iters;
+  // update_fluid_sources in three parallel passes (marker_kernels.cu): what the emitting pass
+  // needs of the state before the bookkeeping pass advanced it
+  unsigned long long src_n0, src_state0, src_allow;
 };
 
 // The MAC-grid stage kernels (grid_kernels.cu) stream only the 512 x 32-cell tiles that can hold a

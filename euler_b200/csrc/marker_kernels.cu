@@ -550,13 +550,48 @@ __global__ void k_sources_prep(DevScalars* sc, const double* __restrict__ gather
 
 // Row-major over source cells; the k-th cell that needs a marker uses draws 2k and 2k+1 of
 // the stream (y jitter first: gcc evaluates v2f's second argument first, see oracle).
-__global__ void __launch_bounds__(1024) k_sources(
-    Grid g, float h, const unsigned int* __restrict__ cells, size_t ncells,
-    uint8_t* __restrict__ count, float2* __restrict__ markers, size_t max_markers_global,
-    const unsigned long long* __restrict__ jump, DevScalars* sc, int distributed) {
+// Three passes so that a scenario with 10^5..10^6 source cells (waterfall at 4096^2: 270 000) does
+// not run on one block (it took 1.25 ms of a 6 ms sub-step there): (1) needy cells per block of
+// 1024 source cells, (2) one block scans those counts and does the sequential loop's bookkeeping
+// (marker total, RNG state after all draws, the MAX_MARKER_COUNT-1 latch), (3) every block emits
+// its markers at rank = cells-before-me, each with its own jump-ahead of the stream.
+constexpr int SRC_CHUNK = 1024;
+
+__global__ void __launch_bounds__(SRC_CHUNK) k_sources_need(const unsigned int* __restrict__ cells, size_t ncells,
+                                                            const uint8_t* __restrict__ count,
+                                                            unsigned int* __restrict__ block_need) {
+  const size_t i = (size_t)blockIdx.x * SRC_CHUNK + threadIdx.x;
+  const bool need = i < ncells && count[cells[i]] < 4;       // main.c:287
+  const int n = __syncthreads_count(need);
+  if (threadIdx.x == 0) block_need[blockIdx.x] = (unsigned int)n;
+}
+
+__global__ void __launch_bounds__(1024) k_sources_scan(const unsigned int* __restrict__ block_need,
+                                                       unsigned int* __restrict__ block_base, int nblocks,
+                                                       size_t max_markers_global,
+                                                       const unsigned long long* __restrict__ jump, DevScalars* sc,
+                                                       int distributed) {
+  // exclusive scan of the per-block counts (contiguous chunk per thread + Hillis-Steele over 1024 sums)
+  const int per = (nblocks + 1023) / 1024;
+  const int lo = min(nblocks, per * (int)threadIdx.x), hi = min(nblocks, lo + per);
+  unsigned int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += block_need[i];
+  __shared__ unsigned int sh[1024];
+  sh[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const unsigned int v = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned int run = sh[threadIdx.x] - sum;
+  for (int i = lo; i < hi; ++i) { block_base[i] = run; run += block_need[i]; }
+  if (threadIdx.x != 1023) return;
   // single GPU: ranks start at 0 and the global marker count is the local one.  Slab mode:
   // this slab's needy cells come after those of the slabs below it (row-major order), the
   // MAX_MARKER_COUNT-1 latch (main.c:281,290) looks at the global count.
+  const unsigned long long carry = sh[1023];
   const unsigned long long n0 = sc->n_markers;
   const unsigned long long nglob = distributed ? sc->n_markers_global : n0;
   const unsigned long long rank0 = distributed ? sc->src_base : 0ull;
@@ -564,54 +599,49 @@ __global__ void __launch_bounds__(1024) k_sources(
   const bool exhausted0 = sc->source_exhausted || nglob == cap;
   const unsigned long long allow = exhausted0 ? 0 : cap - nglob;
   const unsigned long long state0 = sc->rng_state;
-  __shared__ unsigned int warp_tot[32];
-  __shared__ unsigned long long carry_sh;
-  if (threadIdx.x == 0) carry_sh = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (size_t base = 0; base < ncells; base += 1024) {
-    const size_t i = base + threadIdx.x;
-    bool need = false;
-    unsigned int cell = 0;
-    if (i < ncells) {
-      cell = cells[i];
-      need = count[cell] < 4;                                // main.c:287
-    }
-    const unsigned int bal = __ballot_sync(EULER_FULL_MASK, need);
-    if (lane == 0) warp_tot[wid] = __popc(bal);
-    __syncthreads();
-    unsigned int woff = 0, total = 0;
-    for (int wv = 0; wv < 32; ++wv) {
-      const unsigned int t = warp_tot[wv];
-      if (wv < wid) woff += t;
-      total += t;
-    }
-    const unsigned long long lrank = carry_sh + woff + __popc(bal & ((1u << lane) - 1u));
-    const unsigned long long rank = rank0 + lrank;
-    if (need && rank < allow) {
-      unsigned long long s = rng_jump(jump, state0, 2 * rank);
-      s = rng_step(s);
-      const float jy = rng_float(s);
-      s = rng_step(s);
-      const float jx = rng_float(s);
-      const int y = (int)(cell / (unsigned int)g.pitch), x = (int)(cell % (unsigned int)g.pitch);
-      markers[n0 + lrank] = make_float2(h * (x + jx), h * (y + g.yoff + jy));   // main.c:288
-      count[cell] += 1;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) carry_sh += total;
-    __syncthreads();
+  sc->src_n0 = n0; sc->src_state0 = state0; sc->src_allow = allow;
+  // markers this slab appends: its needy cells whose global rank is below `allow`
+  unsigned long long mine = carry;
+  if (rank0 >= allow) mine = 0;
+  else if (rank0 + mine > allow) mine = allow - rank0;
+  const unsigned long long need_all = distributed ? (unsigned long long)sc->part[2] : carry;
+  const unsigned long long added_all = need_all < allow ? need_all : allow;
+  sc->n_markers = n0 + mine;
+  sc->rng_state = rng_jump(jump, state0, 2 * added_all);
+  sc->source_exhausted = (exhausted0 || (nglob + added_all == cap)) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(SRC_CHUNK) k_sources_emit(
+    Grid g, float h, const unsigned int* __restrict__ cells, size_t ncells, uint8_t* __restrict__ count,
+    float2* __restrict__ markers, const unsigned int* __restrict__ block_base,
+    const unsigned long long* __restrict__ jump, const DevScalars* sc, int distributed) {
+  const unsigned long long n0 = sc->src_n0, state0 = sc->src_state0, allow = sc->src_allow;
+  const unsigned long long rank0 = distributed ? sc->src_base : 0ull;
+  const size_t i = (size_t)blockIdx.x * SRC_CHUNK + threadIdx.x;
+  bool need = false;
+  unsigned int cell = 0;
+  if (i < ncells) {
+    cell = cells[i];
+    need = count[cell] < 4;                                  // main.c:287
   }
-  if (threadIdx.x == 0) {
-    // markers this slab appended: its needy cells whose global rank is below `allow`
-    unsigned long long mine = carry_sh;
-    if (rank0 >= allow) mine = 0;
-    else if (rank0 + mine > allow) mine = allow - rank0;
-    const unsigned long long need_all = distributed ? (unsigned long long)sc->part[2] : carry_sh;
-    const unsigned long long added_all = need_all < allow ? need_all : allow;
-    sc->n_markers = n0 + mine;
-    sc->rng_state = rng_jump(jump, state0, 2 * added_all);
-    sc->source_exhausted = (exhausted0 || (nglob + added_all == cap)) ? 1 : 0;
+  __shared__ unsigned int warp_tot[SRC_CHUNK / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned int bal = __ballot_sync(EULER_FULL_MASK, need);
+  if (lane == 0) warp_tot[wid] = __popc(bal);
+  __syncthreads();
+  unsigned int woff = 0;
+  for (int wv = 0; wv < wid; ++wv) woff += warp_tot[wv];
+  const unsigned long long lrank = (unsigned long long)block_base[blockIdx.x] + woff + __popc(bal & ((1u << lane) - 1u));
+  const unsigned long long rank = rank0 + lrank;
+  if (need && rank < allow) {
+    unsigned long long s = rng_jump(jump, state0, 2 * rank);
+    s = rng_step(s);
+    const float jy = rng_float(s);
+    s = rng_step(s);
+    const float jx = rng_float(s);
+    const int y = (int)(cell / (unsigned int)g.pitch), x = (int)(cell % (unsigned int)g.pitch);
+    markers[n0 + lrank] = make_float2(h * (x + jx), h * (y + g.yoff + jy));   // main.c:288
+    count[cell] += 1;
   }
 }
 
@@ -665,10 +695,21 @@ void launch_refresh_counts(Ctx& c) {
 void launch_sources(Ctx& c) {
   if (c.n_source_cells_global == 0) return;
   ProfScope ps(c, KC_SOURCES);
-  k_sources<<<1, 1024, 0, c.stream>>>(c.g, c.h, c.source_cells, c.n_source_cells, c.count,
-                                      c.markers, c.max_markers_global, c.rng_jump, c.sc,
-                                      c.distributed);
+  // (seg_count / seg_offset: the compaction scratch of refresh_marker_counts, free at this point;
+  // one entry per 1024 markers of capacity >= one per 1024 source cells)
+  const int nb = (int)((c.n_source_cells + SRC_CHUNK - 1) / SRC_CHUNK);
+  if (nb > 0) {
+    k_sources_need<<<nb, SRC_CHUNK, 0, c.stream>>>(c.source_cells, c.n_source_cells, c.count, c.seg_count);
+    c.launches += 1;
+  }
+  k_sources_scan<<<1, 1024, 0, c.stream>>>(c.seg_count, c.seg_offset, nb, c.max_markers_global, c.rng_jump, c.sc,
+                                           c.distributed);
   c.launches += 1;
+  if (nb > 0) {
+    k_sources_emit<<<nb, SRC_CHUNK, 0, c.stream>>>(c.g, c.h, c.source_cells, c.n_source_cells, c.count, c.markers,
+                                                   c.seg_offset, c.rng_jump, c.sc, c.distributed);
+    c.launches += 1;
+  }
 }
 
 void launch_sources_count(Ctx& c) {

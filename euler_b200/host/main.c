@@ -226,6 +226,7 @@ int main(int argc, char **argv) {
   if (headless && frames < 0) frames = 100;
   if (ranks > 1) {
     if (!headless || !rdv || rank < 0 || rank >= ranks || load_path || save_path || prm.rainbow) {
+      /* (the library transports --rainbow colours on slabs; this program's rank-0 report only assembles the count plane) */
       fprintf(stderr, "--ranks needs --headless, --rank 0..N-1 and --rendezvous DIR (no --load/--save/--rainbow)\n");
       return 1;
     }

@@ -176,7 +176,8 @@ typedef struct euler_params {
   int   slab_rows;
   /* --rainbow (main.c:76, 984-993): transport a passive RGB colour with the fluid — colorize()
    * at create/reinit (main.c:271-273), extrapolate(P) (:859-863), source colours (:292-294) and
-   * advect_p (:873-882) every sub-step.  Six more fp32 planes; single-GPU handles only.
+   * advect_p (:873-882) every sub-step.  Six more fp32 planes.  Works on slab handles too (halo
+   * rows of the three colour planes are exchanged once per sub-step).
    * Default 0, like the reference. */
   int   rainbow;
   /* mixed-precision PCG (enum euler_pcg_dtype); default EULER_PCG_FP64, like the reference */

@@ -282,9 +282,7 @@ def test_rainbow_off_and_errors():
     with pytest.raises(G.EulerGpuError):
         g.run_stage(G.S_ADVECT_COLOR, 0.01)
     g.close()
-    with pytest.raises(G.EulerGpuError):      # slabs do not carry the colour planes yet
-        G.EulerGpu.from_scenario(Scenario(shipped_text("block"), 100, 40), precon=1, marker_mode=1,
-                                 rainbow=1, slab_row0=0, slab_rows=20)
+    # (slab handles carry the colour planes since round 2: tests/test_gpu_multi.py::test_rainbow_on_slabs)
 
 
 def test_host_program_rainbow_matches_golden(tmp_path):

@@ -253,3 +253,54 @@ def test_host_program_two_ranks_match_one(no_p2p, tmp_path):
     for key in ("fnv_count", "markers", "substeps", "rng_state", "solves"):
         assert got[key] == want[key], key
     assert abs(got["pcg_iterations"] - want["pcg_iterations"]) <= got["solves"]    # +-1 per solve at the tolerance
+
+
+def _rainbow_worker(rank, nranks, uid, text, nx, ny, substeps, out_dir):
+    sys.path.insert(0, ROOT)
+    from euler_b200 import gpu as G
+    scn = Scenario(text, nx, ny)
+    row0, rows = G.slab_partition(ny, nranks, rank)
+    g = G.EulerGpu.from_scenario(scn, precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST, device=rank,
+                                 slab_row0=row0, slab_rows=rows, rainbow=1, max_iterations=0)
+    g.comm_init(rank, nranks, uid)
+    g.comm_p2p_import(_exchange_blobs(out_dir, rank, nranks, g.comm_p2p_export()))
+    for _ in range(substeps):
+        g.substep(g.calculate_timestep(0.1))
+    np.savez(os.path.join(out_dir, "rb%d.npz" % rank), row0=row0, rows=rows, count=g.get(G.F_COUNT),
+             cr=g.get(G.F_CR), cg=g.get(G.F_CG), cb=g.get(G.F_CB))
+    g.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+@pytest.mark.parametrize("name,nx,ny,substeps", [("waterfall", 160, 96, 60), ("block", 100, 64, 60)])
+def test_rainbow_on_slabs(name, nx, ny, substeps, nranks, tmp_path):
+    """--rainbow colour transport (main.c:187-201, 424-438, 859-863, 873-882, 292-294) on row slabs
+    against the ORACLE's --rainbow run (itself pinned to the reference's), iteration cap 0 on both
+    sides so that the velocities are bit-determined: the colours of every fluid cell — what
+    draw_rows() reads (main.c:938) — and the count plane bit for bit, with fluid, source colours and
+    newly wet cells crossing the slab boundaries."""
+    if _gpu_count() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    import torch.multiprocessing as mp
+    from euler_b200 import gpu as G
+    from oracle.oracle import Oracle
+    text = resample(shipped_text(name), nx - 2, ny - 2)
+    uid = G.comm_unique_id()
+    mp.spawn(_rainbow_worker, args=(nranks, uid, text, nx, ny, substeps, str(tmp_path)), nprocs=nranks, join=True)
+    o = Oracle(nx, ny, text, rainbow=True)
+    o.c.precon_mode = 1; o.c.quirk_marker_dt_leak = 0; o.c.max_iterations = 0
+    for _ in range(substeps):
+        o.substep(o.calculate_timestep(0.1))
+    parts = [np.load(os.path.join(str(tmp_path), "rb%d.npz" % r)) for r in range(nranks)]
+
+    def merged(field, dtype):
+        out = np.zeros((ny, nx), dtype)
+        for p in parts:
+            r0, n = int(p["row0"]), int(p["rows"])
+            out[r0:r0 + n] = p[field][r0:r0 + n]
+        return out
+    assert same_bits(merged("count", np.uint8), o.count)
+    fl = o.count != 0
+    assert fl.any()
+    for f, ref in (("cr", o.cr), ("cg", o.cg), ("cb", o.cb)):
+        assert same_bits(merged(f, np.float32)[fl], ref[fl]), f
