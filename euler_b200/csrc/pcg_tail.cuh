@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
   __shared__ pipe::JobIter prod_sh;
   __shared__ int pstage_sh, pphase_sh;           // next stage to fill, parity its `empty` must have passed
   if (producer) { prod_sh = cons; pstage_sh = 0; pphase_sh = 1; }
+  bool more_rows = cons.valid;                   // (a register: only the producer lane may touch prod_sh)
 
   auto issue = [&]() {                           // producer lane only
     pipe::JobIter prod = prod_sh;
@@ -129,9 +130,10 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     if (++pstage == NS) { pstage = 0; pphase ^= 1; }
     prod.next(g, T, th, active.list);
     prod_sh = prod; pstage_sh = pstage; pphase_sh = pphase;
+    more_rows = prod.valid;
   };
   if (producer)
-    for (int i = 0; i < NS - 1 && prod_sh.valid; ++i) issue();   // NS-1 rows ahead from here on
+    for (int i = 0; i < NS - 1 && more_rows; ++i) issue();       // NS-1 rows ahead from here on
 
   TailLane<C> t;
 #pragma unroll
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
   size_t rowp = 0;
 
   while (cons.valid) {
-    if (producer && prod_sh.valid) issue();
+    if (producer && more_rows) issue();
     const pipe::Piece& pz = cons.p;
     const int yy = cons.yy;                      // row whose inputs arrive in this step
     const int rel = yy - pz.y0;                  // -2 at the first row of a piece
