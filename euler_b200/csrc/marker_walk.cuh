@@ -48,18 +48,9 @@ __device__ __forceinline__ float2 walk_marker(const Grid& g, const InterpLimits&
   const int off_x = vx < 0 ? -1 : 0;
   const int off_y = vy < 0 ? -1 : 0;
   float gx = line_x * h, gy = line_y * h;
-  // Most markers cross no grid line in a sub-step (displacement <= 0.75 h, main.c:838).  Then
-  // t_next = min(tx, ty) >= dt, the loop below does not run and the result is p + dt v (or p, when
-  // both components are exactly 0: the same value).  That case is certified WITHOUT the two IEEE
-  // divisions of time_to (main.c:451-457): |line - p| >= dt |v| (1 + 2^-20), evaluated in fp32 with
-  // its own roundings (each < 2^-23 relative), implies fl((line - p) / v) > dt.  Anything closer
-  // than that, NaNs included, takes the reference's path verbatim.
-  {
-    const float ax = fabsf(vx), ay = fabsf(vy);
-    const bool clear_x = !(ax > 0.f) ? !(ax != ax) : fabsf(gx - px) >= (dt * ax) * 1.000001f;
-    const bool clear_y = !(ay > 0.f) ? !(ay != ay) : fabsf(gy - py) >= (dt * ay) * 1.000001f;
-    if (clear_x && clear_y && dt > 0.f) return make_float2(px + dt * vx, py + dt * vy);
-  }
+  // (certifying "no grid line is crossed" without the two IEEE divisions of time_to — |line - p| >=
+  // dt |v| (1 + 2^-20) implies fl((line - p) / v) > dt — and returning p + dt v at once was measured:
+  // bit-identical, but advect_markers 2.80 -> 3.00 ms at 16384^2; the divisions are not what limits it)
   float tx = time_until(px, gx, vx);
   float ty = time_until(py, gy, vy);
 

@@ -89,19 +89,6 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
   }
   __syncthreads();
 
-  double alpha = sc->alpha, alpha_prev = sc->alpha_prev;
-  if (split_it) {
-    // split-phase exchange (p2p.cuh): every block consumes the {z.s} partials the search/apply
-    // kernel posted and forms alpha itself (main.c:752); block 0 records it
-    double zs, unused;
-    const bool ok = p2p_collect(dist, false, zs, unused);
-    const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
-    if (!ok) { if (writer) { sc->comm_timeout = 1; sc->done = 1; } return; }
-    alpha = sc->sigma_s[(split_it + 1) & 1] / zs;
-    alpha_prev = sc->alpha_s[(split_it + 1) & 1];          // the previous iteration's
-    if (writer) { sc->alpha_s[split_it & 1] = alpha; sc->zs = zs; sc->alpha_prev = alpha_prev; sc->alpha = alpha; }
-  }
-  const double neg_alpha = -alpha;
   const int th = g.th;
   const size_t pitch = (size_t)g.pitch;
   const pipe::Tiles T = pipe::tiles_of(g, th);
@@ -134,6 +121,23 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
   };
   if (producer)
     for (int i = 0; i < NS - 1 && more_rows; ++i) issue();       // NS-1 rows ahead from here on
+
+  double alpha = sc->alpha, alpha_prev = sc->alpha_prev;
+  if (split_it) {
+    // split-phase exchange (p2p.cuh): every block consumes the {z.s} partials the search/apply
+    // kernel posted and forms alpha itself (main.c:752); block 0 records it.  The first rows of the
+    // ring are already in flight: none of this kernel's inputs comes from another rank.
+    double zs, unused;
+    const bool ok = p2p_collect(dist, false, zs, unused);
+    const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
+    // a peer that never showed up (bounded poll): flag it — every later kernel returns at once — but
+    // finish this launch normally (bulk copies are in flight into this block's shared memory)
+    if (!ok && writer) { sc->comm_timeout = 1; sc->done = 1; }
+    alpha = sc->sigma_s[(split_it + 1) & 1] / zs;
+    alpha_prev = sc->alpha_s[(split_it + 1) & 1];          // the previous iteration's
+    if (writer) { sc->alpha_s[split_it & 1] = alpha; sc->zs = zs; sc->alpha_prev = alpha_prev; sc->alpha = alpha; }
+  }
+  const double neg_alpha = -alpha;
 
   TailLane<C> t;
 #pragma unroll
@@ -205,8 +209,9 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
             if (own_row && m) {
               if (mode == 1) pv.v[k] = pv.v[k] + spv.v[k] * alpha_prev;         // the previous iteration's main.c:753
               if (mode) pv.v[k] = pv.v[k] + sv.v[k] * alpha;                    // fmadd(s, alpha, p), main.c:753
-              const double a = fabs(rn);
-              if (a > mx && acc_row) mx = a;                                     // NaN-dropping max, main.c:659-662
+              // NaN-dropping max like main.c:659-662 (`if (a > max) max = a`): fmax returns the other
+              // operand for a NaN, and |r'| >= +0 so the sign of a zero cannot matter
+              if (acc_row) mx = fmax(mx, fabs(rn));
             }
           }
           if (par0) red_w(std::integral_constant<int, 1>{}); else red_w(std::integral_constant<int, 0>{});
