@@ -243,8 +243,8 @@ def run_gpu(args):
     n = args.grid
     precon = G.PRECON_REDBLACK if args.precon == "rb" else G.PRECON_IC0_WAVEFRONT
     mixed = args.pcg_dtype == "fp32"
-    if mixed and (world > 1 or args.precon != "rb"):
-        raise SystemExit("--pcg-dtype fp32 is a single-GPU mode of the red-black solve")
+    if mixed and args.precon != "rb":
+        raise SystemExit("--pcg-dtype fp32 is a mode of the red-black solve")
     alg_bytes = dict(ALG_BYTES_PER_CELL, **ALG_BYTES_PER_CELL_FP32) if mixed else ALG_BYTES_PER_CELL
 
     t_host0 = time.perf_counter()

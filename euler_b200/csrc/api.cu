@@ -453,7 +453,10 @@ int dist_after_backward(euler_gpu* h, bool init) {
   // of the new z that the next iteration's search/apply kernel starts from
   CM(comm_group_begin());
   CM(comm_gather_scalars(c, h->cm, c.sc->part));
-  if (c.fused) CM(comm_halo(c, h->cm, c.z, 8, SLAB_HALO));
+  if (c.fused) {
+    if (c.mixed) CM(comm_halo(c, h->cm, c.z32, 4, SLAB_HALO));
+    else CM(comm_halo(c, h->cm, c.z, 8, SLAB_HALO));
+  }
   CM(comm_group_end());
   launch_dist_beta(c, h->cm.gather, h->cm.nranks, init, h->prm.tol);
   return 0;
@@ -485,6 +488,9 @@ int dist_iteration(euler_gpu* h, bool first, int it) {
     return 0;
   }
   launch_axpy(c, h->prm.tol, c.fused != 0, c.fused == 1 ? ((it & 1) ? 0 : 1) : 2);
+  // mixed precision: r <- b - A p in fp64 (p is complete after an even iteration, and kept current
+  // on the +-3 halo rows by the redundant updates there)
+  if (c.mixed && h->prm.pcg_refresh_every > 0 && it % h->prm.pcg_refresh_every == 0) launch_true_residual(c);
   int rc = dist_precon_apply(h, false);
   if (rc) return rc;
   if (!c.fused) launch_update_search(c);
@@ -506,13 +512,15 @@ int run_project_dist(euler_gpu* h, float dt) {
     launch_pcg_reset(c);
     launch_rb_build(c);
     CM(comm_halo(c, h->cm, c.r, 8, SLAB_HALO));      // b is only valid one row into the halo
+    if (c.mixed) CM(comm_halo(c, h->cm, c.r32, 4, SLAB_HALO));
     rc = dist_precon_apply(h, true);
     if (rc) return rc;
     if (!c.fused) launch_copy_search(c);
     bool first = true;
     int remaining = h->prm.max_iterations;
     const int every = h->prm.pcg_check_every > 0 ? h->prm.pcg_check_every : 8;
-    const double* s_odd = c.s2;                      // where iteration 1 leaves its s
+    // where iteration 1 leaves its s
+    const void* s_odd = c.mixed ? static_cast<const void*>(c.s32b) : static_cast<const void*>(c.s2);
     int it = 0;
     bool first_chunk = true;
     while (remaining > 0) {
@@ -709,9 +717,9 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
     return fail(EULER_E_INVALID, "unknown pcg_dtype %d", prm.pcg_dtype);
   const bool mixed = prm.pcg_dtype == EULER_PCG_FP32;
   if (mixed) {
-    if (prm.precon != EULER_PRECON_REDBLACK || prm.dot_mode != EULER_DOT_TREE || prm.stencil_variant != 0 || slab)
+    if (prm.precon != EULER_PRECON_REDBLACK || prm.dot_mode != EULER_DOT_TREE || prm.stencil_variant != 0)
       return fail(EULER_E_UNSUPPORTED, "pcg_dtype=FP32 needs precon=REDBLACK, dot_mode=TREE, stencil_variant=0 "
-                  "on a single-GPU handle (it is a mode of the fused red-black iteration)");
+                  "(it is a mode of the fused red-black iteration)");
     if (prm.pcg_refresh_every < 0 || (prm.pcg_refresh_every & 1))
       return fail(EULER_E_INVALID, "pcg_refresh_every must be even (p is complete after even iterations) or 0, got %d",
                   prm.pcg_refresh_every);
@@ -815,7 +823,8 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   if (mixed) {
     // fp64: p and b (in the r plane) only; everything the iteration streams is fp32
     TRY(alloc_plane(h, &c.p)); TRY(alloc_plane(h, &c.r));
-    TRY(alloc_plane(h, &c.r32)); TRY(alloc_plane(h, &c.z32)); TRY(alloc_plane(h, &c.s32));
+    TRY(alloc_plane(h, &c.r32)); TRY(alloc_plane(h, &c.z32)); h->z_raw = h->allocs.back();
+    TRY(alloc_plane(h, &c.s32));
     TRY(alloc_plane(h, &c.s32b)); TRY(alloc_plane(h, &c.q32)); TRY(alloc_plane(h, &c.pc32));
   } else {
     TRY(alloc_plane(h, &c.precon)); TRY(alloc_plane(h, &c.q)); TRY(alloc_plane(h, &c.p));
@@ -1243,10 +1252,10 @@ int euler_gpu_comm_p2p_import(euler_gpu* h, const void* blobs) {
   if (!h->slab || !h->comm_ready || !h->pp.mine) return fail(EULER_E_INVALID, "comm_p2p_export first");
   if (!blobs) return fail(EULER_E_INVALID, "blobs is NULL");
   CU(cudaStreamSynchronize(h->c.stream));
-  if (p2p_import(h->c, h->cm, h->pp, blobs)) return fail(EULER_E_COMM, "%s", comm_last_error());
+  if (p2p_import(h->c, h->cm, h->pp, blobs, h->c.mixed ? 4 : 8)) return fail(EULER_E_COMM, "%s", comm_last_error());
   if (h->c.fused == 1) {
     const char* e = getenv("EULER_P2P_SEPARATE");
-    h->c.p2p_mode = (e && atoi(e)) ? 1 : 2;
+    h->c.p2p_mode = (e && atoi(e) && !h->c.mixed) ? 1 : 2;
     // split-phase scalar exchange (post in the producing kernel, collect in every block of the
     // consuming one; needs the fused tail kernel).  Measured on the 16384^2 workload, same boxes,
     // back to back (profiles/r02b_*): 56.26 -> 55.94 ms at N = 2, 31.39 -> 31.11 at N = 4,

@@ -278,7 +278,7 @@ int p2p_export(Ctx& c, Comm& cm, P2P& pp, void* z_raw_base, void* blob) {
   return 0;
 }
 
-int p2p_import(Ctx& c, Comm& cm, P2P& pp, const void* blobs) {
+int p2p_import(Ctx& c, Comm& cm, P2P& pp, const void* blobs, int z_elem) {
   if (cm.nranks > P2P_MAX_RANKS) { snprintf(g_cerr, sizeof g_cerr, "p2p: more than %d ranks", P2P_MAX_RANKS); return -1; }
   const char* base = reinterpret_cast<const char*>(blobs);
   for (int r = 0; r < cm.nranks; ++r) {
@@ -292,7 +292,9 @@ int p2p_import(Ctx& c, Comm& cm, P2P& pp, const void* blobs) {
     if (r == cm.rank - 1 || r == cm.rank + 1) {
       void* zp = nullptr;
       CUQ(cudaIpcOpenMemHandle(&zp, b.z, cudaIpcMemLazyEnablePeerAccess));
-      double* row0 = reinterpret_cast<double*>(reinterpret_cast<char*>(zp) + b.z_off) + (size_t)GUARD_ROWS * c.g.pitch;
+      // (typed double* whatever the element size: the launchers bias it in bytes)
+      double* row0 = reinterpret_cast<double*>(reinterpret_cast<char*>(zp) + b.z_off +
+                                               (size_t)GUARD_ROWS * c.g.pitch * (size_t)z_elem);
       if (r == cm.rank - 1) { pp.z_dn = row0; pp.dn_own1 = b.own1; }
       else { pp.z_up = row0; pp.up_own0 = b.own0; }
     }

@@ -62,7 +62,8 @@ struct P2P {
 };
 
 int p2p_export(Ctx& c, Comm& cm, P2P& pp, void* z_raw_base, void* blob /*P2P_BLOB_BYTES*/);
-int p2p_import(Ctx& c, Comm& cm, P2P& pp, const void* blobs /*nranks * P2P_BLOB_BYTES*/);
+// z_elem: element size of the exchanged z plane (8: fp64 solve, 4: pcg_dtype = FP32)
+int p2p_import(Ctx& c, Comm& cm, P2P& pp, const void* blobs /*nranks * P2P_BLOB_BYTES*/, int z_elem = 8);
 void p2p_close(P2P& pp, Comm& cm);
 // The exchanges as separate small kernels (Ctx::p2p_mode 1; A/B against the fused epilogues):
 // stores the top/bottom `depth` owned rows of z into the neighbours' halo rows

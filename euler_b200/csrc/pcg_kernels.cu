@@ -941,7 +941,7 @@ void launch_axpy(Ctx& c, double tol, bool as_in_q, int mode) {
   const size_t o = (size_t)(v.s - c.s);
   if (c.mixed)                    // fused red-black iteration only: A s is in q32
     launch_pdl(k_axpy<float>, pcg_blocks(c, k_axpy<float>), TT, 0, c.stream, v.g, TL, v.s32, c.s32b + o,
-               v.q32, v.fluid, v.p, v.r32, c.partials, c.sc, tol, 0, v.a0, v.a1, mode);
+               v.q32, v.fluid, v.p, v.r32, c.partials, c.sc, tol, c.distributed ? 1 : 0, v.a0, v.a1, mode);
   else
     launch_pdl(k_axpy<double>, pcg_blocks(c, k_axpy<double>), TT, 0, c.stream, v.g, TL, v.s, c.s2 ? c.s2 + o : v.s,
                as_in_q ? v.q : v.z, v.fluid, v.p, v.r, c.partials, c.sc, tol, c.distributed ? 1 : 0, v.a0, v.a1,
@@ -1035,15 +1035,22 @@ void launch_rb_backward(Ctx& c, bool init) {
     constexpr int C = CPT_MIXED;
     DistArgs d;
     memset(&d, 0, sizeof d);
+    if (c.p2p_mode == 2) {        // NVLink path on slabs: the neighbours' fp32 z planes, biased in BYTES
+      d = c.dist;
+      d.depth = P2P_HALO_DEPTH;
+      const long lo = (long)((v.z32 - c.z32) / c.g.pitch);
+      if (d.z_dn) d.z_dn = reinterpret_cast<double*>(reinterpret_cast<char*>(d.z_dn) + (lo + c.p2p_dn_own1 - c.own0) * (long)c.g.pitch * 4);
+      if (d.z_up) d.z_up = reinterpret_cast<double*>(reinterpret_cast<char*>(d.z_up) + (lo + c.p2p_up_own0 - c.own1) * (long)c.g.pitch * 4);
+    }
 #define BWD32(N) { constexpr int sb = pipe::smem_bytes<3, 1, N, float>(); \
     launch_pdl(k_rb_backward_pipe<N, C, float>, pcg_blocks(c, k_rb_backward_pipe<N, C, float>, sb, TW / C), \
-               TW / C, sb, c.stream, v.g, TL, v.q32, v.r32, v.fluid, v.pc32, v.z32, c.partials, c.sc, init ? 1 : 0, 0, \
-               v.a0, v.a1, c.tol, d); }
+               TW / C, sb, c.stream, v.g, TL, v.q32, v.r32, v.fluid, v.pc32, v.z32, c.partials, c.sc, init ? 1 : 0, \
+               dotflag(c), v.a0, v.a1, c.tol, d); }
     if (c.mixed_blocks == 8) {
       constexpr int sb = pipe::smem_bytes<3, 1, 4, float>();
       auto k = k_rb_backward_pipe<4, C, float, 8>;
       launch_pdl(k, pcg_blocks(c, k, sb, TW / C, true), TW / C, sb, c.stream, v.g, TL, v.q32, v.r32, v.fluid, v.pc32,
-                 v.z32, c.partials, c.sc, init ? 1 : 0, 0, v.a0, v.a1, c.tol, d);
+                 v.z32, c.partials, c.sc, init ? 1 : 0, dotflag(c), v.a0, v.a1, c.tol, d);
     } else if (c.ns_mixed[1] == 8) BWD32(8) else if (c.ns_mixed[1] == 6) BWD32(6) else BWD32(4)
 #undef BWD32
   } else if (c.use_pipe) {
@@ -1098,16 +1105,18 @@ void launch_fused_search_apply(Ctx& c, bool init, int split_it) {
   memset(&d, 0, sizeof d);
   if (c.mixed) {
     constexpr int C = CPT_MIXED;
+    if (c.p2p_mode == 2) d = c.dist;   // slabs, NVLink path: {z.s} finished across ranks in the last block
+    const int xf = c.distributed ? 2 : 0;
 #define KA32(N) { constexpr int smem = pipe::smem_bytes<2, 2, N, float>(); \
     launch_pdl(k_fused_search_apply<N, C, float>, \
                pcg_blocks(c, k_fused_search_apply<N, C, float>, smem, TW / C), TW / C, smem, c.stream, \
-               v.g, TL, v.z32, v.s32, v.fluid, v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0, \
+               v.g, TL, v.z32, v.s32, v.fluid, v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, xf, \
                v.a0, v.a1, d, 0, 0.0); }
     if (c.mixed_blocks == 8) {
       constexpr int smem = pipe::smem_bytes<2, 2, 4, float>();
       auto k = k_fused_search_apply<4, C, float, 8>;
       launch_pdl(k, pcg_blocks(c, k, smem, TW / C, true), TW / C, smem, c.stream, v.g, TL, v.z32, v.s32, v.fluid,
-                 v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, 0, v.a0, v.a1, d, 0, 0.0);
+                 v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, xf, v.a0, v.a1, d, 0, 0.0);
     } else if (c.ns_mixed[2] == 8) KA32(8) else if (c.ns_mixed[2] == 6) KA32(6) else KA32(4)
 #undef KA32
     c.launches += 1;

@@ -74,8 +74,8 @@ enum euler_pcg_dtype {
                          to fp32 rounding of u, v (measured <= 1e-7 relative on the shipped
                          scenarios); a solve cut off at max_iterations is a different, equally
                          unconverged iterate.  Needs precon = REDBLACK, dot_mode = TREE,
-                         stencil_variant = 0; single-GPU handles only.  CPU mirror:
-                         oracle/euler_oracle.c pcg_mixed. */
+                         stencil_variant = 0.  Works on slab handles (fp32 halo rows of z over
+                         NVLink / NCCL).  CPU mirror: oracle/euler_oracle.c pcg_mixed. */
 };
 
 /* How the marker array is kept. */

@@ -70,16 +70,15 @@ def test_product_does_not_import_oracle():
 
 
 def test_pcg_dtype_parameter_validation():
-    """pcg_dtype = FP32 is a mode of the fused red-black iteration on a single-GPU handle:
-    every other combination is refused before any device work (so this runs without a GPU)."""
+    """pcg_dtype = FP32 is a mode of the fused red-black iteration (single GPU or slabs): every
+    other combination is refused before any device work (so this runs without a GPU)."""
     import numpy as np
     from euler_b200 import gpu as G
     z = np.zeros((16, 16), np.uint8)
     m = np.zeros((0, 2), np.float32)
     bad = [dict(pcg_dtype=G.PCG_FP32),                                          # default precon is IC(0)
            dict(pcg_dtype=G.PCG_FP32, precon=G.PRECON_REDBLACK, dot_mode=G.DOT_REFERENCE_ORDER),
-           dict(pcg_dtype=G.PCG_FP32, precon=G.PRECON_REDBLACK, stencil_variant=1),
-           dict(pcg_dtype=G.PCG_FP32, precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST, slab_row0=0, slab_rows=8)]
+           dict(pcg_dtype=G.PCG_FP32, precon=G.PRECON_REDBLACK, stencil_variant=1)]
     for kw in bad:
         with pytest.raises(G.EulerGpuError) as e:
             G.EulerGpu(16, 16, z, z, z, m, **kw)

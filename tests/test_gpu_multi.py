@@ -304,3 +304,61 @@ def test_rainbow_on_slabs(name, nx, ny, substeps, nranks, tmp_path):
     assert fl.any()
     for f, ref in (("cr", o.cr), ("cg", o.cg), ("cb", o.cb)):
         assert same_bits(merged(f, np.float32)[fl], ref[fl]), f
+
+
+def _mixed_worker(rank, nranks, uid, text, nx, ny, frames, out_dir, p2p):
+    sys.path.insert(0, ROOT)
+    from euler_b200 import gpu as G
+    scn = Scenario(text, nx, ny)
+    row0, rows = G.slab_partition(ny, nranks, rank)
+    g = G.EulerGpu.from_scenario(scn, precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST, device=rank,
+                                 slab_row0=row0, slab_rows=rows, pcg_dtype=G.PCG_FP32, max_iterations=400)
+    g.comm_init(rank, nranks, uid)
+    if p2p:
+        g.comm_p2p_import(_exchange_blobs(out_dir, rank, nranks, g.comm_p2p_export()))
+    subs = [g.step_frame() for _ in range(frames)]
+    st = g.stats()
+    np.savez(os.path.join(out_dir, "mx%d.npz" % rank), row0=row0, rows=rows, count=g.get(G.F_COUNT),
+             u=g.get(G.F_U), v=g.get(G.F_V), p=g.get(G.F_P), subs=np.array(subs), iters=st.pcg_iterations,
+             markers=np.uint64(st.n_markers), rng=np.uint64(st.rng_state))
+    g.close()
+
+
+@pytest.mark.parametrize("p2p", [True, False])
+@pytest.mark.parametrize("nranks,name,nx,ny,frames", [(2, "block", 100, 40, 12), (2, "waterfall", 160, 96, 20),
+                                                      (4, "waterfall", 160, 96, 20)])
+def test_mixed_precision_on_slabs(nranks, name, nx, ny, frames, p2p, tmp_path):
+    """pcg_dtype = FP32 (fp32 PCG vectors, fp64 pressure and dot products, residual replacement:
+    an opt-in mode that is not in the reference) on row slabs against the same mode on one GPU:
+    classification bit-exact, marker totals, RNG state and sub-step counts equal, u, v and p within
+    1e-5 (converged solves; the two runs differ in the summation order of the dot products only)."""
+    if _gpu_count() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    import torch.multiprocessing as mp
+    from euler_b200 import gpu as G
+    text = shipped_text(name)
+    if (nx, ny) != (100, 40):
+        text = resample(text, nx - 2, ny - 2)
+    uid = G.comm_unique_id()
+    mp.spawn(_mixed_worker, args=(nranks, uid, text, nx, ny, frames, str(tmp_path), p2p), nprocs=nranks, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), "mx%d.npz" % r)) for r in range(nranks)]
+    ref = G.EulerGpu.from_scenario(Scenario(text, nx, ny), precon=G.PRECON_REDBLACK, marker_mode=G.MARKERS_FAST,
+                                   pcg_dtype=G.PCG_FP32, max_iterations=400)
+    subs = [ref.step_frame() for _ in range(frames)]
+
+    def merged(field, dtype):
+        out = np.zeros((ny, nx), dtype)
+        for p in parts:
+            r0, n = int(p["row0"]), int(p["rows"])
+            out[r0:r0 + n] = p[field][r0:r0 + n]
+        return out
+    st = ref.stats()
+    assert all(list(p["subs"]) == subs for p in parts)
+    assert same_bits(merged("count", np.uint8), ref.get(G.F_COUNT))
+    assert sum(int(p["markers"]) for p in parts) == int(st.n_markers)
+    assert all(int(p["rng"]) == int(st.rng_state) for p in parts)
+    assert abs(int(parts[0]["iters"]) - int(st.pcg_iterations)) <= max(4, int(0.02 * st.pcg_iterations))
+    for f, fld in (("u", G.F_U), ("v", G.F_V), ("p", G.F_P)):
+        a, b = merged(f, np.float64 if f == "p" else np.float32), ref.get(fld)
+        assert float(np.abs(a - b).max()) <= 1e-5 * max(1.0, float(np.abs(b).max())), f
+    ref.close()
