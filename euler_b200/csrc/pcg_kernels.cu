@@ -879,7 +879,9 @@ static PV pview(const Ctx& c) {
   v.a0 = c.own0 - lo; v.a1 = c.own1 - lo;
   // tiles are only the unit of the "contains fluid" flags; the persistent kernels split the
   // active tiles' ROWS evenly over their blocks, so a thin slab needs no smaller tile
-  v.g.th = TH;
+  // (EULER_PCG_TH: A/B knob — taller tiles halve the halo rows the fused tail recomputes per tile)
+  static const int pcg_th = env_int("EULER_PCG_TH", 2 * TH);
+  v.g.th = pcg_th;
   v.fluid = c.count + o; v.adiag = c.adiag + o;
   v.s = c.s + o; v.z = c.z + o; v.r = c.r + o; v.p = c.p + o; v.q = c.q + o; v.precon = c.precon + o;
   v.s32 = v.z32 = v.r32 = v.q32 = v.pc32 = nullptr;

@@ -40,11 +40,11 @@ namespace tail {
 
 constexpr int HALO = 2;                 // halo columns of the value planes (== pipe::Elem<double>::HX)
 constexpr int ABW = TW + 2 * HALO;      // doubles per row of the rolling neighbour buffer
-constexpr int NSLOT = 5;                // steps j-3 .. j are live; a fast warp may already write step j+1
+constexpr int NSLOT = 6;                // steps j-4 .. j are live; a fast warp may already write step j+1
 
 template <int NS>
 constexpr int smem_bytes() {
-  return NS * pipe::Layout<3, 1>::stage_bytes + 2 * NS * 8 + NSLOT * ABW * 8;
+  return NS * pipe::Layout<3, 1>::stage_bytes + 2 * NS * 8 + 2 * NSLOT * ABW * 8;
 }
 
 }  // namespace tail
@@ -54,8 +54,9 @@ constexpr int smem_bytes() {
 // word per row, shifted along with the register window.
 template <int NC>
 struct TailLane {
-  double r1[NC], pc1[NC], r2[NC], pc2[NC], q2[NC];    // r', pc of rows yy-1 / yy-2, q of row yy-2
-  unsigned mw0, mw1, mw2, mw3;                        // rows yy, yy-1, yy-2, yy-3
+  double pc1[NC];                                     // pc of row yy-1
+  double pc2[NC], q2[NC], pc3[NC], q3[NC];            // pc, q of rows yy-2 / yy-3
+  unsigned mw0, mw1, mw2, mw3, mw4;                   // rows yy .. yy-4
 };
 
 __device__ __forceinline__ bool tbit(unsigned w, int i) { return (w >> i) & 1u; }
@@ -78,6 +79,8 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NS * L::stage_bytes);
   uint64_t* empty = full + NS;
   double* ab = reinterpret_cast<double*>(empty + NS) + tail::HALO;          // [NSLOT][ABW], index slot*ABW + col
+  double* rb = ab + tail::NSLOT * tail::ABW;     // r' of the same rows (stage 2 and 3 read their own cells back:
+                                                 // three rows of r' in registers would not fit next to the rest)
 
   const int tid = threadIdx.x, lane = tid & 31;
   const bool is_main = tid < NMAIN;
@@ -138,20 +141,29 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     if (writer) { sc->alpha_s[split_it & 1] = alpha; sc->zs = zs; sc->alpha_prev = alpha_prev; sc->alpha = alpha; }
   }
   const double neg_alpha = -alpha;
+  // alpha and alpha_prev are needed by the p update only (even iterations): block-wide constants kept
+  // in shared memory rather than in four registers of every thread
+  __shared__ double alpha_sh[2];
+  if (tid == 0) { alpha_sh[0] = alpha; alpha_sh[1] = alpha_prev; }
+  __syncthreads();
 
   TailLane<C> t;
 #pragma unroll
-  for (int k = 0; k < C; ++k) t.r1[k] = t.pc1[k] = t.r2[k] = t.pc2[k] = t.q2[k] = 0.0;
-  t.mw0 = t.mw1 = t.mw2 = t.mw3 = 0u;
+  for (int k = 0; k < C; ++k) t.pc1[k] = t.pc2[k] = t.q2[k] = t.pc3[k] = t.q3[k] = 0.0;
+  t.mw0 = t.mw1 = t.mw2 = t.mw3 = t.mw4 = 0u;
   double acc = 0.0, mx = 0.0;
   bool peer_stored = false;
   double* __restrict__ z_dn = dist.z_dn;
   double* __restrict__ z_up = dist.z_up;
   const bool has_peer = z_dn || z_up;
-  // rolling row slots of the neighbour buffer, as element offsets: steps j, j-1, j-2, j-3 and the
-  // free one.  No barrier separates stage 3 of one step from stage 1 of the next: with 5 slots the
-  // one a fast warp already overwrites (step j-4's) is one nobody still reads.
-  int o0 = 0, o1 = tail::ABW, o2 = 2 * tail::ABW, o3 = 3 * tail::ABW, of = 4 * tail::ABW;
+  // rolling row slots of the neighbour buffer, as element offsets: steps j .. j-4 and the free one.
+  // ONE barrier per step: stage 2 works on row yy-1 (needs the red entries of rows yy-2 .. yy, the
+  // last written by this step's stage 1, hence the barrier), stage 3 on row yy-3 (needs the black
+  // entries of rows yy-4 .. yy-2, all written by EARLIER steps' stage 2), so the two run back to
+  // back without a barrier between them; with 6 slots the one a fast warp already overwrites in
+  // the next step's stage 1 (step j-5's) is one nobody still reads.  The last row of a piece is
+  // finished by a second stage-3 pass in the piece's last step, behind one extra barrier.
+  int o0 = 0, o1 = tail::ABW, o2 = 2 * tail::ABW, o3 = 3 * tail::ABW, o4 = 4 * tail::ABW, of = 5 * tail::ABW;
   int cstage = 0, cphase = 0;                    // consumer: ring stage of this step, its parity
   // per piece: this thread's first column / cell count, global parity base, element offset of
   // (x0 + col, yy) in the planes
@@ -172,6 +184,7 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     const int par0 = (par_base + yy) & 1;        // parity of (col, yy): 0 = red
     const bool own_row = (unsigned)rel < (unsigned)(pz.y1 - pz.y0);
     const bool acc_row = yy >= acc0 && yy < acc1;
+    const bool last_step = yy == pz.y1 + 1;      // block-uniform
 
     // the element-wise operands of the p update, issued before the wait on the ring
     const bool do_p = mode != 0 && own_row && is_main && ncol > 0;
@@ -207,20 +220,23 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
             const double rn = m ? rr.v[k] + aa.v[k] * neg_alpha : rr.v[k];      // fmadd(z, -alpha, r), main.c:754
             r0[k] = rn; pc0[k] = pp.v[k];
             if (own_row && m) {
-              if (mode == 1) pv.v[k] = pv.v[k] + spv.v[k] * alpha_prev;         // the previous iteration's main.c:753
-              if (mode) pv.v[k] = pv.v[k] + sv.v[k] * alpha;                    // fmadd(s, alpha, p), main.c:753
+              if (mode == 1) pv.v[k] = pv.v[k] + spv.v[k] * alpha_sh[1];        // the previous iteration's main.c:753
+              if (mode) pv.v[k] = pv.v[k] + sv.v[k] * alpha_sh[0];              // fmadd(s, alpha, p), main.c:753
               // NaN-dropping max like main.c:659-662 (`if (a > max) max = a`): fmax returns the other
               // operand for a NaN, and |r'| >= +0 so the sign of a zero cannot matter
               if (acc_row) mx = fmax(mx, fabs(rn));
             }
           }
           if (par0) red_w(std::integral_constant<int, 1>{}); else red_w(std::integral_constant<int, 0>{});
-          if (own_row) {
+          {
             DV<C> o;
 #pragma unroll
             for (int k = 0; k < C; ++k) o.v[k] = r0[k];
-            stv<C>(r_new + rowp, o);
-            if (do_p) stv<C>(p + rowp, pv);
+            stv<C>(rb + o0 + col, o);
+            if (own_row) {
+              stv<C>(r_new + rowp, o);
+              if (do_p) stv<C>(p + rowp, pv);
+            }
           }
         } else {
 #pragma unroll
@@ -235,6 +251,7 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
           const double rr = in.d[0][col], aa = in.d[1][col], pp = in.d[2][col];
           const double rn = tbit(mw, 1) ? rr + aa * neg_alpha : rr;
           r0[0] = rn; pc0[0] = pp;
+          rb[o0 + col] = rn;
           if (par0 == 0) ab[o0 + col] = pp * (rn * pp);
         }
       }
@@ -252,13 +269,14 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     for (int k = 0; k < C; ++k) q1[k] = 0.0;
     if (rel >= 0 && ncol) {
       if (is_main) {
+        const DV<C> r1 = ldsv<C>(rb + o1 + col);
         auto fwd = [&](auto parc) {
           constexpr int PAR = decltype(parc)::value;
 #pragma unroll
           for (int k = 0; k < C; ++k) {
             if (!tbit(t.mw1, k + 1)) continue;
             const int cc = col + k;
-            double v = t.r1[k];
+            double v = r1.v[k];
             const bool black = ((PAR + k) & 1) == 0;                 // row yy-1: the colours of row yy swapped (folds after unrolling)
             if (black) {                                             // + red neighbours: l, r, d, u
               if (tbit(t.mw1, k)) v = v + ab[o1 + cc - 1];
@@ -274,7 +292,7 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
         if (par0) fwd(std::integral_constant<int, 1>{}); else fwd(std::integral_constant<int, 0>{});
       } else if ((lane == 1 || lane == 2) && tbit(t.mw1, 1) && par0 == 0) {
         // inner halo columns -1 and w: only a black cell's zb is ever asked for
-        double v = t.r1[0];
+        double v = rb[o1 + col];
         if (tbit(t.mw1, 0)) v = v + ab[o1 + col - 1];
         if (tbit(t.mw1, 2)) v = v + ab[o1 + col + 1];
         if (tbit(t.mw2, 1)) v = v + ab[o2 + col];
@@ -282,55 +300,67 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
         ab[o1 + col] = (v * t.pc1[0]) * t.pc1[0];
       }
     }
-    __syncthreads();
 
-    // ---- stage 3: z(yy-2), z.r': rows y0 .. y1-1 -------------------------------------------
-    if (is_main && ncol && rel >= 2) {
-      const int y2r = yy - 2;
-      const bool acc2 = y2r >= acc0 && y2r < acc1;
+    // ---- stage 3: z(row), z.r' for a row whose neighbours' zb are complete ------------------
+    // `back` = how many rows behind yy (3, or 2 in the second pass of a piece's last step); the
+    // row's own q / pc / r', its mask words (centre, below, above) and buffer rows come with it
+    auto stage3 = [&](int back, const double (&qv)[C], const double (&pcv)[C], unsigned mc,
+                      unsigned mdn, unsigned mup, int oc, int odn, int oup) {
+      const int yrow = yy - back;
+      const bool accr = yrow >= acc0 && yrow < acc1;
+      const DV<C> rv = ldsv<C>(rb + oc + col);
       DV<C> out;
-      const unsigned any = t.mw2 & (((1u << C) - 1u) << 1);
+      const unsigned any = mc & (((1u << C) - 1u) << 1);
       auto bwd = [&](auto parc) {
-        constexpr int PAR = decltype(parc)::value;
+        constexpr int PAR = decltype(parc)::value;   // 1: cell 0 of this row is black
 #pragma unroll
         for (int k = 0; k < C; ++k) {
           out.v[k] = 0.0;
-          if (!tbit(t.mw2, k + 1)) continue;
+          if (!tbit(mc, k + 1)) continue;
           const int cc = col + k;
-          const double pk = t.pc2[k];
+          const double pk = pcv[k];
           double zc;
-          if ((PAR + k) & 1) {                                       // row yy-2 has the colours of row yy
-            zc = t.q2[k] * pk;                                       // black: q*pc
+          if (((PAR + k) & 1) != 0) {
+            zc = qv[k] * pk;                                         // black: q*pc
           } else {
-            double v = t.q2[k];
-            if (tbit(t.mw2, k)) v = v + pk * ab[o2 + cc - 1];
-            if (tbit(t.mw2, k + 2)) v = v + pk * ab[o2 + cc + 1];
-            if (tbit(t.mw3, k + 1)) v = v + pk * ab[o3 + cc];
-            if (tbit(t.mw1, k + 1)) v = v + pk * ab[o1 + cc];
+            double v = qv[k];
+            if (tbit(mc, k)) v = v + pk * ab[oc + cc - 1];
+            if (tbit(mc, k + 2)) v = v + pk * ab[oc + cc + 1];
+            if (tbit(mdn, k + 1)) v = v + pk * ab[odn + cc];
+            if (tbit(mup, k + 1)) v = v + pk * ab[oup + cc];
             zc = v * pk;
           }
           out.v[k] = zc;
-          if (acc2) acc += zc * t.r2[k];
+          if (accr) acc += zc * rv.v[k];
         }
       };
-      if (par0) bwd(std::integral_constant<int, 1>{}); else bwd(std::integral_constant<int, 0>{});
+      // colour of cell 0 in row yy - back: that of row yy when back is even
+      if (((par0 + back) & 1) != 0) bwd(std::integral_constant<int, 1>{}); else bwd(std::integral_constant<int, 0>{});
       // only the owned rows are stored: the halo rows of z belong to the neighbouring slabs
-      if (any && acc2) {
-        const size_t c2 = rowp - 2 * pitch;
+      if (any && accr) {
+        const size_t c2 = rowp - (size_t)back * pitch;
         stv<C>(z + c2, out);
         if (has_peer) {
-          if (z_dn && y2r < acc0 + dist.depth) { stv<C>(z_dn + c2, out); peer_stored = true; }
-          if (z_up && y2r >= acc1 - dist.depth) { stv<C>(z_up + c2, out); peer_stored = true; }
+          if (z_dn && yrow < acc0 + dist.depth) { stv<C>(z_dn + c2, out); peer_stored = true; }
+          if (z_up && yrow >= acc1 - dist.depth) { stv<C>(z_up + c2, out); peer_stored = true; }
         }
       }
+    };
+    const bool main_live = is_main && ncol > 0;
+    if (main_live && rel >= 3) stage3(3, t.q3, t.pc3, t.mw3, t.mw4, t.mw2, o3, o4, o2);
+    if (last_step) {
+      // the piece ends here: its last row (yy-2) still needs the zb this step's stage 2 just wrote
+      __syncthreads();
+      if (main_live && rel >= 2) stage3(2, t.q2, t.pc2, t.mw2, t.mw3, t.mw1, o2, o3, o1);
     }
     // shift the register window and the row slots
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-      t.r2[k] = t.r1[k]; t.pc2[k] = t.pc1[k]; t.q2[k] = q1[k]; t.r1[k] = r0[k]; t.pc1[k] = pc0[k];
+      t.pc3[k] = t.pc2[k]; t.q3[k] = t.q2[k];
+      t.pc2[k] = t.pc1[k]; t.q2[k] = q1[k]; t.pc1[k] = pc0[k];
     }
-    t.mw3 = t.mw2; t.mw2 = t.mw1; t.mw1 = t.mw0;
-    { const int f = o3; o3 = o2; o2 = o1; o1 = o0; o0 = of; of = f; }
+    t.mw4 = t.mw3; t.mw3 = t.mw2; t.mw2 = t.mw1; t.mw1 = t.mw0;
+    { const int f = o4; o4 = o3; o3 = o2; o2 = o1; o1 = o0; o0 = of; of = f; }
     rowp += pitch;
     cons.next(g, T, th, active.list);
   }
