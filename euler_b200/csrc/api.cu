@@ -226,6 +226,11 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
   memset(h->host_sc, 0, sizeof(DevScalars));
   h->host_sc->n_markers = h->slab ? 0 : n_markers;
   h->host_sc->rng_state = rng_state;
+  if (c.trace) {
+    const char* tk = getenv("EULER_TRACE_BLOCKS");      // 1 search+apply, 2 tail
+    h->host_sc->trace_blk = c.trace + (size_t)c.trace_cap * TRACE_WORDS;
+    h->host_sc->trace_kind = tk ? atoi(tk) : 0;
+  }
   CU(cudaMemcpyAsync(c.sc, h->host_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, c.stream));
   if (!h->slab) {
     if (n_markers > c.max_markers) return fail(EULER_E_INVALID, "too many markers");
@@ -872,6 +877,16 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
     TRYCU(cudaStreamSynchronize(c.stream));
   }
   if (slab) TRY(alloc_array(h, &h->n_keep, 1));
+  {
+    // EULER_TRACE=<slots>: in-kernel timeline of the PCG iteration kernels (euler_gpu_trace_read)
+    const char* te = getenv("EULER_TRACE");
+    const int slots = te ? atoi(te) : 0;
+    c.trace = nullptr; c.trace_cap = 0; c.trace_n = 0;
+    if (slots > 0) {
+      TRY(alloc_array(h, &c.trace, (size_t)slots * TRACE_WORDS + (size_t)TRACE_BLK_MAX * TRACE_BLK_WORDS));
+      c.trace_cap = slots;
+    }
+  }
   // (slab handles: the halo rows of the count plane are filled by comm_init's halo exchange)
   TRY(load_state(h, solid, source, sink, markers_xy, n_markers, prm.rng_state, true));
 #undef TRY
@@ -1198,6 +1213,26 @@ const char* euler_gpu_kernel_class_name(int i) {
       "update_search", "pressure_update", "misc", "fused_search_apply_a", "fused_axpy_forward",
       "rb_forward", "rb_backward", "color_transport", "true_residual", "fused_tail"};
   return (i >= 0 && i < KC__COUNT) ? names[i] : nullptr;
+}
+
+int euler_gpu_trace_read(euler_gpu* h, unsigned long long* out, size_t max_slots, size_t* n_slots) {
+  ENTER(h);
+  if (!n_slots) return fail(EULER_E_INVALID, "n_slots is NULL");
+  Ctx& c = h->c;
+  CU(cudaStreamSynchronize(c.stream));
+  size_t n = (size_t)c.trace_n;
+  if (n > max_slots) n = max_slots;
+  if (n && !out) return fail(EULER_E_INVALID, "out is NULL");
+  if (n) CU(cudaMemcpy(out, c.trace, n * TRACE_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  *n_slots = n;
+  // per-block records of the last traced launch of kernel EULER_TRACE_BLOCKS, behind the slots
+  if (c.trace && out && max_slots >= n + (size_t)TRACE_BLK_MAX * TRACE_BLK_WORDS / TRACE_WORDS)
+    CU(cudaMemcpy(out + n * TRACE_WORDS, c.trace + (size_t)c.trace_cap * TRACE_WORDS,
+                  (size_t)TRACE_BLK_MAX * TRACE_BLK_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  // start over: the next launch records into slot 0 again
+  if (c.trace) CU(cudaMemsetAsync(c.trace, 0, (size_t)c.trace_cap * TRACE_WORDS * sizeof(unsigned long long), c.stream));
+  c.trace_n = 0;
+  return 0;
 }
 
 int euler_gpu_synchronize(euler_gpu* h) {

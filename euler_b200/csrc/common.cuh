@@ -78,6 +78,9 @@ struct DevScalars {
   // update_fluid_sources in three parallel passes (marker_kernels.cu): what the emitting pass
   // needs of the state before the bookkeeping pass advanced it
   unsigned long long src_n0, src_state0, src_allow;
+  // diagnostics (EULER_TRACE): per-block records of the last traced launch of kernel `trace_kind`
+  unsigned long long* trace_blk;
+  int trace_kind, pad5;
 };
 
 // The MAC-grid stage kernels (grid_kernels.cu) stream only the 512 x 32-cell tiles that can hold a
@@ -203,6 +206,32 @@ __device__ __forceinline__ bool grid_reduce_last_block_all(double block_value, d
   __syncthreads();
   total = total_sh;
   return true;
+}
+// ---- in-kernel timeline of the two PCG iteration kernels (diagnostics, EULER_TRACE=<slots>) ----
+// One 16-word slot per launch; thread 0 of every block folds %globaltimer (ns) into (min, max) pairs:
+//   words 0/1 block start, 2/3 scalars known (after the cross-rank collect), 4/5 rows done,
+//   6/7 block exit (max = the last block's, after the reduction / post); minima are stored
+//   complemented so that one atomicMax serves both.  Word 8 = kernel kind, 9 = iteration.
+// A null slot pointer (the default) costs one uniform predicate per mark.
+constexpr int TRACE_WORDS = 16;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_mark(unsigned long long* slot, int pair) {
+  if (!slot || threadIdx.x != 0) return;
+  const unsigned long long t = global_ns();
+  atomicMax(slot + 2 * pair, ~t);
+  atomicMax(slot + 2 * pair + 1, t);
+}
+// per-block record of one launch: {start ns, rows-done ns, SM id, 0}
+constexpr int TRACE_BLK_WORDS = 4, TRACE_BLK_MAX = 4096;
+__device__ __forceinline__ void trace_block(unsigned long long* slot, const DevScalars* sc, int kind, int word) {
+  if (!slot || threadIdx.x != 0 || sc->trace_kind != kind || blockIdx.x >= TRACE_BLK_MAX) return;
+  unsigned long long* b = sc->trace_blk + (size_t)TRACE_BLK_WORDS * blockIdx.x;
+  b[word] = global_ns();
+  if (word == 0) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); b[2] = smid; }
 }
 #endif  // __CUDACC__
 

@@ -96,7 +96,15 @@ struct Ctx {
   DistArgs dist;                  // z_dn / z_up here are row 0 of the neighbours' planes
   int p2p_dn_own1, p2p_up_own0;   // the neighbours' owned-row bounds in their local rows
   double tol;                     // PCG stop tolerance (main.c:736)
+  // in-kernel timeline of the iteration kernels (common.cuh trace_mark): EULER_TRACE=<slots>
+  unsigned long long* trace;      // trace_cap slots of TRACE_WORDS words, or null
+  int trace_cap, trace_n;
 };
+// next free trace slot (null when tracing is off or the buffer is full)
+inline unsigned long long* trace_slot(Ctx& c) {
+  if (!c.trace || c.trace_n >= c.trace_cap) return nullptr;
+  return c.trace + (size_t)TRACE_WORDS * (size_t)c.trace_n++;
+}
 
 // RAII: when profiling is on, brackets the launches of one kernel class with CUDA events on
 // ctx.stream; prof_collect() (after a stream sync) folds them into Prof::ms.

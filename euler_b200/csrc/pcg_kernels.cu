@@ -735,9 +735,11 @@ __global__ void __launch_bounds__(TW / C, MB) k_fused_search_apply(
     Grid g, TileList active, const T* __restrict__ z, const T* __restrict__ s,
     const uint8_t* __restrict__ fluid, const int8_t* __restrict__ adiag, T* __restrict__ s_new,
     T* __restrict__ as, double* partials, DevScalars* sc, int init, int exact, int acc0, int acc1,
-    const __grid_constant__ DistArgs dist, int split_it, double tol) {
+    const __grid_constant__ DistArgs dist, int split_it, double tol, unsigned long long* tr) {
   pdl_prologue();
   if (sc->done) return;
+  trace_mark(tr, 0);
+  if (tr && blockIdx.x == 0 && threadIdx.x == 0) { tr[8] = 1; tr[9] = (unsigned long long)split_it; }
   double beta = sc->beta;
   if (split_it) {
     // split-phase exchange (p2p.cuh): this kernel's blocks consume {z.r, ||r||inf} that the
@@ -755,22 +757,28 @@ __global__ void __launch_bounds__(TW / C, MB) k_fused_search_apply(
       if (writer) { sc->beta = beta; sc->sigma_s[(split_it + 1) & 1] = zr; }
     }
   }
+  trace_mark(tr, 1);
+  trace_block(tr, sc, 1, 0);
   FusedSearchApply<C, T> op{g, s_new, as, (T)beta, init != 0, 0.0, acc0, acc1};
   pipe::Planes<2, 2, T> in;
   in.d[0] = z; in.d[1] = s; in.b[0] = fluid; in.b[1] = reinterpret_cast<const uint8_t*>(adiag);
   pipe::run<2, 2, NS, TH, FusedSearchApply<C, T>, C, T>(g, active.list, (int)*active.count, in, op);
+  trace_mark(tr, 2);
+  trace_block(tr, sc, 1, 1);
   const double bsum = block_reduce<false>(op.acc);
   double total;
-  if (!grid_reduce_last_block_all<false>(bsum, partials, &sc->ctr[CTR_ZS], total)) return;
+  if (!grid_reduce_last_block_all<false>(bsum, partials, &sc->ctr[CTR_ZS], total)) { trace_mark(tr, 3); return; }
   if (dist.mine) {                                           // {z.s} over NVLink -> alpha
     if (split_it) p2p_post(dist, total, 0.0, false);
     else p2p_finish(dist, sc, 0, 0, 0.0, total, false);
+    trace_mark(tr, 3);
     return;
   }
   if (threadIdx.x != 0) return;
   if (exact == 2) { sc->part[0] = total; return; }
   sc->zs = total;
   sc->alpha_prev = sc->alpha; sc->alpha = sc->sigma / total;                             // main.c:752
+  trace_mark(tr, 3);
 }
 
 template <int NS>
@@ -1113,12 +1121,12 @@ void launch_fused_search_apply(Ctx& c, bool init, int split_it) {
     launch_pdl(k_fused_search_apply<N, C, float>, \
                pcg_blocks(c, k_fused_search_apply<N, C, float>, smem, TW / C), TW / C, smem, c.stream, \
                v.g, TL, v.z32, v.s32, v.fluid, v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, xf, \
-               v.a0, v.a1, d, 0, 0.0); }
+               v.a0, v.a1, d, 0, 0.0, (unsigned long long*)nullptr); }
     if (c.mixed_blocks == 8) {
       constexpr int smem = pipe::smem_bytes<2, 2, 4, float>();
       auto k = k_fused_search_apply<4, C, float, 8>;
       launch_pdl(k, pcg_blocks(c, k, smem, TW / C, true), TW / C, smem, c.stream, v.g, TL, v.z32, v.s32, v.fluid,
-                 v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, xf, v.a0, v.a1, d, 0, 0.0);
+                 v.adiag, c.s32b + o, v.q32, c.partials, c.sc, init ? 1 : 0, xf, v.a0, v.a1, d, 0, 0.0, (unsigned long long*)nullptr);
     } else if (c.ns_mixed[2] == 8) KA32(8) else if (c.ns_mixed[2] == 6) KA32(6) else KA32(4)
 #undef KA32
     c.launches += 1;
@@ -1126,11 +1134,12 @@ void launch_fused_search_apply(Ctx& c, bool init, int split_it) {
     return;
   }
   if (c.p2p_mode == 2) d = c.dist;
+  unsigned long long* tr = trace_slot(c);
 #define KA(N, C) { constexpr int smem = pipe::smem_bytes<2, 2, N>(); \
   launch_pdl(k_fused_search_apply<N, C>, pcg_blocks(c, k_fused_search_apply<N, C>, smem, TW / C), TW / C, smem, c.stream, \
              v.g, TL, v.z, v.s, v.fluid, v.adiag, c.s2 + o, v.q, c.partials, c.sc, init ? 1 : 0, \
-             c.distributed ? 2 : 0, v.a0, v.a1, d, split_it, c.tol); }
-  if (cpt == 2) { if (ns == 6) KA(6, 2) else if (ns == 5) KA(5, 2) else KA(4, 2) }
+             c.distributed ? 2 : 0, v.a0, v.a1, d, split_it, c.tol, tr); }
+  if (cpt == 2) { if (ns == 10) KA(10, 2) else if (ns == 8) KA(8, 2) else if (ns == 6) KA(6, 2) else if (ns == 5) KA(5, 2) else KA(4, 2) }
   else { if (ns == 6) KA(6, 4) else if (ns == 5) KA(5, 4) else KA(4, 4) }
 #undef KA
   c.launches += 1;
@@ -1166,6 +1175,7 @@ void launch_fused_tail(Ctx& c, double tol, int mode, int split_it) {
     if (d.z_dn) d.z_dn += (lo + c.p2p_dn_own1 - c.own0) * (long)c.g.pitch;
     if (d.z_up) d.z_up += (lo + c.p2p_up_own0 - c.own1) * (long)c.g.pitch;
   }
+  unsigned long long* tr = trace_slot(c);
   static const int cpt = env_int("EULER_CPT_TAIL", 2);
   static const int ns = env_int("EULER_NS_TAIL", 3);
   // resident blocks per SM the compiler must allow.  Measured at 16384^2 (same box, profiles/r02a):
@@ -1175,7 +1185,7 @@ void launch_fused_tail(Ctx& c, double tol, int mode, int split_it) {
 #define TAIL(N, C, MB) { constexpr int smem = tail::smem_bytes<N>(); constexpr int threads = TW / C + 32; \
     k_fused_tail<N, C, MB><<<pcg_blocks(c, k_fused_tail<N, C, MB>, smem, threads), threads, smem, c.stream>>>( \
         v.g, TL, v.r, v.q, v.precon, v.fluid, v.s, c.s2 + o, v.p, c.r2 + o, v.z, c.partials, c.sc, tol, mode, \
-        dotflag(c), v.a0, v.a1, d, split_it); }
+        dotflag(c), v.a0, v.a1, d, split_it, tr); }
   if (cpt == 4) { if (ns == 4) TAIL(4, 4, 3) else TAIL(3, 4, 3) }
   else if (mb == 2) { if (ns == 5) TAIL(5, 2, 2) else if (ns == 4) TAIL(4, 2, 2) else TAIL(3, 2, 2) }
   else { if (ns == 4) TAIL(4, 2, 3) else TAIL(3, 2, 3) }

@@ -70,6 +70,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// L2 prefetch of a contiguous global range by the bulk-copy engine (no destination, no mbarrier):
+// for operands that are read with plain loads a few rows later
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(src)), "r"(bytes)
+               : "memory");
+}
 
 #endif  // __CUDACC__
 

@@ -40,6 +40,10 @@ namespace tail {
 
 constexpr int HALO = 2;                 // halo columns of the value planes (== pipe::Elem<double>::HX)
 constexpr int ABW = TW + 2 * HALO;      // doubles per row of the rolling neighbour buffer
+#ifndef EULER_TAIL_PF_ROWS
+#define EULER_TAIL_PF_ROWS -1
+#endif
+constexpr int PF_ROWS = EULER_TAIL_PF_ROWS;   // rows ahead of the ring's newest row the p-update operands are prefetched to L2
 constexpr int NSLOT = 6;                // steps j-4 .. j are live; a fast warp may already write step j+1
 
 template <int NS>
@@ -69,11 +73,13 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     const double* __restrict__ precon, const uint8_t* __restrict__ fluid, const double* __restrict__ s,
     const double* __restrict__ s_prev, double* __restrict__ p, double* __restrict__ r_new,
     double* __restrict__ z, double* partials, DevScalars* sc, double tol, int mode, int exact,
-    int acc0, int acc1, const __grid_constant__ DistArgs dist, int split_it) {
+    int acc0, int acc1, const __grid_constant__ DistArgs dist, int split_it, unsigned long long* tr) {
   using L = pipe::Layout<3, 1>;
   constexpr int NMAIN = TW / C;                  // main threads: C cells each
   constexpr int ROWT = L::ROWT;
   if (sc->done) return;
+  trace_mark(tr, 0);
+  if (tr && blockIdx.x == 0 && threadIdx.x == 0) { tr[8] = 2; tr[9] = (unsigned long long)split_it; }
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* stages = smem_raw;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NS * L::stage_bytes);
@@ -117,6 +123,24 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     pipe::bulk_g2s(dst + ROWT, as + row - tail::HALO, b8, full + pstage);
     pipe::bulk_g2s(dst + 2 * ROWT, precon + row - tail::HALO, b8, full + pstage);
     pipe::bulk_g2s(dst + 3 * ROWT, fluid + row - pipe::HX1, b1, full + pstage);
+    // the element-wise operands of the p update are read with plain loads when the row is consumed:
+    // pull them into L2 now (even iterations, owned rows only)
+    // pull them into L2 PF rows before that (even iterations, owned rows only; the first PF rows of
+    // a piece go out with its first halo row)
+    if (mode != 0) {
+      constexpr int PF = tail::PF_ROWS;
+      const uint32_t bp = (uint32_t)prod.p.w * 8u;
+      auto pf = [&](int y) {
+        const long o = (long)y * g.pitch + prod.p.x0;
+        pipe::bulk_prefetch_l2(s + o, bp);
+        pipe::bulk_prefetch_l2(p + o, bp);
+        if (mode == 1) pipe::bulk_prefetch_l2(s_prev + o, bp);
+      };
+      if (PF > 2 && prod.yy == prod.p.y0 - 2)
+        for (int y = prod.p.y0; y < prod.p.y0 + PF - 2 && y < prod.p.y1; ++y) pf(y);
+      const int t = prod.yy + PF;
+      if (t >= prod.p.y0 + (PF > 2 ? PF - 2 : 0) && t < prod.p.y1) pf(t);
+    }
     if (++pstage == NS) { pstage = 0; pphase ^= 1; }
     prod.next(g, T, th, active.list);
     prod_sh = prod; pstage_sh = pstage; pphase_sh = pphase;
@@ -140,6 +164,8 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     alpha_prev = sc->alpha_s[(split_it + 1) & 1];          // the previous iteration's
     if (writer) { sc->alpha_s[split_it & 1] = alpha; sc->zs = zs; sc->alpha_prev = alpha_prev; sc->alpha = alpha; }
   }
+  trace_mark(tr, 1);
+  trace_block(tr, sc, 2, 0);
   const double neg_alpha = -alpha;
   // alpha and alpha_prev are needed by the p update only (even iterations): block-wide constants kept
   // in shared memory rather than in four registers of every thread
@@ -365,6 +391,8 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     cons.next(g, T, th, active.list);
   }
 
+  trace_mark(tr, 2);
+  trace_block(tr, sc, 2, 1);
   if (peer_stored) __threadfence_system();
   const double bsum = block_reduce<false>(acc);
   const double bmax = block_reduce<true>(mx);
@@ -379,7 +407,7 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
     last_sh = atomicAdd(&sc->ctr[CTR_ZR], 1u) == nblocks - 1;
   }
   __syncthreads();
-  if (!last_sh) return;
+  if (!last_sh) { trace_mark(tr, 3); return; }
   __threadfence();
   double a = 0.0, m = 0.0;
   for (unsigned int i = tid; i < nblocks; i += blockDim.x) {
@@ -392,10 +420,11 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
   __syncthreads();
   const double total = tot_sh[0], norm = tot_sh[1];
   if (dist.mine) {                                           // halo flags + {z.r, ||r||inf} over NVLink
-    if (split_it) { p2p_post(dist, total, norm, true); return; }
+    if (split_it) { p2p_post(dist, total, norm, true); trace_mark(tr, 3); return; }
     if (tid == 0) sc->part[1] = norm;
     __syncthreads();
     p2p_finish(dist, sc, 1, 0, tol, total, true);
+    trace_mark(tr, 3);
     return;
   }
   if (tid != 0) return;
@@ -405,4 +434,5 @@ __global__ void __launch_bounds__(TW / C + 32, MB) k_fused_tail(
   if (norm <= tol) { sc->done = 1; return; }                 // main.c:756-758
   sc->beta = total / sc->sigma;                              // main.c:762-765
   sc->sigma = total;
+  trace_mark(tr, 3);
 }

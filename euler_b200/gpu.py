@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libeuler_gpu.so")
+# (EULER_GPU_LIB: an A/B build of the same library, tools only)
+LIB_PATH = os.environ.get("EULER_GPU_LIB") or os.path.join(_HERE, "lib", "libeuler_gpu.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError("%s is missing — build it with `make gpu` (there is no CPU fallback)" % LIB_PATH)
@@ -102,6 +103,7 @@ _L.euler_gpu_set_max_iterations.argtypes = [_H, C.c_int]
 _L.euler_gpu_stats.argtypes = [_H, C.POINTER(Stats)]
 _L.euler_gpu_check.argtypes = [_H, C.POINTER(Check)]
 _L.euler_gpu_set_profiling.argtypes = [_H, C.c_int]
+_L.euler_gpu_trace_read.argtypes = [_H, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
 _L.euler_gpu_synchronize.argtypes = [_H]
 _L.euler_gpu_reset_profile.argtypes = [_H]
 _L.euler_gpu_kernel_class_name.restype = C.c_char_p
@@ -230,6 +232,13 @@ class EulerGpu:
     def run_stage(self, stage, dt=0.0): _ck(_L.euler_gpu_run_stage(self._h, stage, np.float32(dt)))
     def pcg_iterations(self, n): _ck(_L.euler_gpu_pcg_iterations(self._h, n))
     def synchronize(self): _ck(_L.euler_gpu_synchronize(self._h))
+    def trace_read(self, max_slots=65536):
+        """Timeline slots recorded since the last call (EULER_TRACE=<slots>): array [n, 16] of uint64."""
+        out = np.zeros((max_slots, 16), dtype=np.uint64)
+        n = C.c_size_t(0)
+        _ck(_L.euler_gpu_trace_read(self._h, out.ctypes.data_as(C.c_void_p), C.c_size_t(max_slots), C.byref(n)))
+        self.trace_blocks = out[n.value:n.value + 1024].reshape(-1, 4) if max_slots >= n.value + 1024 else None
+        return out[:n.value]
     def set_profiling(self, on): _ck(_L.euler_gpu_set_profiling(self._h, 1 if on else 0))
     def reset_profile(self): _ck(_L.euler_gpu_reset_profile(self._h))
 

@@ -311,6 +311,15 @@ int euler_gpu_set_profiling(euler_gpu *h, int enabled);
 const char *euler_gpu_kernel_class_name(int i);
 /* Zero the profiling accumulators. */
 int euler_gpu_reset_profile(euler_gpu *h);
+/* Diagnostics (the new build's counterpart of the reference's debug helpers, misc/debug.c): with
+ * EULER_TRACE=<slots> in the environment when the handle is created, the two kernels of a red-black
+ * PCG iteration record a timeline per launch — 16 words: %globaltimer ns as (~min, max) over the
+ * blocks for {block start, scalars known, rows done, block exit}, word 8 = kernel (1 search+apply,
+ * 2 tail), word 9 = iteration (slab runs).  Copies the recorded slots out (up to max_slots) and
+ * starts over; *n_slots = 0 when tracing is off.  With EULER_TRACE_BLOCKS=<kernel> and room for
+ * 1024 more slots in `out`, the per-block records {start ns, rows-done ns, SM id, 0} x 4096 of that
+ * kernel's last launch follow the slots. */
+int euler_gpu_trace_read(euler_gpu *h, unsigned long long *out, size_t max_slots, size_t *n_slots);
 int euler_gpu_synchronize(euler_gpu *h);
 /* The CUDA stream (cudaStream_t) the handle enqueues on, for event timing by the caller. */
 void *euler_gpu_stream(euler_gpu *h);
