@@ -54,6 +54,10 @@ struct euler_gpu {
   bool comm_ready;
   unsigned long long* n_keep;    // device scratch of the marker partition
   size_t source_cap;             // capacity of Ctx::source_cells
+  unsigned int* src_rows;        // per stored row: source cells, then their offset in the list (load_state)
+  unsigned long long* src_totals;
+  cudaStream_t up_stream;        // sim_init hand-over: uploads next to the zeroing of the planes
+  cudaEvent_t up_event;
   P2P pp;                        // NVLink peer-to-peer fast path of the per-iteration exchanges
   void* z_raw;                   // cudaMalloc base of the z plane (for the IPC handle)
   bool own_stream;
@@ -142,11 +146,11 @@ FieldInfo field_info(euler_gpu* h, int f) {
 }
 
 // host arrays always have the GLOBAL shape [ny][nx]; the handle takes the rows it stores
-int upload_plane(euler_gpu* h, void* dst, const void* src, size_t elem) {
+int upload_plane(euler_gpu* h, void* dst, const void* src, size_t elem, cudaStream_t stream) {
   const Grid& g = h->c.g;
   const char* from = reinterpret_cast<const char*>(src) + (size_t)h->lo * g.nx * elem;
   CU(cudaMemcpy2DAsync(dst, g.pitch * elem, from, (size_t)g.nx * elem, (size_t)g.nx * elem, g.ny,
-                       cudaMemcpyHostToDevice, h->c.stream));
+                       cudaMemcpyHostToDevice, stream));
   return 0;
 }
 
@@ -201,7 +205,16 @@ int color_halos(euler_gpu* h) {
 int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const uint8_t* sink,
                const float* markers_xy, size_t n_markers, uint64_t rng_state, bool fresh) {
   Ctx& c = h->c;
-  const int nx = h->nx, ny = h->ny;
+  // The uploads go out on a second stream, next to the zeroing of the dynamic planes on the main one
+  // (copy engine and SMs: at 16384^2 the memsets are 39 GB, the uploads 2.5 GB over PCIe).  They
+  // start after everything already enqueued on the main stream (a fresh handle's allocation memsets
+  // clear the very planes the uploads fill).
+  if (!h->up_stream) {
+    CU(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->up_event, cudaEventDisableTiming));
+  }
+  CU(cudaEventRecord(h->up_event, c.stream));
+  CU(cudaStreamWaitEvent(h->up_stream, h->up_event, 0));
   if (!fresh) {
     int rc = 0;
     rc |= zero_plane(h, c.u); rc |= zero_plane(h, c.v); rc |= zero_plane(h, c.utmp); rc |= zero_plane(h, c.vtmp);
@@ -218,11 +231,18 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
     h->max_valid = false;
   }
   int rc;
-  if ((rc = upload_plane(h, c.solid, solid, 1))) return rc;
-  if ((rc = upload_plane(h, c.source, source, 1))) return rc;
-  if ((rc = upload_plane(h, c.sink, sink, 1))) return rc;
+  if ((rc = upload_plane(h, c.solid, solid, 1, h->up_stream))) return rc;
+  if ((rc = upload_plane(h, c.source, source, 1, h->up_stream))) return rc;
+  if ((rc = upload_plane(h, c.sink, sink, 1, h->up_stream))) return rc;
 
-  c.gt_hist = c.gt_sparse = c.gt_prev_sparse = 0;           // the grid stages start over all tiles
+  // Every dynamic plane is zero now, so "zero outside the tiles that hold or border fluid" — what the
+  // tile list of the grid stages relies on (common.cuh GridTiles) — holds from the first sub-step:
+  // the two "previous sub-step" flag planes start empty instead of forcing two passes over all tiles.
+  // (The first count fold still runs over all tiles: gt_prev_sparse.)
+  for (int i = 0; i < 3; ++i)
+    CU(cudaMemsetAsync(c.gt_flags[i], 0, (size_t)c.gt_tx * c.gt_ty, c.stream));
+  c.gt_hist = 2;
+  c.gt_sparse = c.gt_prev_sparse = 0;
   memset(h->host_sc, 0, sizeof(DevScalars));
   h->host_sc->n_markers = h->slab ? 0 : n_markers;
   h->host_sc->rng_state = rng_state;
@@ -235,8 +255,11 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
   if (!h->slab) {
     if (n_markers > c.max_markers) return fail(EULER_E_INVALID, "too many markers");
     if (n_markers)
-      CU(cudaMemcpyAsync(c.markers, markers_xy, n_markers * sizeof(float2), cudaMemcpyHostToDevice, c.stream));
-  } else {
+      CU(cudaMemcpyAsync(c.markers, markers_xy, n_markers * sizeof(float2), cudaMemcpyHostToDevice, h->up_stream));
+  }
+  CU(cudaEventRecord(h->up_event, h->up_stream));
+  CU(cudaStreamWaitEvent(c.stream, h->up_event, 0));
+  if (h->slab) {
     // keep the markers whose cell row this slab owns: the global array streams through the
     // scratch marker array in chunks and a kernel appends the owned ones (order is free in
     // FAST marker mode, the only one slabs support)
@@ -246,45 +269,25 @@ int load_state(euler_gpu* h, const uint8_t* solid, const uint8_t* source, const 
       CU(cudaMemcpyAsync(c.markers_alt, markers_xy + 2 * off, n * sizeof(float2), cudaMemcpyHostToDevice, c.stream));
       launch_filter_markers(c, c.markers_alt, n, h->row0, h->row0 + h->rows);
     }
-    unsigned long long kept = 0;
-    CU(cudaMemcpyAsync(&kept, &c.sc->n_markers, sizeof kept, cudaMemcpyDeviceToHost, c.stream));
-    CU(cudaStreamSynchronize(c.stream));
-    if (kept > c.max_markers) return fail(EULER_E_INVALID, "too many markers in slab");
   }
 
-  // static row-major list of source cells (main.c:284-286 visits them in this order); rows
-  // are scanned a machine word at a time: almost all of them hold no source.  A slab handle
-  // looks only at the rows it stores; whether ANY rank has a source is agreed on below.
-  std::vector<unsigned int> cells;
-  size_t n_src_global = 0;
-  const int scan0 = h->slab ? h->lo : 0, scan1 = h->slab ? h->lo + c.g.ny : ny;
-  for (int y = scan0; y < scan1; ++y) {
-    const uint8_t* row = source + (size_t)y * nx;
-    const bool mine = y >= h->row0 && y < h->row0 + h->rows;
-    for (int x = 0; x < nx;) {
-      if (x + 8 <= nx) {
-        uint64_t w;
-        memcpy(&w, row + x, 8);
-        if (!w) { x += 8; continue; }
-      }
-      const int xe = x + 8 <= nx ? x + 8 : nx;
-      for (; x < xe; ++x)
-        if (row[x]) {
-          n_src_global++;
-          if (mine) cells.push_back((unsigned int)((size_t)(y - h->lo) * c.g.pitch + x));
-        }
-    }
-  }
-  c.n_source_cells = cells.size();
-  c.n_source_cells_global = n_src_global;
-  if (cells.size() > h->source_cap || !c.source_cells) {
-    int arc = alloc_array(h, &c.source_cells, cells.size());
+  // static row-major list of source cells (main.c:284-286 visits them in this order), built on the
+  // device from the uploaded plane (marker_kernels.cu k_src_row_*).  A slab handle lists the rows it
+  // owns and counts the rows it stores; whether ANY rank has a source is agreed on below.
+  launch_source_rows_count(c, h->src_rows, h->src_totals);
+  unsigned long long tot[2] = {0, 0}, kept = 0;
+  CU(cudaMemcpyAsync(tot, h->src_totals, sizeof tot, cudaMemcpyDeviceToHost, c.stream));
+  if (h->slab) CU(cudaMemcpyAsync(&kept, &c.sc->n_markers, sizeof kept, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));      // also: pageable host buffers may go out of scope after this
+  if (h->slab && kept > c.max_markers) return fail(EULER_E_INVALID, "too many markers in slab");
+  c.n_source_cells = (size_t)tot[0];
+  c.n_source_cells_global = (size_t)tot[1];
+  if (c.n_source_cells > h->source_cap || !c.source_cells) {
+    int arc = alloc_array(h, &c.source_cells, c.n_source_cells);
     if (arc) return arc;
-    h->source_cap = cells.size();
+    h->source_cap = c.n_source_cells;
   }
-  if (!cells.empty())
-    CU(cudaMemcpyAsync(c.source_cells, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice, c.stream));
-  CU(cudaStreamSynchronize(c.stream));      // `cells` and pageable host buffers go out of scope
+  if (c.n_source_cells) launch_source_rows_write(c, h->src_rows);
 
   launch_refresh_counts(c);                                  // sim_init, main.c:268
   launch_colorize(c);                                        // --rainbow, main.c:271-273
@@ -691,6 +694,7 @@ int euler_gpu_destroy(euler_gpu* h) {
     for (int i = 0; i < 2 * h->c.prof.cap; ++i) if (h->c.prof.ev[i]) cudaEventDestroy(h->c.prof.ev[i]);
     delete[] h->c.prof.ev; delete[] h->c.prof.cls;
   }
+  if (h->up_stream) { cudaStreamDestroy(h->up_stream); cudaEventDestroy(h->up_event); }
   if (h->own_stream && h->c.stream) cudaStreamDestroy(h->c.stream);
   delete h;
   return 0;
@@ -757,6 +761,7 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
   h->host_sc = nullptr; h->device_bytes = 0; h->max_valid = false;
   h->frames = h->substeps = h->solves = h->solves_skipped = h->pcg_iterations = h->markers_migrated = 0;
   h->last_iterations = 0; h->last_residual = 0; h->last_dt = 0; h->profiling = false; h->poll_hint = 0;
+  h->up_stream = nullptr; h->up_event = nullptr; h->src_rows = nullptr; h->src_totals = nullptr;
   h->split = false;
   h->ms_markers = h->ms_grid = h->ms_project = 0;
   for (int i = 0; i < 4; ++i) h->ev[i] = nullptr;
@@ -877,6 +882,8 @@ int euler_gpu_create(euler_gpu** out, int nx, int ny, const uint8_t* solid, cons
     TRYCU(cudaStreamSynchronize(c.stream));
   }
   if (slab) TRY(alloc_array(h, &h->n_keep, 1));
+  TRY(alloc_array(h, &h->src_rows, (size_t)c.g.ny + 1));
+  TRY(alloc_array(h, &h->src_totals, 2));
   {
     // EULER_TRACE=<slots>: in-kernel timeline of the PCG iteration kernels (euler_gpu_trace_read)
     const char* te = getenv("EULER_TRACE");
@@ -1088,7 +1095,7 @@ int euler_gpu_set(euler_gpu* h, int field, const void* src, size_t bytes) {
   if (!fi.ptr) return fail(EULER_E_INVALID, "field %d unknown or not allocated on this handle (params.rainbow / pcg_dtype)", field);
   const size_t want = (size_t)g.nx * h->ny * fi.elem;
   if (bytes != want) return fail(EULER_E_INVALID, "field %d: %zu bytes given, %zu needed", field, bytes, want);
-  int rc = upload_plane(h, fi.ptr, src, fi.elem);
+  int rc = upload_plane(h, fi.ptr, src, fi.elem, h->c.stream);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->c.stream));
   if (field == EULER_F_U || field == EULER_F_V) h->max_valid = false;

@@ -156,6 +156,10 @@ void launch_advect_markers(Ctx& c, float dt, int mode);      // in: markers, out
 void launch_refresh_counts(Ctx& c);                          // prev<-cur, re-bin, delete in sink/solid
 void launch_sources(Ctx& c);                                 // update_fluid_sources
 void launch_sources_count(Ctx& c);
+// sim_init: the ordered list of source cells from the uploaded source plane.  rows_scratch: g.ny
+// words; totals2[0] = cells in owned rows (the list), [1] = in all stored rows
+void launch_source_rows_count(Ctx& c, unsigned int* rows_scratch, unsigned long long* totals2);
+void launch_source_rows_write(Ctx& c, const unsigned int* rows_scratch);
 void launch_sources_prep(Ctx& c, const double* gathered, int rank, int nranks);
 // slab mode: advect + hand the markers that left rows [own_lo, own_hi) to the staging buffers
 // (null = no neighbour on that side); they are deleted locally by the next refresh_marker_counts

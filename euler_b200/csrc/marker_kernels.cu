@@ -695,6 +695,100 @@ void launch_refresh_counts(Ctx& c) {
   c.launches += 5;
 }
 
+// ---- the static row-major list of source cells (main.c:284-286 visits them in this order), built
+// on the device from the uploaded source plane: per-row counts, one scan over the rows, ordered
+// writes.  (Round 1 scanned the plane on the host: 35 ms per sim_init hand-over at 16384^2.)
+namespace {
+__device__ __forceinline__ int nonzero_bytes(unsigned w) {
+  return __popc((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u);
+}
+// one block per stored row; padding columns of the plane are zero
+__global__ void __launch_bounds__(256) k_src_row_count(Grid g, const uint8_t* __restrict__ source,
+                                                       unsigned int* __restrict__ row_count) {
+  __shared__ int tot;
+  if (threadIdx.x == 0) tot = 0;
+  __syncthreads();
+  const uint4* row = reinterpret_cast<const uint4*>(source + (size_t)blockIdx.x * g.pitch);
+  int n = 0;
+  for (int i = threadIdx.x; i < g.pitch / 16; i += blockDim.x) {
+    const uint4 w = row[i];
+    if (w.x | w.y | w.z | w.w) n += nonzero_bytes(w.x) + nonzero_bytes(w.y) + nonzero_bytes(w.z) + nonzero_bytes(w.w);
+  }
+  if (n) atomicAdd(&tot, n);
+  __syncthreads();
+  if (threadIdx.x == 0) row_count[blockIdx.x] = (unsigned int)tot;
+}
+// exclusive scan of the OWNED rows' counts (in place), totals[0] = cells in owned rows,
+// totals[1] = cells in all stored rows
+__global__ void __launch_bounds__(1024) k_src_row_scan(int ny, int own0, int own1, unsigned int* __restrict__ row_count,
+                                                       unsigned long long* __restrict__ totals) {
+  __shared__ unsigned long long sh[1024];
+  __shared__ unsigned long long all_sh;
+  const int per = (ny + 1023) / 1024;
+  const int lo = min(ny, per * (int)threadIdx.x), hi = min(ny, lo + per);
+  unsigned long long own = 0, all = 0;
+  for (int y = lo; y < hi; ++y) { all += row_count[y]; if (y >= own0 && y < own1) own += row_count[y]; }
+  if (threadIdx.x == 0) all_sh = 0;
+  sh[threadIdx.x] = own;
+  __syncthreads();
+  if (all) atomicAdd(&all_sh, all);
+  for (int d = 1; d < 1024; d <<= 1) {
+    const unsigned long long v = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned long long run = sh[threadIdx.x] - own;
+  for (int y = lo; y < hi; ++y) {
+    const unsigned int c = (y >= own0 && y < own1) ? row_count[y] : 0u;
+    row_count[y] = c ? (unsigned int)run : 0xffffffffu;       // rows without (owned) sources are skipped
+    run += c;
+  }
+  if (threadIdx.x == 1023) { totals[0] = sh[1023]; totals[1] = all_sh; }
+}
+// one block per stored row that has sources: cells in ascending x
+__global__ void __launch_bounds__(256) k_src_row_write(Grid g, const uint8_t* __restrict__ source,
+                                                       const unsigned int* __restrict__ row_offset,
+                                                       unsigned int* __restrict__ cells) {
+  const unsigned int base0 = row_offset[blockIdx.x];
+  if (base0 == 0xffffffffu) return;
+  __shared__ int wsum[8];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const unsigned* row = reinterpret_cast<const unsigned*>(source + (size_t)blockIdx.x * g.pitch);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < g.pitch / 4; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const unsigned w = i < g.pitch / 4 ? row[i] : 0u;
+    const int n = nonzero_bytes(w);
+    int inc = n;                                               // inclusive scan over the block
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(EULER_FULL_MASK, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    int before = carry;
+    for (int k = 0; k < wid; ++k) before += wsum[k];
+    int pos = before + inc - n;
+    for (int b = 0; b < 4; ++b)
+      if ((w >> (8 * b)) & 0xffu) cells[base0 + pos++] = (unsigned int)((size_t)blockIdx.x * g.pitch + 4 * i + b);
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = before + inc;
+    __syncthreads();
+  }
+}
+}  // namespace
+
+void launch_source_rows_count(Ctx& c, unsigned int* rows_scratch, unsigned long long* totals2) {
+  k_src_row_count<<<c.g.ny, 256, 0, c.stream>>>(c.g, c.source, rows_scratch);
+  k_src_row_scan<<<1, 1024, 0, c.stream>>>(c.g.ny, c.own0, c.own1, rows_scratch, totals2);
+  c.launches += 2;
+}
+void launch_source_rows_write(Ctx& c, const unsigned int* rows_scratch) {
+  k_src_row_write<<<c.g.ny, 256, 0, c.stream>>>(c.g, c.source, rows_scratch, c.source_cells);
+  c.launches += 1;
+}
+
 void launch_sources(Ctx& c) {
   if (c.n_source_cells_global == 0) return;
   ProfScope ps(c, KC_SOURCES);
