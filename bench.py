@@ -380,6 +380,7 @@ def run_gpu(args):
     barrier()
     t0 = time.perf_counter()
     sim.reinit(solid_h, source_h, sink_h, markers_h, scn.rng_state)
+    t_reinit = time.perf_counter() - t0          # (euler_gpu_reinit returns after a stream synchronize)
     for _ in range(args.steps):
         one_step(sim)
         if args.e2e_read == "plane":
@@ -415,7 +416,7 @@ def run_gpu(args):
     sim.close()
     del sim, keep
 
-    t = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, t_e2e * 1e3, t_reinit * 1e3], dtype=torch.float64, device="cuda")
     it = torch.tensor([launches, h2d_rank, d2h_rank, active_cells], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -423,7 +424,7 @@ def run_gpu(args):
     h2d = float(it[1]) / args.steps
     d2h = float(it[2])
     active_cells_all = int(it[3])     # halo-row tiles are counted by both neighbours: slightly above the N=1 figure
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, reinit_ms_max = float(t[0]), float(t[1]), float(t[2])
     ksum = torch.tensor([sum(v[0] for v in prof.values()) / args.steps], dtype=torch.float64, device="cuda")
     ksums = [torch.zeros_like(ksum) for _ in range(world)]
     if world > 1:
@@ -502,6 +503,7 @@ def run_gpu(args):
             "gpu_launches": launches_all,
             "e2e": {"value": cells * args.steps / (e2e_ms_max * 1e-3), "unit": "cell-updates/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "reinit_ms": round(reinit_ms_max, 2), "steps_ms": round(e2e_ms_max - reinit_ms_max, 2),
                     "note": "euler_gpu_reinit (sim_init hand-over: H2D of masks + seeded markers from pinned host arrays) "
                             "+ K sub-steps + per-step D2H of " + ("the whole count plane" if args.e2e_read == "plane" else
                             "the window of the count plane that draw_rows() reads (main.c:917-920, 240x67 terminal: "
