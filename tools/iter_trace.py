@@ -9,7 +9,6 @@ the row loop, the spread of block ends and the epilogue (fence + reduction + pos
         tools/iter_trace.py [NX] [NY]                                      # N row slabs
 """
 import os, sys
-os.environ.setdefault("EULER_TRACE", "4096")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
@@ -44,6 +43,7 @@ def analyse(tr):
 
 
 def main():
+    os.environ.setdefault("EULER_TRACE", "4096")      # read by the library when the handle is created
     nx = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     ny = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
